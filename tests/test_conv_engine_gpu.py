@@ -1,0 +1,184 @@
+"""GPU parity of the convolution engine (tcgen05 implicit GEMM + SIMT) through the C ABI.
+
+Checker: torch conv3d in fp32 (TF32 off) on the same bf16-rounded operands.  Every case runs and is
+logged to gpurun_out/conv_engine.log so that one GPU call shows all failures at once.
+"""
+import os
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+pytestmark = pytest.mark.gpu
+
+LOG = []
+
+
+def _log(msg):
+    LOG.append(msg)
+    print(msg, flush=True)
+
+
+def _ref_conv(x, w, k, bias=None):
+    # x (N,D,H,W,Cin) bf16, w (Cout,taps,Cin) bf16 -> fp32 (N,D,H,W,Cout)
+    Cout, taps, Cin = w.shape
+    w5 = w.float().view(Cout, k[0], k[1], k[2], Cin).permute(0, 4, 1, 2, 3).contiguous()
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w5, bias, padding=(k[0] // 2, k[1] // 2, k[2] // 2))
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+def _rel(a, b):
+    return float((a.float() - b.float()).abs().max() / (b.float().abs().max() + 1e-12))
+
+
+FPROP_CASES = [
+    # N, D, H, W, Cin, Cout, k
+    (4, 1, 8, 8, 64, 64, (1, 3, 3)),
+    (2, 4, 8, 8, 64, 128, (3, 3, 3)),
+    (64, 1, 2, 2, 128, 256, (1, 3, 3)),
+    (16, 1, 1, 1, 1024, 512, (1, 1, 1)),
+    (16, 1, 1, 1, 1024, 512, (3, 3, 3)),
+    (8, 1, 16, 16, 32, 32, (1, 3, 3)),
+    (8, 1, 16, 16, 16, 48, (1, 3, 3)),
+    (2, 2, 8, 8, 16, 64, (3, 3, 3)),
+    (3, 3, 6, 10, 64, 64, (3, 3, 3)),
+    (8, 8, 16, 16, 64, 64, (3, 3, 3)),
+    (2, 1, 64, 64, 32, 16, (1, 3, 3)),
+    (4, 2, 4, 4, 256, 512, (3, 3, 3)),
+    (5, 1, 1, 1, 1280, 16, (1, 1, 1)),
+]
+
+
+def _mk(N, D, H, W, Cin, Cout, k, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((N, D, H, W, Cin), device="cuda", generator=g).to(torch.bfloat16)
+    taps = k[0] * k[1] * k[2]
+    w = (torch.randn((Cout, taps, Cin), device="cuda", generator=g) / (taps * Cin) ** 0.5).to(torch.bfloat16)
+    return x, w
+
+
+@pytest.fixture(scope="module", autouse=True)
+def _setup():
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    yield
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/conv_engine.log", "a") as f:
+        f.write("\n".join(LOG) + "\n")
+
+
+@pytest.mark.parametrize("algo", [1, 2], ids=["tc", "simt"])
+@pytest.mark.parametrize("case", FPROP_CASES)
+def test_fprop(case, algo):
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k = case
+    x, w = _mk(*case)
+    y = K.conv_fprop(x, w, k=k, algo=algo)
+    torch.cuda.synchronize()
+    ref = _ref_conv(x, w, k)
+    e = _rel(y, ref)
+    _log("fprop algo=%d case=%s rel=%.3e" % (algo, case, e))
+    assert e < 1.5e-2
+
+
+@pytest.mark.parametrize("algo", [1, 2], ids=["tc", "simt"])
+def test_fprop_epilogue(algo):
+    from txt2vid_b200 import kernels as K
+    case = (2, 4, 8, 8, 64, 128, (3, 3, 3))
+    x, w = _mk(*case, seed=1)
+    bias = torch.randn(128, device="cuda")
+    res = torch.randn((2, 4, 8, 8, 128), device="cuda").to(torch.bfloat16)
+    y = K.conv_fprop(x, w, bias=bias, residual=res, k=case[6], relu=True, out_f32=True, algo=algo)
+    ref = torch.relu(_ref_conv(x, w, case[6], bias) + res.float())
+    e = _rel(y, ref)
+    _log("fprop epilogue algo=%d rel=%.3e" % (algo, e))
+    assert y.dtype == torch.float32 and e < 2e-3
+
+
+@pytest.mark.parametrize("algo", [1, 2], ids=["tc", "simt"])
+@pytest.mark.parametrize("case", FPROP_CASES[:4] + FPROP_CASES[8:10])
+def test_dgrad(case, algo):
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k = case
+    x, w = _mk(*case, seed=2)
+    dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
+    wT = K.pack_dgrad_weight(w.float())
+    dx = K.conv_dgrad(dy, wT, k=k, algo=algo)
+    xr = x.float().requires_grad_(True)
+    yr = _ref_conv(xr, w, k)
+    (gr,) = torch.autograd.grad(yr, xr, dy.float())
+    e = _rel(dx, gr)
+    _log("dgrad algo=%d case=%s rel=%.3e" % (algo, case, e))
+    assert e < 1.5e-2
+
+
+WGRAD_CASES = [
+    (4, 1, 8, 8, 64, 64, (1, 3, 3)),
+    (2, 4, 8, 8, 64, 128, (3, 3, 3)),
+    (64, 1, 2, 2, 128, 256, (1, 3, 3)),
+    (16, 1, 1, 1, 1024, 512, (3, 3, 3)),
+    (3, 3, 6, 10, 64, 64, (3, 3, 3)),
+    (8, 8, 16, 16, 64, 64, (3, 3, 3)),
+    (32, 1, 1, 1, 512, 1024, (1, 1, 1)),
+]
+
+
+@pytest.mark.parametrize("algo", [1, 2], ids=["tc", "simt"])
+@pytest.mark.parametrize("case", WGRAD_CASES + [(8, 1, 16, 16, 32, 48, (1, 3, 3)), (4, 2, 4, 4, 3, 5, (3, 3, 3))])
+def test_wgrad(case, algo):
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k = case
+    if algo == 1 and (Cin % 64 or Cout % 64):
+        pytest.skip("tcgen05 wgrad needs 64-multiples")
+    x, w = _mk(*case, seed=3)
+    dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
+    dw = K.conv_wgrad(dy, x, k=k, algo=algo)
+    wr = w.float().requires_grad_(True)
+    yr = _ref_conv(x, wr, k)
+    (gr,) = torch.autograd.grad(yr, wr, dy.float())
+    e = _rel(dw, gr)
+    _log("wgrad algo=%d case=%s rel=%.3e" % (algo, case, e))
+    assert e < 2e-3
+    dw2 = K.conv_wgrad(dy, x, k=k, out=dw.clone(), accumulate=True, algo=algo)
+    e2 = _rel(dw2, 2 * gr)
+    assert e2 < 2e-3
+
+
+def test_simt_odd_channels():
+    from txt2vid_b200 import kernels as K
+    case = (4, 2, 4, 4, 3, 5, (3, 3, 3))
+    x, w = _mk(*case, seed=4)
+    y = K.conv_fprop(x, w, k=case[6], algo=0)
+    e = _rel(y, _ref_conv(x, w, case[6]))
+    _log("simt odd rel=%.3e" % e)
+    assert e < 1.5e-2
+
+
+def test_perf_probe():
+    """Not a parity test: first timing of the engine on representative TGANv2 shapes."""
+    from txt2vid_b200 import kernels as K
+    shapes = [
+        ("D stem conv2 3^3 64->64 L0 B=256", (256, 16, 8, 8, 64, 64, (3, 3, 3))),
+        ("D down0 conv2 64->128 B=256", (256, 8, 4, 4, 64, 128, (3, 3, 3))),
+        ("G up0 conv1 1024->512 @2x2", (4096, 1, 2, 2, 1024, 512, (1, 3, 3))),
+        ("G up2 conv1 256->128 @8x8", (4096, 1, 8, 8, 256, 128, (1, 3, 3))),
+        ("clstm gate gemm 1024->4096", (256, 1, 1, 1, 1024, 4096, (1, 1, 1))),
+    ]
+    for name, case in shapes:
+        N, D, H, W, Cin, Cout, k = case
+        x, w = _mk(*case, seed=5)
+        dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
+        for what, fn in (("fprop", lambda: K.conv_fprop(x, w, k=k, algo=1)),
+                         ("wgrad", lambda: K.conv_wgrad(dy, x, k=k, algo=1))):
+            for _ in range(3):
+                fn()
+            t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            t0.record()
+            for _ in range(10):
+                fn()
+            t1.record()
+            torch.cuda.synchronize()
+            ms = t0.elapsed_time(t1) / 10
+            live = [kk if ext > 1 else 1 for kk, ext in zip(k, (D, H, W))]
+            fl = 2.0 * N * D * H * W * Cin * Cout * live[0] * live[1] * live[2]
+            _log("perf %-36s %s %.3f ms  %.1f TFLOP/s (live taps)" % (name, what, ms, fl / ms / 1e9))

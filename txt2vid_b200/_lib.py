@@ -1,0 +1,89 @@
+"""ctypes binding of libt2v_b200.so (the C ABI declared in include/t2v.h).
+
+There is no CPU fallback: importing this module without the built library, or calling a kernel
+without a CUDA device, raises.  Build with `python -c "import __graft_entry__ as g; g.build()"`
+(or `make -C txt2vid_b200/csrc`).
+"""
+import ctypes
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libt2v_b200.so")
+
+T2V_OK = 0
+ALGO_AUTO, ALGO_TC, ALGO_SIMT = 0, 1, 2
+EPI_RELU, EPI_OUT_F32 = 1, 2
+
+
+class ConvGeom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "D", "H", "W", "Cin", "Cout", "kd", "kh", "kw")]
+
+
+class T2VError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def lib():
+    """Load the shared library once; fail loudly when it is missing."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise T2VError(
+                "libt2v_b200.so is not built (%s). Run __graft_entry__.build(); there is no fallback path."
+                % LIB_PATH)
+        _lib = ctypes.CDLL(LIB_PATH)
+        _declare(_lib)
+    return _lib
+
+
+c_void_p, c_int, c_i64, c_u32, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32,
+                                          ctypes.c_float)
+_P = c_void_p
+
+# name -> argtypes (restype is int unless listed in _RESTYPES); kept in one table so the CPU test
+# can check that every symbol of include/t2v.h is exported.
+SIGNATURES = {
+    "t2v_version": [],
+    "t2v_launch_count": [],
+    "t2v_conv_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, c_u32, c_int, _P],
+    "t2v_conv_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, c_int, _P],
+    "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],
+    "t2v_cast_f32_to_bf16": [_P, _P, c_i64, _P],
+    "t2v_cast_bf16_to_f32": [_P, _P, c_i64, _P],
+    "t2v_pack_dgrad_weight": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
+}
+_RESTYPES = {"t2v_launch_count": ctypes.c_ulonglong}
+
+
+def _declare(l):
+    for name, argtypes in SIGNATURES.items():
+        fn = getattr(l, name)
+        fn.argtypes = argtypes
+        fn.restype = _RESTYPES.get(name, c_int)
+
+
+def ptr(t):
+    """Device pointer of a tensor (None -> NULL)."""
+    if t is None:
+        return None
+    return ctypes.c_void_p(t.data_ptr())
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def check(rc, what):
+    if rc != T2V_OK:
+        raise T2VError("%s failed with T2V error %d" % (what, rc))
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise T2VError("txt2vid_b200 kernels need CUDA tensors (got %s); there is no CPU path" % t.device)

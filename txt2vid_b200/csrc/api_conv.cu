@@ -1,0 +1,110 @@
+// C-ABI entry points of the convolution engine (declared in include/t2v.h).
+#include "t2v_common.cuh"
+
+namespace t2v {
+unsigned long long g_launch_count = 0;
+
+bool igemm_fprop_supported(const t2v_conv_geom* g);
+bool igemm_wgrad_supported(const t2v_conv_geom* g);
+int igemm_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
+                       uint32_t, cudaStream_t);
+int igemm_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
+                      uint32_t, cudaStream_t);
+int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+
+__global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
+  const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (i + 3 < n) {
+    const float4 v = *reinterpret_cast<const float4*>(s + i);
+    uint2 o;
+    o.x = pack_bf16x2(v.x, v.y);
+    o.y = pack_bf16x2(v.z, v.w);
+    *reinterpret_cast<uint2*>(d + i) = o;
+  } else {
+    for (long long j = i; j < n; ++j) d[j] = f2bf(s[j]);
+  }
+}
+__global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float* __restrict__ d, long long n) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) d[i] = bf2f(s[i]);
+}
+// wT[ci][taps-1-tap][co] = w[co][tap][ci]
+__global__ void pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wT, int Cout,
+                                  int taps, int Cin) {
+  __shared__ float tile[32][33];
+  const int tap = blockIdx.z;
+  const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int co = co0 + r, ci = ci0 + threadIdx.x;
+    tile[r][threadIdx.x] = (co < Cout && ci < Cin) ? w[((long long)co * taps + tap) * Cin + ci] : 0.f;
+  }
+  __syncthreads();
+  for (int r = threadIdx.y; r < 32; r += blockDim.y) {
+    const int ci = ci0 + r, co = co0 + threadIdx.x;
+    if (ci < Cin && co < Cout)
+      wT[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = f2bf(tile[threadIdx.x][r]);
+  }
+}
+}  // namespace t2v
+
+using namespace t2v;
+
+extern "C" {
+
+int t2v_version(void) { return 100; }
+unsigned long long t2v_launch_count(void) { return g_launch_count; }
+
+int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
+                   const void* residual, void* y, uint32_t epi_flags, int algo, void* stream) {
+  if (!g || !x || !w || !y) return T2V_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool tc_ok = igemm_fprop_supported(g);
+  if (algo == T2V_ALGO_TC && !tc_ok) return T2V_ERR_ARG;
+  if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
+  return igemm_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
+}
+
+int t2v_conv_dgrad(const t2v_conv_geom* g, const void* dy, const void* wT, const void* residual,
+                   void* dx, uint32_t epi_flags, int algo, void* stream) {
+  if (!g) return T2V_ERR_ARG;
+  t2v_conv_geom gt = *g;
+  gt.Cin = g->Cout;
+  gt.Cout = g->Cin;
+  return t2v_conv_fprop(&gt, dy, wT, nullptr, residual, dx, epi_flags, algo, stream);
+}
+
+int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
+                   int algo, void* stream) {
+  if (!g || !dy || !x || !dw) return T2V_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const bool tc_ok = igemm_wgrad_supported(g);
+  if (algo == T2V_ALGO_TC && !tc_ok) return T2V_ERR_ARG;
+  if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_wgrad_launch(g, dy, x, dw, accumulate, s);
+  return igemm_wgrad_launch(g, dy, x, dw, accumulate, s);
+}
+
+int t2v_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {
+  if (n <= 0) return T2V_OK;
+  const long long thr = (n + 3) / 4;
+  cast_f32_bf16_kernel<<<(unsigned)((thr + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, reinterpret_cast<__nv_bfloat16*>(dst), n);
+  count_launch();
+  return check_last("cast");
+}
+int t2v_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
+  if (n <= 0) return T2V_OK;
+  cast_bf16_f32_kernel<<<(unsigned)((n + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(src), dst, n);
+  count_launch();
+  return check_last("cast");
+}
+int t2v_pack_dgrad_weight(const float* w, void* wT, int32_t Cout, int32_t taps, int32_t Cin, void* stream) {
+  dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps), block(32, 8);
+  pack_dgrad_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(wT), Cout, taps, Cin);
+  count_launch();
+  return check_last("pack_dgrad");
+}
+
+}  // extern "C"

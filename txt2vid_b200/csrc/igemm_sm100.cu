@@ -1,0 +1,538 @@
+// Implicit-GEMM convolution engine for sm_100a: TMA-fed tcgen05.mma with TMEM accumulators.
+//
+// Replaces every F.conv2d / F.conv3d / F.linear call site on the TGANv2 path of the reference
+// (txt2vid/models/layers.py:174-183,231-237,251; resnet3d.py:12-17; conv_lstm.py:32-38 centre-tap
+// GEMM; tganv2_cond/gen.py:39 Linear) -- all of them stride-1, "same"-padded, kernel 1 or 3.
+//
+// Layout trick: activations are channels-last [N][D][H][W][C] bf16.  A 5-D TMA box
+// (C=BLOCK_K, bw, bh, bd, bn) with bw*bh*bd*bn = 128 lands in shared memory as 128 rows of
+// BLOCK_K*2 bytes -- exactly the canonical K-major swizzled UMMA operand -- and a filter tap is just
+// a coordinate offset; halo / padding comes from TMA out-of-bounds zero fill.  So im2col never
+// exists in memory and the tensor core reads what TMA wrote.
+//
+//   fprop : D[128 pos x BN cout] += A[pos, (tap,ci)] * W[cout, (tap,ci)]      (both K-major)
+//   dgrad : same kernel on dy with the flipped/transposed weight pack
+//   wgrad : D[128 cout x BN cin]  += dy[pos, cout]^T * x[pos+tap, cin]        (both MN-major),
+//           split over position tiles, fp32 atomics into dw[cout][tap][cin]
+//
+// Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
+// warps 2-5 = epilogue (TMEM -> registers -> global).
+#include "t2v_common.cuh"
+
+namespace t2v {
+
+struct IgemmParams {
+  int N, D, H, W, Cin, Cout;
+  int kd, kh, kw, pd, ph, pw;
+  int bn, bd, bh, bw;          // position box (product = rows per k-block)
+  int tn, td, th, tw;          // number of boxes per dim
+  int BN;                      // GEMM-N tile (<= 256, multiple of 16)
+  int lo_d, hi_d, lo_h, hi_h, lo_w, hi_w;  // live tap ranges (dead taps read only padding)
+  int cblocks;                 // Cin / BLOCK_K
+  int num_k_blocks;
+  int stages;
+  uint32_t stage_bytes, a_bytes, b_bytes;
+  uint32_t idesc, tmem_cols;
+  const float* bias;
+  const __nv_bfloat16* residual;
+  void* out;
+  int out_f32, relu;
+  // wgrad only
+  float* dw;
+  int taps_total, splits, tiles_total, atomic_out;
+};
+
+static constexpr int kThreads = 192;
+
+template <int BLOCK_K>
+struct SwizzleOf {
+  static constexpr uint32_t layout = BLOCK_K == 64 ? 2u : (BLOCK_K == 32 ? 4u : 6u);
+  static constexpr uint32_t sbo = 8u * BLOCK_K * 2u;
+};
+
+// ------------------------------------------------------------------------------------ fprop
+template <int BLOCK_K>
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* accum_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  // tile coordinates
+  int mt = blockIdx.x;
+  const int tw_i = mt % p.tw; mt /= p.tw;
+  const int th_i = mt % p.th; mt /= p.th;
+  const int td_i = mt % p.td; mt /= p.td;
+  const int n0 = mt * p.bn, d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
+  const int col0 = blockIdx.y * p.BN;
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nkw = p.hi_w - p.lo_w, nkh = p.hi_h - p.lo_h;
+      for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        int t = kb / p.cblocks;
+        const int c0 = (kb - t * p.cblocks) * BLOCK_K;
+        const int a_w = t % nkw + p.lo_w; t /= nkw;
+        const int a_h = t % nkh + p.lo_h; t /= nkh;
+        const int a_d = t + p.lo_d;
+        const int tap = (a_d * p.kh + a_h) * p.kw + a_w;
+        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+        tma_load_5d(sa, &tmA, &full_bar[stage], c0, w0 + a_w - p.pw, h0 + a_h - p.ph,
+                    d0 + a_d - p.pd, n0);
+        tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + c0, col0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+      mbar_wait(&full_bar[stage], phase);
+      tc_fence_after();
+      if (lane == 0) {
+        const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t sb = sa + p.a_bytes;
+        const uint64_t adesc = make_smem_desc(sa, 0, SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
+        const uint64_t bdesc = make_smem_desc(sb, 0, SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+          umma_bf16_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
+                       (kb | k) != 0 ? 1u : 0u);
+        }
+        umma_commit(&empty_bar[stage]);
+        if (kb == p.num_k_blocks - 1) umma_commit(accum_bar);
+      }
+      __syncwarp();
+      if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes [32*(w%4), +32) = accumulator rows
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int r = row;
+    const int iw = r % p.bw; r /= p.bw;
+    const int ih = r % p.bh; r /= p.bh;
+    const int id = r % p.bd; r /= p.bd;
+    const int n = n0 + r, d = d0 + id, h = h0 + ih, w = w0 + iw;
+    const bool row_ok = (n < p.N) && (d < p.D) && (h < p.H) && (w < p.W);
+    const size_t pos = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
+    mbar_wait(accum_bar, 0);
+    tc_fence_after();
+    for (int c = 0; c < p.BN; c += 16) {
+      uint32_t v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+      tmem_ld_wait();
+      const int col = col0 + c;
+      if (row_ok && col < p.Cout) {
+        float f[16];
+#pragma unroll
+        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+        if (p.bias != nullptr) {
+#pragma unroll
+          for (int j = 0; j < 16; j += 4) {
+            const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+          }
+        }
+        if (p.residual != nullptr) {
+          const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pos * p.Cout + col);
+#pragma unroll
+          for (int j = 0; j < 2; ++j) {
+            const uint4 u = rp[j];
+            const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z),
+                         dd = unpack_bf16x2(u.w);
+            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+            f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += dd.x; f[8 * j + 7] += dd.y;
+          }
+        }
+        if (p.relu) {
+#pragma unroll
+          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+        }
+        if (p.out_f32) {
+          float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pos * p.Cout + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+        } else {
+          uint4* op = reinterpret_cast<uint4*>(reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.Cout + col);
+#pragma unroll
+          for (int j = 0; j < 2; ++j)
+            op[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ wgrad
+// One CTA: output tile dW[co0:co0+128, tap, ci0:ci0+BN] partial-summed over a range of position
+// boxes (64 positions per k-block).  dy box -> A (MN-major, two 64-channel atoms), shifted x box -> B.
+static constexpr int kWgradPos = 64;
+
+__global__ void __launch_bounds__(kThreads, 1)
+igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
+                   const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* accum_bar = empty_bar + p.stages;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum_bar + 1);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int co0 = blockIdx.x * 128;
+  const int ci0 = blockIdx.y * p.BN;
+  const int split = blockIdx.z % p.splits;
+  int t = blockIdx.z / p.splits;
+  const int nkw = p.hi_w - p.lo_w, nkh = p.hi_h - p.lo_h;
+  const int a_w = t % nkw + p.lo_w; t /= nkw;
+  const int a_h = t % nkh + p.lo_h; t /= nkh;
+  const int a_d = t + p.lo_d;
+  const int tap = (a_d * p.kh + a_h) * p.kw + a_w;
+  // position boxes handled by this split
+  const int per = (p.tiles_total + p.splits - 1) / p.splits;
+  const int t_begin = split * per;
+  const int t_end = min(p.tiles_total, t_begin + per);
+  const int nkb = max(0, t_end - t_begin);
+  constexpr uint32_t kBoxBytes = kWgradPos * 128;  // 64 positions x 64 channels x bf16
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmDy);
+    tma_prefetch_desc(&tmX);
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    mbar_init(accum_bar, 1);
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (nkb > 0) {
+    if (warp == 0) {
+      if (lane == 0) {
+        int stage = 0;
+        uint32_t phase = 0;
+        const int nb_boxes = p.BN / 64;
+        for (int kb = 0; kb < nkb; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          int mt = t_begin + kb;
+          const int tw_i = mt % p.tw; mt /= p.tw;
+          const int th_i = mt % p.th; mt /= p.th;
+          const int td_i = mt % p.td; mt /= p.td;
+          const int n0 = mt * p.bn, d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + 2 * kBoxBytes;
+          mbar_expect_tx(&full_bar[stage], (2 + nb_boxes) * kBoxBytes);
+          tma_load_5d(sa, &tmDy, &full_bar[stage], co0, w0, h0, d0, n0);
+          tma_load_5d(sa + kBoxBytes, &tmDy, &full_bar[stage], co0 + 64, w0, h0, d0, n0);
+          for (int j = 0; j < nb_boxes; ++j)
+            tma_load_5d(sb + j * kBoxBytes, &tmX, &full_bar[stage], ci0 + 64 * j, w0 + a_w - p.pw,
+                        h0 + a_h - p.ph, d0 + a_d - p.pd, n0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    } else if (warp == 1) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        if (lane == 0) {
+          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
+          const uint32_t sb = sa + 2 * kBoxBytes;
+          // MN-major, 128B swizzle: atom = 64 channels x 8 positions (1024 B); SBO = next 8 positions,
+          // LBO = next 64-channel atom (one TMA box further).
+          const uint64_t adesc = make_smem_desc(sa, kBoxBytes, 1024, 2);
+          const uint64_t bdesc = make_smem_desc(sb, kBoxBytes, 1024, 2);
+#pragma unroll
+          for (int k = 0; k < kWgradPos / 16; ++k) {
+            // 16 positions further = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
+            umma_bf16_ss(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), p.idesc,
+                         (kb | k) != 0 ? 1u : 0u);
+          }
+          umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(accum_bar);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    } else {
+      const int q = warp & 3;
+      const int co = co0 + q * 32 + lane;
+      mbar_wait(accum_bar, 0);
+      tc_fence_after();
+      for (int c = 0; c < p.BN; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)c, v);
+        tmem_ld_wait();
+        const int ci = ci0 + c;
+        if (co < p.Cout && ci < p.Cin) {
+          float* dst = p.dw + ((size_t)co * p.taps_total + tap) * p.Cin + ci;
+          if (p.atomic_out) {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              reinterpret_cast<float4*>(dst)[j] =
+                  make_float4(__uint_as_float(v[4 * j]), __uint_as_float(v[4 * j + 1]),
+                              __uint_as_float(v[4 * j + 2]), __uint_as_float(v[4 * j + 3]));
+          }
+        }
+      }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ host side
+typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                        const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                        const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                        CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static PFN_tmapEncodeTiled get_encode() {
+  static PFN_tmapEncodeTiled fn = nullptr;
+  static bool tried = false;
+  if (!tried) {
+    tried = true;
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_tmapEncodeTiled>(ptr);
+  }
+  return fn;
+}
+
+static CUtensorMapSwizzle swizzle_for(int inner_bytes) {
+  return inner_bytes == 128 ? CU_TENSOR_MAP_SWIZZLE_128B
+                            : (inner_bytes == 64 ? CU_TENSOR_MAP_SWIZZLE_64B : CU_TENSOR_MAP_SWIZZLE_32B);
+}
+
+// activation CL [N][D][H][W][C] bf16, box (bc, bw, bh, bd, bn)
+static int make_act_map(CUtensorMap* m, const void* base, int N, int D, int H, int W, int C, int bc,
+                        int bw, int bh, int bd, int bn) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return T2V_ERR_DRIVER;
+  cuuint64_t gdim[5] = {(cuuint64_t)C, (cuuint64_t)W, (cuuint64_t)H, (cuuint64_t)D, (cuuint64_t)N};
+  cuuint64_t gstr[4] = {(cuuint64_t)C * 2, (cuuint64_t)W * C * 2, (cuuint64_t)H * W * C * 2,
+                        (cuuint64_t)D * H * W * C * 2};
+  cuuint32_t box[5] = {(cuuint32_t)bc, (cuuint32_t)bw, (cuuint32_t)bh, (cuuint32_t)bd, (cuuint32_t)bn};
+  cuuint32_t es[5] = {1, 1, 1, 1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 5, const_cast<void*>(base), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bc * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? T2V_OK : T2V_ERR_ARG;
+}
+
+// weight [rows][K] bf16 (K contiguous), box (bk, brows)
+static int make_w_map(CUtensorMap* m, const void* base, int rows, int K, int bk, int brows) {
+  PFN_tmapEncodeTiled enc = get_encode();
+  if (!enc) return T2V_ERR_DRIVER;
+  cuuint64_t gdim[2] = {(cuuint64_t)K, (cuuint64_t)rows};
+  cuuint64_t gstr[1] = {(cuuint64_t)K * 2};
+  cuuint32_t box[2] = {(cuuint32_t)bk, (cuuint32_t)brows};
+  cuuint32_t es[2] = {1, 1};
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstr, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle_for(bk * 2), CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS ? T2V_OK : T2V_ERR_ARG;
+}
+
+static int pow2_floor(int v) {
+  int r = 1;
+  while (r * 2 <= v) r *= 2;
+  return r;
+}
+static int pow2_ceil(int v) {
+  int r = 1;
+  while (r < v) r *= 2;
+  return r;
+}
+
+// Choose a position box (bn,bd,bh,bw) with product == rows (a power of two).
+static void choose_box(int rows, int N, int D, int H, int W, int* bn, int* bd, int* bh, int* bw) {
+  int rem = rows;
+  *bw = pow2_ceil(W) < rem ? pow2_ceil(W) : rem; rem /= *bw;
+  *bh = pow2_ceil(H) < rem ? pow2_ceil(H) : rem; rem /= *bh;
+  *bd = pow2_ceil(D) < rem ? pow2_ceil(D) : rem; rem /= *bd;
+  *bn = rem;
+  (void)N;
+}
+
+static void live_taps(int k, int extent, int* lo, int* hi) {
+  // a +-1 tap along an axis of extent 1 only ever reads padding
+  if (k == 3 && extent == 1) { *lo = 1; *hi = 2; }
+  else { *lo = 0; *hi = k; }
+}
+
+bool igemm_fprop_supported(const t2v_conv_geom* g) {
+  if (g->Cin % 16 || g->Cout % 16) return false;
+  if (g->Cin <= 0 || g->Cout <= 0 || g->N <= 0) return false;
+  auto okk = [](int k) { return k == 1 || k == 3; };
+  return okk(g->kd) && okk(g->kh) && okk(g->kw);
+}
+
+bool igemm_wgrad_supported(const t2v_conv_geom* g) {
+  return igemm_fprop_supported(g) && g->Cin % 64 == 0 && g->Cout % 64 == 0;
+}
+
+static int fill_common(IgemmParams& p, const t2v_conv_geom* g) {
+  p.N = g->N; p.D = g->D; p.H = g->H; p.W = g->W; p.Cin = g->Cin; p.Cout = g->Cout;
+  p.kd = g->kd; p.kh = g->kh; p.kw = g->kw;
+  p.pd = g->kd / 2; p.ph = g->kh / 2; p.pw = g->kw / 2;
+  live_taps(g->kd, g->D, &p.lo_d, &p.hi_d);
+  live_taps(g->kh, g->H, &p.lo_h, &p.hi_h);
+  live_taps(g->kw, g->W, &p.lo_w, &p.hi_w);
+  p.taps_total = g->kd * g->kh * g->kw;
+  return (p.hi_d - p.lo_d) * (p.hi_h - p.lo_h) * (p.hi_w - p.lo_w);
+}
+
+int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
+                       const void* residual, void* y, uint32_t flags, cudaStream_t stream) {
+  if (!igemm_fprop_supported(g)) return T2V_ERR_ARG;
+  IgemmParams p{};
+  const int ntaps = fill_common(p, g);
+  const int BLOCK_K = (g->Cin % 64 == 0) ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
+  choose_box(128, g->N, g->D, g->H, g->W, &p.bn, &p.bd, &p.bh, &p.bw);
+  p.tn = (g->N + p.bn - 1) / p.bn; p.td = (g->D + p.bd - 1) / p.bd;
+  p.th = (g->H + p.bh - 1) / p.bh; p.tw = (g->W + p.bw - 1) / p.bw;
+  p.BN = g->Cout >= 128 ? 128 : g->Cout;
+  p.cblocks = g->Cin / BLOCK_K;
+  p.num_k_blocks = ntaps * p.cblocks;
+  p.a_bytes = 128u * BLOCK_K * 2u;
+  p.b_bytes = (uint32_t)p.BN * BLOCK_K * 2u;
+  p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
+  int stages = (int)(196608u / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  if (stages > p.num_k_blocks) stages = p.num_k_blocks < 2 ? 2 : p.num_k_blocks;
+  p.stages = stages;
+  p.idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);
+  p.tmem_cols = (uint32_t)(pow2_ceil(p.BN) < 32 ? 32 : pow2_ceil(p.BN));
+  p.bias = bias;
+  p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
+  p.out = y;
+  p.out_f32 = (flags & T2V_EPI_OUT_F32) ? 1 : 0;
+  p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
+
+  CUtensorMap tmA, tmB;
+  int rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, g->Cin, BLOCK_K, p.bw, p.bh, p.bd, p.bn);
+  if (rc) return rc;
+  rc = make_w_map(&tmB, w, g->Cout, p.taps_total * g->Cin, BLOCK_K, p.BN);
+  if (rc) return rc;
+
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
+  dim3 grid(p.tn * p.td * p.th * p.tw, (g->Cout + p.BN - 1) / p.BN, 1);
+  auto launch = [&](auto kern) {
+    cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+  };
+  if (BLOCK_K == 64) launch(igemm_fprop_kernel<64>);
+  else if (BLOCK_K == 32) launch(igemm_fprop_kernel<32>);
+  else launch(igemm_fprop_kernel<16>);
+  count_launch();
+  return check_last("igemm_fprop");
+}
+
+int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
+                       cudaStream_t stream) {
+  if (!igemm_wgrad_supported(g)) return T2V_ERR_ARG;
+  IgemmParams p{};
+  const int ntaps = fill_common(p, g);
+  choose_box(kWgradPos, g->N, g->D, g->H, g->W, &p.bn, &p.bd, &p.bh, &p.bw);
+  p.tn = (g->N + p.bn - 1) / p.bn; p.td = (g->D + p.bd - 1) / p.bd;
+  p.th = (g->H + p.bh - 1) / p.bh; p.tw = (g->W + p.bw - 1) / p.bw;
+  p.tiles_total = p.tn * p.td * p.th * p.tw;
+  p.BN = g->Cin >= 128 ? 128 : 64;
+  const int mtiles = (g->Cout + 127) / 128, ntiles = (g->Cin + p.BN - 1) / p.BN;
+  const int base_ctas = mtiles * ntiles * ntaps;
+  int splits = (2 * 148 + base_ctas - 1) / base_ctas;
+  const int max_splits = (p.tiles_total + 3) / 4;  // keep >= 4 k-blocks per CTA
+  if (splits > max_splits) splits = max_splits;
+  if (splits < 1) splits = 1;
+  p.splits = splits;
+  p.a_bytes = 2u * kWgradPos * 128u;
+  p.b_bytes = (uint32_t)(p.BN / 64) * kWgradPos * 128u;
+  p.stage_bytes = p.a_bytes + p.b_bytes;
+  int stages = (int)(196608u / p.stage_bytes);
+  if (stages > 8) stages = 8;
+  p.stages = stages;
+  p.idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
+  p.tmem_cols = (uint32_t)(p.BN < 32 ? 32 : p.BN);
+  p.dw = dw;
+  p.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
+
+  const size_t dw_elems = (size_t)g->Cout * p.taps_total * g->Cin;
+  if (!accumulate && (p.atomic_out || ntaps < p.taps_total))
+    cudaMemsetAsync(dw, 0, dw_elems * sizeof(float), stream);
+
+  CUtensorMap tmDy, tmX;
+  int rc = make_act_map(&tmDy, dy, g->N, g->D, g->H, g->W, g->Cout, 64, p.bw, p.bh, p.bd, p.bn);
+  if (rc) return rc;
+  rc = make_act_map(&tmX, x, g->N, g->D, g->H, g->W, g->Cin, 64, p.bw, p.bh, p.bd, p.bn);
+  if (rc) return rc;
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
+  dim3 grid(mtiles, ntiles, ntaps * splits);
+  cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  igemm_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDy, tmX, p);
+  count_launch();
+  return check_last("igemm_wgrad");
+}
+
+}  // namespace t2v
