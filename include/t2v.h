@@ -71,9 +71,80 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
 /* fp32 master weight [Cout][taps][Cin] -> bf16 same layout (fprop operand)                    */
 int t2v_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int t2v_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
-/* fp32 master weight [Cout][taps][Cin] -> bf16 [Cin][taps reversed][Cout] (dgrad operand)     */
-int t2v_pack_dgrad_weight(const float* w, void* wT, int32_t Cout, int32_t taps, int32_t Cin,
+/* fp32 master weight [Cout][taps][Cin] -> bf16 [CinP][taps reversed][CoutP] (dgrad operand); the
+ * destination must be pre-zeroed when CinP > Cin or CoutP > Cout                                 */
+int t2v_pack_dgrad_weight(const float* w, void* wT, int32_t Cout, int32_t taps, int32_t Cin, int32_t CoutP,
                           void* stream);
+/* channel-padded operand packs for the convs whose channel count is not a multiple of 16
+ * (RGB stem conv resnet3d.py:12,17; render conv layers.py:251; attention 1x1 convs)              */
+int t2v_pack_weight_padded(const float* w, void* dst, int32_t Cout, int32_t taps, int32_t Cin, int32_t CinP,
+                           void* stream);
+int t2v_unpack_wgrad_padded(const float* src, float* dst, int32_t Cout, int32_t taps, int32_t Cin, int32_t CinP,
+                            void* stream);
+
+/* activations / pooling / layout (HBM-bound; all tensors bf16 CL unless noted) ---------------- */
+/* nn.ReLU: layers.py:172,176,230,232,250; n = element count (multiple of 8)                      */
+int t2v_relu_fwd(const void* x, void* y, int64_t n, void* stream);
+/* dx = dy * (ref > 0); ref = the ReLU's input or output                                          */
+int t2v_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, void* stream);
+/* F.avg_pool3d, count_include_pad, kernel <= stride (layers.py:202-217, resnet3d.py:16,18);
+ * in_shape = {N,D,H,W,C}; y = pool(x) (+ residual, y-shaped, may be NULL)                        */
+int t2v_avgpool_fwd(const void* x, const void* residual, void* y, const int32_t* in_shape, const int32_t* kernel,
+                    const int32_t* stride, const int32_t* pad, void* stream);
+int t2v_avgpool_bwd(const void* dy, void* dx, const int32_t* in_shape, const int32_t* kernel, const int32_t* stride,
+                    const int32_t* pad, void* stream);
+/* nn.Upsample(scale_factor=2) nearest on (N,H,W,C) (layers.py:168,180) and its adjoint            */
+int t2v_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int t2v_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+/* fp32 (N,C,S) <-> bf16 (N,S,Cp) with zero channel padding (D input / G output boundary)         */
+int t2v_nchw_to_cl(const float* x, void* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
+int t2v_cl_to_nchw(const void* x, float* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
+/* out[c] = sum_rows x[row,c] (bias gradients)                                                    */
+int t2v_sum_rows(const void* x, float* out, int64_t P, int32_t C, void* stream);
+/* torch.sum(x,[2,3,4]) resnet3d.py:48: out fp32 (N,C) = sum_s x (N,S,C); and its adjoint          */
+int t2v_sum_spatial(const void* x, float* out, int64_t N, int64_t S, int32_t C, void* stream);
+int t2v_broadcast_spatial(const float* g, void* y, int64_t N, int64_t S, int32_t C, void* stream);
+
+/* BatchNorm2d in train() fused with ReLU and nearest x2 (layers.py:171-173,175-176,249-250) ---- */
+/* stats fp32 [2C] = {sum, sum of squares} over P rows                                            */
+int t2v_bn_stats(const void* x, float* stats, int64_t P, int32_t C, void* stream);
+/* mean_invstd [2C], scale_shift [2C]; updates running stats in place (NULL to skip)               */
+int t2v_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
+                    float* running_var, float* mean_invstd, float* scale_shift, int32_t C, int64_t count,
+                    float eps, float momentum, void* stream);
+/* y (N,up*H,up*W,C) = [relu](x*scale+shift) nearest-upsampled by up in {1,2}                      */
+int t2v_bn_apply(const void* x, const float* scale_shift, void* y, int64_t N, int32_t H, int32_t W, int32_t C,
+                 int32_t relu, int32_t up, void* stream);
+/* red fp32 [2C] = {dbeta, dgamma}; dx (N,H,W,C)                                                   */
+int t2v_bn_bwd(const void* dy, const void* x, const float* scale_shift, const float* mean_invstd, float* red,
+               void* dx, int64_t N, int32_t H, int32_t W, int32_t C, int32_t relu, int32_t up, void* stream);
+
+/* RenderBlock tail: tanh + (B*T,H,W,Cp) bf16 -> (B,C,T,H,W) fp32 (layers.py:252, gen.py:116-119)  */
+int t2v_render_fwd(const void* pre, float* y, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, int32_t Cp,
+                   void* stream);
+int t2v_render_bwd(const float* dy, const float* y, void* dpre, int32_t B, int32_t T, int32_t H, int32_t W,
+                   int32_t C, int32_t Cp, void* stream);
+
+/* bit-exact index kernels ------------------------------------------------------------------- */
+/* Subsample x[::sn, :, bt::st] (layers.py:106-111) on merged-frame maps of frame_bytes each;
+ * scatter = 1 runs the adjoint (y = zero-filled source-shaped gradient)                           */
+int t2v_gather_frames(const void* x, void* y, int32_t B, int32_t T, int64_t frame_bytes, int32_t sn, int32_t st,
+                      int32_t bt, int32_t scatter, void* stream);
+/* one level of the real-video pyramid (gan/trainer.py:131-165): fp32 (B,C,T,H,W) ->
+ * (ceil(B/sn), C, ceil((T-bt)/st), Ho, Wo) with nearest resize src = floor(dst*in/out)            */
+int t2v_pyramid_level(const float* x, float* y, const int32_t* in_shape, int32_t Ho, int32_t Wo, int32_t sn,
+                      int32_t st, int32_t bt, void* stream);
+
+/* LSTM cell update (conv_lstm.py:32-38; txt/basic.py:56 nn.LSTM): gates fp32 (P,4H) = [i|f|g|o]   */
+int t2v_lstm_cell_fwd(const float* gates, const float* c_prev, float* c, void* h, float* h32, int64_t P, int32_t Hd,
+                      void* stream);
+int t2v_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c, const float* dh, const float* dc_next,
+                      void* dgates, float* dc_prev, int64_t P, int32_t Hd, void* stream);
+
+/* torch.optim.Adam (train/gan.py:93-94), multi-tensor: host arrays of `count` device pointers      */
+int t2v_adam_step(int32_t count, float* const* host_params, const float* const* host_grads, float* const* host_m,
+                  float* const* host_v, const int64_t* host_sizes, float lr, float beta1, float beta2, float eps,
+                  int32_t step, float grad_scale, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,257 @@
+"""TEST-ONLY executable specification of txt2vid_b200/kernels.py in plain PyTorch.
+
+Same function names, argument meaning, layouts and rounding points (bf16 storage, fp32 math) as the
+C-ABI wrappers, but runs on any device.  Two uses:
+  * `-m "not gpu"` tests monkeypatch `txt2vid_b200.ops.K` with this module to check the autograd
+    formulas (incl. the double backward the gradient penalty needs) against the oracle on CPU;
+  * `-m gpu` tests compare every real kernel against these functions on the same inputs.
+The product never imports this file.
+"""
+import torch
+import torch.nn.functional as F
+
+F32 = torch.float32
+# Storage dtype of activations / operand packs.  bf16 = the product's rounding points; the CPU tests also
+# run with float32 storage to check the autograd formulas against the oracle at the fp32 bar (1e-3).
+STORE = torch.bfloat16
+
+
+def set_store_dtype(dt):
+    global STORE
+    STORE = dt
+
+
+def _w5(w, k):
+    Cout, taps, Cin = w.shape
+    return w.float().view(Cout, k[0], k[1], k[2], Cin).permute(0, 4, 1, 2, 3)
+
+
+def _pad(k):
+    return (k[0] // 2, k[1] // 2, k[2] // 2)
+
+
+def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=False, algo=0):
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), _w5(w, k), bias, padding=_pad(k)).permute(0, 2, 3, 4, 1)
+    if residual is not None:
+        y = y + residual.float()
+    if relu:
+        y = torch.relu(y)
+    y = y.contiguous()
+    return y if out_f32 else y.to(STORE)
+
+
+def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0):
+    # wT (Cin,taps,Cout) with reversed taps == the forward weight of the adjoint convolution
+    return conv_fprop(dy, wT, None, residual, k, relu, out_f32)
+
+
+def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
+    Cout, Cin = dy.shape[-1], x.shape[-1]
+    taps = k[0] * k[1] * k[2]
+    xin = x.float().permute(0, 4, 1, 2, 3)
+    g = torch.nn.grad.conv3d_weight(xin, (Cout, Cin) + tuple(k), dy.float().permute(0, 4, 1, 2, 3), padding=_pad(k))
+    g = g.permute(0, 2, 3, 4, 1).reshape(Cout, taps, Cin).contiguous()
+    if out is None:
+        return g
+    if accumulate:
+        out += g
+    else:
+        out.copy_(g)
+    return out
+
+
+def cast_bf16(src):
+    return src.to(STORE)
+
+
+def cast_f32(src):
+    return src.float()
+
+
+def pack_weight(w, CoutP=None, CinP=None):
+    Cout, taps, Cin = w.shape
+    CoutP, CinP = CoutP or Cout, CinP or Cin
+    dst = torch.zeros((CoutP, taps, CinP), dtype=STORE, device=w.device)
+    dst[:Cout, :, :Cin] = w.to(STORE)
+    return dst
+
+
+def pack_dgrad_weight(w, CoutP=None, CinP=None):
+    Cout, taps, Cin = w.shape
+    CoutP, CinP = CoutP or Cout, CinP or Cin
+    wT = torch.zeros((CinP, taps, CoutP), dtype=STORE, device=w.device)
+    wT[:Cin, :, :Cout] = w.to(STORE).flip(1).permute(2, 1, 0)
+    return wT
+
+
+def unpack_wgrad(dwp, Cout, Cin):
+    return dwp[:Cout, :, :Cin].contiguous()
+
+
+def relu_fwd(x):
+    return torch.relu(x)
+
+
+def relu_bwd(dy, ref):
+    return torch.where(ref > 0, dy, torch.zeros_like(dy))
+
+
+def pool_out_shape(in_shape, kernel, stride, pad):
+    N, D, H, W, C = in_shape
+    o = [(s + 2 * p - k) // st + 1 for s, k, st, p in zip((D, H, W), kernel, stride, pad)]
+    return (N, o[0], o[1], o[2], C)
+
+
+def avgpool_fwd(x, kernel, stride, pad, residual=None):
+    y = F.avg_pool3d(x.float().permute(0, 4, 1, 2, 3), tuple(kernel), tuple(stride), tuple(pad)).permute(0, 2, 3, 4, 1)
+    if residual is not None:
+        y = y + residual.float()
+    return y.contiguous().to(STORE)
+
+
+def avgpool_bwd(dy, in_shape, kernel, stride, pad):
+    with torch.enable_grad():
+        x = torch.zeros((in_shape[0], in_shape[4], in_shape[1], in_shape[2], in_shape[3]), requires_grad=True,
+                        device=dy.device)
+        y = F.avg_pool3d(x, tuple(kernel), tuple(stride), tuple(pad))
+        (g,) = torch.autograd.grad(y, x, dy.detach().float().permute(0, 4, 1, 2, 3))
+    return g.permute(0, 2, 3, 4, 1).contiguous().to(STORE)
+
+
+def upsample2x_fwd(x):
+    return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3).contiguous()
+
+
+def upsample2x_bwd(dy):
+    N, D, H2, W2, C = dy.shape
+    return dy.float().view(N, D, H2 // 2, 2, W2 // 2, 2, C).sum(dim=(3, 5)).to(STORE)
+
+
+def nchw_to_cl(x, Cp):
+    N, C, D, H, W = x.shape
+    y = torch.zeros((N, D, H, W, Cp), dtype=STORE, device=x.device)
+    y[..., :C] = x.permute(0, 2, 3, 4, 1).to(STORE)
+    return y
+
+
+def cl_to_nchw(x, C):
+    return x[..., :C].permute(0, 4, 1, 2, 3).float().contiguous()
+
+
+def sum_rows(x):
+    return x.float().reshape(-1, x.shape[-1]).sum(0)
+
+
+def sum_spatial(x):
+    return x.float().reshape(x.shape[0], -1, x.shape[-1]).sum(1)
+
+
+def broadcast_spatial(g, shape):
+    N, C = g.shape
+    return g.view(N, 1, 1, 1, C).expand(tuple(shape)).to(STORE).contiguous()
+
+
+def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, momentum=0.1, training=True):
+    N, D, H, W, C = x.shape
+    xf = x.float().reshape(-1, C)
+    if training:
+        P = xf.shape[0]
+        mean = xf.mean(0)
+        var = (xf * xf).mean(0) - mean * mean
+        var = var.clamp_min(0)
+        if running_mean is not None:
+            unbiased = var * P / (P - 1) if P > 1 else var
+            running_mean.mul_(1 - momentum).add_(momentum * mean)
+            running_var.mul_(1 - momentum).add_(momentum * unbiased)
+    else:
+        mean, var = running_mean.float(), running_var.float()
+    invstd = torch.rsqrt(var + eps)
+    scale = gamma * invstd
+    shift = beta - mean * scale
+    y = x.float() * scale + shift
+    if relu:
+        y = torch.relu(y)
+    y = y.to(STORE)
+    if up == 2:
+        y = upsample2x_fwd(y)
+    return y.contiguous(), torch.cat((mean, invstd)), torch.cat((scale, shift))
+
+
+def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
+    N, D, H, W, C = x.shape
+    mean, invstd = mean_invstd[:C], mean_invstd[C:]
+    scale, shift = scale_shift[:C], scale_shift[C:]
+    g = dy.float()
+    if up == 2:
+        g = g.view(N, D, H, 2, W, 2, C).sum(dim=(3, 5))
+    xf = x.float()
+    if relu:
+        g = torch.where(xf * scale + shift > 0, g, torch.zeros_like(g))
+    xhat = (xf - mean) * invstd
+    P = N * D * H * W
+    dbeta = g.reshape(-1, C).sum(0)
+    dgamma = (g * xhat).reshape(-1, C).sum(0)
+    dx = scale * (g - dbeta / P - xhat * dgamma / P)
+    return dx.to(STORE), dgamma, dbeta
+
+
+def render_fwd(pre, B, T, C):
+    BT, D, H, W, Cp = pre.shape
+    return torch.tanh(pre.float()[..., :C]).view(B, T, H, W, C).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def render_bwd(dy, y, Cp):
+    B, C, T, H, W = y.shape
+    g = (dy * (1 - y * y)).permute(0, 2, 3, 4, 1).reshape(B * T, 1, H, W, C)
+    out = torch.zeros((B * T, 1, H, W, Cp), dtype=STORE, device=y.device)
+    out[..., :C] = g.to(STORE)
+    return out
+
+
+def gather_frames(x, B, T, bt, sn=2, st=2):
+    x5 = x.view((B, T) + tuple(x.shape[1:]))
+    y = x5[::sn, bt::st]
+    return y.reshape((-1,) + tuple(x.shape[1:])).contiguous()
+
+
+def scatter_frames(dy, B, T, bt, sn=2, st=2):
+    dx = torch.zeros((B, T) + tuple(dy.shape[1:]), dtype=dy.dtype, device=dy.device)
+    Bo = (B + sn - 1) // sn
+    dx[::sn, bt::st] = dy.view((Bo, -1) + tuple(dy.shape[1:]))
+    return dx.view((B * T,) + tuple(dy.shape[1:]))
+
+
+def pyramid_level(x, Ho, Wo, sn=1, st=1, bt=0):
+    B, C, T, H, W = x.shape
+    ih = (torch.arange(Ho, device=x.device) * H) // Ho
+    iw = (torch.arange(Wo, device=x.device) * W) // Wo
+    return x[::sn, :, bt::st][:, :, :, ih][:, :, :, :, iw].contiguous()
+
+
+def lstm_cell_fwd(gates, c_prev, want_h32=False):
+    gi, gf, gg, go = gates.chunk(4, dim=-1)
+    cp = c_prev if c_prev is not None else torch.zeros_like(gi)
+    c = torch.sigmoid(gf) * cp + torch.sigmoid(gi) * torch.tanh(gg)
+    h = torch.sigmoid(go) * torch.tanh(c)
+    return c.contiguous(), h.to(STORE).contiguous(), (h.contiguous() if want_h32 else None)
+
+
+def lstm_cell_bwd(gates, c_prev, c, dh, dc_next):
+    gi, gf, gg, go = [t for t in gates.chunk(4, dim=-1)]
+    i, f, g, o = torch.sigmoid(gi), torch.sigmoid(gf), torch.tanh(gg), torch.sigmoid(go)
+    cp = c_prev if c_prev is not None else torch.zeros_like(c)
+    tc = torch.tanh(c)
+    dhv = dh if dh is not None else torch.zeros_like(c)
+    dc = (dc_next if dc_next is not None else torch.zeros_like(c)) + dhv * o * (1 - tc * tc)
+    dg = torch.cat((dc * g * i * (1 - i), dc * cp * f * (1 - f), dc * i * (1 - g * g), dhv * tc * o * (1 - o)), dim=-1)
+    return dg.to(STORE).contiguous(), (dc * f).contiguous()
+
+
+def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
+    with torch.no_grad():
+        for p, g, m, v in zip(params, grads, ms, vs):
+            g = g * grad_scale
+            m.mul_(beta1).add_(g, alpha=1 - beta1)
+            v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
+            p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)

@@ -44,6 +44,9 @@ def lib():
 c_void_p, c_int, c_i64, c_u32, c_float = (ctypes.c_void_p, ctypes.c_int, ctypes.c_int64, ctypes.c_uint32,
                                           ctypes.c_float)
 _P = c_void_p
+c_i32 = ctypes.c_int32
+_I32P = ctypes.POINTER(ctypes.c_int32)
+_PP = ctypes.POINTER(ctypes.c_void_p)
 
 # name -> argtypes (restype is int unless listed in _RESTYPES); kept in one table so the CPU test
 # can check that every symbol of include/t2v.h is exported.
@@ -55,7 +58,32 @@ SIGNATURES = {
     "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],
     "t2v_cast_f32_to_bf16": [_P, _P, c_i64, _P],
     "t2v_cast_bf16_to_f32": [_P, _P, c_i64, _P],
-    "t2v_pack_dgrad_weight": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
+    "t2v_pack_dgrad_weight": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
+    "t2v_pack_weight_padded": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
+    "t2v_unpack_wgrad_padded": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
+    "t2v_relu_fwd": [_P, _P, c_i64, _P],
+    "t2v_relu_bwd": [_P, _P, _P, c_i64, _P],
+    "t2v_avgpool_fwd": [_P, _P, _P, _I32P, _I32P, _I32P, _I32P, _P],
+    "t2v_avgpool_bwd": [_P, _P, _I32P, _I32P, _I32P, _I32P, _P],
+    "t2v_upsample2x_fwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_upsample2x_bwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_nchw_to_cl": [_P, _P, c_i64, c_i32, c_i64, c_i32, _P],
+    "t2v_cl_to_nchw": [_P, _P, c_i64, c_i32, c_i64, c_i32, _P],
+    "t2v_sum_rows": [_P, _P, c_i64, c_i32, _P],
+    "t2v_sum_spatial": [_P, _P, c_i64, c_i64, c_i32, _P],
+    "t2v_broadcast_spatial": [_P, _P, c_i64, c_i64, c_i32, _P],
+    "t2v_bn_stats": [_P, _P, c_i64, c_i32, _P],
+    "t2v_bn_finalize": [_P, _P, _P, _P, _P, _P, _P, c_i32, c_i64, c_float, c_float, _P],
+    "t2v_bn_apply": [_P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_bn_bwd": [_P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_render_fwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_render_bwd": [_P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_gather_frames": [_P, _P, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_pyramid_level": [_P, _P, _I32P, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_lstm_cell_fwd": [_P, _P, _P, _P, _P, c_i64, c_i32, _P],
+    "t2v_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, _P],
+    "t2v_adam_step": [c_i32, _PP, _PP, _PP, _PP, ctypes.POINTER(c_i64), c_float, c_float, c_float, c_float, c_i32,
+                      c_float, _P],
 }
 _RESTYPES = {"t2v_launch_count": ctypes.c_ulonglong}
 

@@ -29,9 +29,9 @@ __global__ void cast_bf16_f32_kernel(const __nv_bfloat16* __restrict__ s, float*
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i < n) d[i] = bf2f(s[i]);
 }
-// wT[ci][taps-1-tap][co] = w[co][tap][ci]
+// wT[ci][taps-1-tap][co] = w[co][tap][ci]; destination is [CinP][taps][CoutP] (padding pre-zeroed by caller)
 __global__ void pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ wT, int Cout,
-                                  int taps, int Cin) {
+                                  int taps, int Cin, int CoutP) {
   __shared__ float tile[32][33];
   const int tap = blockIdx.z;
   const int co0 = blockIdx.y * 32, ci0 = blockIdx.x * 32;
@@ -43,8 +43,26 @@ __global__ void pack_dgrad_kernel(const float* __restrict__ w, __nv_bfloat16* __
   for (int r = threadIdx.y; r < 32; r += blockDim.y) {
     const int ci = ci0 + r, co = co0 + threadIdx.x;
     if (ci < Cin && co < Cout)
-      wT[((long long)ci * taps + (taps - 1 - tap)) * Cout + co] = f2bf(tile[threadIdx.x][r]);
+      wT[((long long)ci * taps + (taps - 1 - tap)) * CoutP + co] = f2bf(tile[threadIdx.x][r]);
   }
+}
+// dst bf16 [CoutP][taps][CinP] <- src fp32 [Cout][taps][Cin] (padding pre-zeroed by caller)
+__global__ void pack_pad_kernel(const float* __restrict__ w, __nv_bfloat16* __restrict__ dst, int taps, int Cin,
+                                int CinP, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = (int)(i % Cin);
+  const long long r = i / Cin;  // co*taps + tap
+  dst[r * CinP + ci] = f2bf(w[i]);
+}
+// dst fp32 [Cout][taps][Cin] <- src fp32 [CoutP][taps][CinP]
+__global__ void unpack_pad_kernel(const float* __restrict__ src, float* __restrict__ dst, int taps, int Cin,
+                                  int CinP, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = (int)(i % Cin);
+  const long long r = i / Cin;
+  dst[i] = src[r * CinP + ci];
 }
 }  // namespace t2v
 
@@ -99,12 +117,31 @@ int t2v_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream) {
   count_launch();
   return check_last("cast");
 }
-int t2v_pack_dgrad_weight(const float* w, void* wT, int32_t Cout, int32_t taps, int32_t Cin, void* stream) {
+int t2v_pack_dgrad_weight(const float* w, void* wT, int32_t Cout, int32_t taps, int32_t Cin, int32_t CoutP,
+                          void* stream) {
   dim3 grid((Cin + 31) / 32, (Cout + 31) / 32, taps), block(32, 8);
   pack_dgrad_kernel<<<grid, block, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
-      w, reinterpret_cast<__nv_bfloat16*>(wT), Cout, taps, Cin);
+      w, reinterpret_cast<__nv_bfloat16*>(wT), Cout, taps, Cin, CoutP);
   count_launch();
   return check_last("pack_dgrad");
+}
+int t2v_pack_weight_padded(const float* w, void* dst, int32_t Cout, int32_t taps, int32_t Cin, int32_t CinP,
+                           void* stream) {
+  const long long total = (long long)Cout * taps * Cin;
+  if (total == 0) return T2V_OK;
+  pack_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      w, reinterpret_cast<__nv_bfloat16*>(dst), taps, Cin, CinP, total);
+  count_launch();
+  return check_last("pack_pad");
+}
+int t2v_unpack_wgrad_padded(const float* src, float* dst, int32_t Cout, int32_t taps, int32_t Cin, int32_t CinP,
+                            void* stream) {
+  const long long total = (long long)Cout * taps * Cin;
+  if (total == 0) return T2V_OK;
+  unpack_pad_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      src, dst, taps, Cin, CinP, total);
+  count_launch();
+  return check_last("unpack_pad");
 }
 
 }  // extern "C"

@@ -1,0 +1,153 @@
+"""Host-side input handling that sits on the hot path: caption token indexing (bit-exact mirror of
+txt2vid/data/__init__.py:260-355 Vocab / collate_fn), a pinned-memory prefetcher with the reference's
+`data_prefetcher.next()` contract (:131-156), and synthetic batches of the shapes SURVEY.md 8(d) names.
+The reference's file/LMDB datasets, DALI hooks and caches are out of scope.
+"""
+import torch
+
+
+class Vocab(object):
+    START, END, UNKNOWN, PAD = '<start>', '<end>', '<unk>', '<pad>'   # PAD is always index 0
+
+    def __init__(self):
+        self.word2idx, self.idx2word, self.idx = {}, {}, 0
+        for w in (self.PAD, self.START, self.END, self.UNKNOWN):
+            self.add_word(w)
+
+    def add_word(self, word):
+        word = word.lower()
+        if word not in self.word2idx:
+            self.word2idx[word] = self.idx
+            self.idx2word[self.idx] = word
+            self.idx += 1
+
+    def get_word(self, idx):
+        return self.idx2word.get(idx, self.UNKNOWN)
+
+    def __call__(self, word):
+        return self.word2idx.get(word.lower(), self.word2idx[self.UNKNOWN])
+
+    def __len__(self):
+        return len(self.word2idx)
+
+    def tokenize(self, sentence):
+        """START, then the words; a word ending in '.' yields the word without it followed by END."""
+        yield self.START
+        for word in sentence.split():
+            if word[-1] == '.':
+                yield word[0:-1]
+                yield self.END
+            else:
+                yield word
+
+    def encode(self, sentence):
+        """Caption part of Dataset.__getitem__ (data/__init__.py:250-254): END appended when missing."""
+        toks = [self(t) for t in self.tokenize(sentence)]
+        if toks[-1] != self(self.END):
+            toks.append(self(self.END))
+        return torch.tensor(toks, dtype=torch.long)
+
+    def to_words(self, tokens):
+        out = u''
+        for i, tok in enumerate(tokens):
+            word = self.get_word(int(tok))
+            if word != self.END and i != 0:
+                out += ' '
+            out += word
+        return out
+
+
+def build_vocab(sentences):
+    vocab = Vocab()
+    for s in sentences:
+        for w in vocab.tokenize(s):
+            vocab.add_word(w)
+    return vocab
+
+
+def collate_fn(data):
+    """[(video, caption)] -> (videos (B,...), tokens (B,Lmax) zero padded, lengths), sorted by caption
+    length, longest first (stable), as pack_padded_sequence requires (data/__init__.py:326-355)."""
+    data.sort(key=lambda item: len(item[1]), reverse=True)
+    vids, caps = zip(*data)
+    lengths = [len(c) for c in caps]
+    tokens = torch.zeros(len(caps), max(lengths)).long()
+    for i, c in enumerate(caps):
+        tokens[i, :lengths[i]] = c[:lengths[i]]
+    return torch.stack(vids, 0), tokens, lengths
+
+
+class data_prefetcher(object):
+    """`x, y = prefetcher.next()` with y = [tokens, lengths] (or []); None, None at the end.  The next
+    batch is staged through pinned memory and copied on a side stream while the current one trains."""
+
+    def __init__(self, loader, device=None):
+        self.loader = iter(loader)
+        self.device = torch.device(device if device is not None else
+                                   ('cuda' if torch.cuda.is_available() else 'cpu'))
+        self.stream = torch.cuda.Stream() if self.device.type == 'cuda' else None
+        self._preload()
+
+    def _to_dev(self, t):
+        if not isinstance(t, torch.Tensor) or self.device.type != 'cuda':
+            return t
+        if not t.is_pinned():
+            t = t.pin_memory()
+        return t.to(self.device, non_blocking=True)
+
+    def _preload(self):
+        try:
+            batch = next(self.loader)
+        except StopIteration:
+            self.next_x = self.next_y = None
+            return
+        if self.stream is not None:
+            with torch.cuda.stream(self.stream):
+                self.next_x = self._to_dev(batch[0])
+                self.next_y = [self._to_dev(a) for a in batch[1:]]
+        else:
+            self.next_x, self.next_y = batch[0], list(batch[1:])
+
+    def next(self):
+        if self.stream is not None:
+            torch.cuda.current_stream().wait_stream(self.stream)
+        x, y = self.next_x, self.next_y
+        if x is not None:
+            if isinstance(x, torch.Tensor) and x.is_cuda:
+                x.record_stream(torch.cuda.current_stream())
+            self._preload()
+        return x, y
+
+
+class SyntheticVideoCaptions(object):
+    """Iterable of `num_batches` synthetic (video (B,T,C,H,W) in [-1,1], tokens, lengths) batches:
+    U(-1,1) clips and MSRVDC-shaped captions (lengths U{4..20}, tokens U{4..V-1}, START/END framed),
+    SURVEY.md 8(d).  Stands in for get_loader(...) in benchmarks and tests."""
+
+    def __init__(self, batch_size, num_batches, vocab_size=1000, frames=16, size=64, channels=3, captions=True,
+                 seed=1234):
+        self.B, self.n, self.V = batch_size, num_batches, vocab_size
+        self.T, self.S, self.C = frames, size, channels
+        self.captions = captions
+        self.seed = seed
+
+    def __len__(self):
+        return self.n
+
+    def batch(self, i):
+        g = torch.Generator().manual_seed(self.seed + i)
+        x = torch.rand(self.B, self.C, self.T, self.S, self.S, generator=g) * 2 - 1
+        x = x.permute(0, 2, 1, 3, 4)                         # loader order (B,T,C,H,W); train() permutes back
+        if not self.captions:
+            return (x,)
+        lengths = sorted([int(v) for v in torch.randint(4, 21, (self.B,), generator=g)], reverse=True)
+        tokens = torch.zeros(self.B, lengths[0], dtype=torch.long)
+        for b, L in enumerate(lengths):
+            tokens[b, 0] = 1
+            tokens[b, 1:L - 1] = torch.randint(4, self.V, (L - 2,), generator=g)
+            tokens[b, L - 1] = 2
+        return x, tokens, lengths
+
+    def __iter__(self):
+        for i in range(self.n):
+            yield self.batch(i)

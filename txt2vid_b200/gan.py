@@ -1,0 +1,304 @@
+"""GAN orchestration and losses: mirror of txt2vid/gan/cond_gan.py and txt2vid/gan/losses.py.
+
+Same classes, method names, keyword arguments and loss arithmetic.  What differs is underneath: the
+discriminator / generator calls run on the sm_100a kernels, and the conditional D step reuses the real
+trunk features for the mismatched-caption pair (the reference's `computed_features` shortcut is dead
+code, tganv2_cond/discrim.py:35,40-41, so it recomputes an identical trunk pass).
+"""
+import numpy as np
+import torch
+import torch.nn as nn
+import torch.nn.functional as F
+
+from .util import gen_perm
+
+
+def get_labels_for(x, label):
+    """gan/losses.py:4-5 with the float fill torch >= 2 needs (SURVEY 8c shim 2)."""
+    return torch.full(x.size(), float(label), device=x.device)
+
+
+class MixedGanLoss(object):
+    def __init__(self, g_loss=None, d_loss=None):
+        self.g_loss = g_loss
+        self.d_loss = d_loss
+
+    def discrim_loss(self, fake=None, real=None):
+        return self.d_loss.discrim_loss(fake=fake, real=real)
+
+    def gen_loss(self, fake=None, real=None):
+        return self.g_loss.gen_loss(fake=fake, real=real)
+
+
+class LabelledGanLoss(object):
+    """NOTE: the reference assigns fake_label <- real_label and real_label <- fake_label
+    (gan/losses.py:26-27); kept, because it is the behaviour users of VanillaGanLoss / HingeGanLoss get."""
+
+    def __init__(self, real_label=None, fake_label=None, underlying_loss=None):
+        assert real_label is not None and fake_label is not None and underlying_loss is not None
+        self.loss = underlying_loss
+        self.fake_label = real_label
+        self.real_label = fake_label
+
+    def _compute_loss(self, x, label):
+        return self.loss(x, get_labels_for(x, label))
+
+    def discrim_loss(self, fake=None, real=None):
+        return self._compute_loss(fake, self.fake_label) + self._compute_loss(real, self.real_label)
+
+    def gen_loss(self, fake=None, real=None):
+        return self._compute_loss(fake, self.real_label)
+
+
+class VanillaGanLoss(LabelledGanLoss):
+    def __init__(self, bce_loss=True, reduction='mean'):
+        loss = nn.BCEWithLogitsLoss(reduction=reduction) if bce_loss else nn.CrossEntropyLoss(reduction=reduction)
+        super().__init__(underlying_loss=loss, real_label=1, fake_label=0)
+
+
+class HingeGanLoss(LabelledGanLoss):
+    def __init__(self, margin=2.0):
+        super().__init__(underlying_loss=nn.HingeEmbeddingLoss(margin=margin), real_label=1, fake_label=-1)
+
+
+class WassersteinGanLoss(object):
+    def discrim_loss(self, fake=None, real=None):
+        return -(real.mean() - fake.mean())
+
+    def gen_loss(self, fake=None, real=None):
+        return -fake.mean()
+
+
+class RSGANLoss(object):
+    """Relativistic standard GAN (gan/losses.py:74-85): BCE-with-logits against ones of (r - f) / (f - r),
+    i.e. mean softplus(-(r - f))."""
+
+    def __init__(self, bce_loss=True):
+        self.bce = bce_loss
+        if not bce_loss:
+            self.loss = nn.CrossEntropyLoss()
+
+    def _rel(self, a, b):
+        if self.bce:
+            return F.softplus(b - a).mean()
+        return self.loss(a - b, get_labels_for(a, 1))
+
+    def discrim_loss(self, fake=None, real=None):
+        return self._rel(real, fake)
+
+    def gen_loss(self, fake=None, real=None):
+        return self._rel(fake, real)
+
+
+class RaSGANLoss(object):
+    """The reference's RaSGANLoss reads self.fake_labels / self.real_labels, which it never defines
+    (gan/losses.py:91-96): every call raises AttributeError.  Same here, with a clearer message."""
+
+    def __init__(self, bce_loss=True):
+        self.loss = nn.BCEWithLogitsLoss() if bce_loss else nn.CrossEntropyLoss()
+        self.fake_label = 0
+        self.real_label = 1
+
+    def _broken(self):
+        raise AttributeError("'RaSGANLoss' object has no attribute 'fake_labels' (unusable in the reference too: "
+                             "txt2vid/gan/losses.py:95-96)")
+
+    def discrim_loss(self, fake=None, real=None):
+        self._broken()
+
+    def gen_loss(self, fake=None, real=None):
+        self._broken()
+
+
+class RaLSGANLoss(object):
+    """Relativistic average LSGAN (gan/losses.py:113-133)."""
+
+    def discrim_loss(self, fake=None, real=None):
+        return (torch.mean((real - torch.mean(fake) - 1) ** 2) + torch.mean((fake - torch.mean(real) + 1) ** 2)) / 2
+
+    def gen_loss(self, fake=None, real=None):
+        return (torch.mean((real - torch.mean(fake) + 1) ** 2) + torch.mean((fake - torch.mean(real) - 1) ** 2)) / 2
+
+
+def _gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xbar=None, real_cond=None,
+                      fake_cond=None, zero_center=False, combine=torch.mean):
+    """gan/losses.py:135-186.  alpha ~ U(0,1) per sample from the CPU generator (created on CPU, then moved,
+    :140-145); only d/dx_hat is kept (:178); the second derivative runs through ops.Conv*F etc."""
+    B = real_x.size(0)
+    assert real_x.dim() in (4, 5)
+    alpha = torch.rand(*([B] + [1] * (real_x.dim() - 1)))
+    a = alpha.to(real_x.device)
+    xh = (a * real_x + (1 - a) * fake_x).requires_grad_(True)
+    xbarh = None
+    if real_xbar is not None and fake_xbar is not None:
+        ab = alpha.view([B] + [1] * (real_xbar.dim() - 1)).to(real_xbar.device)
+        xbarh = (ab * real_xbar + (1 - ab) * fake_xbar).requires_grad_(True)
+    ch = None
+    if real_cond is not None and fake_cond is not None:
+        ac = alpha.view(B, 1).to(real_cond.device)
+        ch = (ac * real_cond + (1 - ac) * fake_cond).requires_grad_(True)
+    u, c, _ = discrim(x=xh, cond=ch, xbar=xbarh)
+    outs = [u] + ([c] if c is not None else [])
+    ins = [xh] + ([ch] if ch is not None else []) + ([xbarh] if xbarh is not None else [])
+    g = torch.autograd.grad(outputs=outs, inputs=ins, grad_outputs=[torch.ones_like(o) for o in outs],
+                            create_graph=True, retain_graph=True, only_inputs=True)[0]
+    n2 = g.reshape(B, -1).pow(2).sum(dim=1)
+    return combine(n2) if zero_center else combine((n2.sqrt() - 1) ** 2)
+
+
+def gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xbar=None, real_cond=None,
+                     fake_cond=None):
+    """gan/losses.py:188-209: multi-scale D -> zero-centred penalty summed over samples and levels."""
+    if not hasattr(discrim, 'sub_discrims'):
+        return _gradient_penalty(discrim, real_x=real_x, real_xbar=real_xbar, fake_x=fake_x, fake_xbar=fake_xbar,
+                                 real_cond=real_cond, fake_cond=fake_cond)
+    total = []
+    for i in range(len(real_x)):
+        rc = fc = rxb = fxb = None
+        if real_cond is not None:
+            rc, fc = real_cond[i], fake_cond[i]
+            rxb = real_xbar[i] if real_xbar is not None else None
+            fxb = fake_xbar[i] if fake_xbar is not None else None
+        total.append(_gradient_penalty(discrim.sub_discrims[i], real_x=real_x[i], real_xbar=rxb, real_cond=rc,
+                                       fake_x=fake_x[i], fake_xbar=fxb, fake_cond=fc, zero_center=True,
+                                       combine=torch.sum))
+    return torch.stack(total).sum()
+
+
+class CondGan(object):
+    """gan/cond_gan.py:7-217."""
+
+    def __init__(self, gen=None, discrims=None, cond_encoder=None, discrim_names=None, sample_mapping=None,
+                 discrim_lambdas=None):
+        assert gen is not None and discrims is not None and len(discrims) >= 1
+        if discrim_names is None:
+            discrim_names = ['discrim-%d' % i for i in range(len(discrims))]
+        self.gen = gen
+        self.discrims = discrims
+        self.sample_mapping = sample_mapping
+        self.cond_encoder = cond_encoder
+        self.discrim_names = discrim_names
+        self.discrim_lambdas = discrim_lambdas
+
+    def _map_input(self, x):
+        return self.sample_mapping(x) if self.sample_mapping is not None and x is not None else None
+
+    def _discrim_weighted_sum(self, losses):
+        if self.discrim_lambdas is None:
+            return torch.mean(losses)
+        return torch.sum(torch.tensor(self.discrim_lambdas, device=losses.device) * losses)
+
+    @staticmethod
+    def _mean_over_levels(loss, fakes, reals, idx):
+        return torch.stack([loss(fake=f[idx], real=r[idx]) for f, r in zip(fakes, reals)]).mean()
+
+    def discrim_forward(self, name=None, discrim=None, real=None, real_mapping=None, fake=None, fake_mapping=None,
+                        real_cond=None, fake_cond=None, loss=None, gp_lambda=-1):
+        """(x_r,c_r) / (x_r,c_f) / (x_f,c_r) pairs and their per-level loss average (cond_gan.py:34-87)."""
+        fake_pred = real_pred = l = None
+        if real_cond is not None and fake_cond is not None:
+            real_cc = discrim(x=real, cond=real_cond, xbar=real_mapping)
+            real_pred = real_cc
+            if loss is not None:
+                real_ic = discrim(x=real, cond=fake_cond, xbar=real_mapping,
+                                  computed_features=[t[-1] for t in real_cc])
+                fake_cc = discrim(x=fake, cond=real_cond, xbar=fake_mapping)
+                l_u = self._mean_over_levels(loss, fake_cc, real_cc, 0)
+                l_c = (self._mean_over_levels(loss, fake_cc, real_cc, 1) +
+                       self._mean_over_levels(loss, real_ic, real_cc, 1)) / 2
+                l = (l_u + l_c) / 2.0
+        else:
+            if real is not None:
+                real_pred = [r[0] for r in discrim(x=real, cond=None, xbar=real_mapping)]
+            if fake is not None:
+                fake_pred = [f[0] for f in discrim(x=fake, cond=None, xbar=fake_mapping)]
+            if loss is not None and fake_pred is not None and real_pred is not None:
+                l = torch.stack([loss(fake=f, real=r) for f, r in zip(fake_pred, real_pred)]).mean()
+        if l is not None and gp_lambda > 0:
+            l = l + gp_lambda * gradient_penalty(discrim, real_x=real, real_xbar=real_mapping, fake_x=fake,
+                                                 fake_xbar=fake_mapping, real_cond=real_cond, fake_cond=fake_cond)
+        return l, fake_pred, real_pred
+
+    def gen_step(self, fake=None, real_pred=None, cond=None, loss=None):
+        """cond_gan.py:90-118 (unconditional branch: element [0] of each tuple -- the reference passes the
+        tuples themselves and raises, cond_gan.py:102-106; documented adapter)."""
+        self.gen.zero_grad()
+        if self.cond_encoder is not None:
+            self.cond_encoder.zero_grad()
+        fake_mapping = self._map_input(fake)
+        losses = []
+        for r, name, discrim in zip(real_pred, self.discrim_names, self.discrims):
+            fake_cc = discrim(x=fake, cond=cond, xbar=fake_mapping)
+            if cond is None:
+                pick = lambda t: t[0] if isinstance(t, (tuple, list)) else t
+                losses.append(torch.stack([loss(fake=pick(ff), real=pick(rr)) for ff, rr in zip(fake_cc, r)]).mean())
+            else:
+                l_u = self._mean_over_levels(loss, fake_cc, r, 0)
+                l_c = self._mean_over_levels(loss, fake_cc, r, 1)
+                losses.append((l_c + l_u) / 2.0)
+        return self._discrim_weighted_sum(torch.stack(losses))
+
+    def all_discrim_forward(self, fake=None, real=None, cond=None, loss=None, gp_lambda=-1):
+        """cond_gan.py:121-154: mismatched captions = a non-identity permutation of the level-0 captions
+        (numpy RNG), truncated per level."""
+        losses, real_pred, fake_pred = [], [], []
+        real_mapping, fake_mapping = self._map_input(real), self._map_input(fake)
+        for name, discrim in zip(self.discrim_names, self.discrims):
+            fake_cond = None
+            if cond is not None:
+                perm = torch.as_tensor(gen_perm(cond[0].size(0)), device=cond[0].device)
+                shuffled = cond[0][perm]
+                fake_cond = [shuffled[0:r.size(0)] for r in cond]
+            l, f, r = self.discrim_forward(name=name, discrim=discrim, real=real, real_cond=cond,
+                                           real_mapping=real_mapping, fake=fake, fake_cond=fake_cond,
+                                           fake_mapping=fake_mapping, loss=loss, gp_lambda=gp_lambda)
+            losses.append(l)
+            fake_pred.append(f)
+            real_pred.append(r)
+        return losses, fake_pred, real_pred
+
+    def discrim_step(self, real=None, fake=None, cond=None, loss=None, gp_lambda=-1):
+        for discrim in self.discrims:
+            discrim.zero_grad()
+        if self.cond_encoder is not None:
+            self.cond_encoder.zero_grad()
+        losses, _, _ = self.all_discrim_forward(real=real, fake=fake, cond=cond, loss=loss, gp_lambda=gp_lambda)
+        return self._discrim_weighted_sum(torch.stack(losses))
+
+    def count_params(self):
+        from .util import count_params
+        n = int(np.sum([count_params(d) for d in self.discrims])) + count_params(self.gen)
+        if self.cond_encoder is not None:
+            n += count_params(self.cond_encoder)
+        if self.sample_mapping is not None:
+            n += count_params(self.sample_mapping)
+        return n
+
+    def __call__(self, *args, **kwargs):
+        return self.gen(*args, **kwargs)
+
+    @property
+    def discrims_params(self):
+        return [d.parameters() for d in self.discrims]
+
+    def save_dict(self):
+        res = {'gen': self.gen.state_dict()}
+        if self.cond_encoder is not None:
+            res['cond'] = self.cond_encoder.state_dict()
+        if self.sample_mapping is not None:
+            res['sample_mapping'] = self.sample_mapping.state_dict()
+        for name, discrim in zip(self.discrim_names, self.discrims):
+            res[name] = discrim.state_dict()
+        return res
+
+    def load_from_dict(self, to_load):
+        self.gen.load_state_dict(to_load['gen'])
+        if 'cond' in to_load:
+            assert self.cond_encoder is not None
+            self.cond_encoder.load_state_dict(to_load['cond'])
+        if 'sample_mapping' in to_load:
+            assert self.sample_mapping is not None
+            self.sample_mapping.load_state_dict(to_load['sample_mapping'])
+        for name, discrim in zip(self.discrim_names, self.discrims):
+            if name in to_load:
+                discrim.load_state_dict(to_load[name])

@@ -2,7 +2,8 @@
 
 Tensors here are in the kernels' native layouts ("CL" = contiguous (N, D, H, W, C) bf16; 2-D
 feature maps use D = 1).  Everything above this file (ops.py autograd formulas, the module mirrors)
-only talks to the GPU through these functions.
+only talks to the GPU through these functions.  There is no CPU path: every function raises on
+non-CUDA tensors (tests/cpu_kernels.py is a test-only stand-in used to check the autograd formulas).
 """
 import ctypes
 
@@ -12,6 +13,7 @@ from . import _lib
 from ._lib import ConvGeom, check, lib, ptr, require_cuda, stream
 
 BF16 = torch.bfloat16
+F32 = torch.float32
 
 
 def _geom(N, D, H, W, Cin, Cout, k):
@@ -19,6 +21,11 @@ def _geom(N, D, H, W, Cin, Cout, k):
     return ConvGeom(N, D, H, W, Cin, Cout, kd, kh, kw)
 
 
+def _i32(*vals):
+    return (ctypes.c_int32 * len(vals))(*vals)
+
+
+# ------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=False, algo=0):
     """x (N,D,H,W,Cin) bf16, w (Cout,taps,Cin) bf16 -> y (N,D,H,W,Cout) bf16|f32."""
     require_cuda(x, w, bias, residual)
@@ -26,7 +33,9 @@ def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=
     Cout = w.shape[0]
     assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == BF16 and w.dtype == BF16
-    y = torch.empty((N, D, H, W, Cout), device=x.device, dtype=torch.float32 if out_f32 else BF16)
+    assert bias is None or (bias.dtype == F32 and bias.numel() == Cout)
+    assert residual is None or (residual.dtype == BF16 and residual.is_contiguous())
+    y = torch.empty((N, D, H, W, Cout), device=x.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
     flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0)
     check(lib().t2v_conv_fprop(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), flags, algo,
@@ -39,8 +48,8 @@ def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, al
     require_cuda(dy, wT, residual)
     N, D, H, W, Cout = dy.shape
     Cin = wT.shape[0]
-    assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous()
-    dx = torch.empty((N, D, H, W, Cin), device=dy.device, dtype=torch.float32 if out_f32 else BF16)
+    assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and dy.dtype == BF16
+    dx = torch.empty((N, D, H, W, Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
     flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0)
     check(lib().t2v_conv_dgrad(ctypes.byref(g), ptr(dy), ptr(wT), ptr(residual), ptr(dx), flags, algo, stream()),
@@ -54,10 +63,11 @@ def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
     N, D, H, W, Cout = dy.shape
     Cin = x.shape[-1]
     assert x.shape[:4] == dy.shape[:4] and dy.is_contiguous() and x.is_contiguous()
+    assert dy.dtype == BF16 and x.dtype == BF16
     taps = k[0] * k[1] * k[2]
     if out is None:
         assert not accumulate
-        out = torch.empty((Cout, taps, Cin), device=x.device, dtype=torch.float32)
+        out = torch.empty((Cout, taps, Cin), device=x.device, dtype=F32)
     g = _geom(N, D, H, W, Cin, Cout, k)
     check(lib().t2v_conv_wgrad(ctypes.byref(g), ptr(dy), ptr(x), ptr(out), 1 if accumulate else 0, algo, stream()),
           "t2v_conv_wgrad")
@@ -66,7 +76,7 @@ def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
 
 def cast_bf16(src):
     require_cuda(src)
-    assert src.dtype == torch.float32 and src.is_contiguous()
+    assert src.dtype == F32 and src.is_contiguous()
     dst = torch.empty(src.shape, device=src.device, dtype=BF16)
     check(lib().t2v_cast_f32_to_bf16(ptr(src), ptr(dst), src.numel(), stream()), "t2v_cast_f32_to_bf16")
     return dst
@@ -75,16 +85,293 @@ def cast_bf16(src):
 def cast_f32(src):
     require_cuda(src)
     assert src.dtype == BF16 and src.is_contiguous()
-    dst = torch.empty(src.shape, device=src.device, dtype=torch.float32)
+    dst = torch.empty(src.shape, device=src.device, dtype=F32)
     check(lib().t2v_cast_bf16_to_f32(ptr(src), ptr(dst), src.numel(), stream()), "t2v_cast_bf16_to_f32")
     return dst
 
 
-def pack_dgrad_weight(w):
-    """w (Cout,taps,Cin) fp32 -> (Cin,taps,Cout) bf16 with the tap order reversed."""
+def pack_weight(w, CoutP=None, CinP=None):
+    """w (Cout,taps,Cin) fp32 -> bf16 (CoutP,taps,CinP), zero padded (plain cast when unpadded)."""
     require_cuda(w)
-    assert w.dtype == torch.float32 and w.is_contiguous() and w.dim() == 3
+    assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
     Cout, taps, Cin = w.shape
-    wT = torch.empty((Cin, taps, Cout), device=w.device, dtype=BF16)
-    check(lib().t2v_pack_dgrad_weight(ptr(w), ptr(wT), Cout, taps, Cin, stream()), "t2v_pack_dgrad_weight")
+    CoutP, CinP = CoutP or Cout, CinP or Cin
+    if CoutP == Cout and CinP == Cin:
+        return cast_bf16(w)
+    dst = torch.zeros((CoutP, taps, CinP), device=w.device, dtype=BF16)
+    check(lib().t2v_pack_weight_padded(ptr(w), ptr(dst), Cout, taps, Cin, CinP, stream()), "t2v_pack_weight_padded")
+    return dst
+
+
+def pack_dgrad_weight(w, CoutP=None, CinP=None):
+    """w (Cout,taps,Cin) fp32 -> (CinP,taps,CoutP) bf16 with the tap order reversed."""
+    require_cuda(w)
+    assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
+    Cout, taps, Cin = w.shape
+    CoutP, CinP = CoutP or Cout, CinP or Cin
+    alloc = torch.empty if (CoutP == Cout and CinP == Cin) else torch.zeros
+    wT = alloc((CinP, taps, CoutP), device=w.device, dtype=BF16)
+    check(lib().t2v_pack_dgrad_weight(ptr(w), ptr(wT), Cout, taps, Cin, CoutP, stream()), "t2v_pack_dgrad_weight")
     return wT
+
+
+def unpack_wgrad(dwp, Cout, Cin):
+    """(CoutP,taps,CinP) fp32 -> (Cout,taps,Cin) fp32 (crop of the channel padding)."""
+    require_cuda(dwp)
+    CoutP, taps, CinP = dwp.shape
+    if CoutP == Cout and CinP == Cin:
+        return dwp
+    dst = torch.empty((Cout, taps, Cin), device=dwp.device, dtype=F32)
+    check(lib().t2v_unpack_wgrad_padded(ptr(dwp), ptr(dst), Cout, taps, Cin, CinP, stream()),
+          "t2v_unpack_wgrad_padded")
+    return dst
+
+
+# ------------------------------------------------------------------------------------- pointwise / pooling
+def relu_fwd(x):
+    require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().t2v_relu_fwd(ptr(x), ptr(y), x.numel(), stream()), "t2v_relu_fwd")
+    return y
+
+
+def relu_bwd(dy, ref):
+    require_cuda(dy, ref)
+    assert dy.dtype == BF16 and ref.dtype == BF16 and dy.is_contiguous() and ref.is_contiguous()
+    dx = torch.empty_like(dy)
+    check(lib().t2v_relu_bwd(ptr(dy), ptr(ref), ptr(dx), dy.numel(), stream()), "t2v_relu_bwd")
+    return dx
+
+
+def pool_out_shape(in_shape, kernel, stride, pad):
+    N, D, H, W, C = in_shape
+    o = [(s + 2 * p - k) // st + 1 for s, k, st, p in zip((D, H, W), kernel, stride, pad)]
+    return (N, o[0], o[1], o[2], C)
+
+
+def avgpool_fwd(x, kernel, stride, pad, residual=None):
+    require_cuda(x, residual)
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty(pool_out_shape(x.shape, kernel, stride, pad), device=x.device, dtype=BF16)
+    assert residual is None or (residual.shape == y.shape and residual.is_contiguous())
+    check(lib().t2v_avgpool_fwd(ptr(x), ptr(residual), ptr(y), _i32(*x.shape), _i32(*kernel), _i32(*stride),
+                                _i32(*pad), stream()), "t2v_avgpool_fwd")
+    return y
+
+
+def avgpool_bwd(dy, in_shape, kernel, stride, pad):
+    require_cuda(dy)
+    assert dy.dtype == BF16 and dy.is_contiguous()
+    assert tuple(dy.shape) == tuple(pool_out_shape(in_shape, kernel, stride, pad))
+    dx = torch.empty(tuple(in_shape), device=dy.device, dtype=BF16)
+    check(lib().t2v_avgpool_bwd(ptr(dy), ptr(dx), _i32(*in_shape), _i32(*kernel), _i32(*stride), _i32(*pad),
+                                stream()), "t2v_avgpool_bwd")
+    return dx
+
+
+def upsample2x_fwd(x):
+    require_cuda(x)
+    N, D, H, W, C = x.shape
+    assert D == 1 and x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty((N, 1, 2 * H, 2 * W, C), device=x.device, dtype=BF16)
+    check(lib().t2v_upsample2x_fwd(ptr(x), ptr(y), N, H, W, C, stream()), "t2v_upsample2x_fwd")
+    return y
+
+
+def upsample2x_bwd(dy):
+    require_cuda(dy)
+    N, D, H2, W2, C = dy.shape
+    assert D == 1 and dy.dtype == BF16 and dy.is_contiguous()
+    dx = torch.empty((N, 1, H2 // 2, W2 // 2, C), device=dy.device, dtype=BF16)
+    check(lib().t2v_upsample2x_bwd(ptr(dy), ptr(dx), N, H2 // 2, W2 // 2, C, stream()), "t2v_upsample2x_bwd")
+    return dx
+
+
+def nchw_to_cl(x, Cp):
+    """fp32 (N,C,D,H,W) -> bf16 (N,D,H,W,Cp), padded channels zero."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
+    N, C, D, H, W = x.shape
+    y = torch.empty((N, D, H, W, Cp), device=x.device, dtype=BF16)
+    check(lib().t2v_nchw_to_cl(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_nchw_to_cl")
+    return y
+
+
+def cl_to_nchw(x, C):
+    """bf16 (N,D,H,W,Cp) -> fp32 (N,C,D,H,W) (first C channels)."""
+    require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 5
+    N, D, H, W, Cp = x.shape
+    y = torch.empty((N, C, D, H, W), device=x.device, dtype=F32)
+    check(lib().t2v_cl_to_nchw(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_cl_to_nchw")
+    return y
+
+
+def sum_rows(x):
+    """bf16 (..., C) -> fp32 (C,) sum over all leading dims."""
+    require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    C = x.shape[-1]
+    out = torch.empty((C,), device=x.device, dtype=F32)
+    check(lib().t2v_sum_rows(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows")
+    return out
+
+
+def sum_spatial(x):
+    """bf16 (N,D,H,W,C) -> fp32 (N,C)."""
+    require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    N, C = x.shape[0], x.shape[-1]
+    out = torch.empty((N, C), device=x.device, dtype=F32)
+    check(lib().t2v_sum_spatial(ptr(x), ptr(out), N, x.numel() // (N * C), C, stream()), "t2v_sum_spatial")
+    return out
+
+
+def broadcast_spatial(g, shape):
+    """fp32 (N,C) -> bf16 `shape` = (N,D,H,W,C)."""
+    require_cuda(g)
+    assert g.dtype == F32 and g.is_contiguous()
+    N, C = g.shape
+    y = torch.empty(tuple(shape), device=g.device, dtype=BF16)
+    check(lib().t2v_broadcast_spatial(ptr(g), ptr(y), N, y.numel() // (N * C), C, stream()),
+          "t2v_broadcast_spatial")
+    return y
+
+
+# ------------------------------------------------------------------------------------- BatchNorm (train)
+def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, momentum=0.1, training=True):
+    """x (N,1,H,W,C) bf16 -> y (N,1,up*H,up*W,C), plus (mean_invstd, scale_shift) fp32 [2C] for backward.
+    training=False normalises with the running statistics (no update)."""
+    require_cuda(x, gamma, beta)
+    N, D, H, W, C = x.shape
+    assert D == 1 and x.dtype == BF16 and x.is_contiguous()
+    dev = x.device
+    mean_invstd = torch.empty((2 * C,), device=dev, dtype=F32)
+    scale_shift = torch.empty((2 * C,), device=dev, dtype=F32)
+    if training:
+        stats = torch.empty((2 * C,), device=dev, dtype=F32)
+        P = N * H * W
+        check(lib().t2v_bn_stats(ptr(x), ptr(stats), P, C, stream()), "t2v_bn_stats")
+        check(lib().t2v_bn_finalize(ptr(stats), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
+                                    ptr(mean_invstd), ptr(scale_shift), C, P, eps, momentum, stream()),
+              "t2v_bn_finalize")
+    else:
+        # stats := {P*mean, P*(var+mean^2)} with P = 1 reproduces mean / var in the finalize kernel
+        stats = torch.cat((running_mean, running_var + running_mean * running_mean)).contiguous()
+        check(lib().t2v_bn_finalize(ptr(stats), ptr(gamma), ptr(beta), None, None, ptr(mean_invstd),
+                                    ptr(scale_shift), C, 1, eps, momentum, stream()), "t2v_bn_finalize")
+    y = torch.empty((N, 1, up * H, up * W, C), device=dev, dtype=BF16)
+    check(lib().t2v_bn_apply(ptr(x), ptr(scale_shift), ptr(y), N, H, W, C, 1 if relu else 0, up, stream()),
+          "t2v_bn_apply")
+    return y, mean_invstd, scale_shift
+
+
+def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
+    """-> dx (x-shaped bf16), dgamma fp32 [C], dbeta fp32 [C]."""
+    require_cuda(dy, x)
+    N, D, H, W, C = x.shape
+    assert dy.is_contiguous() and dy.dtype == BF16 and tuple(dy.shape) == (N, 1, up * H, up * W, C)
+    red = torch.empty((2 * C,), device=x.device, dtype=F32)
+    dx = torch.empty_like(x)
+    check(lib().t2v_bn_bwd(ptr(dy), ptr(x), ptr(scale_shift), ptr(mean_invstd), ptr(red), ptr(dx), N, H, W, C,
+                           1 if relu else 0, up, stream()), "t2v_bn_bwd")
+    return dx, red[C:], red[:C]
+
+
+# ------------------------------------------------------------------------------------- render / index
+def render_fwd(pre, B, T, C):
+    """pre (B*T,1,H,W,Cp) bf16 -> tanh -> fp32 (B,C,T,H,W)."""
+    require_cuda(pre)
+    BT, D, H, W, Cp = pre.shape
+    assert BT == B * T and D == 1 and pre.dtype == BF16 and pre.is_contiguous()
+    y = torch.empty((B, C, T, H, W), device=pre.device, dtype=F32)
+    check(lib().t2v_render_fwd(ptr(pre), ptr(y), B, T, H, W, C, Cp, stream()), "t2v_render_fwd")
+    return y
+
+
+def render_bwd(dy, y, Cp):
+    require_cuda(dy, y)
+    B, C, T, H, W = y.shape
+    assert dy.dtype == F32 and dy.is_contiguous() and y.is_contiguous()
+    dpre = torch.empty((B * T, 1, H, W, Cp), device=y.device, dtype=BF16)
+    check(lib().t2v_render_bwd(ptr(dy), ptr(y), ptr(dpre), B, T, H, W, C, Cp, stream()), "t2v_render_bwd")
+    return dpre
+
+
+def gather_frames(x, B, T, bt, sn=2, st=2):
+    """x (B*T,1,H,W,C) merged-frame map -> frames (b*sn, bt + t*st): (Bo*To,1,H,W,C)."""
+    require_cuda(x)
+    assert x.is_contiguous() and x.shape[0] == B * T
+    Bo = (B + sn - 1) // sn
+    To = (T - bt + st - 1) // st if T > bt else 0
+    y = torch.empty((Bo * To,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
+    fb = x[0].numel() * x.element_size()
+    check(lib().t2v_gather_frames(ptr(x), ptr(y), B, T, fb, sn, st, bt, 0, stream()), "t2v_gather_frames")
+    return y
+
+
+def scatter_frames(dy, B, T, bt, sn=2, st=2):
+    """adjoint of gather_frames: zero-filled (B*T, ...) with the gathered frames written back."""
+    require_cuda(dy)
+    assert dy.is_contiguous()
+    dx = torch.empty((B * T,) + tuple(dy.shape[1:]), device=dy.device, dtype=dy.dtype)
+    fb = dy[0].numel() * dy.element_size() if dy.shape[0] else dx[0].numel() * dx.element_size()
+    check(lib().t2v_gather_frames(ptr(dy), ptr(dx), B, T, fb, sn, st, bt, 1, stream()), "t2v_gather_frames")
+    return dx
+
+
+def pyramid_level(x, Ho, Wo, sn=1, st=1, bt=0):
+    """fp32 (B,C,T,H,W) -> (ceil(B/sn), C, ceil((T-bt)/st), Ho, Wo): batch/frame subsampling composed
+    with nearest resize (src = floor(dst*in/out)); either part can be the identity."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
+    B, C, T, H, W = x.shape
+    Bo = (B + sn - 1) // sn
+    To = (T - bt + st - 1) // st if T > bt else 0
+    y = torch.empty((Bo, C, To, Ho, Wo), device=x.device, dtype=F32)
+    check(lib().t2v_pyramid_level(ptr(x), ptr(y), _i32(B, C, T, H, W), Ho, Wo, sn, st, bt, stream()),
+          "t2v_pyramid_level")
+    return y
+
+
+# ------------------------------------------------------------------------------------- LSTM cell / Adam
+def lstm_cell_fwd(gates, c_prev, want_h32=False):
+    """gates fp32 (..., 4H) [i|f|g|o], c_prev fp32 (..., H) or None -> (c fp32, h bf16, h32|None)."""
+    require_cuda(gates, c_prev)
+    assert gates.dtype == F32 and gates.is_contiguous()
+    Hd = gates.shape[-1] // 4
+    shp = tuple(gates.shape[:-1]) + (Hd,)
+    c = torch.empty(shp, device=gates.device, dtype=F32)
+    h = torch.empty(shp, device=gates.device, dtype=BF16)
+    h32 = torch.empty(shp, device=gates.device, dtype=F32) if want_h32 else None
+    check(lib().t2v_lstm_cell_fwd(ptr(gates), ptr(c_prev), ptr(c), ptr(h), ptr(h32), c.numel() // Hd, Hd, stream()),
+          "t2v_lstm_cell_fwd")
+    return c, h, h32
+
+
+def lstm_cell_bwd(gates, c_prev, c, dh, dc_next):
+    """-> (dgates bf16 (...,4H), dc_prev fp32 (...,H)); dh / dc_next fp32 or None."""
+    require_cuda(gates, c)
+    Hd = c.shape[-1]
+    dgates = torch.empty(gates.shape, device=gates.device, dtype=BF16)
+    dc_prev = torch.empty_like(c)
+    check(lib().t2v_lstm_cell_bwd(ptr(gates), ptr(c_prev), ptr(c), ptr(dh), ptr(dc_next), ptr(dgates), ptr(dc_prev),
+                                  c.numel() // Hd, Hd, stream()), "t2v_lstm_cell_bwd")
+    return dgates, dc_prev
+
+
+def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0):
+    """In-place multi-tensor Adam on fp32 tensors that share memory layout pairwise."""
+    n = len(params)
+    if n == 0:
+        return
+    require_cuda(*params)
+    arr = ctypes.c_void_p * n
+    sizes = (ctypes.c_int64 * n)(*[p.numel() for p in params])
+    for p, g, m, v in zip(params, grads, ms, vs):
+        assert p.dtype == F32 and g.dtype == F32 and p.stride() == g.stride() == m.stride() == v.stride(), \
+            (p.shape, p.stride(), g.stride())
+    check(lib().t2v_adam_step(n, arr(*[p.data_ptr() for p in params]), arr(*[g.data_ptr() for g in grads]),
+                              arr(*[m.data_ptr() for m in ms]), arr(*[v.data_ptr() for v in vs]), sizes, lr, beta1,
+                              beta2, eps, step, grad_scale, stream()), "t2v_adam_step")

@@ -1,0 +1,566 @@
+"""Differentiable ops of the TGANv2 training step on top of the sm_100a kernels.
+
+Every Function's backward is written in terms of other Functions of this file, so the graph is
+closed under differentiation where the reference needs it: the gradient penalty
+(txt2vid/gan/losses.py:135-209) differentiates d(D)/d(x_hat) a second time, which here means
+conv_fprop <-> conv_dgrad <-> conv_wgrad, ReLU masks, avg-pool/broadcast adjoint pairs.
+
+Activations are "CL" tensors: contiguous (N, D, H, W, C) bf16 (2-D maps: D = 1).  Parameters stay
+fp32 `nn.Parameter`s with the reference's logical shapes; conv weights are re-homed once into
+channels-last memory ([Cout][taps][Cin]) so that packing is a cast and the weight gradient the
+kernels write is the parameter gradient's memory.
+"""
+import torch
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import kernels as K   # tests replace this module attribute with tests/cpu_kernels.py
+
+BF16 = torch.bfloat16
+F32 = torch.float32
+
+_EPOCH = [0]
+
+
+def bump_weight_epoch():
+    """Called after an optimiser writes parameters through raw pointers (no autograd version bump)."""
+    _EPOCH[0] += 1
+
+
+def round16(c):
+    return (c + 15) // 16 * 16
+
+
+# ------------------------------------------------------------------------------------- weight handling
+def kernel_of(weight):
+    """(kd,kh,kw) of a Linear / Conv2d / Conv3d weight."""
+    if weight.dim() == 2:
+        return (1, 1, 1)
+    if weight.dim() == 4:
+        return (1, weight.shape[2], weight.shape[3])
+    return tuple(weight.shape[2:])
+
+
+def w3_view(weight):
+    """fp32 (Cout, taps, Cin) VIEW of a parameter, re-homing it to channels-last memory if needed."""
+    if weight.dim() == 2:
+        assert weight.is_contiguous()
+        return weight.view(weight.shape[0], 1, weight.shape[1])
+    fmt = torch.channels_last_3d if weight.dim() == 5 else torch.channels_last
+    if not weight.is_contiguous(memory_format=fmt) or (weight.numel() and weight.stride(1) != 1):
+        with torch.no_grad():
+            weight.data = _to_cl_memory(weight.data)
+    perm = (0, 2, 3, 4, 1) if weight.dim() == 5 else (0, 2, 3, 1)
+    wp = weight.permute(*perm)
+    return wp.reshape(weight.shape[0], -1, weight.shape[1])
+
+
+def _to_cl_memory(t):
+    perm = (0, 2, 3, 4, 1) if t.dim() == 5 else (0, 2, 3, 1)
+    inv = (0, 4, 1, 2, 3) if t.dim() == 5 else (0, 3, 1, 2)
+    return t.permute(*perm).contiguous().permute(*inv)
+
+
+def grad_like_weight(dw3, weight):
+    """(Cout,taps,Cin) fp32 -> tensor with the parameter's logical shape sharing dw3's memory."""
+    if weight.dim() == 2:
+        return dw3.view(weight.shape)
+    Cout, Cin = weight.shape[0], weight.shape[1]
+    if weight.dim() == 4:
+        return dw3.view(Cout, weight.shape[2], weight.shape[3], Cin).permute(0, 3, 1, 2)
+    return dw3.view(Cout, weight.shape[2], weight.shape[3], weight.shape[4], Cin).permute(0, 4, 1, 2, 3)
+
+
+class _PackCache(object):
+    """bf16 operand packs per parameter, rebuilt when the parameter changes."""
+
+    def __init__(self):
+        self.store = {}
+
+    def _key(self, w):
+        return (w._version, w.data_ptr(), _EPOCH[0])
+
+    def get(self, w, kind, CoutP, CinP):
+        ent = self.store.get(id(w))
+        key = self._key(w)
+        if ent is None or ent[0] != key:
+            ent = (key, {})
+            self.store[id(w)] = ent
+        slot = (kind, CoutP, CinP)
+        if slot not in ent[1]:
+            with torch.no_grad():
+                w3 = w3_view(w).detach()       # may re-home the parameter's memory (channels-last)
+            if kind == "fprop":
+                ent[1][slot] = K.pack_weight(w3, CoutP, CinP)
+            else:
+                ent[1][slot] = K.pack_dgrad_weight(w3, CoutP, CinP)
+            ent = (self._key(w), ent[1])          # w3_view may have re-homed the parameter
+            self.store[id(w)] = ent
+        return ent[1][slot]
+
+    def clear(self):
+        self.store.clear()
+
+
+PACKS = _PackCache()
+
+
+def _pad_bias(bias, CoutP):
+    if bias is None:
+        return None
+    b = bias.detach()
+    if b.numel() == CoutP:
+        return b
+    out = torch.zeros((CoutP,), device=b.device, dtype=F32)
+    out[:b.numel()] = b
+    return out
+
+
+# ------------------------------------------------------------------------------------- convolution
+class ConvF(Function):
+    """y = [relu](conv(x, w) + b [+ residual]);  x CL (.., CinP) -> y CL (.., CoutP)."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, residual, relu):
+        k = kernel_of(weight)
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        CinP, CoutP = x.shape[-1], round16(Cout)
+        assert CinP >= Cin and CinP % 16 == 0, (CinP, Cin)
+        wp = PACKS.get(weight, "fprop", CoutP, CinP)
+        y = K.conv_fprop(x, wp, _pad_bias(bias, CoutP), residual, k, relu)
+        ctx.relu = relu
+        ctx.has_bias = bias is not None
+        ctx.has_res = residual is not None
+        ctx.save_for_backward(x, weight, y if relu else None)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight, y = ctx.saved_tensors
+        dy = dy.contiguous()
+        if ctx.relu:
+            dy = ReluBwdF.apply(dy, y)
+        dx = dw = db = dres = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvDgradF.apply(dy, weight, x.shape[-1])
+        if ctx.needs_input_grad[1]:
+            dw = ConvWgradF.apply(dy, x, weight)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = SumRowsF.apply(dy)[:weight.shape[0]]
+        if ctx.has_res and ctx.needs_input_grad[3]:
+            dres = dy
+        return dx, dw, db, dres, None
+
+
+class ConvDgradF(Function):
+    """dx = conv_transpose(dy, w)  (the data gradient of ConvF, itself differentiable)."""
+
+    @staticmethod
+    def forward(ctx, dy, weight, CinP):
+        k = kernel_of(weight)
+        wT = PACKS.get(weight, "dgrad", dy.shape[-1], CinP)
+        ctx.save_for_backward(dy, weight)
+        return K.conv_dgrad(dy, wT, k)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        dy, weight = ctx.saved_tensors
+        ddx = ddx.contiguous()
+        g_dy = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_dy = ConvF.apply(ddx, weight, None, None, False)
+        if ctx.needs_input_grad[1]:
+            g_w = ConvWgradF.apply(dy, ddx, weight)
+        return g_dy, g_w, None
+
+
+class ConvWgradF(Function):
+    """dw = sum_pos dy (x) x, returned with the parameter's logical shape (channels-last memory)."""
+
+    @staticmethod
+    def forward(ctx, dy, x, weight):
+        k = kernel_of(weight)
+        dwp = K.conv_wgrad(dy, x, k)
+        dw3 = K.unpack_wgrad(dwp, weight.shape[0], weight.shape[1])
+        ctx.save_for_backward(dy, x)
+        ctx.k = k
+        ctx.wshape = tuple(weight.shape)
+        return grad_like_weight(dw3, weight)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ddw):
+        # d/d(dy) = conv(x, ddw), d/dx = conv_transpose(dy, ddw): only reached by third-order graphs
+        dy, x = ctx.saved_tensors
+        Cout, Cin = ctx.wshape[0], ctx.wshape[1]
+        w3 = w3_view(ddw.detach().clone())
+        g_dy = g_x = None
+        if ctx.needs_input_grad[0]:
+            g_dy = K.conv_fprop(x, K.pack_weight(w3, dy.shape[-1], x.shape[-1]), None, None, ctx.k)
+        if ctx.needs_input_grad[1]:
+            g_x = K.conv_dgrad(dy, K.pack_dgrad_weight(w3, dy.shape[-1], x.shape[-1]), ctx.k)
+        return g_dy, g_x, None
+
+
+class SumRowsF(Function):
+    """fp32 (C,) = sum over positions (bias gradient)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return K.sum_rows(x)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, g):
+        N = ctx.shape[0]
+        return K.broadcast_spatial(g.view(1, -1).expand(N, -1).contiguous(), ctx.shape)
+
+
+def conv(x, weight, bias=None, residual=None, relu=False):
+    return ConvF.apply(x, weight, bias, residual, relu)
+
+
+# ------------------------------------------------------------------------------------- ReLU
+class ReluF(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.relu_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return ReluBwdF.apply(dy.contiguous(), y)
+
+
+class ReluBwdF(Function):
+    """dx = dy * (ref > 0); linear in dy, piecewise constant in ref."""
+
+    @staticmethod
+    def forward(ctx, dy, ref):
+        ctx.save_for_backward(ref)
+        return K.relu_bwd(dy, ref)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        (ref,) = ctx.saved_tensors
+        return ReluBwdF.apply(ddx.contiguous(), ref), None
+
+
+def relu(x):
+    return ReluF.apply(x)
+
+
+# ------------------------------------------------------------------------------------- avg-pool
+class PoolF(Function):
+    """y = avg_pool3d(x, kernel, stride, pad, count_include_pad) [+ residual]."""
+
+    @staticmethod
+    def forward(ctx, x, residual, kernel, stride, pad):
+        ctx.cfg = (tuple(x.shape), tuple(kernel), tuple(stride), tuple(pad))
+        ctx.has_res = residual is not None
+        return K.avgpool_fwd(x, kernel, stride, pad, residual)
+
+    @staticmethod
+    def backward(ctx, dy):
+        shape, kernel, stride, pad = ctx.cfg
+        dy = dy.contiguous()
+        dx = PoolBwdF.apply(dy, shape, kernel, stride, pad) if ctx.needs_input_grad[0] else None
+        return dx, (dy if ctx.has_res else None), None, None, None
+
+
+class PoolBwdF(Function):
+    @staticmethod
+    def forward(ctx, dy, shape, kernel, stride, pad):
+        ctx.cfg = (kernel, stride, pad)
+        return K.avgpool_bwd(dy, shape, kernel, stride, pad)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        kernel, stride, pad = ctx.cfg
+        return PoolF.apply(ddx.contiguous(), None, kernel, stride, pad), None, None, None, None
+
+
+def avg_pool(x, kernel, stride, pad=(0, 0, 0), residual=None):
+    return PoolF.apply(x, residual, kernel, stride, pad)
+
+
+def down_sample_cfg(shape):
+    """kernel/stride/pad of the reference's DownSample (models/layers.py:202-217) for a CL shape."""
+    k, s, p = [1, 1, 1], [1, 1, 1], [0, 0, 0]
+    for i in range(3):
+        size = shape[1 + i]
+        if size == 1:
+            continue
+        k[i] = s[i] = 2
+        if size % 2:
+            p[i] = 1
+    return tuple(k), tuple(s), tuple(p)
+
+
+# ------------------------------------------------------------------------------------- nearest x2
+class UpsampleF(Function):
+    @staticmethod
+    def forward(ctx, x):
+        return K.upsample2x_fwd(x)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return UpsampleBwdF.apply(dy.contiguous())
+
+
+class UpsampleBwdF(Function):
+    @staticmethod
+    def forward(ctx, dy):
+        return K.upsample2x_bwd(dy)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        return UpsampleF.apply(ddx.contiguous())
+
+
+def upsample2x(x):
+    return UpsampleF.apply(x)
+
+
+# ------------------------------------------------------------------------------------- layout boundary
+class ToCLF(Function):
+    """fp32 (N,C,D,H,W) -> CL bf16 (N,D,H,W,Cp) (zero channel padding)."""
+
+    @staticmethod
+    def forward(ctx, x, Cp):
+        ctx.C = x.shape[1]
+        ctx.Cp = Cp
+        return K.nchw_to_cl(x.contiguous(), Cp)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return FromCLF.apply(dy.contiguous(), ctx.C), None
+
+
+class FromCLF(Function):
+    """CL bf16 (N,D,H,W,Cp) -> fp32 (N,C,D,H,W)."""
+
+    @staticmethod
+    def forward(ctx, x, C):
+        ctx.Cp = x.shape[-1]
+        return K.cl_to_nchw(x, C)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return ToCLF.apply(dy.contiguous(), ctx.Cp), None
+
+
+def to_cl(x, Cp=None):
+    return ToCLF.apply(x, Cp or round16(x.shape[1]))
+
+
+def from_cl(x, C):
+    return FromCLF.apply(x, C)
+
+
+# ------------------------------------------------------------------------------------- sum-pool head
+class SumSpatialF(Function):
+    """torch.sum(x, [2,3,4]) (models/resnet3d.py:48): CL bf16 -> fp32 (N, C)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        ctx.shape = tuple(x.shape)
+        return K.sum_spatial(x)
+
+    @staticmethod
+    def backward(ctx, g):
+        return BroadcastSpatialF.apply(g.contiguous(), ctx.shape)
+
+
+class BroadcastSpatialF(Function):
+    @staticmethod
+    def forward(ctx, g, shape):
+        return K.broadcast_spatial(g, shape)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return SumSpatialF.apply(dy.contiguous()), None
+
+
+def sum_spatial(x):
+    return SumSpatialF.apply(x)
+
+
+# ------------------------------------------------------------------------------------- BatchNorm(+ReLU+Up)
+class BnReluUpF(Function):
+    """[nearest x2]([relu](BatchNorm2d(x))) with batch statistics in train(); updates the running
+    statistics in place (models/layers.py:171-173,175-176,249-250)."""
+
+    @staticmethod
+    def forward(ctx, x, gamma, beta, running_mean, running_var, relu, up, training, eps, momentum):
+        y, mean_invstd, scale_shift = K.bn_forward(x, gamma.detach(), beta.detach(), running_mean, running_var, relu,
+                                                   up, eps, momentum, training)
+        ctx.cfg = (relu, up, training)
+        ctx.save_for_backward(x, mean_invstd, scale_shift)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        relu, up, training = ctx.cfg
+        x, mean_invstd, scale_shift = ctx.saved_tensors
+        assert training, "eval-mode BatchNorm backward is not on the training path"
+        dx, dgamma, dbeta = K.bn_backward(dy.contiguous(), x, mean_invstd, scale_shift, relu, up)
+        return dx, dgamma, dbeta, None, None, None, None, None, None, None
+
+
+def bn_relu_up(x, bn, relu=True, up=1):
+    """bn: an nn.BatchNorm2d parameter container."""
+    return BnReluUpF.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, relu, up, bn.training, bn.eps,
+                           bn.momentum)
+
+
+# ------------------------------------------------------------------------------------- render tail
+class RenderF(Function):
+    """tanh + (B*T,1,H,W,Cp) bf16 -> fp32 (B,C,T,H,W) (layers.py:252; tganv2_cond/gen.py:116-119)."""
+
+    @staticmethod
+    def forward(ctx, pre, B, T, C):
+        y = K.render_fwd(pre, B, T, C)
+        ctx.Cp = pre.shape[-1]
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.render_bwd(dy.contiguous(), y, ctx.Cp), None, None, None
+
+
+def render_tail(pre, B, T, C=3):
+    return RenderF.apply(pre, B, T, C)
+
+
+# ------------------------------------------------------------------------------------- frame subsampling
+class GatherFramesF(Function):
+    """Subsample x[::2, :, bt::2] (layers.py:106-111) on a merged-frame CL map (B*T, 1, H, W, C)."""
+
+    @staticmethod
+    def forward(ctx, x, B, T, bt):
+        ctx.cfg = (B, T, bt)
+        return K.gather_frames(x, B, T, bt)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        B, T, bt = ctx.cfg
+        return K.scatter_frames(dy.contiguous(), B, T, bt), None, None, None
+
+
+def gather_frames(x, B, T, bt):
+    return GatherFramesF.apply(x, B, T, bt)
+
+
+# ------------------------------------------------------------------------------------- ConvLSTM
+class ConvLstmF(Function):
+    """The whole TGANv2 temporal generator (models/conv_lstm.py:32-38,75-97): `steps` LSTM steps on a
+    (B, 1, fh, fw, C) CL plane.  Step 0 sees the input, later steps see zeros (so Wx*(0) = bias);
+    peepholes are identically zero in the reference.  Per step: ONE gate GEMM on the tensor cores
+    ([i|f|g|o] packed along Cout) + one fused cell-update kernel.  Output: (B*steps, 1, fh, fw, C)
+    merged-frame map in (b, t) order (tganv2_cond/gen.py:75-76,91-96)."""
+
+    @staticmethod
+    def forward(ctx, x, wx, wh, bx, steps):
+        # wx, wh: fp32 (4*Hd, taps, Cin|Hd) stacked [i|f|g|o] views/copies; bx fp32 (4*Hd,)
+        B, D, fh, fw, Cin = x.shape
+        Hd = wh.shape[0] // 4
+        taps = wx.shape[1]
+        k = (1, 3, 3) if taps == 9 else (1, 1, 1)
+        wx_p = K.pack_weight(wx.detach().contiguous())
+        wh_p = K.pack_weight(wh.detach().contiguous())
+        gates, cs, hs = [], [], []
+        h = c = None
+        for t in range(steps):
+            src = x if t == 0 else h
+            wp = wx_p if t == 0 else wh_p
+            g = K.conv_fprop(src, wp, bx.detach(), None, k, False, True)           # fp32 (B,1,fh,fw,4Hd)
+            c, h, _ = K.lstm_cell_fwd(g, c)
+            gates.append(g)
+            cs.append(c)
+            hs.append(h)
+        out = torch.stack(hs, dim=1).reshape(B * steps, 1, fh, fw, Hd)              # (b, t) frame order
+        ctx.save_for_backward(x, wx, wh, *gates, *cs, *hs)
+        ctx.cfg = (steps, k, Hd)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        steps, k, Hd = ctx.cfg
+        saved = ctx.saved_tensors
+        x, wx, wh = saved[0], saved[1], saved[2]
+        gates = saved[3:3 + steps]
+        cs = saved[3 + steps:3 + 2 * steps]
+        hs = saved[3 + 2 * steps:3 + 3 * steps]
+        B, D, fh, fw, Cin = x.shape
+        dout = dout.reshape(B, steps, 1, fh, fw, Hd)
+        whT = K.pack_dgrad_weight(wh.detach().contiguous())
+        dh_rec = None                      # bf16 gradient flowing into h_{t} from step t+1
+        dc = None
+        dgs = [None] * steps
+        for t in range(steps - 1, -1, -1):
+            dh = dout[:, t].float()
+            if dh_rec is not None:
+                dh = dh + dh_rec.float()
+            dg, dc = K.lstm_cell_bwd(gates[t], cs[t - 1] if t > 0 else None, cs[t], dh.contiguous(), dc)
+            dgs[t] = dg
+            if t > 0:
+                dh_rec = K.conv_dgrad(dg, whT, k)
+        # weight gradients: Wh over steps 1.., Wx from step 0, bias over all steps
+        dwh = torch.zeros(wh.shape, device=x.device, dtype=F32)
+        if steps > 1:
+            dg_all = torch.cat(dgs[1:], dim=0)
+            h_all = torch.cat(hs[:steps - 1], dim=0)
+            dwh = K.conv_wgrad(dg_all, h_all, k)
+        dwx = K.conv_wgrad(dgs[0], x, k)
+        db = K.sum_rows(torch.cat(dgs, dim=0))
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_dgrad(dgs[0], K.pack_dgrad_weight(wx.detach().contiguous()), k)
+        return dx, dwx, dwh, db, None
+
+
+# ------------------------------------------------------------------------------------- non-local block
+def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2)):
+    """SA-GAN / non-local block (models/layers.py:23-36 2-D, :52-68 3-D) on a CL tensor.
+
+    The four 1x1(x1) convs run on the tcgen05 engine (channel counts < 16 are zero-padded).  ROUND-1
+    INTERIM: the attention core (max-pool, theta^T phi, softmax, beta g) is plain torch (cuBLAS bmm +
+    ATen softmax) in fp32 -- < 0.1 % of the step's FLOPs -- and is double-differentiable as the
+    gradient penalty requires.  DESIGN.md lists the fused kernel that replaces it."""
+    import torch.nn.functional as Fnn
+    N, D, H, W, C = x.shape
+    c8, c2 = w_theta.shape[0], w_g.shape[0]
+    theta = conv(x, w_theta)[..., :c8].float()
+    phi = conv(x, w_phi)[..., :c8].float()
+    g = conv(x, w_g)[..., :c2].float()
+
+    def mp(t):
+        t = Fnn.max_pool3d(t.permute(0, 4, 1, 2, 3), list(pool))
+        return t.permute(0, 2, 3, 4, 1)
+    theta = theta.reshape(N, D * H * W, c8)
+    phi = mp(phi).reshape(N, -1, c8)
+    g = mp(g).reshape(N, -1, c2)
+    beta = torch.softmax(torch.bmm(theta, phi.transpose(1, 2)), -1)
+    o = torch.bmm(beta, g).reshape(N, D, H, W, c2)
+    c2p = round16(c2)
+    if c2p != c2:
+        o = Fnn.pad(o, (0, c2p - c2))
+    o = conv(o.to(x.dtype).contiguous(), w_o)
+    return gamma.to(x.dtype) * o + x
+
+
+def head_linear(feat, weight, bias):
+    """fc_uncond / fc heads (models/resnet3d.py:50-55) on fp32 (B, F) features.  ROUND-1 INTERIM: ATen
+    (a (B,F)x(F,1) product); the fused sum-pool + two-dot-product kernel is listed in DESIGN.md."""
+    import torch.nn.functional as Fnn
+    return Fnn.linear(feat, weight, bias)

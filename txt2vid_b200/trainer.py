@@ -1,0 +1,242 @@
+"""Training / sampling loop: mirror of txt2vid/gan/trainer.py (train, test, add_params_to_parser,
+save_frames, save_sentences) with the same parameters and iteration order, driving the B200-native
+modules.  Differences that do not change results:
+  * the real-video pyramid (trainer.py:131-165) runs as bit-exact index kernels on the GPU;
+  * `real_pred` for the G step is computed without recording a D-parameter graph: the reference
+    back-propagates the G loss into D's (already stepped, about to be zeroed) gradients
+    (trainer.py:247,262) -- wasted work with no observable effect on lossG, G's gradients or D;
+  * an optional `dist` argument (txt2vid_b200.parallel) all-reduces gradients before each optimiser step.
+"""
+import sys
+
+import torch
+
+from . import kernels as K
+from .blocks import Subsample
+from .util import RollingAvg, Stopwatch, ensure_exists, status
+
+
+def add_params_to_parser(parser):
+    """Same flags, defaults and (inverted) store_false quirks as gan/trainer.py:15-42."""
+    a = parser.add_argument
+    a('--data_is_imgs', action='store_true', default=False, help='is the data images? If not, assume it is videos')
+    a('--img_model', action='store_true', default=False, help='does the GAN only do images?')
+    a('--log_period', type=int, default=20, help='period to log')
+    a('--loss_window_size', type=int, default=20, help='window size for logging')
+    a('--no_mean_discrim_loss', action='store_false', default=True,
+      help='divides each discrim step loss by discrim_steps')
+    a('--no_mean_gen_loss', action='store_false', default=True, help='divides each gen step loss by gen_steps')
+    a('--sample_batch_size', type=int, default=None, help='batch size to gen samples')
+    a('--discrim_steps', type=int, default=1, help='Number of discriminator steps to use per iteration')
+    a('--gen_steps', type=int, default=1, help='Number of generator steps to use per iteration')
+    a('--gp_lambda', type=float, default=-1, help='GP lambda hyper-param (negative to disable GP)')
+    a('--save_initial', action='store_true', default=False, help='save initial model')
+    a('--save_initial_examples', action='store_true', default=False, help='save initial sample')
+    a('--save_model_period', type=int, default=100, help='number of iters until model is saved')
+    a('--save_example_period', type=int, default=100, help='number of iters until model is saved')
+    a('--use_writer', action='store_true', default=False, help='write losses to SummaryWriter (tensorboardX)')
+    a('--out', type=str, default='out', help='dir output path')
+    a('--out_samples', type=str, default='out_samples', help='dir output path')
+    a('--subsample_input', action='store_true', default=False, help='should subsampling be applied to the input?')
+    return parser
+
+
+def multiscale_data(x, cond, frame_sizes, subsample_input, subsampler=None):
+    """Real-video pyramid (gan/trainer.py:131-165): level i < last = nearest resize of the CURRENT
+    (already subsampled) clip to frame_sizes[i]; last = the clip; after every level (the last one
+    included: its draw is discarded) x <- x[::2, :, bt::2], cond <- cond[::2] when subsample_input."""
+    n = len(frame_sizes)
+    if n == 1:
+        return [x], (None if cond is None else [cond])
+    subsampler = subsampler or Subsample()
+    xs, conds = [], []
+    for i in range(n):
+        if i != n - 1:
+            fs = frame_sizes[i]
+            if x.is_cuda:
+                xs.append(K.pyramid_level(x.contiguous(), fs, fs))
+            else:
+                xs.append(torch.nn.functional.interpolate(x, size=(x.size(2), fs, fs)))
+        else:
+            xs.append(x)
+        if cond is not None:
+            conds.append(cond)
+        if subsample_input:
+            x, _ = subsampler(x)
+            if cond is not None:
+                cond = cond[::2]
+    return xs, (conds if conds else None)
+
+
+def save_frames(frames, path=None, channel_first=True, is_images=False):
+    import torchvision.utils as vutils
+    if channel_first:
+        if is_images:
+            frames = frames.unsqueeze(2)
+        frames = frames.permute(0, 2, 1, 3, 4).contiguous()
+    n = frames.size(1)
+    vutils.save_image(frames.view(-1, frames.size(2), frames.size(3), frames.size(4)), path, normalize=True, nrow=n)
+
+
+def save_sentences(captions, path=None, vocab=None):
+    with open(path, 'w') as f:
+        for cap in captions:
+            f.write(vocab.to_words(cap))
+            f.write('\n')
+
+
+def test(gan=None, num_samples=1, dataset=None, device=None, params=None, channel_first=True, vocab=None):
+    """Eval-mode sampling (gan/trainer.py:44-90): one batch per sample index, full-resolution output."""
+    ensure_exists(params.out_samples)
+    gan.gen.eval()
+    for i in range(num_samples):
+        for j, data in enumerate(dataset):
+            x = data[0]
+            B = x.size(0)
+            if channel_first:
+                x = x.permute(0, 2, 1, 3, 4)
+            y = [a.to(device) if isinstance(a, torch.Tensor) else a for a in data[1:]]
+            cond = None
+            if gan.cond_encoder is not None and len(y) >= 2:
+                _, _, cond = gan.cond_encoder.encode(y[0], y[1])
+            z = torch.randn(B, gan.gen.latent_size, device=device)
+            with torch.no_grad():
+                fake = gan(z, cond=cond)
+            save_frames(x, path='%s/real_%d.png' % (params.out_samples, i), channel_first=channel_first,
+                        is_images=params.img_model)
+            if cond is not None:
+                save_sentences(y[0], path='%s/sentences_%d_%d.txt' % (params.out_samples, i, j), vocab=vocab)
+            for f in fake:
+                h, w = (f.size(2), f.size(3)) if params.img_model else (f.size(3), f.size(4))
+                path = '%s/%dx%d_%d_%d.jpg' % (params.out_samples, h, w, i, j)
+                status("saving to %s" % path)
+                save_frames(f, path=path, channel_first=channel_first, is_images=params.img_model)
+            break
+
+
+def train_iteration(gan, x, y, device, optD, optG, params, losses, channel_first=True, end2end=True, dist=None,
+                    z=None):
+    """Body of one `train()` iteration (gan/trainer.py:199-267).  x: (B,T,C,H,W) loader order.
+    Returns (lossD, lossG, fake) with the losses as 0-d device tensors (no host sync here)."""
+    B = x.size(0)
+    if not params.data_is_imgs and channel_first:
+        x = x.permute(0, 2, 1, 3, 4)
+    if params.img_model and not params.data_is_imgs:
+        x = x.squeeze(2)
+    cond = None
+    if gan.cond_encoder is not None and len(y) >= 2:
+        _, _, cond = gan.cond_encoder.encode(y[0], y[1])
+        if not end2end:
+            cond = cond.detach()
+    x, cond = multiscale_data(x, cond, params.frame_sizes, params.subsample_input)
+    if z is None:
+        z = torch.randn(B, gan.gen.latent_size, device=device)
+    fake = gan(z, cond=cond[0] if cond is not None else None)
+
+    total_d = 0
+    for j in range(params.discrim_steps):
+        loss = gan.discrim_step(real=x, fake=[f.detach() for f in fake], cond=cond, loss=losses.discrim_loss,
+                                gp_lambda=params.gp_lambda)
+        if not params.no_mean_discrim_loss:
+            loss = loss / params.discrim_steps
+        loss.backward(retain_graph=j != params.discrim_steps - 1 or end2end)
+        if dist is not None:
+            dist.reduce_grads(optD)
+        optD.step()
+        total_d = total_d + loss.detach()
+
+    # trainer.py:247 -- draws the caption permutation again (numpy RNG) although only real_pred is used
+    with torch.no_grad():
+        _, _, real_pred = gan.all_discrim_forward(real=x, cond=cond, fake=None, loss=None)
+
+    total_g = 0
+    for j in range(params.gen_steps):
+        if j != 0:
+            fake = gan(z, cond=cond[0] if cond is not None else None)
+        for d in gan.discrims:                     # D's parameter gradients are not needed here
+            for p_ in d.parameters():
+                p_.requires_grad_(False)
+        try:
+            loss = gan.gen_step(fake=fake, real_pred=real_pred, cond=cond, loss=losses.gen_loss)
+            if not params.no_mean_gen_loss:
+                loss = loss / params.gen_steps
+            loss.backward(retain_graph=j != params.gen_steps - 1)
+        finally:
+            for d in gan.discrims:
+                for p_ in d.parameters():
+                    p_.requires_grad_(True)
+        if dist is not None:
+            dist.reduce_grads(optG)
+        optG.step()
+        total_g = total_g + loss.detach()
+    return total_d, total_g, fake, x, cond
+
+
+def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=None, params=None, vocab=None,
+          losses=None, channel_first=True, end2end=True, dist=None):
+    """gan/trainer.py:111-333."""
+    if getattr(params, 'debug', False):
+        status("Parameter settings:")
+        print(locals())
+    if params.sample_batch_size is None:
+        params.sample_batch_size = params.batch_size
+    ensure_exists(params.out)
+    ensure_exists(params.out_samples)
+    from .data import data_prefetcher
+
+    gen_loss, discrim_loss = RollingAvg(params.loss_window_size), RollingAvg(params.loss_window_size)
+    avg_data_load, avg_iter = RollingAvg(params.log_period), RollingAvg(params.log_period)
+    data_load_watch, iter_watch = Stopwatch(), Stopwatch()
+
+    for epoch in range(num_epoch):
+        if params.log_period > 0:
+            status('Epoch %d started' % (epoch + 1))
+        data_load_watch.start()
+        iter_watch.start()
+        i = 0
+        prefetcher = data_prefetcher(dataset, device=device)
+        x, y = prefetcher.next()
+        while x is not None:
+            iteration = epoch * len(dataset) + i + 1
+            data_load_watch.stop()
+            avg_data_load.update(data_load_watch.elapsed_time)
+
+            ld, lg, fake, xs, cond = train_iteration(gan, x, y, device, optD, optG, params, losses,
+                                                     channel_first=channel_first, end2end=end2end, dist=dist)
+            discrim_loss.update(float(ld))          # the reference's two host syncs per iteration
+            gen_loss.update(float(lg))
+
+            if (iteration == 1 and params.save_initial) or iteration % params.save_example_period == 0:
+                to_save = {'optG': optG.state_dict(), 'optD': optD.state_dict()}
+                to_save.update(gan.save_dict())
+                torch.save(to_save, '%s/iter_%d_lossG_%.4f_lossD_%.4f' % (params.out, iteration, gen_loss.get(),
+                                                                          discrim_loss.get()))
+                del to_save
+            if params.log_period > 0 and iteration % params.log_period == 0:
+                sys.stdout.flush()
+                mem = (torch.cuda.max_memory_allocated() / 1e9, torch.cuda.max_memory_reserved() / 1e9) \
+                    if torch.cuda.is_available() else (0.0, 0.0)
+                status('[%d/%d; %d/%d] - Iter %d, Loss_D: %.4f Loss_G: %.4f (%.2fGB used; %.2fGB cached) - '
+                       '%.4f sec/iter; %.4f sec/batch load' % (epoch, num_epoch, i, len(dataset), iteration,
+                                                                discrim_loss.get(), gen_loss.get(), mem[0], mem[1],
+                                                                avg_iter.get(), avg_data_load.get()))
+                if torch.cuda.is_available():
+                    torch.cuda.reset_peak_memory_stats()
+            if params.save_example_period > 0 and ((iteration == 1 and params.save_initial_examples) or
+                                                   iteration % params.save_example_period == 0):
+                status('saving to %s (iteration %d)' % (params.out_samples, iteration))
+                save_frames(xs[0], '%s/real_samples.png' % params.out_samples, is_images=params.img_model)
+                for f in fake:
+                    h, w = (f.size(2), f.size(3)) if params.img_model else (f.size(3), f.size(4))
+                    save_frames(f.detach(), path='%s/fake_samples_epoch_%03d_iter_%06d_%dx%d.png' %
+                                (params.out_samples, epoch, iteration, h, w), channel_first=channel_first,
+                                is_images=params.img_model)
+                if cond is not None and vocab is not None:
+                    save_sentences(y[0], path='%s/sentences_epoch%03d_iter_%06d.txt' % (params.out_samples, epoch,
+                                                                                       iteration), vocab=vocab)
+            data_load_watch.start()
+            iter_watch.stop()
+            avg_iter.update(iter_watch.elapsed_time)
+            iter_watch.start()
+            x, y = prefetcher.next()
+            i += 1
