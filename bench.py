@@ -1,0 +1,296 @@
+#!/usr/bin/env python
+"""bench.py -- TGANv2-conditional G+D training step throughput (videos/s) on B200.
+
+    python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
+    python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+
+Workload (BASELINE.json configs[3], the configuration the metric is quoted on): TGANv2 conditional,
+64x64x16 clips, Bi-LSTM caption encoder, non-local blocks, RSGAN loss + zero-centred gradient penalty
+(lambda 0.5), Adam(2e-4, (0.5, 0.999)), 1 D step + 1 G step per iteration, synthetic U(-1,1) clips and
+MSRVDC-shaped captions.  One "step" = one full training iteration over one batch.
+
+Prints ONE JSON line (rank 0).  `value` = videos/s with inputs resident in HBM, device-timed (CUDA events,
+max over ranks); `e2e` = the same through the public train_iteration() API with host (pinned) inputs
+copied in and the two losses read back every step; `roofline` = the conv engine's tcgen05 kernel timed per
+launch with CUDA events (t2v_profile_*) in a profiled pass of the same step right after the timed region;
+`cpu_baseline` = the oracle (CPU restatement of the reference) on the host cores, bounded sample.
+"""
+import argparse
+import contextlib
+import io
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+from types import SimpleNamespace
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+GFLOP_PER_VIDEO_NOMINAL = 55.4      # config 4 incl. gradient penalty, padded taps counted
+WORKLOAD = "TGANv2-cond 64x64x16 G+D train step (RSGAN + GP 0.5, Adam), synthetic clips + captions"
+
+
+def peaks():
+    p = {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0, "source": "fallback"}
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            m = json.load(f)
+        p.update({k: m[k] for k in ("hbm_gbs", "bf16_tflops", "bf16_tflops_sustained") if k in m})
+        p["source"] = "measured"
+    except Exception:
+        pass
+    return p
+
+
+class ClockSampler(object):
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md recipe)."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index=0):
+        self.rows, self.proc, self.index = [], None, index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], None, set()
+        for r in self.rows:
+            try:
+                sm.append(float(r[1]))
+                mx = float(r[2])
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            except Exception:
+                pass
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def train_params(gp_lambda):
+    return SimpleNamespace(data_is_imgs=False, img_model=False, frame_sizes=[8, 16, 32, 64], subsample_input=True,
+                           discrim_steps=1, gen_steps=1, gp_lambda=gp_lambda, no_mean_discrim_loss=False,
+                           no_mean_gen_loss=True)
+
+
+# =========================================================================================== reference arm
+def run_reference(args):
+    """The reference's algorithm on the host CPU cores (oracle port: /root/reference is Python and does not
+    travel to the GPU box).  Rank 0 only; bounded sample: batch 8 per step."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    out = cpu_baseline(steps=max(1, args.steps), warmup=max(1, min(args.warmup, 1)), batch=args.cpu_batch)
+    line = {"metric": "TGANv2-cond G+D train videos/sec", "value": out["value"], "unit": "videos/s",
+            "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": out["ms_per_step"], "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "impl": "reference",
+            "config": {"workload": WORKLOAD, "batch_per_step": args.cpu_batch, "device": "cpu"},
+            "cpu_baseline": {k: out[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": out["value"], "unit": "videos/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}
+    print(json.dumps(line), flush=True)
+
+
+def cpu_baseline(steps=2, warmup=1, batch=8):
+    import numpy as np
+    import torch
+    import oracle.txt2vid_oracle as O
+    from txt2vid_b200.factory import build_models as build_product_models
+    from txt2vid_b200.data import SyntheticVideoCaptions
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    V = 1000
+    with contextlib.redirect_stdout(io.StringIO()):
+        txt, gen, dis = build_product_models(True, vocab_size=V, seed=100)     # same constructors/init as the reference
+    sd_g, sd_d, sd_t = (O.as_leaves({k: v.detach().clone() for k, v in m.state_dict().items()}) for m in (gen, dis, txt))
+    del txt, gen, dis
+    opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
+    opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
+    times = []
+    for it in range(warmup + steps):
+        x, tokens, lengths = SyntheticVideoCaptions(batch, 1, vocab_size=V, seed=1234 + it).batch(0)
+        x = x.permute(0, 2, 1, 3, 4).contiguous()
+        t0 = time.perf_counter()
+        bt_real = O.draw_real(4, True)
+        z = torch.randn(batch, 256)
+        draws = O.draw_rest([batch, batch // 2, batch // 4, batch // 8], conditional=True, gp=True)
+        draws["bt_real"] = bt_real
+        O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
+        dt = time.perf_counter() - t0
+        if it >= warmup:
+            times.append(dt)
+    per = sum(times) / len(times)
+    return {"value": batch / per, "unit": "videos/s", "cores": cores, "kind": "port", "ms_per_step": per * 1e3,
+            "sample": "%d timed iterations of batch %d (same model/loss/optimiser, fp32, torch CPU threads=%d)"
+                      % (len(times), batch, cores)}
+
+
+# =========================================================================================== B200 arm
+def run_b200(args):
+    import numpy as np
+    import torch
+    from txt2vid_b200 import _lib, ops
+    from txt2vid_b200.data import SyntheticVideoCaptions
+    from txt2vid_b200.gan import CondGan, MixedGanLoss, RSGANLoss
+    from txt2vid_b200.optim import FusedAdam
+    from txt2vid_b200.parallel import DistContext
+    from txt2vid_b200.trainer import train_iteration
+    from txt2vid_b200.factory import build_models as build_product_models
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the product has no CPU path (use --impl reference)")
+    dist = DistContext()
+    rank, world = dist.rank, dist.world
+    torch.cuda.set_device(dist.local_rank)
+    device = torch.device("cuda", dist.local_rank)
+    b = args.batch
+    V = 1000
+    with contextlib.redirect_stdout(io.StringIO()):
+        txt, gen, dis = build_product_models(True, vocab_size=V, seed=100)
+    txt, gen, dis = txt.to(device), gen.to(device), dis.to(device)
+    torch.manual_seed(100)                       # CPU generator: identical frame offsets on every rank
+    torch.cuda.manual_seed(100 + rank)
+    np.random.seed(100 + rank)
+    gan = CondGan(gen=gen, discrims=[dis], cond_encoder=txt, discrim_names=["video"])
+    losses = MixedGanLoss(g_loss=RSGANLoss(), d_loss=RSGANLoss())
+    optD = FusedAdam([{"params": dis.parameters()}], lr=2e-4, betas=(0.5, 0.999))
+    optG = FusedAdam([{"params": gen.parameters()}], lr=2e-4, betas=(0.5, 0.999))
+    params = train_params(0.5 * dist.gp_scale)
+    ddp = dist if dist.enabled else None
+
+    nb = 4
+    data = SyntheticVideoCaptions(b, nb, vocab_size=V, seed=1234 + 1000 * rank)
+    host = [data.batch(i) for i in range(nb)]
+    host = [(x.contiguous().pin_memory(), t.pin_memory(), l) for x, t, l in host]
+    dev = [(x.to(device), t.to(device), l) for x, t, l in host]
+
+    def step_resident(i):
+        x, t, l = dev[i % nb]
+        return train_iteration(gan, x, [t, l], device, optD, optG, params, losses, end2end=False, dist=ddp)
+
+    def step_e2e(i):
+        x, t, l = host[i % nb]
+        xd = x.to(device, non_blocking=True)
+        td = t.to(device, non_blocking=True)
+        ld, lg, _, _, _ = train_iteration(gan, xd, [td, l], device, optD, optG, params, losses, end2end=False,
+                                          dist=ddp)
+        return float(ld), float(lg)                     # the device->host read of the step's result
+
+    def timed(fn, n):
+        dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for i in range(n):
+            fn(i)
+        e1.record()
+        torch.cuda.synchronize()
+        dist.barrier()
+        return dist.all_reduce_max(e0.elapsed_time(e1) / 1e3)
+
+    lib = _lib.lib()
+    for i in range(max(3, args.warmup)):
+        step_resident(i)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(dist.local_rank)
+    if rank == 0:
+        clocks.start()
+    l0 = lib.t2v_launch_count()
+    t_res = timed(step_resident, args.steps)
+    launches = int(lib.t2v_launch_count() - l0)
+    clk = clocks.stop() if rank == 0 else None
+    t_e2e = timed(step_e2e, args.steps)
+
+    # ---- roofline pass: per-launch CUDA-event timing of the conv engine over the same step
+    import ctypes
+    prof_steps = min(args.steps, 3)
+    lib.t2v_profile_enable(1)
+    t_prof = timed(step_resident, prof_steps)
+    lib.t2v_profile_enable(0)
+    buf = (ctypes.c_double * 6)()
+    lib.t2v_profile_read(buf)
+    fp_ms, fp_fl, fp_n, wg_ms, wg_fl, wg_n = list(buf)
+    mem_gb = torch.cuda.max_memory_allocated() / 1e9
+
+    if rank != 0:
+        return
+    pk = peaks()
+    videos = world * b * args.steps
+    value = videos / t_res
+    e2e = videos / t_e2e
+    x0, t0_, _ = host[0]
+    h2d = x0.numel() * x0.element_size() + t0_.numel() * t0_.element_size()
+    step_ms_prof = t_prof / prof_steps * 1e3
+    roof = {"bound": "tensor", "kernel": "igemm_fprop_kernel (tcgen05 implicit GEMM: conv fprop + dgrad)",
+            "achieved": fp_fl / (fp_ms * 1e-3) / 1e12 if fp_ms > 0 else None, "peak": pk["bf16_tflops_sustained"],
+            "unit": "TFLOP/s", "traffic": None,
+            "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), %s" % pk["source"],
+            "launches_per_step": fp_n / prof_steps, "ms_per_step_in_kernel": fp_ms / prof_steps,
+            "share_of_step": fp_ms / prof_steps / step_ms_prof if step_ms_prof > 0 else None,
+            "flops_counted": "useful MACs x2 (live taps only, padded channels included)",
+            "wgrad_kernel": {"achieved": wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else None,
+                             "launches_per_step": wg_n / prof_steps, "ms_per_step_in_kernel": wg_ms / prof_steps,
+                             "share_of_step": wg_ms / prof_steps / step_ms_prof if step_ms_prof > 0 else None},
+            "step_nominal_tflops_per_gpu": value / world * GFLOP_PER_VIDEO_NOMINAL / 1e3,
+            "step_nominal_frac_of_sustained_peak": value / world * GFLOP_PER_VIDEO_NOMINAL / 1e3 / pk["bf16_tflops_sustained"]}
+    roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
+    cpu = None
+    if not args.no_cpu_baseline:
+        c = cpu_baseline(steps=2, warmup=1, batch=args.cpu_batch)
+        cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
+    line = {"metric": "TGANv2-cond G+D train videos/sec", "value": value, "unit": "videos/s", "n_gpus": world,
+            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "batch_per_gpu": b, "global_batch": world * b,
+                       "parallelism": "dp%d" % world, "l2": "per-step working set (%.1f GB peak allocated) >> 126 MB L2; "
+                       "%d distinct resident batches cycled" % (mem_gb, nb)},
+            "e2e": {"value": e2e, "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                    "ms_per_step": t_e2e / args.steps * 1e3},
+            "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
+            "peak_mem_gb": mem_gb}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="videos per GPU per step (multiple of 8)")
+    ap.add_argument("--cpu_batch", type=int, default=8)
+    ap.add_argument("--no_cpu_baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

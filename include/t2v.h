@@ -54,6 +54,10 @@ typedef struct {
 int t2v_version(void);
 /* number of kernels launched by this library since load (bench.py: "gpu_launches") */
 unsigned long long t2v_launch_count(void);
+/* optional CUDA-event timing of every conv-engine launch (bench.py roofline); read returns
+ * host_out6 = {fprop+dgrad ms, useful FLOPs, launches, wgrad ms, useful FLOPs, launches} and resets */
+int t2v_profile_enable(int on);
+int t2v_profile_read(double* host_out6);
 
 /* convolution engine (tcgen05 implicit GEMM; replaces F.conv2d/conv3d/linear = cuDNN/cuBLAS)  */
 /* y[n,d,h,w,co] = sum_{taps,ci} x[n,d+a-pd,h+b-ph,w+c-pw,ci] * w[co,a,b,c,ci] + bias[co] (+ residual)
@@ -145,6 +149,10 @@ int t2v_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c, c
 int t2v_adam_step(int32_t count, float* const* host_params, const float* const* host_grads, float* const* host_m,
                   float* const* host_v, const int64_t* host_sizes, float lr, float beta1, float beta2, float eps,
                   int32_t step, float grad_scale, void* stream);
+
+/* gradient bucket pack / unpack for the data-parallel all-reduce (fp32, memory order): dst[i][:] = src[i][:]  */
+int t2v_multi_copy(int32_t count, const float* const* host_src, float* const* host_dst, const int64_t* host_sizes,
+                   void* stream);
 
 #ifdef __cplusplus
 }

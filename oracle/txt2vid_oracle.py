@@ -510,7 +510,7 @@ def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN
     ld = discrim_loss(sd_d, xs, [f.detach() for f in fake], conds, fake_cond, draws["alphas"], loss, gp_lambda)
     d_names = param_names(sd_d)
     d_grads = torch.autograd.grad(ld, [sd_d[n] for n in d_names], allow_unused=True)
-    out["lossD"] = float(ld)
+    out["lossD"] = float(ld.detach())
     out["gradD"] = {n: g for n, g in zip(d_names, d_grads) if g is not None}
     if opt_d is not None:
         opt_d.step(sd_d, out["gradD"])
@@ -519,7 +519,7 @@ def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN
     lg = gen_loss(sd_d, fake, real_pred, conds, loss)
     g_names = param_names(sd_g)
     g_grads = torch.autograd.grad(lg, [sd_g[n] for n in g_names], allow_unused=True)
-    out["lossG"] = float(lg)
+    out["lossG"] = float(lg.detach())
     out["gradG"] = {n: g for n, g in zip(g_names, g_grads) if g is not None}
     if opt_g is not None:
         opt_g.step(sd_g, out["gradG"])

@@ -255,3 +255,10 @@ def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0
             m.mul_(beta1).add_(g, alpha=1 - beta1)
             v.mul_(beta2).addcmul_(g, g, value=1 - beta2)
             p.addcdiv_(m, v.sqrt() / (bc2 ** 0.5) + eps, value=-lr / bc1)
+
+
+def multi_copy(srcs, dsts):
+    with torch.no_grad():
+        for s, d in zip(srcs, dsts):
+            d.view(-1)[:] = torch.as_strided(s, (s.numel(),), (1,), s.storage_offset()) if not s.is_contiguous() \
+                else s.reshape(-1)

@@ -37,22 +37,8 @@ def checksum(t):
 
 def build_product_models(conditional, V=1000, seed=100, width=64, height=64, num_frames=16):
     """Construction + init order of txt2vid/train/gan.py:28-70, on the product classes."""
-    from txt2vid_b200 import tganv2, text
-    from txt2vid_b200.util import init
-    seed_all(seed)
-    txt = None
-    with contextlib.redirect_stdout(io.StringIO()):
-        if conditional:
-            txt = text.Seq2Seq(vocab_size=V)
-            init(txt, "xavier")
-            gen = tganv2.MultiScaleGen(width=width, height=height, cond_dim=256, num_frames=num_frames)
-            dis = tganv2.MultiScaleDiscrim(cond_dim=256)
-        else:
-            gen = tganv2.MultiScaleGenUncond(width=width, height=height, cond_dim=0, num_frames=num_frames)
-            dis = tganv2.MultiScaleDiscrimUncond(cond_dim=0)
-    init(gen, "xavier")
-    init(dis, "xavier")
-    return txt, gen, dis
+    from txt2vid_b200.factory import build_models
+    return build_models(conditional, vocab_size=V, seed=seed, width=width, height=height, num_frames=num_frames)
 
 
 def synth_batch(B, V, T=16, S=64, seed=1234):

@@ -1,0 +1,166 @@
+"""GPU: every non-conv kernel of the C ABI against its executable specification (tests/cpu_kernels.py,
+run on the same CUDA tensors with torch ops).  Index / layout kernels must be bit-exact."""
+import pytest
+import torch
+
+import cpu_kernels as C
+
+pytestmark = pytest.mark.gpu
+BF = torch.bfloat16
+
+
+def K():
+    from txt2vid_b200 import kernels
+    return kernels
+
+
+def rnd(*shape, dtype=BF, scale=1.0):
+    return (torch.randn(*shape, device="cuda") * scale).to(dtype)
+
+
+def close(a, b, tol=1e-2):
+    a, b = a.float(), b.float()
+    err = float((a - b).abs().max() / (b.abs().max() + 1e-12))
+    assert err < tol, err
+
+
+def test_relu():
+    x, dy = rnd(3, 2, 5, 7, 16), rnd(3, 2, 5, 7, 16)
+    assert torch.equal(K().relu_fwd(x), C.relu_fwd(x))
+    assert torch.equal(K().relu_bwd(dy, x), C.relu_bwd(dy, x))
+
+
+@pytest.mark.parametrize("shape,k,s,p", [((2, 4, 8, 8, 32), (2, 2, 2), (2, 2, 2), (0, 0, 0)),
+                                         ((3, 1, 4, 4, 64), (1, 2, 2), (1, 2, 2), (0, 0, 0)),
+                                         ((2, 8, 8, 8, 16), (1, 2, 2), (2, 2, 2), (0, 0, 0)),
+                                         ((2, 3, 5, 7, 16), (2, 2, 2), (2, 2, 2), (1, 1, 1)),
+                                         ((4, 2, 1, 1, 128), (2, 1, 1), (2, 1, 1), (0, 0, 0))])
+def test_avgpool(shape, k, s, p):
+    x = rnd(*shape)
+    y = K().avgpool_fwd(x, k, s, p)
+    close(y, C.avgpool_fwd(x, k, s, p), 5e-3)
+    res = rnd(*y.shape)
+    close(K().avgpool_fwd(x, k, s, p, res), C.avgpool_fwd(x, k, s, p, res), 5e-3)
+    dy = rnd(*y.shape)
+    close(K().avgpool_bwd(dy, shape, k, s, p), C.avgpool_bwd(dy, shape, k, s, p), 5e-3)
+
+
+def test_upsample():
+    x = rnd(5, 1, 4, 6, 32)
+    assert torch.equal(K().upsample2x_fwd(x), C.upsample2x_fwd(x))
+    dy = rnd(5, 1, 8, 12, 32)
+    close(K().upsample2x_bwd(dy), C.upsample2x_bwd(dy), 5e-3)
+
+
+def test_layout_roundtrip():
+    x = torch.randn(3, 3, 4, 5, 6, device="cuda")
+    y = K().nchw_to_cl(x, 16)
+    assert torch.equal(y, C.nchw_to_cl(x, 16))
+    assert torch.equal(K().cl_to_nchw(y, 3), C.cl_to_nchw(y, 3))
+
+
+def test_reductions():
+    x = rnd(7, 2, 3, 5, 96)
+    close(K().sum_rows(x), C.sum_rows(x), 1e-3)
+    close(K().sum_spatial(x), C.sum_spatial(x), 1e-3)
+    g = torch.randn(7, 96, device="cuda")
+    assert torch.equal(K().broadcast_spatial(g, x.shape), C.broadcast_spatial(g, x.shape))
+
+
+@pytest.mark.parametrize("up", [1, 2])
+@pytest.mark.parametrize("relu", [True, False])
+def test_batchnorm(up, relu):
+    N, H, W, Cc = 6, 8, 8, 64
+    x = rnd(N, 1, H, W, Cc, scale=1.5) + 0.25
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.3
+    rm1, rv1 = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    y, mi, ss = K().bn_forward(x, gamma, beta, rm1, rv1, relu, up)
+    y2, mi2, ss2 = C.bn_forward(x, gamma, beta, rm2, rv2, relu, up)
+    close(mi, mi2, 1e-4), close(ss, ss2, 1e-4), close(rm1, rm2, 1e-4), close(rv1, rv2, 1e-4)
+    close(y, y2, 1e-2)
+    dy = rnd(N, 1, H * up, W * up, Cc)
+    dx, dg, db = K().bn_backward(dy, x, mi2, ss2, relu, up)
+    dx2, dg2, db2 = C.bn_backward(dy, x, mi2, ss2, relu, up)
+    close(dx, dx2, 1e-2), close(dg, dg2, 1e-3), close(db, db2, 1e-3)
+    # eval mode
+    ye, _, _ = K().bn_forward(x, gamma, beta, rm2, rv2, relu, up, training=False)
+    ye2, _, _ = C.bn_forward(x, gamma, beta, rm2, rv2, relu, up, training=False)
+    close(ye, ye2, 1e-2)
+
+
+def test_render():
+    B, T, H, W = 3, 4, 8, 8
+    pre = rnd(B * T, 1, H, W, 16)
+    y = K().render_fwd(pre, B, T, 3)
+    close(y, C.render_fwd(pre, B, T, 3), 1e-5)
+    dy = torch.randn_like(y)
+    close(K().render_bwd(dy, y, 16), C.render_bwd(dy, y, 16), 1e-2)
+
+
+@pytest.mark.parametrize("B,T,bt", [(8, 16, 0), (8, 16, 1), (5, 7, 1), (1, 1, 1), (2, 2, 0)])
+def test_gather_scatter_frames_bit_exact(B, T, bt):
+    x = rnd(B * T, 1, 4, 4, 32)
+    y = K().gather_frames(x, B, T, bt)
+    assert torch.equal(y, C.gather_frames(x, B, T, bt))
+    assert torch.equal(K().scatter_frames(y, B, T, bt), C.scatter_frames(y, B, T, bt))
+
+
+def test_pyramid_bit_exact_vs_reference_semantics():
+    """x[::2, :, bt::2] and F.interpolate(nearest) must be reproduced bit for bit."""
+    import torch.nn.functional as F
+    x = torch.randn(8, 3, 16, 64, 64, device="cuda")
+    for fs in (8, 16, 32):
+        assert torch.equal(K().pyramid_level(x, fs, fs), F.interpolate(x, size=(16, fs, fs)))
+    for bt in (0, 1):
+        assert torch.equal(K().pyramid_level(x, 64, 64, 2, 2, bt), x[::2, :, bt::2].contiguous())
+    x = torch.randn(5, 2, 7, 20, 10, device="cuda")
+    assert torch.equal(K().pyramid_level(x, 7, 16), F.interpolate(x, size=(7, 7, 16)))
+    assert torch.equal(K().pyramid_level(x, 20, 10, 2, 2, 1), x[::2, :, 1::2].contiguous())
+
+
+def test_lstm_cell():
+    P, Hd = 37, 128
+    gates = torch.randn(P, 4 * Hd, device="cuda")
+    cp = torch.randn(P, Hd, device="cuda")
+    c, h, h32 = K().lstm_cell_fwd(gates, cp, True)
+    c2, h2, h322 = C.lstm_cell_fwd(gates, cp, True)
+    close(c, c2, 1e-5), close(h, h2, 1e-2), close(h32, h322, 1e-5)
+    dh, dc = torch.randn(P, Hd, device="cuda"), torch.randn(P, Hd, device="cuda")
+    dg, dcp = K().lstm_cell_bwd(gates, cp, c2, dh, dc)
+    dg2, dcp2 = C.lstm_cell_bwd(gates, cp, c2, dh, dc)
+    close(dg, dg2, 1e-2), close(dcp, dcp2, 1e-5)
+    c0, h0, _ = K().lstm_cell_fwd(gates, None)
+    c02, h02, _ = C.lstm_cell_fwd(gates, None)
+    close(c0, c02, 1e-5)
+
+
+def test_adam():
+    shapes = [(1024, 27, 64), (64,), (3, 5), (1000, 256)] * 20          # > one AdamChunk
+    ps = [torch.randn(s, device="cuda") for s in shapes]
+    gs = [torch.randn(s, device="cuda") * 0.1 for s in shapes]
+    ms = [torch.zeros_like(p) for p in ps]
+    vs = [torch.zeros_like(p) for p in ps]
+    ps2, ms2, vs2 = [p.clone() for p in ps], [m.clone() for m in ms], [v.clone() for v in vs]
+    for step in (1, 2, 3):
+        K().adam_step(ps, gs, ms, vs, 2e-4, 0.5, 0.999, 1e-8, step)
+        C.adam_step(ps2, gs, ms2, vs2, 2e-4, 0.5, 0.999, 1e-8, step)
+    for a, b in zip(ps, ps2):
+        assert float((a - b).abs().max()) < 2e-6
+
+
+def test_weight_packs():
+    w = torch.randn(3, 27, 3, device="cuda")
+    assert torch.equal(K().pack_weight(w, 16, 16), C.pack_weight(w, 16, 16))
+    assert torch.equal(K().pack_dgrad_weight(w, 16, 16), C.pack_dgrad_weight(w, 16, 16))
+    w = torch.randn(128, 9, 64, device="cuda")
+    assert torch.equal(K().pack_weight(w), C.pack_weight(w))
+    assert torch.equal(K().pack_dgrad_weight(w), C.pack_dgrad_weight(w))
+    dwp = torch.randn(16, 27, 16, device="cuda")
+    assert torch.equal(K().unpack_wgrad(dwp, 3, 3), C.unpack_wgrad(dwp, 3, 3))
+
+
+def test_no_cpu_fallback():
+    from txt2vid_b200._lib import T2VError
+    with pytest.raises(T2VError):
+        K().relu_fwd(torch.zeros(8, dtype=BF))

@@ -53,6 +53,8 @@ _PP = ctypes.POINTER(ctypes.c_void_p)
 SIGNATURES = {
     "t2v_version": [],
     "t2v_launch_count": [],
+    "t2v_profile_enable": [c_int],
+    "t2v_profile_read": [ctypes.POINTER(ctypes.c_double)],
     "t2v_conv_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],
@@ -82,6 +84,7 @@ SIGNATURES = {
     "t2v_pyramid_level": [_P, _P, _I32P, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_lstm_cell_fwd": [_P, _P, _P, _P, _P, c_i64, c_i32, _P],
     "t2v_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, _P],
+    "t2v_multi_copy": [c_i32, _PP, _PP, ctypes.POINTER(c_i64), _P],
     "t2v_adam_step": [c_i32, _PP, _PP, _PP, _PP, ctypes.POINTER(c_i64), c_float, c_float, c_float, c_float, c_i32,
                       c_float, _P],
 }

@@ -512,6 +512,24 @@ __global__ void adam_kernel(const AdamChunk ch, float lr, float b1, float b2, fl
   }
 }
 
+// ------------------------------------------------------------------------------------ multi-tensor copy
+struct CopyChunk {
+  static constexpr int kMax = 96;
+  const float* src[kMax];
+  float* dst[kMax];
+  long long n[kMax];
+  int count;
+};
+__global__ void multi_copy_kernel(const CopyChunk ch) {
+  const int t = blockIdx.y;
+  if (t >= ch.count) return;
+  const float* s = ch.src[t];
+  float* d = ch.dst[t];
+  const long long n = ch.n[t];
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+    d[i] = s[i];
+}
+
 }  // namespace t2v
 
 using namespace t2v;
@@ -759,6 +777,27 @@ int t2v_adam_step(int32_t count, float* const* host_params, const float* const* 
     count_launch();
   }
   return check_last("adam_step");
+}
+
+int t2v_multi_copy(int32_t count, const float* const* host_src, float* const* host_dst, const int64_t* host_sizes,
+                   void* stream) {
+  for (int base = 0; base < count; base += CopyChunk::kMax) {
+    CopyChunk ch;
+    ch.count = count - base < CopyChunk::kMax ? count - base : CopyChunk::kMax;
+    long long maxn = 0;
+    for (int i = 0; i < ch.count; ++i) {
+      ch.src[i] = host_src[base + i];
+      ch.dst[i] = host_dst[base + i];
+      ch.n[i] = host_sizes[base + i];
+      if (ch.n[i] > maxn) maxn = ch.n[i];
+    }
+    long long bx = (maxn + 256 * 4 - 1) / (256 * 4);
+    if (bx > 1024) bx = 1024;
+    if (bx < 1) bx = 1;
+    multi_copy_kernel<<<dim3((unsigned)bx, ch.count, 1), 256, 0, STREAM>>>(ch);
+    count_launch();
+  }
+  return check_last("multi_copy");
 }
 
 }  // extern "C"

@@ -17,6 +17,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> global).
+#include <vector>
+
 #include "t2v_common.cuh"
 
 namespace t2v {
@@ -341,6 +343,31 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
 }
 
 // ------------------------------------------------------------------------------------ host side
+// Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every
+// engine launch; t2v_profile_read() sums elapsed time and useful (live-tap) FLOPs per kernel kind.
+struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
+static bool g_prof_on = false;
+static std::vector<ProfRec> g_prof;
+void prof_enable(int on) { g_prof_on = on != 0; }
+static void prof_begin(cudaStream_t s, ProfRec* r, int kind, double flops) {
+  r->kind = kind; r->flops = flops;
+  cudaEventCreate(&r->a); cudaEventCreate(&r->b);
+  cudaEventRecord(r->a, s);
+}
+static void prof_end(cudaStream_t s, ProfRec* r) { cudaEventRecord(r->b, s); g_prof.push_back(*r); }
+// out[kind*3 + {0,1,2}] = {milliseconds, flops, launches}, kind 0 = fprop/dgrad, 1 = wgrad
+void prof_read(double* out) {
+  for (int i = 0; i < 6; ++i) out[i] = 0.0;
+  for (auto& r : g_prof) {
+    cudaEventSynchronize(r.b);
+    float ms = 0.f;
+    cudaEventElapsedTime(&ms, r.a, r.b);
+    out[r.kind * 3 + 0] += ms; out[r.kind * 3 + 1] += r.flops; out[r.kind * 3 + 2] += 1.0;
+    cudaEventDestroy(r.a); cudaEventDestroy(r.b);
+  }
+  g_prof.clear();
+}
+
 typedef CUresult (*PFN_tmapEncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                         const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
                                         const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -483,9 +510,13 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
   };
+  ProfRec rec;
+  if (g_prof_on)
+    prof_begin(stream, &rec, 0, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps);
   if (BLOCK_K == 64) launch(igemm_fprop_kernel<64>);
   else if (BLOCK_K == 32) launch(igemm_fprop_kernel<32>);
   else launch(igemm_fprop_kernel<16>);
+  if (g_prof_on) prof_end(stream, &rec);
   count_launch();
   return check_last("igemm_fprop");
 }
@@ -530,7 +561,11 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
   dim3 grid(mtiles, ntiles, ntaps * splits);
   cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ProfRec rec;
+  if (g_prof_on)
+    prof_begin(stream, &rec, 1, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps);
   igemm_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDy, tmX, p);
+  if (g_prof_on) prof_end(stream, &rec);
   count_launch();
   return check_last("igemm_wgrad");
 }

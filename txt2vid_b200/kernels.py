@@ -375,3 +375,17 @@ def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0
     check(lib().t2v_adam_step(n, arr(*[p.data_ptr() for p in params]), arr(*[g.data_ptr() for g in grads]),
                               arr(*[m.data_ptr() for m in ms]), arr(*[v.data_ptr() for v in vs]), sizes, lr, beta1,
                               beta2, eps, step, grad_scale, stream()), "t2v_adam_step")
+
+
+def multi_copy(srcs, dsts):
+    """dst[i].memory <- src[i].memory for lists of equally laid-out fp32 tensors (gradient buckets)."""
+    n = len(srcs)
+    if n == 0:
+        return
+    require_cuda(*srcs)
+    arr = ctypes.c_void_p * n
+    sizes = (ctypes.c_int64 * n)(*[s.numel() for s in srcs])
+    for s, d in zip(srcs, dsts):
+        assert s.dtype == F32 and d.dtype == F32 and s.numel() == d.numel()
+    check(lib().t2v_multi_copy(n, arr(*[s.data_ptr() for s in srcs]), arr(*[d.data_ptr() for d in dsts]), sizes,
+                               stream()), "t2v_multi_copy")

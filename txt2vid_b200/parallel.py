@@ -1,0 +1,88 @@
+"""Data parallelism: one process per GPU, weights resident, ONE bucketed NCCL all-reduce per optimiser
+step (D gradients after the D backward, G gradients after the G backward), SURVEY.md 8(e).
+
+Replaces the reference's per-call torch.nn.parallel.data_parallel / nn.DataParallel replicate-scatter-
+gather (models/tganv2_cond/gen.py:111,116; discrim.py:15), which re-broadcasts 29 M parameters 24 times
+per iteration.  Per-rank semantics match the reference's own multi-GPU behaviour: BatchNorm statistics,
+`x[::2]` batch striding and the caption permutation act on the local shard; the frame offsets `bt` come
+from an identically seeded CPU generator on every rank; the gradient-penalty term (a SUM over samples,
+gan/losses.py:203) is multiplied by the world size so that averaging gradients reproduces the reference's
+full-batch loss.
+"""
+import os
+
+import torch
+import torch.distributed as dist
+
+from . import kernels as K
+
+
+class DistContext(object):
+    def __init__(self, backend=None):
+        self.world = int(os.environ.get("WORLD_SIZE", "1"))
+        self.rank = int(os.environ.get("RANK", "0"))
+        self.local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+        self.enabled = self.world > 1
+        self._flat = {}
+        if self.enabled and not dist.is_initialized():
+            if backend is None:
+                backend = "nccl" if torch.cuda.is_available() else "gloo"
+            if backend == "nccl":
+                torch.cuda.set_device(self.local_rank)
+            dist.init_process_group(backend=backend, init_method="env://")
+
+    @property
+    def gp_scale(self):
+        """factor for gp_lambda under gradient averaging (see module docstring)"""
+        return float(self.world)
+
+    def barrier(self):
+        if self.enabled:
+            dist.barrier()
+
+    def reduce_grads(self, optimizer):
+        """Average the gradients of every parameter of `optimizer` across ranks, in place."""
+        if not self.enabled:
+            return
+        params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
+        if not params:
+            return
+        key = id(optimizer)
+        total = sum(p.numel() for p in params)
+        flat = self._flat.get(key)
+        if flat is None or flat.numel() != total or flat.device != params[0].device:
+            flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
+            self._flat[key] = flat
+        views, off = [], 0
+        for p in params:
+            views.append(flat[off:off + p.numel()])
+            off += p.numel()
+        grads = [p.grad for p in params]
+        if flat.is_cuda:
+            K.multi_copy(grads, views)
+        else:                                   # gloo / CPU tests of the host logic
+            for g, v in zip(grads, views):
+                v.copy_(_memory_order(g))
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM)
+        if hasattr(optimizer, "grad_scale"):
+            optimizer.grad_scale = 1.0 / self.world           # the 1/N is folded into the fused Adam kernel
+        else:
+            flat.mul_(1.0 / self.world)
+        if flat.is_cuda:
+            K.multi_copy(views, grads)
+        else:
+            for g, v in zip(grads, views):
+                _memory_order(g).copy_(v)
+
+    def all_reduce_max(self, value):
+        if not self.enabled:
+            return value
+        t = torch.tensor([value], dtype=torch.float64, device="cuda" if torch.cuda.is_available() and
+                         dist.get_backend() == "nccl" else "cpu")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t[0])
+
+
+def _memory_order(t):
+    """1-D view of a dense tensor in memory order (works for channels-last parameter gradients)."""
+    return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
