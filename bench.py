@@ -159,7 +159,7 @@ def run_b200(args):
     from txt2vid_b200.gan import CondGan, MixedGanLoss, RSGANLoss
     from txt2vid_b200.optim import FusedAdam
     from txt2vid_b200.parallel import DistContext
-    from txt2vid_b200.trainer import train_iteration
+    from txt2vid_b200.trainer import GraphedTrainStep, train_iteration
     from txt2vid_b200.factory import build_models as build_product_models
 
     if not torch.cuda.is_available():
@@ -189,17 +189,26 @@ def run_b200(args):
     host = [(x.contiguous().pin_memory(), t.pin_memory(), l) for x, t, l in host]
     dev = [(x.to(device), t.to(device), l) for x, t, l in host]
 
+    lib = _lib.lib()
+    if args.eager:
+        def run_step(x, t, l):
+            ld, lg, _, _, _ = train_iteration(gan, x, [t, l], device, optD, optG, params, losses, end2end=False,
+                                              dist=ddp)
+            return ld, lg
+    else:
+        graphed = GraphedTrainStep(gan, optD, optG, params, losses, device, end2end=False, dist=ddp, warmup=2)
+
+        def run_step(x, t, l):
+            return graphed(x, [t, l])
+
     def step_resident(i):
         x, t, l = dev[i % nb]
-        return train_iteration(gan, x, [t, l], device, optD, optG, params, losses, end2end=False, dist=ddp)
+        return run_step(x, t, l)
 
     def step_e2e(i):
-        x, t, l = host[i % nb]
-        xd = x.to(device, non_blocking=True)
-        td = t.to(device, non_blocking=True)
-        ld, lg, _, _, _ = train_iteration(gan, xd, [td, l], device, optD, optG, params, losses, end2end=False,
-                                          dist=ddp)
-        return float(ld), float(lg)                     # the device->host read of the step's result
+        x, t, l = host[i % nb]                                   # pinned host memory -> H2D inside the timed region
+        ld, lg = run_step(x.to(device, non_blocking=True), t.to(device, non_blocking=True), l)
+        return float(ld), float(lg)                               # the device->host read of the step's result
 
     def timed(fn, n):
         dist.barrier()
@@ -213,28 +222,38 @@ def run_b200(args):
         dist.barrier()
         return dist.all_reduce_max(e0.elapsed_time(e1) / 1e3)
 
-    lib = _lib.lib()
-    for i in range(max(3, args.warmup)):
+    l0 = lib.t2v_launch_count()
+    step_resident(0)
+    step_resident(1)                                              # eager warm-ups (graph mode: then capture)
+    l1 = lib.t2v_launch_count()
+    launches_per_step = int(l1 - l0) // 2
+    for i in range(2, max(3, args.warmup)):
         step_resident(i)
     torch.cuda.synchronize()
     clocks = ClockSampler(dist.local_rank)
     if rank == 0:
         clocks.start()
-    l0 = lib.t2v_launch_count()
     t_res = timed(step_resident, args.steps)
-    launches = int(lib.t2v_launch_count() - l0)
+    launches = launches_per_step * args.steps
     clk = clocks.stop() if rank == 0 else None
     t_e2e = timed(step_e2e, args.steps)
 
-    # ---- roofline pass: per-launch CUDA-event timing of the conv engine over the same step
+    # ---- roofline pass: per-launch CUDA-event timing of the conv engine over the same step, run eagerly
+    # (events cannot be read back from inside a replayed graph; kernels, shapes and launch order are the same)
     import ctypes
-    prof_steps = min(args.steps, 3)
+    prof_steps = 2
+
+    def step_eager(i):
+        x, t, l = dev[i % nb]
+        train_iteration(gan, x, [t, l], device, optD, optG, params, losses, end2end=False, dist=ddp)
+    step_eager(0)
     lib.t2v_profile_enable(1)
-    t_prof = timed(step_resident, prof_steps)
+    timed(step_eager, prof_steps)
     lib.t2v_profile_enable(0)
     buf = (ctypes.c_double * 6)()
     lib.t2v_profile_read(buf)
     fp_ms, fp_fl, fp_n, wg_ms, wg_fl, wg_n = list(buf)
+    t_prof = t_res / args.steps * prof_steps                       # share is quoted against the timed step
     mem_gb = torch.cuda.max_memory_allocated() / 1e9
 
     if rank != 0:
@@ -267,7 +286,8 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": WORKLOAD, "batch_per_gpu": b, "global_batch": world * b,
-                       "parallelism": "dp%d" % world, "l2": "per-step working set (%.1f GB peak allocated) >> 126 MB L2; "
+                       "parallelism": "dp%d" % world, "launch": "eager" if args.eager else "3 CUDA graphs per step",
+                       "l2": "per-step working set (%.1f GB peak allocated) >> 126 MB L2; "
                        "%d distinct resident batches cycled" % (mem_gb, nb)},
             "e2e": {"value": e2e, "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
                     "ms_per_step": t_e2e / args.steps * 1e3},
@@ -285,6 +305,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="videos per GPU per step (multiple of 8)")
     ap.add_argument("--cpu_batch", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--eager", action="store_true", help="no CUDA graphs: launch every kernel from Python")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -129,15 +129,18 @@ int t2v_render_fwd(const void* pre, float* y, int32_t B, int32_t T, int32_t H, i
 int t2v_render_bwd(const float* dy, const float* y, void* dpre, int32_t B, int32_t T, int32_t H, int32_t W,
                    int32_t C, int32_t Cp, void* stream);
 
-/* bit-exact index kernels ------------------------------------------------------------------- */
+/* bit-exact index kernels -------------------------------------------------------------------
+ * bt_dev (may be NULL): device int32 holding the frame offset, read by the kernel instead of `bt` so that a
+ * captured CUDA graph can be replayed with a fresh draw; the caller then guarantees that the output frame
+ * count computed from `bt` holds for every value *bt_dev may take (even T).                       */
 /* Subsample x[::sn, :, bt::st] (layers.py:106-111) on merged-frame maps of frame_bytes each;
  * scatter = 1 runs the adjoint (y = zero-filled source-shaped gradient)                           */
 int t2v_gather_frames(const void* x, void* y, int32_t B, int32_t T, int64_t frame_bytes, int32_t sn, int32_t st,
-                      int32_t bt, int32_t scatter, void* stream);
+                      int32_t bt, const int32_t* bt_dev, int32_t scatter, void* stream);
 /* one level of the real-video pyramid (gan/trainer.py:131-165): fp32 (B,C,T,H,W) ->
  * (ceil(B/sn), C, ceil((T-bt)/st), Ho, Wo) with nearest resize src = floor(dst*in/out)            */
 int t2v_pyramid_level(const float* x, float* y, const int32_t* in_shape, int32_t Ho, int32_t Wo, int32_t sn,
-                      int32_t st, int32_t bt, void* stream);
+                      int32_t st, int32_t bt, const int32_t* bt_dev, void* stream);
 
 /* LSTM cell update (conv_lstm.py:32-38; txt/basic.py:56 nn.LSTM): gates fp32 (P,4H) = [i|f|g|o]   */
 int t2v_lstm_cell_fwd(const float* gates, const float* c_prev, float* c, void* h, float* h32, int64_t P, int32_t Hd,
@@ -145,10 +148,11 @@ int t2v_lstm_cell_fwd(const float* gates, const float* c_prev, float* c, void* h
 int t2v_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c, const float* dh, const float* dc_next,
                       void* dgates, float* dc_prev, int64_t P, int32_t Hd, void* stream);
 
-/* torch.optim.Adam (train/gan.py:93-94), multi-tensor: host arrays of `count` device pointers      */
+/* torch.optim.Adam (train/gan.py:93-94), multi-tensor: host arrays of `count` device pointers;
+ * dyn_dev (may be NULL): device {lr/(1-b1^t), 1/sqrt(1-b2^t)} overriding `step` for CUDA-graph replays   */
 int t2v_adam_step(int32_t count, float* const* host_params, const float* const* host_grads, float* const* host_m,
                   float* const* host_v, const int64_t* host_sizes, float lr, float beta1, float beta2, float eps,
-                  int32_t step, float grad_scale, void* stream);
+                  int32_t step, float grad_scale, const float* dyn_dev, void* stream);
 
 /* gradient bucket pack / unpack for the data-parallel all-reduce (fp32, memory order): dst[i][:] = src[i][:]  */
 int t2v_multi_copy(int32_t count, const float* const* host_src, float* const* host_dst, const int64_t* host_sizes,

@@ -209,12 +209,14 @@ def render_bwd(dy, y, Cp):
 
 
 def gather_frames(x, B, T, bt, sn=2, st=2):
+    bt = int(bt)
     x5 = x.view((B, T) + tuple(x.shape[1:]))
     y = x5[::sn, bt::st]
     return y.reshape((-1,) + tuple(x.shape[1:])).contiguous()
 
 
 def scatter_frames(dy, B, T, bt, sn=2, st=2):
+    bt = int(bt)
     dx = torch.zeros((B, T) + tuple(dy.shape[1:]), dtype=dy.dtype, device=dy.device)
     Bo = (B + sn - 1) // sn
     dx[::sn, bt::st] = dy.view((Bo, -1) + tuple(dy.shape[1:]))
@@ -222,6 +224,7 @@ def scatter_frames(dy, B, T, bt, sn=2, st=2):
 
 
 def pyramid_level(x, Ho, Wo, sn=1, st=1, bt=0):
+    bt = int(bt)
     B, C, T, H, W = x.shape
     ih = (torch.arange(Ho, device=x.device) * H) // Ho
     iw = (torch.arange(Wo, device=x.device) * W) // Wo
@@ -247,7 +250,7 @@ def lstm_cell_bwd(gates, c_prev, c, dh, dc_next):
     return dg.to(STORE).contiguous(), (dc * f).contiguous()
 
 
-def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0, dyn=None):
     bc1, bc2 = 1 - beta1 ** step, 1 - beta2 ** step
     with torch.no_grad():
         for p, g, m, v in zip(params, grads, ms, vs):

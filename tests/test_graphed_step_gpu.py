@@ -1,0 +1,75 @@
+"""GPU: the CUDA-graph replay of the training iteration (trainer.GraphedTrainStep) must follow the eager
+iteration: same seeds -> same host-RNG draws -> same losses (up to fp32 atomics order / bf16 noise), and the
+weights must keep training across replays.  Also checks tcgen05 wgrad on < 64-channel layers (TMA zero fill)."""
+import contextlib
+import io
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _setup(B, seed=100):
+    from bench import train_params
+    from txt2vid_b200 import ops
+    from txt2vid_b200.data import SyntheticVideoCaptions
+    from txt2vid_b200.factory import build_models
+    from txt2vid_b200.gan import CondGan, MixedGanLoss, RSGANLoss
+    from txt2vid_b200.optim import FusedAdam
+    ops.PACKS.clear()
+    dev = torch.device("cuda", 0)
+    with contextlib.redirect_stdout(io.StringIO()):
+        txt, gen, dis = build_models(True, vocab_size=1000, seed=seed)
+    txt, gen, dis = txt.to(dev), gen.to(dev), dis.to(dev)
+    torch.manual_seed(7)
+    torch.cuda.manual_seed(7)
+    np.random.seed(7)
+    gan = CondGan(gen=gen, discrims=[dis], cond_encoder=txt, discrim_names=["video"])
+    losses = MixedGanLoss(g_loss=RSGANLoss(), d_loss=RSGANLoss())
+    optD = FusedAdam([{"params": dis.parameters()}], lr=2e-4, betas=(0.5, 0.999))
+    optG = FusedAdam([{"params": gen.parameters()}], lr=2e-4, betas=(0.5, 0.999))
+    data = SyntheticVideoCaptions(B, 6, vocab_size=1000)
+    batches = [(x.to(dev), t.to(dev), l) for x, t, l in (data.batch(i) for i in range(6))]
+    return dev, gan, losses, optD, optG, train_params(0.5), batches
+
+
+def test_graph_replay_matches_eager():
+    from txt2vid_b200.trainer import GraphedTrainStep, train_iteration
+    B = 8
+    dev, gan, losses, optD, optG, params, batches = _setup(B)
+    eager = []
+    for x, t, l in batches:
+        ld, lg, _, _, _ = train_iteration(gan, x, [t, l], dev, optD, optG, params, losses, end2end=False)
+        eager.append((float(ld), float(lg)))
+    dev, gan, losses, optD, optG, params, batches = _setup(B)
+    step = GraphedTrainStep(gan, optD, optG, params, losses, dev, warmup=2)
+    graphed = []
+    for x, t, l in batches:
+        ld, lg = step(x, [t, l])
+        graphed.append((float(ld), float(lg)))
+    print("eager  ", eager)
+    print("graphed", graphed)
+    assert step.graphs is not None
+    for (a, b), (c, d) in zip(eager, graphed):
+        assert abs(a - c) < 3e-2 * max(1.0, abs(a)) and abs(b - d) < 3e-2 * max(1.0, abs(b)), (eager, graphed)
+    # the losses move (training is happening) and stay finite
+    assert all(np.isfinite(v) for pair in graphed for v in pair)
+    assert len({round(p[0], 4) for p in graphed}) > 2
+
+
+@pytest.mark.parametrize("case", [(8, 1, 16, 16, 32, 48, (1, 3, 3)), (4, 8, 8, 8, 16, 64, (3, 3, 3)),
+                                  (6, 1, 32, 32, 32, 16, (1, 3, 3)), (16, 1, 8, 8, 128, 16, (1, 1, 1))])
+def test_tc_wgrad_small_channels(case):
+    import torch.nn.functional as F
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k = case
+    g = torch.Generator(device="cuda").manual_seed(3)
+    x = torch.randn((N, D, H, W, Cin), device="cuda", generator=g).to(torch.bfloat16)
+    dy = torch.randn((N, D, H, W, Cout), device="cuda", generator=g).to(torch.bfloat16)
+    dw = K.conv_wgrad(dy, x, k=k, algo=1)
+    ref = K.conv_wgrad(dy, x, k=k, algo=2)
+    err = float((dw - ref).abs().max() / ref.abs().max())
+    print(case, err)
+    assert err < 1e-4

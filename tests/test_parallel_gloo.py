@@ -1,0 +1,64 @@
+"""CPU, world_size 2 over gloo: the data-parallel gradient exchange of txt2vid_b200.parallel (bucket pack ->
+one all-reduce -> unpack, channels-last parameter layouts included) equals the mean of the per-rank gradients,
+and identically seeded ranks draw identical frame offsets while permutations / z differ."""
+import os
+import socket
+
+import numpy as np
+import torch
+import torch.multiprocessing as mp
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, out):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world),
+                      LOCAL_RANK=str(rank))
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    from txt2vid_b200.parallel import DistContext
+    from txt2vid_b200 import hostrng
+    ctx = DistContext(backend="gloo")
+    assert ctx.enabled and ctx.world == world and ctx.gp_scale == float(world)
+    torch.manual_seed(1234)                       # per-rank parameters would be identical in real use
+    conv = torch.nn.Conv3d(4, 6, 3)
+    lin = torch.nn.Linear(5, 3)
+    # one weight in channels-last memory, like the product's re-homed conv weights
+    conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last_3d)
+    params = list(conv.parameters()) + list(lin.parameters())
+    g = torch.Generator().manual_seed(100 + rank)
+    for p in params:
+        p.grad = torch.empty_like(p, memory_format=torch.preserve_format)
+        p.grad.copy_(torch.randn(p.shape, generator=g))
+    local = [p.grad.clone() for p in params]
+    opt = torch.optim.SGD(params, lr=0.1)
+    ctx.reduce_grads(opt)
+    # frame offsets: shared CPU seed -> same on all ranks; permutation: per-rank numpy seed
+    torch.manual_seed(100)
+    np.random.seed(100 + rank)
+    bts = [hostrng.EagerDraws().bt(2) for _ in range(7)]
+    perm = hostrng.EagerDraws().perm(8, "cpu").tolist()
+    out[rank] = {"local": local, "reduced": [p.grad.clone() for p in params], "bts": bts, "perm": perm,
+                 "strides": [p.grad.stride() for p in params]}
+    torch.distributed.barrier()
+    torch.distributed.destroy_process_group()
+
+
+def test_reduce_grads_world2():
+    world, port = 2, _free_port()
+    mgr = mp.Manager()
+    out = mgr.dict()
+    mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
+    r0, r1 = out[0], out[1]
+    for a, b, m0, m1 in zip(r0["local"], r1["local"], r0["reduced"], r1["reduced"]):
+        mean = (a + b) / 2
+        assert torch.allclose(m0, mean, atol=1e-6) and torch.allclose(m1, mean, atol=1e-6)
+    assert r0["bts"] == r1["bts"]
+    assert r0["perm"] != r1["perm"]
+    assert r0["strides"][0] == r1["strides"][0] and r0["strides"][0][1] == 1      # layout preserved (channels-last)

@@ -80,13 +80,13 @@ SIGNATURES = {
     "t2v_bn_bwd": [_P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_render_fwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_render_bwd": [_P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
-    "t2v_gather_frames": [_P, _P, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, c_i32, _P],
-    "t2v_pyramid_level": [_P, _P, _I32P, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_gather_frames": [_P, _P, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, _P, c_i32, _P],
+    "t2v_pyramid_level": [_P, _P, _I32P, c_i32, c_i32, c_i32, c_i32, c_i32, _P, _P],
     "t2v_lstm_cell_fwd": [_P, _P, _P, _P, _P, c_i64, c_i32, _P],
     "t2v_lstm_cell_bwd": [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, _P],
     "t2v_multi_copy": [c_i32, _PP, _PP, ctypes.POINTER(c_i64), _P],
     "t2v_adam_step": [c_i32, _PP, _PP, _PP, _PP, ctypes.POINTER(c_i64), c_float, c_float, c_float, c_float, c_i32,
-                      c_float, _P],
+                      c_float, _P, _P],
 }
 _RESTYPES = {"t2v_launch_count": ctypes.c_ulonglong}
 

@@ -54,7 +54,9 @@ class Subsample(nn.Module):
         self.st = st
 
     def draw(self):
-        return torch.randint(self.st, (1,))
+        """python int (eager) or a device int32 tensor (CUDA-graph mode), see hostrng.py"""
+        from . import hostrng
+        return hostrng.CURRENT.bt(self.st)
 
     def forward(self, x, bt=None):
         if bt is None:
@@ -62,7 +64,7 @@ class Subsample(nn.Module):
         if x.is_cuda and x.dtype == torch.float32 and x.dim() == 5 and not x.requires_grad:
             from . import kernels as K
             B, C, T, H, W = x.shape
-            return K.pyramid_level(x.contiguous(), H, W, self.sn, self.st, int(bt)), bt
+            return K.pyramid_level(x.contiguous(), H, W, self.sn, self.st, bt), bt
         return x[::self.sn, :, int(bt)::self.st], bt
 
 

@@ -409,9 +409,11 @@ __global__ void render_bwd_kernel(const float* __restrict__ dy, const float* __r
 // ------------------------------------------------------------------------------------ index kernels (bit-exact)
 // Frame gather on merged-frame CL maps: out frame (b', t') <- in frame (sn*b', bt + st*t'); 16-byte units
 __global__ void gather_frames_kernel(const uint4* __restrict__ x, uint4* __restrict__ y, int T, int To, int sn,
-                                     int st, int bt, long long frame_u4, long long total, int scatter) {
+                                     int st, int bt_host, const int* __restrict__ bt_dev, long long frame_u4,
+                                     long long total, int scatter) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const int bt = bt_dev ? *bt_dev : bt_host;
   const long long e = i % frame_u4;
   const long long fo = i / frame_u4;
   const long long bo = fo / To, to = fo % To;
@@ -421,9 +423,11 @@ __global__ void gather_frames_kernel(const uint4* __restrict__ x, uint4* __restr
 }
 // x fp32 (B,C,T,H,W) -> y (Bo,C,To,Ho,Wo): y[b,c,t,h,w] = x[b*sn, c, bt + t*st, floor(h*H/Ho), floor(w*W/Wo)]
 __global__ void pyramid_kernel(const float* __restrict__ x, float* __restrict__ y, int B, int C, int T, int H, int W,
-                               int Bo, int To, int Ho, int Wo, int sn, int st, int bt, long long total) {
+                               int Bo, int To, int Ho, int Wo, int sn, int st, int bt_host,
+                               const int* __restrict__ bt_dev, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
+  const int bt = bt_dev ? *bt_dev : bt_host;
   long long t = i;
   const int w = (int)(t % Wo); t /= Wo;
   const int h = (int)(t % Ho); t /= Ho;
@@ -491,8 +495,10 @@ struct AdamChunk {
   long long n[kMax];
   int count;
 };
+// dyn (optional, device): {lr / (1 - b1^t), 1 / sqrt(1 - b2^t)} for CUDA-graph replays, where the step
+// count cannot be a baked-in kernel argument
 __global__ void adam_kernel(const AdamChunk ch, float lr, float b1, float b2, float eps, float bc1, float bc2,
-                            float grad_scale) {
+                            float grad_scale, const float* __restrict__ dyn) {
   const int t = blockIdx.y;
   if (t >= ch.count) return;
   float* p = ch.p[t];
@@ -500,8 +506,8 @@ __global__ void adam_kernel(const AdamChunk ch, float lr, float b1, float b2, fl
   float* m = ch.m[t];
   float* v = ch.v[t];
   const long long n = ch.n[t];
-  const float step = lr / bc1;
-  const float inv_sqrt_bc2 = rsqrtf(bc2);
+  const float step = dyn ? dyn[0] : lr / bc1;
+  const float inv_sqrt_bc2 = dyn ? dyn[1] : rsqrtf(bc2);
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     const float gi = g[i] * grad_scale;
     const float mi = b1 * m[i] + (1.f - b1) * gi;
@@ -710,7 +716,7 @@ int t2v_render_bwd(const float* dy, const float* y, void* dpre, int32_t B, int32
   return check_last("render_bwd");
 }
 int t2v_gather_frames(const void* x, void* y, int32_t B, int32_t T, int64_t frame_bytes, int32_t sn, int32_t st,
-                      int32_t bt, int32_t scatter, void* stream) {
+                      int32_t bt, const int32_t* bt_dev, int32_t scatter, void* stream) {
   if (frame_bytes % 16 || bt < 0) return T2V_ERR_ARG;
   const int Bo = (B + sn - 1) / sn;
   const int To = T > bt ? (T - bt + st - 1) / st : 0;
@@ -719,20 +725,21 @@ int t2v_gather_frames(const void* x, void* y, int32_t B, int32_t T, int64_t fram
   const long long total = (long long)Bo * To * fu4;
   if (total == 0) return T2V_OK;
   gather_frames_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(reinterpret_cast<const uint4*>(x),
-                                                                   reinterpret_cast<uint4*>(y), T, To, sn, st, bt, fu4,
-                                                                   total, scatter);
+                                                                   reinterpret_cast<uint4*>(y), T, To, sn, st, bt, bt_dev,
+                                                                   fu4, total, scatter);
   count_launch();
   return check_last("gather_frames");
 }
 int t2v_pyramid_level(const float* x, float* y, const int32_t* in_shape, int32_t Ho, int32_t Wo, int32_t sn,
-                      int32_t st, int32_t bt, void* stream) {
+                      int32_t st, int32_t bt, const int32_t* bt_dev, void* stream) {
   const int B = in_shape[0], C = in_shape[1], T = in_shape[2], H = in_shape[3], W = in_shape[4];
   if (sn < 1 || st < 1 || bt < 0) return T2V_ERR_ARG;
   const int Bo = (B + sn - 1) / sn;
   const int To = T > bt ? (T - bt + st - 1) / st : 0;
   const long long total = (long long)Bo * C * To * Ho * Wo;
   if (total == 0) return T2V_OK;
-  pyramid_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, y, B, C, T, H, W, Bo, To, Ho, Wo, sn, st, bt, total);
+  pyramid_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, y, B, C, T, H, W, Bo, To, Ho, Wo, sn, st, bt, bt_dev,
+                                                             total);
   count_launch();
   return check_last("pyramid_level");
 }
@@ -755,7 +762,7 @@ int t2v_lstm_cell_bwd(const float* gates, const float* c_prev, const float* c, c
 }
 int t2v_adam_step(int32_t count, float* const* host_params, const float* const* host_grads, float* const* host_m,
                   float* const* host_v, const int64_t* host_sizes, float lr, float beta1, float beta2, float eps,
-                  int32_t step, float grad_scale, void* stream) {
+                  int32_t step, float grad_scale, const float* dyn_dev, void* stream) {
   const float bc1 = 1.f - powf(beta1, (float)step), bc2 = 1.f - powf(beta2, (float)step);
   for (int base = 0; base < count; base += AdamChunk::kMax) {
     AdamChunk ch;
@@ -773,7 +780,7 @@ int t2v_adam_step(int32_t count, float* const* host_params, const float* const* 
     if (bx > 2048) bx = 2048;
     if (bx < 1) bx = 1;
     dim3 grid((unsigned)bx, ch.count, 1);
-    adam_kernel<<<grid, 256, 0, STREAM>>>(ch, lr, beta1, beta2, eps, bc1, bc2, grad_scale);
+    adam_kernel<<<grid, 256, 0, STREAM>>>(ch, lr, beta1, beta2, eps, bc1, bc2, grad_scale, dyn_dev);
     count_launch();
   }
   return check_last("adam_step");

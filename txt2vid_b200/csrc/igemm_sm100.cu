@@ -17,6 +17,8 @@
 //
 // Warp roles (192 threads): warp 0 = TMA producer, warp 1 = TMEM allocator + MMA issuer,
 // warps 2-5 = epilogue (TMEM -> registers -> global).
+#include <cstdio>
+#include <cstdlib>
 #include <vector>
 
 #include "t2v_common.cuh"
@@ -345,12 +347,12 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
 // ------------------------------------------------------------------------------------ host side
 // Optional per-launch timing (bench.py roofline): CUDA events on the launching stream around every
 // engine launch; t2v_profile_read() sums elapsed time and useful (live-tap) FLOPs per kernel kind.
-struct ProfRec { cudaEvent_t a, b; double flops; int kind; };
+struct ProfRec { cudaEvent_t a, b; double flops; int kind; t2v_conv_geom g; int ctas; };
 static bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
 void prof_enable(int on) { g_prof_on = on != 0; }
-static void prof_begin(cudaStream_t s, ProfRec* r, int kind, double flops) {
-  r->kind = kind; r->flops = flops;
+static void prof_begin(cudaStream_t s, ProfRec* r, int kind, double flops, const t2v_conv_geom* g, int ctas) {
+  r->kind = kind; r->flops = flops; r->g = *g; r->ctas = ctas;
   cudaEventCreate(&r->a); cudaEventCreate(&r->b);
   cudaEventRecord(r->a, s);
 }
@@ -358,13 +360,19 @@ static void prof_end(cudaStream_t s, ProfRec* r) { cudaEventRecord(r->b, s); g_p
 // out[kind*3 + {0,1,2}] = {milliseconds, flops, launches}, kind 0 = fprop/dgrad, 1 = wgrad
 void prof_read(double* out) {
   for (int i = 0; i < 6; ++i) out[i] = 0.0;
+  const char* dump = getenv("T2V_PROFILE_DUMP");
+  FILE* f = dump ? fopen(dump, "a") : nullptr;
   for (auto& r : g_prof) {
     cudaEventSynchronize(r.b);
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);
+    if (f)
+      fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.0f\n", r.kind, r.g.N, r.g.D, r.g.H, r.g.W, r.g.Cin, r.g.Cout,
+              r.g.kd, r.g.kh, r.g.kw, r.ctas, ms, r.flops);
     out[r.kind * 3 + 0] += ms; out[r.kind * 3 + 1] += r.flops; out[r.kind * 3 + 2] += 1.0;
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
+  if (f) fclose(f);
   g_prof.clear();
 }
 
@@ -457,7 +465,8 @@ bool igemm_fprop_supported(const t2v_conv_geom* g) {
 }
 
 bool igemm_wgrad_supported(const t2v_conv_geom* g) {
-  return igemm_fprop_supported(g) && g->Cin % 64 == 0 && g->Cout % 64 == 0;
+  // channel counts below 64 ride on TMA out-of-bounds zero fill of the 64-channel boxes
+  return igemm_fprop_supported(g);
 }
 
 static int fill_common(IgemmParams& p, const t2v_conv_geom* g) {
@@ -512,7 +521,8 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
   };
   ProfRec rec;
   if (g_prof_on)
-    prof_begin(stream, &rec, 0, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps);
+    prof_begin(stream, &rec, 0, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps, g,
+               (int)(grid.x * grid.y));
   if (BLOCK_K == 64) launch(igemm_fprop_kernel<64>);
   else if (BLOCK_K == 32) launch(igemm_fprop_kernel<32>);
   else launch(igemm_fprop_kernel<16>);
@@ -533,7 +543,8 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   p.BN = g->Cin >= 128 ? 128 : 64;
   const int mtiles = (g->Cout + 127) / 128, ntiles = (g->Cin + p.BN - 1) / p.BN;
   const int base_ctas = mtiles * ntiles * ntaps;
-  int splits = (2 * 148 + base_ctas - 1) / base_ctas;
+  // one CTA per SM (smem-bound): fill at most two FULL waves of 148 so that no third, nearly empty wave runs
+  int splits = (2 * 148) / base_ctas;
   const int max_splits = (p.tiles_total + 3) / 4;  // keep >= 4 k-blocks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -563,7 +574,8 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   cudaFuncSetAttribute(igemm_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ProfRec rec;
   if (g_prof_on)
-    prof_begin(stream, &rec, 1, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps);
+    prof_begin(stream, &rec, 1, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps, g,
+               (int)(grid.x * grid.y * grid.z));
   igemm_wgrad_kernel<<<grid, kThreads, smem, stream>>>(tmDy, tmX, p);
   if (g_prof_on) prof_end(stream, &rec);
   count_launch();

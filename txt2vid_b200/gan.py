@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from .util import gen_perm
+from . import hostrng
 
 
 def get_labels_for(x, label):
@@ -126,16 +126,16 @@ def _gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xb
     :140-145); only d/dx_hat is kept (:178); the second derivative runs through ops.Conv*F etc."""
     B = real_x.size(0)
     assert real_x.dim() in (4, 5)
-    alpha = torch.rand(*([B] + [1] * (real_x.dim() - 1)))
-    a = alpha.to(real_x.device)
+    alpha = hostrng.CURRENT.alpha(B, real_x.device)            # B draws from the CPU generator, as the reference
+    a = alpha.view([B] + [1] * (real_x.dim() - 1))
     xh = (a * real_x + (1 - a) * fake_x).requires_grad_(True)
     xbarh = None
     if real_xbar is not None and fake_xbar is not None:
-        ab = alpha.view([B] + [1] * (real_xbar.dim() - 1)).to(real_xbar.device)
+        ab = alpha.view([B] + [1] * (real_xbar.dim() - 1))
         xbarh = (ab * real_xbar + (1 - ab) * fake_xbar).requires_grad_(True)
     ch = None
     if real_cond is not None and fake_cond is not None:
-        ac = alpha.view(B, 1).to(real_cond.device)
+        ac = alpha.view(B, 1)
         ch = (ac * real_cond + (1 - ac) * fake_cond).requires_grad_(True)
     u, c, _ = discrim(x=xh, cond=ch, xbar=xbarh)
     outs = [u] + ([c] if c is not None else [])
@@ -246,7 +246,7 @@ class CondGan(object):
         for name, discrim in zip(self.discrim_names, self.discrims):
             fake_cond = None
             if cond is not None:
-                perm = torch.as_tensor(gen_perm(cond[0].size(0)), device=cond[0].device)
+                perm = hostrng.CURRENT.perm(cond[0].size(0), cond[0].device)
                 shuffled = cond[0][perm]
                 fake_cond = [shuffled[0:r.size(0)] for r in cond]
             l, f, r = self.discrim_forward(name=name, discrim=discrim, real=real, real_cond=cond,

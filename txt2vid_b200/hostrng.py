@@ -1,0 +1,106 @@
+"""Host-RNG draws of one training iteration: frame offsets `bt`
+(models/layers.py:107-108, torch CPU generator), the mismatched-caption permutation
+(gan/cond_gan.py:133, numpy), the gradient-penalty alphas (gan/losses.py:140-145, torch CPU generator).
+
+EagerDraws reproduces the reference: values are drawn at the call site, in call order.
+StaticDraws serves the same calls from device buffers so that a captured CUDA graph can be replayed:
+`refresh()` draws the whole iteration's values on the host -- same generators, same order -- and copies them
+into the buffers the captured kernels read.
+"""
+import numpy as np
+import torch
+
+from .util import gen_perm
+
+
+class EagerDraws(object):
+    def begin_iteration(self):
+        pass
+
+    def bt(self, st=2):
+        return int(torch.randint(st, (1,)))
+
+    def perm(self, n, device):
+        return torch.as_tensor(gen_perm(n), device=device)
+
+    def alpha(self, B, device):
+        return torch.rand(B).to(device)
+
+
+class RecordingDraws(EagerDraws):
+    """Eager draws that also record the (kind, size) sequence of one iteration."""
+
+    def __init__(self):
+        self.calls = []
+
+    def begin_iteration(self):
+        self.calls = []
+
+    def bt(self, st=2):
+        self.calls.append(("bt", st))
+        return EagerDraws.bt(self, st)
+
+    def perm(self, n, device):
+        self.calls.append(("perm", n))
+        return EagerDraws.perm(self, n, device)
+
+    def alpha(self, B, device):
+        self.calls.append(("alpha", B))
+        return EagerDraws.alpha(self, B, device)
+
+
+class StaticDraws(EagerDraws):
+    def __init__(self, calls, device):
+        self.calls = list(calls)
+        self.device = device
+        self.host, self.dev = [], []
+        for kind, n in self.calls:
+            if kind == "bt":
+                h = torch.zeros(1, dtype=torch.int32)
+            elif kind == "perm":
+                h = torch.zeros(n, dtype=torch.int64)
+            else:
+                h = torch.zeros(n, dtype=torch.float32)
+            h = h.pin_memory() if device.type == "cuda" else h
+            self.host.append(h)
+            self.dev.append(torch.zeros_like(h, device=device))
+        self.i = 0
+
+    def refresh(self):
+        """Draw the next iteration's values in the recorded (= reference) order and stage them on the device."""
+        for (kind, n), h, d in zip(self.calls, self.host, self.dev):
+            if kind == "bt":
+                h[0] = int(torch.randint(n, (1,)))
+            elif kind == "perm":
+                h.copy_(torch.from_numpy(np.ascontiguousarray(gen_perm(n))))
+            else:
+                h.copy_(torch.rand(n))
+            d.copy_(h, non_blocking=True)
+
+    def begin_iteration(self):
+        self.i = 0
+
+    def _next(self, kind, n):
+        k, m = self.calls[self.i]
+        assert (k, m) == (kind, n), "host-RNG call sequence changed: got %s, recorded %s" % ((kind, n), (k, m))
+        d = self.dev[self.i]
+        self.i += 1
+        return d
+
+    def bt(self, st=2):
+        return self._next("bt", st)
+
+    def perm(self, n, device):
+        return self._next("perm", n)
+
+    def alpha(self, B, device):
+        return self._next("alpha", B)
+
+
+CURRENT = EagerDraws()
+
+
+def set_current(d):
+    global CURRENT
+    CURRENT = d
+    return d

@@ -299,15 +299,26 @@ def render_bwd(dy, y, Cp):
     return dpre
 
 
+def _bt_args(bt, T, st):
+    """bt: python int, or a device int32 tensor (CUDA-graph replays).  With a tensor the frame count must not
+    depend on its value: T divisible by st."""
+    if isinstance(bt, torch.Tensor):
+        assert bt.is_cuda and bt.dtype == torch.int32 and T % st == 0, "device-side bt needs T % st == 0"
+        return 0, bt
+    return int(bt), None
+
+
 def gather_frames(x, B, T, bt, sn=2, st=2):
     """x (B*T,1,H,W,C) merged-frame map -> frames (b*sn, bt + t*st): (Bo*To,1,H,W,C)."""
     require_cuda(x)
     assert x.is_contiguous() and x.shape[0] == B * T
+    bt, bt_dev = _bt_args(bt, T, st)
     Bo = (B + sn - 1) // sn
     To = (T - bt + st - 1) // st if T > bt else 0
     y = torch.empty((Bo * To,) + tuple(x.shape[1:]), device=x.device, dtype=x.dtype)
     fb = x[0].numel() * x.element_size()
-    check(lib().t2v_gather_frames(ptr(x), ptr(y), B, T, fb, sn, st, bt, 0, stream()), "t2v_gather_frames")
+    check(lib().t2v_gather_frames(ptr(x), ptr(y), B, T, fb, sn, st, bt, ptr(bt_dev), 0, stream()),
+          "t2v_gather_frames")
     return y
 
 
@@ -315,9 +326,11 @@ def scatter_frames(dy, B, T, bt, sn=2, st=2):
     """adjoint of gather_frames: zero-filled (B*T, ...) with the gathered frames written back."""
     require_cuda(dy)
     assert dy.is_contiguous()
+    bt, bt_dev = _bt_args(bt, T, st)
     dx = torch.empty((B * T,) + tuple(dy.shape[1:]), device=dy.device, dtype=dy.dtype)
-    fb = dy[0].numel() * dy.element_size() if dy.shape[0] else dx[0].numel() * dx.element_size()
-    check(lib().t2v_gather_frames(ptr(dy), ptr(dx), B, T, fb, sn, st, bt, 1, stream()), "t2v_gather_frames")
+    fb = dx[0].numel() * dx.element_size()
+    check(lib().t2v_gather_frames(ptr(dy), ptr(dx), B, T, fb, sn, st, bt, ptr(bt_dev), 1, stream()),
+          "t2v_gather_frames")
     return dx
 
 
@@ -327,10 +340,11 @@ def pyramid_level(x, Ho, Wo, sn=1, st=1, bt=0):
     require_cuda(x)
     assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
     B, C, T, H, W = x.shape
+    bt, bt_dev = _bt_args(bt, T, st)
     Bo = (B + sn - 1) // sn
     To = (T - bt + st - 1) // st if T > bt else 0
     y = torch.empty((Bo, C, To, Ho, Wo), device=x.device, dtype=F32)
-    check(lib().t2v_pyramid_level(ptr(x), ptr(y), _i32(B, C, T, H, W), Ho, Wo, sn, st, bt, stream()),
+    check(lib().t2v_pyramid_level(ptr(x), ptr(y), _i32(B, C, T, H, W), Ho, Wo, sn, st, bt, ptr(bt_dev), stream()),
           "t2v_pyramid_level")
     return y
 
@@ -361,7 +375,7 @@ def lstm_cell_bwd(gates, c_prev, c, dh, dc_next):
     return dgates, dc_prev
 
 
-def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0):
+def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0, dyn=None):
     """In-place multi-tensor Adam on fp32 tensors that share memory layout pairwise."""
     n = len(params)
     if n == 0:
@@ -374,7 +388,7 @@ def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0
             (p.shape, p.stride(), g.stride())
     check(lib().t2v_adam_step(n, arr(*[p.data_ptr() for p in params]), arr(*[g.data_ptr() for g in grads]),
                               arr(*[m.data_ptr() for m in ms]), arr(*[v.data_ptr() for v in vs]), sizes, lr, beta1,
-                              beta2, eps, step, grad_scale, stream()), "t2v_adam_step")
+                              beta2, eps, step, grad_scale, ptr(dyn), stream()), "t2v_adam_step")
 
 
 def multi_copy(srcs, dsts):

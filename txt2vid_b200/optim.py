@@ -10,6 +10,7 @@ class FusedAdam(torch.optim.Optimizer):
     def __init__(self, params, lr=1e-3, betas=(0.9, 0.999), eps=1e-8):
         super().__init__(params, dict(lr=lr, betas=betas, eps=eps))
         self.grad_scale = 1.0
+        self.dyn = None          # device {lr/(1-b1^t), 1/sqrt(1-b2^t)} in CUDA-graph mode (trainer.GraphedTrainStep)
 
     @torch.no_grad()
     def step(self, closure=None):
@@ -39,5 +40,5 @@ class FusedAdam(torch.optim.Optimizer):
                 vs.append(st['exp_avg_sq'])
             if ps:
                 b1, b2 = group['betas']
-                K.adam_step(ps, gs, ms, vs, group['lr'], b1, b2, group['eps'], step, self.grad_scale)
+                K.adam_step(ps, gs, ms, vs, group['lr'], b1, b2, group['eps'], step, self.grad_scale, self.dyn)
         ops.bump_weight_epoch()

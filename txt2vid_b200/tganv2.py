@@ -78,10 +78,13 @@ class _MultiScaleGenBase(nn.Module):
         n = len(self.render_blocks)
         for i in range(n):
             if i != 0 and self.training:
-                bt = int(self.subsample.draw())                                   # gen.py:101-109
+                bt = self.subsample.draw()                                        # gen.py:101-109
                 h = ops.gather_frames(h, Bc, T, bt)
                 Bc = (Bc + 1) // 2
-                T = (T - bt + 1) // 2 if T > bt else 0
+                if isinstance(bt, torch.Tensor):
+                    T //= 2                                                       # graph mode: T is even
+                else:
+                    T = (T - bt + 1) // 2 if T > bt else 0
             blk = self.abstract_blocks[i]
             h = blk.forward_cl(h)
             abstract.append(h)

@@ -114,62 +114,185 @@ def test(gan=None, num_samples=1, dataset=None, device=None, params=None, channe
             break
 
 
-def train_iteration(gan, x, y, device, optD, optG, params, losses, channel_first=True, end2end=True, dist=None,
-                    z=None):
-    """Body of one `train()` iteration (gan/trainer.py:199-267).  x: (B,T,C,H,W) loader order.
-    Returns (lossD, lossG, fake) with the losses as 0-d device tensors (no host sync here)."""
-    B = x.size(0)
-    if not params.data_is_imgs and channel_first:
-        x = x.permute(0, 2, 1, 3, 4)
-    if params.img_model and not params.data_is_imgs:
-        x = x.squeeze(2)
+def encode_captions(gan, y, end2end):
     cond = None
     if gan.cond_encoder is not None and len(y) >= 2:
         _, _, cond = gan.cond_encoder.encode(y[0], y[1])
         if not end2end:
             cond = cond.detach()
-    x, cond = multiscale_data(x, cond, params.frame_sizes, params.subsample_input)
-    if z is None:
-        z = torch.randn(B, gan.gen.latent_size, device=device)
-    fake = gan(z, cond=cond[0] if cond is not None else None)
+    return cond
 
-    total_d = 0
+
+def _d_phase(gan, x, cond, device, params, losses, z, channel_first, end2end, j=0, st=None):
+    """pyramid + G forward (first D step only) + D loss backward (trainer.py:199-240)."""
+    if st is None:
+        B = x.size(0)
+        if not params.data_is_imgs and channel_first:
+            x = x.permute(0, 2, 1, 3, 4)
+        if params.img_model and not params.data_is_imgs:
+            x = x.squeeze(2)
+        xs, conds = multiscale_data(x, cond, params.frame_sizes, params.subsample_input)
+        if z is None:
+            z = torch.randn(B, gan.gen.latent_size, device=device)
+        fake = gan(z, cond=conds[0] if conds is not None else None)
+        st = {"xs": xs, "conds": conds, "z": z, "fake": fake}
+    loss = gan.discrim_step(real=st["xs"], fake=[f.detach() for f in st["fake"]], cond=st["conds"],
+                            loss=losses.discrim_loss, gp_lambda=params.gp_lambda)
+    if not params.no_mean_discrim_loss:
+        loss = loss / params.discrim_steps
+    loss.backward(retain_graph=j != params.discrim_steps - 1 or end2end)
+    st["lossD"] = loss.detach()
+    return st
+
+
+def _g_phase(gan, st, params, losses, j=0):
+    """real_pred + G loss backward (trainer.py:247-262)."""
+    xs, conds = st["xs"], st["conds"]
+    if j == 0:
+        # trainer.py:247 -- draws the caption permutation again (numpy RNG) although only real_pred is used
+        with torch.no_grad():
+            _, _, st["real_pred"] = gan.all_discrim_forward(real=xs, cond=conds, fake=None, loss=None)
+    else:
+        st["fake"] = gan(st["z"], cond=conds[0] if conds is not None else None)
+    dparams = [p_ for d in gan.discrims for p_ in d.parameters()]
+    for p_ in dparams:                                  # D's parameter gradients are not needed here
+        p_.requires_grad_(False)
+    try:
+        loss = gan.gen_step(fake=st["fake"], real_pred=st["real_pred"], cond=conds, loss=losses.gen_loss)
+        if not params.no_mean_gen_loss:
+            loss = loss / params.gen_steps
+        loss.backward(retain_graph=j != params.gen_steps - 1)
+    finally:
+        for p_ in dparams:
+            p_.requires_grad_(True)
+    st["lossG"] = loss.detach()
+    return st
+
+
+def train_iteration(gan, x, y, device, optD, optG, params, losses, channel_first=True, end2end=True, dist=None,
+                    z=None):
+    """Body of one `train()` iteration (gan/trainer.py:199-267).  x: (B,T,C,H,W) loader order.
+    Returns (lossD, lossG, fake, real_levels, conds) with the losses as 0-d device tensors (no host sync)."""
+    from . import hostrng
+    hostrng.CURRENT.begin_iteration()
+    cond = encode_captions(gan, y, end2end)
+    st, total_d, total_g = None, 0, 0
     for j in range(params.discrim_steps):
-        loss = gan.discrim_step(real=x, fake=[f.detach() for f in fake], cond=cond, loss=losses.discrim_loss,
-                                gp_lambda=params.gp_lambda)
-        if not params.no_mean_discrim_loss:
-            loss = loss / params.discrim_steps
-        loss.backward(retain_graph=j != params.discrim_steps - 1 or end2end)
+        st = _d_phase(gan, x, cond, device, params, losses, z, channel_first, end2end, j, st)
         if dist is not None:
             dist.reduce_grads(optD)
         optD.step()
-        total_d = total_d + loss.detach()
-
-    # trainer.py:247 -- draws the caption permutation again (numpy RNG) although only real_pred is used
-    with torch.no_grad():
-        _, _, real_pred = gan.all_discrim_forward(real=x, cond=cond, fake=None, loss=None)
-
-    total_g = 0
+        total_d = total_d + st["lossD"]
     for j in range(params.gen_steps):
-        if j != 0:
-            fake = gan(z, cond=cond[0] if cond is not None else None)
-        for d in gan.discrims:                     # D's parameter gradients are not needed here
-            for p_ in d.parameters():
-                p_.requires_grad_(False)
-        try:
-            loss = gan.gen_step(fake=fake, real_pred=real_pred, cond=cond, loss=losses.gen_loss)
-            if not params.no_mean_gen_loss:
-                loss = loss / params.gen_steps
-            loss.backward(retain_graph=j != params.gen_steps - 1)
-        finally:
-            for d in gan.discrims:
-                for p_ in d.parameters():
-                    p_.requires_grad_(True)
+        st = _g_phase(gan, st, params, losses, j)
         if dist is not None:
             dist.reduce_grads(optG)
         optG.step()
-        total_g = total_g + loss.detach()
-    return total_d, total_g, fake, x, cond
+        total_g = total_g + st["lossG"]
+    return total_d, total_g, st["fake"], st["xs"], st["conds"]
+
+
+class GraphedTrainStep(object):
+    """The training iteration as three replayed CUDA graphs (no tracing compiler: the eager iteration above is
+    captured as is).  Segments: [pyramid, G fwd, D fwd/bwd incl. gradient penalty] -> (all-reduce D grads) ->
+    [Adam D, real_pred, G-step fwd/bwd] -> (all-reduce G grads) -> [Adam G].  Everything the host decides per
+    iteration reaches the kernels through device buffers refreshed before each replay: the batch, the caption
+    embedding (the Bi-LSTM runs eagerly -- variable lengths), the host-RNG draws (hostrng.StaticDraws, same
+    generators and order as the reference), Adam's bias corrections.  z comes from the CUDA generator inside
+    the graph.  Needs discrim_steps = gen_steps = 1, a fixed batch shape and an even frame count per level."""
+
+    def __init__(self, gan, optD, optG, params, losses, device, channel_first=True, end2end=False, dist=None,
+                 warmup=2):
+        assert params.discrim_steps == 1 and params.gen_steps == 1 and not end2end
+        self.gan, self.optD, self.optG, self.params, self.losses = gan, optD, optG, params, losses
+        self.device, self.channel_first, self.dist = device, channel_first, dist
+        self.warmup, self.calls, self.graphs = warmup, 0, None
+        self.static_x = self.static_cond = self.draws = None
+        self.side = torch.cuda.Stream(device=device)
+
+    # ---- per-replay host work
+    def _stage_adam(self, opt, step):
+        b1, b2 = opt.param_groups[0]["betas"]
+        opt._dyn_host[0] = opt.param_groups[0]["lr"] / (1.0 - b1 ** step)
+        opt._dyn_host[1] = 1.0 / (1.0 - b2 ** step) ** 0.5
+        opt.dyn.copy_(opt._dyn_host, non_blocking=True)
+
+    def _capture(self, x, cond):
+        """Capture only: nothing executes here.  The caller replays right afterwards."""
+        dev = self.device
+        self.static_x = x.clone()
+        self.static_cond = None if cond is None else cond.clone()
+        for opt in (self.optD, self.optG):
+            opt.dyn = torch.zeros(2, device=dev, dtype=torch.float32)
+            opt._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            opt._step_count = max([st_["step"] for st_ in opt.state.values()] or [0])
+            opt.zero_grad(set_to_none=True)
+        torch.cuda.synchronize()
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        pool = torch.cuda.graph_pool_handle()
+        self.draws.begin_iteration()
+        with torch.cuda.graph(g1, pool=pool, stream=self.side):
+            st = _d_phase(self.gan, self.static_x, self.static_cond, dev, self.params, self.losses, None,
+                          self.channel_first, False)
+        with torch.cuda.graph(g2, pool=pool, stream=self.side):
+            self.optD.step()
+            st = _g_phase(self.gan, st, self.params, self.losses)
+        with torch.cuda.graph(g3, pool=pool, stream=self.side):
+            self.optG.step()
+        self.state = st
+        self.graphs = (g1, g2, g3)
+
+    def __call__(self, x, y):
+        """x (B,T,C,H,W) on the device (or pinned host), y = [tokens, lengths] -> (lossD, lossG) device scalars."""
+        from . import hostrng, ops
+        if not x.is_cuda:
+            x = x.to(self.device, non_blocking=True)
+            y = [a.to(self.device, non_blocking=True) if isinstance(a, torch.Tensor) else a for a in y]
+        self.calls += 1
+        if self.graphs is None and self.calls <= self.warmup:
+            rec = hostrng.set_current(hostrng.RecordingDraws())
+            try:
+                self.side.wait_stream(torch.cuda.current_stream())
+                with torch.cuda.stream(self.side):
+                    ld, lg, _, _, _ = train_iteration(self.gan, x, y, self.device, self.optD, self.optG,
+                                                      self.params, self.losses, self.channel_first, False, self.dist)
+                torch.cuda.current_stream().wait_stream(self.side)
+            finally:
+                hostrng.set_current(hostrng.EagerDraws())
+            self._calls_rec = rec.calls
+            return ld, lg
+        cond = encode_captions(self.gan, y, False)
+        if self.graphs is None:
+            self.draws = hostrng.StaticDraws(self._calls_rec, self.device)
+            hostrng.set_current(self.draws)
+            try:
+                self._capture(x, cond)
+            finally:
+                hostrng.set_current(hostrng.EagerDraws())
+        self.static_x.copy_(x, non_blocking=True)
+        if cond is not None:
+            self.static_cond.copy_(cond)
+        self.draws.refresh()
+        self._stage_adam(self.optD, self.optD._step_count + 1)
+        self._stage_adam(self.optG, self.optG._step_count + 1)
+        g1, g2, g3 = self.graphs
+        g1.replay()
+        if self.dist is not None:
+            self.dist.reduce_grads(self.optD)
+        g2.replay()
+        if self.dist is not None:
+            self.dist.reduce_grads(self.optG)
+        g3.replay()
+        for opt in (self.optD, self.optG):
+            opt._step_count += 1
+        ops.bump_weight_epoch()          # eager users of the modules must re-pack the updated weights
+        return self.state["lossD"], self.state["lossG"]
+
+    def sync_optimizer_state(self):
+        """write the replayed step counts back into the optimisers' state (for checkpoints)"""
+        for opt in (self.optD, self.optG):
+            for st_ in opt.state.values():
+                st_["step"] = opt._step_count
 
 
 def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=None, params=None, vocab=None,
