@@ -302,7 +302,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=64, help="videos per GPU per step (multiple of 8)")
+    ap.add_argument("--batch", type=int, default=1024, help="videos per GPU per step (multiple of 8)")
     ap.add_argument("--cpu_batch", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: launch every kernel from Python")

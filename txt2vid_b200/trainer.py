@@ -311,6 +311,12 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
     avg_data_load, avg_iter = RollingAvg(params.log_period), RollingAvg(params.log_period)
     data_load_watch, iter_watch = Stopwatch(), Stopwatch()
 
+    graphed = None
+    if getattr(params, 'cuda_graphs', False) and torch.device(device).type == 'cuda' and not end2end \
+            and params.discrim_steps == 1 and params.gen_steps == 1:
+        graphed = GraphedTrainStep(gan, optD, optG, params, losses, torch.device(device), channel_first=channel_first,
+                                   end2end=False, dist=dist)
+
     for epoch in range(num_epoch):
         if params.log_period > 0:
             status('Epoch %d started' % (epoch + 1))
@@ -324,8 +330,13 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
             data_load_watch.stop()
             avg_data_load.update(data_load_watch.elapsed_time)
 
-            ld, lg, fake, xs, cond = train_iteration(gan, x, y, device, optD, optG, params, losses,
-                                                     channel_first=channel_first, end2end=end2end, dist=dist)
+            if graphed is not None and x.size(0) == params.batch_size:
+                ld, lg = graphed(x, y)
+                st = getattr(graphed, "state", None) or {}
+                fake, xs, cond = st.get("fake", []), st.get("xs", [x]), st.get("conds")
+            else:
+                ld, lg, fake, xs, cond = train_iteration(gan, x, y, device, optD, optG, params, losses,
+                                                         channel_first=channel_first, end2end=end2end, dist=dist)
             discrim_loss.update(float(ld))          # the reference's two host syncs per iteration
             gen_loss.update(float(lg))
 
