@@ -36,6 +36,7 @@ extern "C" {
 #define T2V_ALGO_AUTO 0   /* tcgen05 implicit GEMM when the shape allows it, else SIMT */
 #define T2V_ALGO_TC 1     /* force the tcgen05/TMEM/TMA kernel (error if shape unsupported) */
 #define T2V_ALGO_SIMT 2   /* force the CUDA-core kernel (cross-check + odd shapes) */
+#define T2V_ALGO_TC_GENERIC 3 /* force the generic tcgen05 implicit GEMM (skip the halo-resident 64-channel kernels) */
 
 /* epilogue flags of t2v_conv_fprop */
 #define T2V_EPI_RELU 1u       /* y = max(y, 0) after bias/residual */
@@ -103,6 +104,13 @@ int t2v_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W
 /* fp32 (N,C,S) <-> bf16 (N,S,Cp) with zero channel padding (D input / G output boundary)         */
 int t2v_nchw_to_cl(const float* x, void* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
 int t2v_cl_to_nchw(const void* x, float* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
+/* RGB stem of the discriminator (resnet3d.py:12, Conv3d(C<=4 -> 64, 3^3)) as im2col + 1x1x1 GEMM:
+ * col bf16 (N,D,H,W,Kp), col[pos][tap*C+c] = x[c][pos+tap-1] (zero padded; Kp >= 27*C, multiple of 8);
+ * t2v_col2im3 is its adjoint (fp32 (N,C,D,H,W) out) for the gradient penalty's d/dx.                */
+int t2v_im2col3(const float* x, void* col, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                void* stream);
+int t2v_col2im3(const void* dcol, float* dx, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                void* stream);
 /* out[c] = sum_rows x[row,c] (bias gradients)                                                    */
 int t2v_sum_rows(const void* x, float* out, int64_t P, int32_t C, void* stream);
 /* torch.sum(x,[2,3,4]) resnet3d.py:48: out fp32 (N,C) = sum_s x (N,S,C); and its adjoint          */

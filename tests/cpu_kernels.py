@@ -138,6 +138,26 @@ def cl_to_nchw(x, C):
     return x[..., :C].permute(0, 4, 1, 2, 3).float().contiguous()
 
 
+def im2col3(x, Kp):
+    N, C, D, H, W = x.shape
+    xp = F.pad(x, (1, 1, 1, 1, 1, 1))
+    col = torch.zeros((N, D, H, W, Kp), dtype=F32, device=x.device)
+    for tap in range(27):
+        a, b, c = tap // 9, (tap // 3) % 3, tap % 3
+        col[..., tap * C:(tap + 1) * C] = xp[:, :, a:a + D, b:b + H, c:c + W].permute(0, 2, 3, 4, 1)
+    return col.to(STORE)
+
+
+def col2im3(dcol, C):
+    N, D, H, W, Kp = dcol.shape
+    dxp = torch.zeros((N, C, D + 2, H + 2, W + 2), dtype=F32, device=dcol.device)
+    g = dcol.float()
+    for tap in range(27):
+        a, b, c = tap // 9, (tap // 3) % 3, tap % 3
+        dxp[:, :, a:a + D, b:b + H, c:c + W] += g[..., tap * C:(tap + 1) * C].permute(0, 4, 1, 2, 3)
+    return dxp[:, :, 1:-1, 1:-1, 1:-1].contiguous()
+
+
 def sum_rows(x):
     return x.float().reshape(-1, x.shape[-1]).sum(0)
 

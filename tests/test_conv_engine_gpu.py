@@ -123,12 +123,24 @@ WGRAD_CASES = [
 ]
 
 
-@pytest.mark.parametrize("algo", [1, 2], ids=["tc", "simt"])
-@pytest.mark.parametrize("case", WGRAD_CASES + [(8, 1, 16, 16, 32, 48, (1, 3, 3)), (4, 2, 4, 4, 3, 5, (3, 3, 3))])
+# shapes that take the halo-resident 64-channel kernels (halo_sm100.cu): ragged extents, partial tiles,
+# both tap-class splits (Cout 64 -> 2 classes, Cout 128 -> 4), 2-D maps, more tiles than CTAs
+HALO_CASES = [
+    (2, 2, 64, 64, 64, 64, (3, 3, 3)),
+    (3, 5, 12, 20, 64, 64, (3, 3, 3)),
+    (40, 16, 8, 8, 64, 64, (3, 3, 3)),
+    (5, 8, 16, 16, 64, 128, (3, 3, 3)),
+    (6, 1, 16, 16, 64, 64, (1, 3, 3)),
+    (3, 1, 36, 24, 64, 128, (1, 3, 3)),
+]
+
+
+@pytest.mark.parametrize("algo", [1, 2, 3], ids=["tc", "simt", "tcgeneric"])
+@pytest.mark.parametrize("case", WGRAD_CASES + HALO_CASES + [(8, 1, 16, 16, 32, 48, (1, 3, 3)), (4, 2, 4, 4, 3, 5, (3, 3, 3))])
 def test_wgrad(case, algo):
     from txt2vid_b200 import kernels as K
     N, D, H, W, Cin, Cout, k = case
-    if algo == 1 and (Cin % 64 or Cout % 64):
+    if algo in (1, 3) and (Cin % 64 or Cout % 64):
         pytest.skip("tcgen05 wgrad needs 64-multiples")
     x, w = _mk(*case, seed=3)
     dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
@@ -159,6 +171,9 @@ def test_perf_probe():
     from txt2vid_b200 import kernels as K
     shapes = [
         ("D stem conv2 3^3 64->64 L0 B=256", (256, 16, 8, 8, 64, 64, (3, 3, 3))),
+        ("D stem conv2 3^3 64->64 L1 B=256", (128, 8, 16, 16, 64, 64, (3, 3, 3))),
+        ("D stem conv2 3^3 64->64 L2 B=256", (64, 4, 32, 32, 64, 64, (3, 3, 3))),
+        ("D stem conv2 3^3 64->64 L3 B=256", (32, 2, 64, 64, 64, 64, (3, 3, 3))),
         ("D down0 conv2 64->128 B=256", (256, 8, 4, 4, 64, 128, (3, 3, 3))),
         ("G up0 conv1 1024->512 @2x2", (4096, 1, 2, 2, 1024, 512, (1, 3, 3))),
         ("G up2 conv1 256->128 @8x8", (4096, 1, 8, 8, 256, 128, (1, 3, 3))),
@@ -169,7 +184,8 @@ def test_perf_probe():
         x, w = _mk(*case, seed=5)
         dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
         for what, fn in (("fprop", lambda: K.conv_fprop(x, w, k=k, algo=1)),
-                         ("wgrad", lambda: K.conv_wgrad(dy, x, k=k, algo=1))):
+                         ("wgrad", lambda: K.conv_wgrad(dy, x, k=k, algo=1)),
+                         ("wgrad-generic", lambda: K.conv_wgrad(dy, x, k=k, algo=3))):
             for _ in range(3):
                 fn()
             t0, t1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -52,6 +52,22 @@ def test_upsample():
     close(K().upsample2x_bwd(dy), C.upsample2x_bwd(dy), 5e-3)
 
 
+@pytest.mark.parametrize("shape", [(3, 3, 4, 5, 6), (2, 1, 2, 8, 8), (1, 3, 16, 8, 8), (2, 3, 1, 3, 2)])
+def test_im2col3_and_adjoint(shape):
+    """RGB-stem im2col (index kernel: bit-exact) and its adjoint, incl. <x, A^T y> == <A x, y>."""
+    x = torch.randn(*shape, device="cuda")
+    Kp = (27 * shape[1] + 31) // 32 * 32
+    col = K().im2col3(x, Kp)
+    assert torch.equal(col, C.im2col3(x, Kp))
+    dcol = rnd(shape[0], shape[2], shape[3], shape[4], Kp)
+    dx = K().col2im3(dcol, shape[1])
+    close(dx, C.col2im3(dcol, shape[1]), 1e-5)
+    xb = x.to(BF).float()
+    lhs = float((K().im2col3(xb, Kp).float() * dcol.float()).sum())
+    rhs = float((xb * dx).sum())
+    assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs)), (lhs, rhs)
+
+
 def test_layout_roundtrip():
     x = torch.randn(3, 3, 4, 5, 6, device="cuda")
     y = K().nchw_to_cl(x, 16)

@@ -13,7 +13,7 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libt2v_b200.so")
 
 T2V_OK = 0
-ALGO_AUTO, ALGO_TC, ALGO_SIMT = 0, 1, 2
+ALGO_AUTO, ALGO_TC, ALGO_SIMT, ALGO_TC_GENERIC = 0, 1, 2, 3
 EPI_RELU, EPI_OUT_F32 = 1, 2
 
 
@@ -71,6 +71,8 @@ SIGNATURES = {
     "t2v_upsample2x_bwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_nchw_to_cl": [_P, _P, c_i64, c_i32, c_i64, c_i32, _P],
     "t2v_cl_to_nchw": [_P, _P, c_i64, c_i32, c_i64, c_i32, _P],
+    "t2v_im2col3": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_col2im3": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_sum_rows": [_P, _P, c_i64, c_i32, _P],
     "t2v_sum_spatial": [_P, _P, c_i64, c_i64, c_i32, _P],
     "t2v_broadcast_spatial": [_P, _P, c_i64, c_i64, c_i32, _P],

@@ -306,8 +306,9 @@ class Resnet3D(nn.Module):
     def features(self, x):
         """fp32 (B,C,T,H,W) -> fp32 (B, F) sum-pooled trunk features."""
         m = self.res_block.inner_module
-        xc = ops.to_cl(x)                                             # RGB padded to 16 channels
-        h = ops.conv(xc, m[0].weight, m[0].bias, relu=True)
+        xc = ops.to_cl(x)                                             # RGB padded to 16 channels (skip path)
+        # first conv (K = 27*3 = 81): im2col once, then a 1x1x1 GEMM on the tensor cores
+        h = ops.conv(ops.im2col3(x), ops.stem_weight_2d(m[0].weight), m[0].bias, relu=True)
         h = ops.conv(h, m[2].weight, m[2].bias)
         c1 = self.res_block.identity_map[1]
         pk, ps = (1, 2, 2), (2, 2, 2)                                 # AvgPool3d((1,2,2), 2): stride 2 in ALL dims

@@ -9,6 +9,11 @@ bool igemm_wgrad_supported(const t2v_conv_geom* g);
 int igemm_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                        uint32_t, cudaStream_t);
 int igemm_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+bool halo_wgrad_supported(const t2v_conv_geom* g);
+bool halo_fprop_supported(const t2v_conv_geom* g);
+int halo_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
+                      uint32_t, cudaStream_t);
+int halo_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
 int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                       uint32_t, cudaStream_t);
 int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
@@ -82,8 +87,9 @@ int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const f
   if (!g || !x || !w || !y) return T2V_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool tc_ok = igemm_fprop_supported(g);
-  if (algo == T2V_ALGO_TC && !tc_ok) return T2V_ERR_ARG;
+  if ((algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) && !tc_ok) return T2V_ERR_ARG;
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
+  if (algo != T2V_ALGO_TC_GENERIC && halo_fprop_supported(g)) return halo_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
   return igemm_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
 }
 
@@ -101,8 +107,9 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
   if (!g || !dy || !x || !dw) return T2V_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool tc_ok = igemm_wgrad_supported(g);
-  if (algo == T2V_ALGO_TC && !tc_ok) return T2V_ERR_ARG;
+  if ((algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) && !tc_ok) return T2V_ERR_ARG;
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_wgrad_launch(g, dy, x, dw, accumulate, s);
+  if (algo != T2V_ALGO_TC_GENERIC && halo_wgrad_supported(g)) return halo_wgrad_launch(g, dy, x, dw, accumulate, s);
   return igemm_wgrad_launch(g, dy, x, dw, accumulate, s);
 }
 

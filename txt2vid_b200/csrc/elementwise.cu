@@ -182,6 +182,64 @@ __global__ void cl_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __
   y[i] = bf2f(x[(n * S + s) * Cp + c]);
 }
 
+// ------------------------------------------------------------------------------------ RGB stem im2col
+// The first discriminator conv (resnet3d.py:12, 3 -> 64 channels, 3^3) has K = 81: too thin for a
+// tap-by-tap implicit GEMM (27 taps x 16 zero-padded channels wasted 5x the tensor work and its weight
+// gradient ran at 29 TFLOP/s).  The input is tiny (3 channels), so im2col it once:
+//   col[pos][tap*C + c] = x[c][pos + tap - 1]   (zero outside the clip, channels >= 27*C are zero)
+// and the conv becomes a 1x1x1 GEMM with Cin = Kp on the tcgen05 engine (fprop, dgrad and wgrad).
+__global__ void im2col3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int C, int D, int H,
+                               int W, int Kp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int chunks = Kp >> 3;
+  const int chunk = (int)(i % chunks);
+  long long pos = i / chunks;
+  const int w = (int)(pos % W); pos /= W;
+  const int h = (int)(pos % H); pos /= H;
+  const int d = (int)(pos % D);
+  const long long n = pos / D;
+  const long long S = (long long)D * H * W;
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = chunk * 8 + j;
+    float val = 0.f;
+    if (k < 27 * C) {
+      const int tap = k / C, c = k - tap * C;
+      const int zd = d + tap / 9 - 1, zh = h + (tap / 3) % 3 - 1, zw = w + tap % 3 - 1;
+      if (zd >= 0 && zd < D && zh >= 0 && zh < H && zw >= 0 && zw < W)
+        val = __ldg(x + (n * C + c) * S + ((long long)zd * H + zh) * W + zw);
+    }
+    v[j] = val;
+  }
+  uint4 o;
+  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
+  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
+  reinterpret_cast<uint4*>(col)[i] = o;
+}
+// adjoint: dx[c][q] = sum_tap dcol[q - (tap - 1)][tap*C + c]; one thread per voxel q, C <= 4
+__global__ void col2im3_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int C, int D, int H,
+                               int W, int Kp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long pos = i;
+  const int w = (int)(pos % W); pos /= W;
+  const int h = (int)(pos % H); pos /= H;
+  const int d = (int)(pos % D);
+  const long long n = pos / D;
+  const long long S = (long long)D * H * W;
+  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  for (int tap = 0; tap < 27; ++tap) {
+    const int zd = d - (tap / 9 - 1), zh = h - ((tap / 3) % 3 - 1), zw = w - (tap % 3 - 1);
+    if (zd < 0 || zd >= D || zh < 0 || zh >= H || zw < 0 || zw >= W) continue;
+    const __nv_bfloat16* row = dcol + ((n * D + zd) * (long long)H * W + (long long)zh * W + zw) * Kp + tap * C;
+    for (int c = 0; c < C; ++c) acc[c] += bf2f(row[c]);
+  }
+  const long long s = ((long long)d * H + h) * W + w;
+  for (int c = 0; c < C; ++c) dx[(n * C + c) * S + s] = acc[c];
+}
+
 // ------------------------------------------------------------------------------------ reductions
 // out[c] (+)= sum over rows of x[row, c]; grid.x = column groups of 64, grid.y = row slices
 __global__ void sum_rows_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ out, long long P, int C,
@@ -623,6 +681,24 @@ int t2v_cl_to_nchw(const void* x, float* y, int64_t N, int32_t C, int64_t S, int
   cl_to_nchw_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(CBF(x), y, C, Cp, S, total);
   count_launch();
   return check_last("cl_to_nchw");
+}
+int t2v_im2col3(const float* x, void* col, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                void* stream) {
+  if (C < 1 || C > 4 || Kp % 8 || Kp < 27 * C) return T2V_ERR_ARG;
+  const long long total = N * D * H * W * (Kp / 8);
+  if (total == 0) return T2V_OK;
+  im2col3_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, BF(col), C, D, H, W, Kp, total);
+  count_launch();
+  return check_last("im2col3");
+}
+int t2v_col2im3(const void* dcol, float* dx, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                void* stream) {
+  if (C < 1 || C > 4 || Kp < 27 * C) return T2V_ERR_ARG;
+  const long long total = N * D * H * W;
+  if (total == 0) return T2V_OK;
+  col2im3_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(CBF(dcol), dx, C, D, H, W, Kp, total);
+  count_launch();
+  return check_last("col2im3");
 }
 static void row_split(long long P, int C, dim3* grid, long long* rows_per_block) {
   const int cg = (C + 63) / 64;

@@ -208,6 +208,26 @@ def cl_to_nchw(x, C):
     return y
 
 
+def im2col3(x, Kp):
+    """fp32 (N,C,D,H,W) -> bf16 (N,D,H,W,Kp), col[..., tap*C + c] = x[c] shifted by tap (3^3, zero padded)."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
+    N, C, D, H, W = x.shape
+    col = torch.empty((N, D, H, W, Kp), device=x.device, dtype=BF16)
+    check(lib().t2v_im2col3(ptr(x), ptr(col), N, C, D, H, W, Kp, stream()), "t2v_im2col3")
+    return col
+
+
+def col2im3(dcol, C):
+    """adjoint of im2col3: bf16 (N,D,H,W,Kp) -> fp32 (N,C,D,H,W)."""
+    require_cuda(dcol)
+    assert dcol.dtype == BF16 and dcol.is_contiguous() and dcol.dim() == 5
+    N, D, H, W, Kp = dcol.shape
+    dx = torch.empty((N, C, D, H, W), device=dcol.device, dtype=F32)
+    check(lib().t2v_col2im3(ptr(dcol), ptr(dx), N, C, D, H, W, Kp, stream()), "t2v_col2im3")
+    return dx
+
+
 def sum_rows(x):
     """bf16 (..., C) -> fp32 (C,) sum over all leading dims."""
     require_cuda(x)

@@ -361,6 +361,48 @@ def from_cl(x, C):
     return FromCLF.apply(x, C)
 
 
+# ------------------------------------------------------------------------------------- RGB stem (im2col)
+class Im2col3F(Function):
+    """fp32 (N,C,D,H,W) clip -> CL bf16 (N,D,H,W,Kp) with the 27 taps of a 3^3 conv unrolled into channels
+    (tap-major, then c; zero padded): the first discriminator conv (resnet3d.py:12) becomes a 1x1x1 GEMM."""
+
+    @staticmethod
+    def forward(ctx, x, Kp):
+        ctx.C = x.shape[1]
+        return K.im2col3(x.contiguous(), Kp)
+
+    @staticmethod
+    def backward(ctx, dcol):
+        return Col2im3F.apply(dcol.contiguous(), ctx.C), None
+
+
+class Col2im3F(Function):
+    @staticmethod
+    def forward(ctx, dcol, C):
+        ctx.Kp = dcol.shape[-1]
+        return K.col2im3(dcol, C)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        return Im2col3F.apply(ddx.contiguous(), ctx.Kp), None
+
+
+def stem_k(C):
+    """channel count of the im2col'ed clip: 27*C rounded up to a multiple of 32 (BLOCK_K of the engine)."""
+    return (27 * C + 31) // 32 * 32
+
+
+def im2col3(x):
+    return Im2col3F.apply(x, stem_k(x.shape[1]))
+
+
+def stem_weight_2d(weight):
+    """(Cout, C, 3,3,3) parameter -> differentiable (Cout, 27*C) VIEW in (tap, c) order (its channels-last
+    memory), i.e. the Linear weight that multiplies an im2col3 row."""
+    w3 = w3_view(weight)                      # re-homes the parameter to channels-last memory once
+    return w3.reshape(w3.shape[0], w3.shape[1] * w3.shape[2])
+
+
 # ------------------------------------------------------------------------------------- sum-pool head
 class SumSpatialF(Function):
     """torch.sum(x, [2,3,4]) (models/resnet3d.py:48): CL bf16 -> fp32 (N, C)."""
