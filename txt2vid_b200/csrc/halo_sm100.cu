@@ -120,38 +120,40 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       int stage = 0;
       uint32_t phase = 0;
       const int ksteps = (p.bd * p.bh) >> 1;     // two 8-voxel lines per MMA (K = 16 positions)
-      // per tap pair: row offset of tap_a and the A-descriptor with LBO = distance to tap_b (both >> 4)
-      uint32_t off_a[8];
-      uint64_t adesc_hi[8];
+      // Everything below is computed by all 32 lanes (warp-uniform) and only the tcgen05 instructions are
+      // predicated on one elected lane, so the descriptors live in uniform registers.
+      // per tap pair: row offset of tap_a (>> 4) and LBO = distance to tap_b
+      uint32_t off_a[8], lbo_a[8];
 #pragma unroll
       for (int q = 0; q < 8; ++q) {
         const int ta = min(t0 + 2 * q, t1 - 1), tb = min(ta + 1, t1 - 1);
         const int ra = halo_tap_row(ta, p.kd3, p.xpitch_d), rb = halo_tap_row(tb, p.kd3, p.xpitch_d);
         off_a[q] = (uint32_t)ra * 8u;                                    // rows * 128 B >> 4
-        adesc_hi[q] = make_smem_desc(0, (uint32_t)(rb - ra) * 128u, (uint32_t)kXW * 128u, 2);
+        lbo_a[q] = (uint32_t)(rb - ra) * 128u;
       }
+      const uint32_t a_hi = desc_hi((uint32_t)kXW * 128u, 2), b_hi = desc_hi(1024, 2);
+      const uint32_t leader = elect_one();
       for (int it = 0; it < ntiles; ++it) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sdy = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sx16 = (sdy + p.dy_bytes) >> 4;
-          const uint64_t bdesc0 = make_smem_desc(sdy, p.dy_box_bytes, 1024, 2);
-          int d = 0, h = 0;
-          for (int j = 0; j < ksteps; ++j) {
-            const uint32_t line16 = (uint32_t)(d * p.xpitch_d + h * kXW) * 8u;
-            const uint64_t bdesc = bdesc0 + (uint64_t)(128 * j);
-            const uint32_t acc = (it | j) != 0 ? 1u : 0u;
+        const uint32_t sdy = smem_u32(smem + (size_t)stage * p.stage_bytes);
+        const uint32_t sx16 = (sdy + p.dy_bytes) >> 4;
+        int d = 0, h = 0;
+        for (int j = 0; j < ksteps; ++j) {
+          const uint32_t line16 = sx16 + (uint32_t)(d * p.xpitch_d + h * kXW) * 8u;
+          const uint32_t b_lo = desc_lo((sdy >> 4) + 128u * (uint32_t)j, p.dy_box_bytes);
+          const uint32_t acc = (it | j) != 0 ? 1u : 0u;
 #pragma unroll
-            for (int q = 0; q < 8; ++q) {
-              if (q < npairs) {
-                const uint64_t adesc = adesc_hi[q] | (uint64_t)((sx16 + line16 + off_a[q]) & 0x3FFFu);
-                umma_bf16_ss(tmem_base + (uint32_t)(q * p.Cout), adesc, bdesc, p.idesc, acc);
-              }
+          for (int q = 0; q < 8; ++q) {
+            if (q < npairs) {
+              const uint32_t a_lo = desc_lo(line16 + off_a[q], lbo_a[q]);
+              if (leader) umma_bf16_ss2(tmem_base + (uint32_t)(q * p.Cout), a_lo, a_hi, b_lo, b_hi, p.idesc, acc);
             }
-            h += 2;
-            if (h >= p.bh) { h = 0; ++d; }
           }
+          h += 2;
+          if (h >= p.bh) { h = 0; ++d; }
+        }
+        if (leader) {
           umma_commit(&empty_bar[stage]);
           if (it == ntiles - 1) umma_commit(accum_bar);
         }
@@ -384,7 +386,10 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     // ---------------- MMA issue
     int st = 0;
     uint32_t ph = 0;
-    const uint64_t adesc_hi = make_smem_desc(0, 0, (uint32_t)p.LS * 128u, 2);
+    // warp-uniform operand computation; only the tcgen05 instructions are predicated on the elected lane
+    const uint32_t a_hi = desc_hi((uint32_t)p.LS * 128u, 2), b_hi = desc_hi(1024, 2);
+    const uint32_t ms16 = (uint32_t)p.MS * 8u;
+    const uint32_t leader = elect_one();
     for (int it = 0; it < p.iters; ++it) {
       const int buf = it & 1;
       const uint32_t par = (uint32_t)(it >> 1) & 1u;
@@ -397,25 +402,28 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       for (int tap = 0; tap < p.ntaps; ++tap) {
         mbar_wait(&w_full[st], ph);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t toff16 = (uint32_t)(a_d * p.Pd + a_h * kXW + a_w) * 8u;
-          const uint64_t bdesc = make_smem_desc(smem_u32(sW + (size_t)st * kWTapBytes), 0, 1024, 2);
-          for (int m = 0; m < p.np; ++m) {
-            const uint32_t row16 = a16 + toff16 + (uint32_t)(m * p.MS) * 8u;
+        const uint32_t row16 = a16 + (uint32_t)(a_d * p.Pd + a_h * kXW + a_w) * 8u;
+        const uint32_t b16 = smem_u32(sW + (size_t)st * kWTapBytes) >> 4;
+#pragma unroll
+        for (int m = 0; m < 4; ++m) {
+          if (m < p.np) {
 #pragma unroll
             for (int k = 0; k < 4; ++k) {
-              const uint64_t adesc = adesc_hi | (uint64_t)((row16 + 2u * k) & 0x3FFFu);
-              umma_bf16_ss(tacc + (uint32_t)(m * 64), adesc, bdesc + (uint64_t)(2 * k), p.idesc,
-                           (tap | k) != 0 ? 1u : 0u);
+              const uint32_t a_lo = desc_lo(row16 + (uint32_t)m * ms16 + 2u * k, 0);
+              const uint32_t b_lo = desc_lo(b16 + 2u * k, 0);
+              if (leader)
+                umma_bf16_ss2(tacc + (uint32_t)(m * 64), a_lo, a_hi, b_lo, b_hi, p.idesc, (tap | k) != 0 ? 1u : 0u);
             }
           }
+        }
+        if (leader) {
           if (cs > 1) umma_commit_mc(&w_empty[st], mask); else umma_commit(&w_empty[st]);
         }
         __syncwarp();
         if (++st == kWStages) { st = 0; ph ^= 1u; }
         if (++a_w == 3) { a_w = 0; if (++a_h == 3) { a_h = 0; ++a_d; } }
       }
-      if (lane == 0) {
+      if (leader) {
         umma_commit(&a_empty[buf]);
         umma_commit(&acc_full[buf]);
       }

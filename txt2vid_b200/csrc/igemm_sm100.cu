@@ -123,20 +123,23 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   } else if (warp == 1) {
     int stage = 0;
     uint32_t phase = 0;
+    // operands are computed warp-uniformly, only the tcgen05 instructions are predicated on the elected lane
+    // (descriptors then stay in uniform registers: no ELECT/R2UR waterfall in front of every UTCHMMA)
+    const uint32_t d_hi = desc_hi(SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
+    const uint32_t leader = elect_one();
     for (int kb = 0; kb < p.num_k_blocks; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
-      if (lane == 0) {
-        const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-        const uint32_t sb = sa + p.a_bytes;
-        const uint64_t adesc = make_smem_desc(sa, 0, SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
-        const uint64_t bdesc = make_smem_desc(sb, 0, SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
+      const uint32_t sa16 = smem_u32(smem + (size_t)stage * p.stage_bytes) >> 4;
+      const uint32_t sb16 = sa16 + (p.a_bytes >> 4);
 #pragma unroll
-        for (int k = 0; k < BLOCK_K / 16; ++k) {
-          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
-          umma_bf16_ss(tmem_base, adesc + (uint64_t)(2 * k), bdesc + (uint64_t)(2 * k), p.idesc,
-                       (kb | k) != 0 ? 1u : 0u);
-        }
+      for (int k = 0; k < BLOCK_K / 16; ++k) {
+        // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+        if (leader)
+          umma_bf16_ss2(tmem_base, desc_lo(sa16 + 2u * k, 0), d_hi, desc_lo(sb16 + 2u * k, 0), d_hi, p.idesc,
+                        (kb | k) != 0 ? 1u : 0u);
+      }
+      if (leader) {
         umma_commit(&empty_bar[stage]);
         if (kb == p.num_k_blocks - 1) umma_commit(accum_bar);
       }
@@ -289,22 +292,23 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
     } else if (warp == 1) {
       int stage = 0;
       uint32_t phase = 0;
+      // MN-major, 128B swizzle: atom = 64 channels x 8 positions (1024 B); SBO = next 8 positions,
+      // LBO = next 64-channel atom (one TMA box further).  Warp-uniform operands, elected-lane issue.
+      const uint32_t d_hi = desc_hi(1024, 2);
+      const uint32_t leader = elect_one();
       for (int kb = 0; kb < nkb; ++kb) {
         mbar_wait(&full_bar[stage], phase);
         tc_fence_after();
-        if (lane == 0) {
-          const uint32_t sa = smem_u32(smem + (size_t)stage * p.stage_bytes);
-          const uint32_t sb = sa + 2 * kBoxBytes;
-          // MN-major, 128B swizzle: atom = 64 channels x 8 positions (1024 B); SBO = next 8 positions,
-          // LBO = next 64-channel atom (one TMA box further).
-          const uint64_t adesc = make_smem_desc(sa, kBoxBytes, 1024, 2);
-          const uint64_t bdesc = make_smem_desc(sb, kBoxBytes, 1024, 2);
+        const uint32_t sa16 = smem_u32(smem + (size_t)stage * p.stage_bytes) >> 4;
+        const uint32_t sb16 = sa16 + ((2 * kBoxBytes) >> 4);
 #pragma unroll
-          for (int k = 0; k < kWgradPos / 16; ++k) {
-            // 16 positions further = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
-            umma_bf16_ss(tmem_base, adesc + (uint64_t)(128 * k), bdesc + (uint64_t)(128 * k), p.idesc,
-                         (kb | k) != 0 ? 1u : 0u);
-          }
+        for (int k = 0; k < kWgradPos / 16; ++k) {
+          // 16 positions further = 16 rows of 128 B = 2048 B -> +128 in the (addr>>4) field
+          if (leader)
+            umma_bf16_ss2(tmem_base, desc_lo(sa16 + 128u * k, kBoxBytes), d_hi, desc_lo(sb16 + 128u * k, kBoxBytes),
+                          d_hi, p.idesc, (kb | k) != 0 ? 1u : 0u);
+        }
+        if (leader) {
           umma_commit(&empty_bar[stage]);
           if (kb == nkb - 1) umma_commit(accum_bar);
         }

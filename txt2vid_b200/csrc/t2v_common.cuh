@@ -191,6 +191,43 @@ __host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint
   return d;
 }
 
+// One elected lane of a fully active warp (same lane every time for the same mask).  Code that feeds
+// tcgen05 instructions should compute its operands in WARP-UNIFORM control flow and only predicate the
+// instruction itself on this: ptxas then keeps descriptors in uniform registers instead of running an
+// ELECT / R2UR.BROADCAST waterfall loop (~18 instructions) in front of every UTCHMMA.
+T2V_DEVINL uint32_t elect_one() {
+  uint32_t pred;
+  asm volatile(
+      "{\n\t"
+      ".reg .pred P;\n\t"
+      "elect.sync _|P, 0xffffffff;\n\t"
+      "selp.u32 %0, 1, 0, P;\n\t"
+      "}"
+      : "=r"(pred));
+  return pred;
+}
+// descriptor halves: lo = start>>4 | (LBO>>4) << 16, hi = SBO>>4 | version 1 << 14 | layout << 29
+T2V_DEVINL uint32_t desc_lo(uint32_t saddr16, uint32_t lbo_bytes) {
+  return (saddr16 & 0x3FFFu) | (((lbo_bytes >> 4) & 0x3FFFu) << 16);
+}
+T2V_DEVINL uint32_t desc_hi(uint32_t sbo_bytes, uint32_t layout_type) {
+  return ((sbo_bytes >> 4) & 0x3FFFu) | (1u << 14) | ((layout_type & 7u) << 29);
+}
+T2V_DEVINL void umma_bf16_ss2(uint32_t tmem_d, uint32_t a_lo, uint32_t a_hi, uint32_t b_lo, uint32_t b_hi,
+                              uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      ".reg .b64 da, db;\n\t"
+      "mov.b64 da, {%1, %2};\n\t"
+      "mov.b64 db, {%3, %4};\n\t"
+      "setp.ne.b32 p, %6, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], da, db, %5, p;\n\t"
+      "}" ::"r"(tmem_d),
+      "r"(a_lo), "r"(a_hi), "r"(b_lo), "r"(b_hi), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+
 // ---------------------------------------------------------------- thread-block clusters
 T2V_DEVINL uint32_t cluster_ctarank() {
   uint32_t r;
