@@ -73,6 +73,26 @@ int t2v_conv_dgrad(const t2v_conv_geom* g, const void* dy, const void* wT, const
  * accumulate = 0 overwrites dw, 1 adds into it.                                              */
 int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float* dw,
                    int accumulate, int algo, void* stream);
+/* General convolution geometry (any kernel / stride / zero padding; 1-D and 2-D use unit extents):
+ * the TGAN / TCWYT layers that are not stride-1 "same" convolutions -- Conv3d/Conv2d k4 s2 p1
+ * (models/tcwyt/video_discrim.py:12-27, frame_discrim.py:8-19), k(1,3,3) and k2 s2 heads
+ * (video_discrim.py:41,46; frame_discrim.py:49), and every ConvTranspose1d/2d/3d (models/tgan/gen.py:21-25,
+ * tgan/temporal_gen.py:16-20, tcwyt/gen.py:14-30).  Do = (Di + 2*pd - kd)/sd + 1, etc.                */
+typedef struct {
+  int32_t N, Di, Hi, Wi, Do, Ho, Wo;
+  int32_t Cin, Cout;           /* channels of the convolution's input / output                      */
+  int32_t kd, kh, kw, sd, sh, sw, pd, ph, pw;
+} t2v_gconv_geom;
+/* y[N,Do,Ho,Wo,Cout] = conv(x[N,Di,Hi,Wi,Cin], w[Cout][taps][Cin]) + bias; y bf16 or fp32 CL        */
+int t2v_gconv_fprop(const t2v_gconv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                    int32_t out_f32, void* stream);
+/* dx[N,Di,Hi,Wi,Cin] = conv_transpose(dy[N,Do,Ho,Wo,Cout], w) (+ bias[Cin]): the data gradient of the
+ * convolution AND the forward of nn.ConvTranspose*d(Cout -> Cin) with the same weight memory           */
+int t2v_gconv_dgrad(const t2v_gconv_geom* g, const void* dy, const void* w, const float* bias, void* dx,
+                    int32_t out_f32, void* stream);
+/* dw[Cout][taps][Cin] (+)= sum_pos dy[pos,co] * x[in(pos,tap),ci]  (fp32)                              */
+int t2v_gconv_wgrad(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
+                    void* stream);
 /* fp32 master weight [Cout][taps][Cin] -> bf16 same layout (fprop operand)                    */
 int t2v_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int t2v_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);
@@ -92,6 +112,12 @@ int t2v_unpack_wgrad_padded(const float* src, float* dst, int32_t Cout, int32_t 
 int t2v_relu_fwd(const void* x, void* y, int64_t n, void* stream);
 /* dx = dy * (ref > 0); ref = the ReLU's input or output                                          */
 int t2v_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, void* stream);
+/* nn.LeakyReLU(slope) (models/tcwyt/gen.py:16, video_discrim.py:9) and tanh on CL bf16 tensors
+ * (models/tgan/temporal_gen.py:33); n elements, multiple of 8; bwd: ref = x or y, y = tanh output     */
+int t2v_leaky_relu_fwd(const void* x, void* y, int64_t n, float slope, void* stream);
+int t2v_leaky_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, float slope, void* stream);
+int t2v_tanh_fwd(const void* x, void* y, int64_t n, void* stream);
+int t2v_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream);
 /* F.avg_pool3d, count_include_pad, kernel <= stride (layers.py:202-217, resnet3d.py:16,18);
  * in_shape = {N,D,H,W,C}; y = pool(x) (+ residual, y-shaped, may be NULL)                        */
 int t2v_avgpool_fwd(const void* x, const void* residual, void* y, const int32_t* in_shape, const int32_t* kernel,
@@ -124,7 +150,8 @@ int t2v_bn_stats(const void* x, float* stats, int64_t P, int32_t C, void* stream
 int t2v_bn_finalize(const float* stats, const float* gamma, const float* beta, float* running_mean,
                     float* running_var, float* mean_invstd, float* scale_shift, int32_t C, int64_t count,
                     float eps, float momentum, void* stream);
-/* y (N,up*H,up*W,C) = [relu](x*scale+shift) nearest-upsampled by up in {1,2}                      */
+/* y (N,up*H,up*W,C) = act(x*scale+shift) nearest-upsampled by up in {1,2};
+ * relu: 0 = identity, 1 = ReLU, 2 = LeakyReLU(0.2) (BatchNorm3d + LeakyReLU of the models/tcwyt files)   */
 int t2v_bn_apply(const void* x, const float* scale_shift, void* y, int64_t N, int32_t H, int32_t W, int32_t C,
                  int32_t relu, int32_t up, void* stream);
 /* red fp32 [2C] = {dbeta, dgamma}; dx (N,H,W,C)                                                   */

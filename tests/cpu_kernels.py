@@ -118,6 +118,52 @@ def avgpool_bwd(dy, in_shape, kernel, stride, pad):
     return g.permute(0, 2, 3, 4, 1).contiguous().to(STORE)
 
 
+def _w5g(w, k):
+    Cout, taps, Cin = w.shape
+    return w.float().view(Cout, k[0], k[1], k[2], Cin).permute(0, 4, 1, 2, 3)
+
+
+def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), _w5g(w, k), bias, stride=tuple(s), padding=tuple(p))
+    y = y.permute(0, 2, 3, 4, 1).contiguous()
+    return y if out_f32 else y.to(STORE)
+
+
+def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
+    osp = [(o - 1) * ss - 2 * pp + kk for o, ss, pp, kk in zip(dy.shape[1:4], s, p, k)]
+    opad = [i - o for i, o in zip(in_sp, osp)]
+    dx = F.conv_transpose3d(dy.float().permute(0, 4, 1, 2, 3), _w5g(w, k), bias, stride=tuple(s), padding=tuple(p),
+                            output_padding=tuple(opad))
+    dx = dx.permute(0, 2, 3, 4, 1).contiguous()
+    return dx if out_f32 else dx.to(STORE)
+
+
+def gconv_wgrad(dy, x, k, s, p):
+    Cout, Cin = dy.shape[-1], x.shape[-1]
+    g = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (Cout, Cin) + tuple(k),
+                                    dy.float().permute(0, 4, 1, 2, 3), stride=tuple(s), padding=tuple(p))
+    return g.permute(0, 2, 3, 4, 1).reshape(Cout, k[0] * k[1] * k[2], Cin).contiguous()
+
+
+def leaky_relu_fwd(x, slope):
+    xf = x.float()
+    return torch.where(xf > 0, xf, xf * slope).to(STORE)
+
+
+def leaky_relu_bwd(dy, ref, slope):
+    g = dy.float()
+    return torch.where(ref.float() > 0, g, g * slope).to(STORE)
+
+
+def tanh_fwd(x):
+    return torch.tanh(x.float()).to(STORE)
+
+
+def tanh_bwd(dy, y):
+    yf = y.float()
+    return (dy.float() * (1 - yf * yf)).to(STORE)
+
+
 def upsample2x_fwd(x):
     return x.repeat_interleave(2, dim=2).repeat_interleave(2, dim=3).contiguous()
 
@@ -189,8 +235,8 @@ def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, mo
     scale = gamma * invstd
     shift = beta - mean * scale
     y = x.float() * scale + shift
-    if relu:
-        y = torch.relu(y)
+    if relu:                                    # activation code: 1 = ReLU, 2 = LeakyReLU(0.2)
+        y = torch.where(y > 0, y, y * (0.0 if relu == 1 else 0.2))
     y = y.to(STORE)
     if up == 2:
         y = upsample2x_fwd(y)
@@ -206,7 +252,7 @@ def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
         g = g.view(N, D, H, 2, W, 2, C).sum(dim=(3, 5))
     xf = x.float()
     if relu:
-        g = torch.where(xf * scale + shift > 0, g, torch.zeros_like(g))
+        g = torch.where(xf * scale + shift > 0, g, g * (0.0 if relu == 1 else 0.2))
     xhat = (xf - mean) * invstd
     P = N * D * H * W
     dbeta = g.reshape(-1, C).sum(0)

@@ -75,12 +75,79 @@ def test_layout_roundtrip():
     assert torch.equal(K().cl_to_nchw(y, 3), C.cl_to_nchw(y, 3))
 
 
+@pytest.mark.parametrize("Cc", [16, 64, 96, 256, 1024, 40])
+def test_sum_rows_paths(Cc):
+    """vectorised column reduction (C/8 a power of two, 256-channel slabs) and the scalar fallback"""
+    x = rnd(37, 1, 3, 5, Cc)
+    close(K().sum_rows(x), C.sum_rows(x), 1e-3)
+    x = rnd(5000, 1, 1, 1, Cc)
+    close(K().sum_rows(x), C.sum_rows(x), 2e-3)
+
+
 def test_reductions():
     x = rnd(7, 2, 3, 5, 96)
     close(K().sum_rows(x), C.sum_rows(x), 1e-3)
     close(K().sum_spatial(x), C.sum_spatial(x), 1e-3)
     g = torch.randn(7, 96, device="cuda")
     assert torch.equal(K().broadcast_spatial(g, x.shape), C.broadcast_spatial(g, x.shape))
+
+
+def test_activations():
+    x, dy = rnd(3, 2, 5, 7, 32), rnd(3, 2, 5, 7, 32)
+    assert torch.equal(K().leaky_relu_fwd(x, 0.2), C.leaky_relu_fwd(x, 0.2))
+    assert torch.equal(K().leaky_relu_bwd(dy, x, 0.2), C.leaky_relu_bwd(dy, x, 0.2))
+    y = K().tanh_fwd(x)
+    close(y, C.tanh_fwd(x), 1e-2)
+    close(K().tanh_bwd(dy, y), C.tanh_bwd(dy, y), 1e-2)
+
+
+GCONV_CASES = [
+    # x shape (N,D,H,W,Cin), Cout, k, s, p
+    ((2, 16, 16, 16, 16), 64, (4, 4, 4), (2, 2, 2), (1, 1, 1)),      # Conv3d k4 s2 p1 (tcwyt/video_discrim.py:12)
+    ((3, 1, 12, 12, 64), 128, (1, 4, 4), (1, 2, 2), (0, 1, 1)),      # Conv2d k4 s2 p1 (frame_discrim.py:12)
+    ((4, 1, 4, 4, 512), 16, (1, 3, 3), (1, 2, 2), (0, 0, 0)),        # head (1,3,3) s2 p0 (video_discrim.py:46)
+    ((4, 2, 3, 3, 80), 16, (1, 3, 3), (1, 1, 1), (0, 0, 0)),         # head (1,3,3) s1 p0 (video_discrim.py:41)
+    ((5, 1, 2, 2, 48), 16, (1, 2, 2), (1, 2, 2), (0, 0, 0)),         # Conv2d k2 s2 (frame_discrim.py:49)
+    ((3, 1, 1, 7, 32), 48, (1, 1, 3), (1, 1, 1), (0, 0, 1)),         # 1-D
+]
+
+
+@pytest.mark.parametrize("case", GCONV_CASES)
+def test_gconv(case):
+    """general strided convolution: fprop, data gradient (= transposed convolution) and weight gradient"""
+    xs, Cout, k, s, p = case
+    x = rnd(*xs)
+    taps = k[0] * k[1] * k[2]
+    w = (torch.randn(Cout, taps, xs[-1], device="cuda") / (taps * xs[-1]) ** 0.5).to(BF)
+    bias = torch.randn(Cout, device="cuda")
+    y = K().gconv_fprop(x, w, bias, k, s, p)
+    y2 = C.gconv_fprop(x, w, bias, k, s, p)
+    assert y.shape == y2.shape
+    close(y, y2, 1e-2)
+    dy = rnd(*y.shape)
+    bias_i = torch.randn(xs[-1], device="cuda")
+    dx = K().gconv_dgrad(dy, w, bias_i, xs[1:4], k, s, p)
+    close(dx, C.gconv_dgrad(dy, w, bias_i, xs[1:4], k, s, p), 1e-2)
+    close(K().gconv_wgrad(dy, x, k, s, p), C.gconv_wgrad(dy, x, k, s, p), 2e-3)
+
+
+@pytest.mark.parametrize("Cc,shape", [(64, (6, 1, 8, 8)), (512, (4, 2, 3, 3)), (1024, (16, 1, 2, 2)), (48, (5, 1, 4, 4))])
+@pytest.mark.parametrize("act", [0, 1, 2])
+def test_batchnorm_any_shape(Cc, shape, act):
+    """BatchNorm1d/2d/3d statistics over all leading dims + fused activation codes (0 none, 1 ReLU, 2 LeakyReLU)"""
+    x = rnd(*shape, Cc, scale=1.5) + 0.25
+    gamma, beta = torch.rand(Cc, device="cuda") + 0.5, torch.randn(Cc, device="cuda") * 0.3
+    rm1, rv1 = torch.zeros(Cc, device="cuda"), torch.ones(Cc, device="cuda")
+    rm2, rv2 = rm1.clone(), rv1.clone()
+    y, mi, ss = K().bn_forward(x, gamma, beta, rm1, rv1, act, 1)
+    y2, mi2, ss2 = C.bn_forward(x, gamma, beta, rm2, rv2, act, 1)
+    assert y.shape == x.shape
+    close(mi, mi2, 1e-4), close(ss, ss2, 1e-4), close(rm1, rm2, 1e-4), close(rv1, rv2, 1e-4)
+    close(y, y2, 1e-2)
+    dy = rnd(*shape, Cc)
+    dx, dg, db = K().bn_backward(dy, x, mi2, ss2, act, 1)
+    dx2, dg2, db2 = C.bn_backward(dy, x, mi2, ss2, act, 1)
+    close(dx, dx2, 1e-2), close(dg, dg2, 2e-3), close(db, db2, 2e-3)
 
 
 @pytest.mark.parametrize("up", [1, 2])

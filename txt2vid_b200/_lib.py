@@ -21,6 +21,11 @@ class ConvGeom(ctypes.Structure):
     _fields_ = [(n, ctypes.c_int32) for n in ("N", "D", "H", "W", "Cin", "Cout", "kd", "kh", "kw")]
 
 
+class GconvGeom(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_int32) for n in ("N", "Di", "Hi", "Wi", "Do", "Ho", "Wo", "Cin", "Cout", "kd", "kh", "kw",
+                                              "sd", "sh", "sw", "pd", "ph", "pw")]
+
+
 class T2VError(RuntimeError):
     pass
 
@@ -58,6 +63,9 @@ SIGNATURES = {
     "t2v_conv_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],
+    "t2v_gconv_fprop": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
+    "t2v_gconv_dgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
+    "t2v_gconv_wgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, c_i32, _P],
     "t2v_cast_f32_to_bf16": [_P, _P, c_i64, _P],
     "t2v_cast_bf16_to_f32": [_P, _P, c_i64, _P],
     "t2v_pack_dgrad_weight": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
@@ -65,6 +73,10 @@ SIGNATURES = {
     "t2v_unpack_wgrad_padded": [_P, _P, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _P],
     "t2v_relu_fwd": [_P, _P, c_i64, _P],
     "t2v_relu_bwd": [_P, _P, _P, c_i64, _P],
+    "t2v_leaky_relu_fwd": [_P, _P, c_i64, c_float, _P],
+    "t2v_leaky_relu_bwd": [_P, _P, _P, c_i64, c_float, _P],
+    "t2v_tanh_fwd": [_P, _P, c_i64, _P],
+    "t2v_tanh_bwd": [_P, _P, _P, c_i64, _P],
     "t2v_avgpool_fwd": [_P, _P, _P, _I32P, _I32P, _I32P, _I32P, _P],
     "t2v_avgpool_bwd": [_P, _P, _I32P, _I32P, _I32P, _I32P, _P],
     "t2v_upsample2x_fwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, _P],

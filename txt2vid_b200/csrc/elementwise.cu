@@ -50,6 +50,46 @@ __global__ void relu_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv
   st8(dx + i * 8, g);
 }
 
+// y = x > 0 ? x : slope * x  (nn.LeakyReLU(0.2), models/tcwyt/*.py) and its gradient (ref = x or y: same sign)
+__global__ void leaky_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, float slope,
+                                 long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  V8 v = ld8(x + i * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v.f[j] = v.f[j] > 0.f ? v.f[j] : slope * v.f[j];
+  st8(y + i * 8, v);
+}
+__global__ void leaky_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ ref,
+                                 __nv_bfloat16* __restrict__ dx, float slope, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  V8 g = ld8(dy + i * 8);
+  const V8 r = ld8(ref + i * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g.f[j] = r.f[j] > 0.f ? g.f[j] : slope * g.f[j];
+  st8(dx + i * 8, g);
+}
+// tanh on a CL tensor (models/tgan/temporal_gen.py:33) and dx = dy * (1 - y^2)
+__global__ void tanh_fwd_kernel(const __nv_bfloat16* __restrict__ x, __nv_bfloat16* __restrict__ y, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  V8 v = ld8(x + i * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v.f[j] = tanhf(v.f[j]);
+  st8(y + i * 8, v);
+}
+__global__ void tanh_bwd_kernel(const __nv_bfloat16* __restrict__ dy, const __nv_bfloat16* __restrict__ y,
+                                __nv_bfloat16* __restrict__ dx, long long n8) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  V8 g = ld8(dy + i * 8);
+  const V8 r = ld8(y + i * 8);
+#pragma unroll
+  for (int j = 0; j < 8; ++j) g.f[j] *= 1.f - r.f[j] * r.f[j];
+  st8(dx + i * 8, g);
+}
+
 // ------------------------------------------------------------------------------------ avg-pool
 struct PoolParams {
   int N, D, H, W, C, Do, Ho, Wo;
@@ -188,39 +228,11 @@ __global__ void cl_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __
 // gradient ran at 29 TFLOP/s).  The input is tiny (3 channels), so im2col it once:
 //   col[pos][tap*C + c] = x[c][pos + tap - 1]   (zero outside the clip, channels >= 27*C are zero)
 // and the conv becomes a 1x1x1 GEMM with Cin = Kp on the tcgen05 engine (fprop, dgrad and wgrad).
-__global__ void im2col3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int C, int D, int H,
-                               int W, int Kp, long long total) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total) return;
-  const int chunks = Kp >> 3;
-  const int chunk = (int)(i % chunks);
-  long long pos = i / chunks;
-  const int w = (int)(pos % W); pos /= W;
-  const int h = (int)(pos % H); pos /= H;
-  const int d = (int)(pos % D);
-  const long long n = pos / D;
-  const long long S = (long long)D * H * W;
-  float v[8];
-#pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int k = chunk * 8 + j;
-    float val = 0.f;
-    if (k < 27 * C) {
-      const int tap = k / C, c = k - tap * C;
-      const int zd = d + tap / 9 - 1, zh = h + (tap / 3) % 3 - 1, zw = w + tap % 3 - 1;
-      if (zd >= 0 && zd < D && zh >= 0 && zh < H && zw >= 0 && zw < W)
-        val = __ldg(x + (n * C + c) * S + ((long long)zd * H + zh) * W + zw);
-    }
-    v[j] = val;
-  }
-  uint4 o;
-  o.x = pack_bf16x2(v[0], v[1]); o.y = pack_bf16x2(v[2], v[3]);
-  o.z = pack_bf16x2(v[4], v[5]); o.w = pack_bf16x2(v[6], v[7]);
-  reinterpret_cast<uint4*>(col)[i] = o;
-}
-// adjoint: dx[c][q] = sum_tap dcol[q - (tap - 1)][tap*C + c]; one thread per voxel q, C <= 4
-__global__ void col2im3_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int C, int D, int H,
-                               int W, int Kp, long long total) {
+// One thread per voxel: the 27*C neighbourhood values are gathered with compile-time tap offsets (the clip is
+// tiny and L1-resident) and written as one contiguous Kp*2-byte row in 16-byte pieces.
+template <int C>
+__global__ void im2col3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ col, int D, int H, int W,
+                               int Kp, long long total) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total) return;
   long long pos = i;
@@ -229,14 +241,56 @@ __global__ void col2im3_kernel(const __nv_bfloat16* __restrict__ dcol, float* __
   const int d = (int)(pos % D);
   const long long n = pos / D;
   const long long S = (long long)D * H * W;
-  float acc[4] = {0.f, 0.f, 0.f, 0.f};
+  const float* xn = x + n * C * S + ((long long)d * H + h) * W + w;
+  constexpr int KR = 27 * C;
+  constexpr int KV = (KR + 7) / 8 * 8;
+  float v[KV];
+#pragma unroll
   for (int tap = 0; tap < 27; ++tap) {
-    const int zd = d - (tap / 9 - 1), zh = h - ((tap / 3) % 3 - 1), zw = w - (tap % 3 - 1);
-    if (zd < 0 || zd >= D || zh < 0 || zh >= H || zw < 0 || zw >= W) continue;
-    const __nv_bfloat16* row = dcol + ((n * D + zd) * (long long)H * W + (long long)zh * W + zw) * Kp + tap * C;
-    for (int c = 0; c < C; ++c) acc[c] += bf2f(row[c]);
+    const int od = tap / 9 - 1, oh = (tap / 3) % 3 - 1, ow = tap % 3 - 1;
+    const bool ok = (unsigned)(d + od) < (unsigned)D && (unsigned)(h + oh) < (unsigned)H &&
+                    (unsigned)(w + ow) < (unsigned)W;
+    const long long off = ((long long)od * H + oh) * W + ow;
+#pragma unroll
+    for (int c = 0; c < C; ++c) v[tap * C + c] = ok ? __ldg(xn + c * S + off) : 0.f;
+  }
+#pragma unroll
+  for (int k = KR; k < KV; ++k) v[k] = 0.f;
+  uint4* dst = reinterpret_cast<uint4*>(col + i * Kp);
+#pragma unroll
+  for (int ch = 0; ch < KV / 8; ++ch)
+    dst[ch] = make_uint4(pack_bf16x2(v[8 * ch], v[8 * ch + 1]), pack_bf16x2(v[8 * ch + 2], v[8 * ch + 3]),
+                         pack_bf16x2(v[8 * ch + 4], v[8 * ch + 5]), pack_bf16x2(v[8 * ch + 6], v[8 * ch + 7]));
+  for (int ch = KV / 8; ch < Kp / 8; ++ch) dst[ch] = make_uint4(0u, 0u, 0u, 0u);
+}
+// adjoint: dx[c][q] = sum_tap dcol[q - (tap - 1)][tap*C + c]; one thread per voxel q
+template <int C>
+__global__ void col2im3_kernel(const __nv_bfloat16* __restrict__ dcol, float* __restrict__ dx, int D, int H, int W,
+                               int Kp, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  long long pos = i;
+  const int w = (int)(pos % W); pos /= W;
+  const int h = (int)(pos % H); pos /= H;
+  const int d = (int)(pos % D);
+  const long long n = pos / D;
+  const long long S = (long long)D * H * W;
+  float acc[C];
+#pragma unroll
+  for (int c = 0; c < C; ++c) acc[c] = 0.f;
+#pragma unroll
+  for (int tap = 0; tap < 27; ++tap) {
+    const int od = tap / 9 - 1, oh = (tap / 3) % 3 - 1, ow = tap % 3 - 1;
+    const bool ok = (unsigned)(d - od) < (unsigned)D && (unsigned)(h - oh) < (unsigned)H &&
+                    (unsigned)(w - ow) < (unsigned)W;
+    if (ok) {
+      const __nv_bfloat16* row = dcol + (i - (((long long)od * H + oh) * W + ow)) * Kp + tap * C;
+#pragma unroll
+      for (int c = 0; c < C; ++c) acc[c] += bf2f(row[c]);
+    }
   }
   const long long s = ((long long)d * H + h) * W + w;
+#pragma unroll
   for (int c = 0; c < C; ++c) dx[(n * C + c) * S + s] = acc[c];
 }
 
@@ -282,6 +336,8 @@ __global__ void broadcast_spatial_kernel(const float* __restrict__ g, __nv_bfloa
 }
 
 // ------------------------------------------------------------------------------------ BatchNorm (train)
+// activation fused behind BatchNorm: 0 = none, 1 = ReLU, 2 = LeakyReLU(0.2)
+T2V_DEVINL float bn_act_slope(int act) { return act == 1 ? 0.f : (act == 2 ? 0.2f : 1.f); }
 // per-channel sum and sum of squares; grid (ceil(C/64), row slices), atomics into stats[0:C], stats[C:2C]
 __global__ void bn_stats_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ stats, long long P, int C,
                                 long long rows_per_block) {
@@ -343,7 +399,7 @@ __global__ void bn_apply_kernel(const __nv_bfloat16* __restrict__ x, const float
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
     float r = fmaf(v.f[j], scale_shift[c + j], scale_shift[C + c + j]);
-    v.f[j] = relu ? fmaxf(r, 0.f) : r;
+    v.f[j] = r > 0.f ? r : r * bn_act_slope(relu);
   }
   st8(y + i * 8, v);
 }
@@ -361,8 +417,8 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
     const float sc = scale_shift[c], sh = scale_shift[C + c], mean = mean_invstd[c], invstd = mean_invstd[C + c];
     for (long long r = a + lr; r < b; r += 4) {
       const float xv = bf2f(x[r * C + c]);
-      const bool on = !relu || fmaf(xv, sc, sh) > 0.f;
-      if (!on) continue;
+      const float am = fmaf(xv, sc, sh) > 0.f ? 1.f : bn_act_slope(relu);
+      if (am == 0.f) continue;
       float g = 0.f;
       if (up == 1) {
         g = bf2f(dy[r * C + c]);
@@ -374,6 +430,7 @@ __global__ void bn_bwd_reduce_kernel(const __nv_bfloat16* __restrict__ dy, const
           for (int v = 0; v < 2; ++v)
             g += bf2f(dy[((n * 2 * H + 2 * h + u) * 2 * W + 2 * w + v) * C + c]);
       }
+      g *= am;
       s1 += g;
       s2 = fmaf(g, (xv - mean) * invstd, s2);
     }
@@ -422,7 +479,7 @@ __global__ void bn_bwd_apply_kernel(const __nv_bfloat16* __restrict__ dy, const 
   for (int j = 0; j < 8; ++j) {
     const float sc = scale_shift[c + j], sh = scale_shift[C + c + j];
     const float mean = mean_invstd[c + j], invstd = mean_invstd[C + c + j];
-    const float gg = (!relu || fmaf(xv.f[j], sc, sh) > 0.f) ? g.f[j] : 0.f;
+    const float gg = fmaf(xv.f[j], sc, sh) > 0.f ? g.f[j] : g.f[j] * bn_act_slope(relu);
     const float xhat = (xv.f[j] - mean) * invstd;
     o.f[j] = sc * (gg - red[c + j] * invP - xhat * red[C + c + j] * invP);  // sc = gamma*invstd
   }
@@ -601,6 +658,109 @@ using namespace t2v;
 #define BF(p) reinterpret_cast<__nv_bfloat16*>(p)
 #define CBF(p) reinterpret_cast<const __nv_bfloat16*>(p)
 
+// ------------------------------------------------------------------------------------ vectorised column reductions
+// Per-channel sums over the rows of a [P][C] bf16 matrix with 16-byte loads: thread = (row slot, 8 channels),
+// C/8 a power of two <= 256.  One kernel body, three uses (bias gradients, BatchNorm statistics, BatchNorm
+// backward reductions); partial sums are combined through shared memory and one atomicAdd per channel and block.
+struct ColRed {
+  long long P;
+  int C, H, W, act, up;                      // H, W, act, up: BatchNorm backward only
+  const __nv_bfloat16* x;
+  const __nv_bfloat16* dy;
+  const float* scale_shift;
+  const float* mean_invstd;
+  float* out;                                 // [C] (mode 0) or [2C] (modes 1, 2)
+  long long rows_per_block;
+};
+template <int MODE>   // 0: sum x   1: sum x, sum x^2   2: BatchNorm backward {sum g, sum g*xhat}
+__global__ void __launch_bounds__(256) colred_v8_kernel(const ColRed p) {
+  __shared__ float sm1[256][9], sm2[256][9];
+  const int Cb = p.C < 256 ? p.C : 256;       // channels per block; blockIdx.y selects the 256-channel slab
+  const int ct = Cb >> 3;
+  const int tc = threadIdx.x % ct, tr = threadIdx.x / ct, rpi = 256 / ct;
+  const long long a = (long long)blockIdx.x * p.rows_per_block, b = min(p.P, a + p.rows_per_block);
+  const int c = blockIdx.y * 256 + tc * 8;
+  float s1[8], s2[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  float sc[8], sh[8], mean[8], invstd[8];
+  if (MODE == 2) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      sc[j] = p.scale_shift[c + j]; sh[j] = p.scale_shift[p.C + c + j];
+      mean[j] = p.mean_invstd[c + j]; invstd[j] = p.mean_invstd[p.C + c + j];
+    }
+  }
+  const float slope = bn_act_slope(p.act);
+#pragma unroll 2
+  for (long long r = a + tr; r < b; r += rpi) {
+    const V8 v = ld8(p.x + r * p.C + c);
+    if (MODE == 0) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) s1[j] += v.f[j];
+    } else if (MODE == 1) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { s1[j] += v.f[j]; s2[j] = fmaf(v.f[j], v.f[j], s2[j]); }
+    } else {
+      V8 g;
+      if (p.up == 1) {
+        g = ld8(p.dy + r * p.C + c);
+      } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) g.f[j] = 0.f;
+        const int w = (int)(r % p.W);
+        const int h = (int)((r / p.W) % p.H);
+        const long long n = r / p.W / p.H;
+#pragma unroll
+        for (int u = 0; u < 2; ++u)
+#pragma unroll
+          for (int q = 0; q < 2; ++q) {
+            const V8 t = ld8(p.dy + ((n * 2 * p.H + 2 * h + u) * 2 * p.W + 2 * w + q) * p.C + c);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) g.f[j] += t.f[j];
+          }
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float gg = fmaf(v.f[j], sc[j], sh[j]) > 0.f ? g.f[j] : g.f[j] * slope;
+        s1[j] += gg;
+        s2[j] = fmaf(gg, (v.f[j] - mean[j]) * invstd[j], s2[j]);
+      }
+    }
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { sm1[threadIdx.x][j] = s1[j]; if (MODE != 0) sm2[threadIdx.x][j] = s2[j]; }
+  __syncthreads();
+  // thread t < C sums channel t over the rpi row slots
+  if ((int)threadIdx.x < Cb) {
+    const int cc = threadIdx.x >> 3, j = threadIdx.x & 7;
+    float t1 = 0.f, t2 = 0.f;
+    for (int q = 0; q < rpi; ++q) { t1 += sm1[q * ct + cc][j]; if (MODE != 0) t2 += sm2[q * ct + cc][j]; }
+    const int co = blockIdx.y * 256 + threadIdx.x;
+    atomicAdd(p.out + co, t1);
+    if (MODE != 0) atomicAdd(p.out + p.C + co, t2);
+  }
+}
+static bool colred_ok(int C) {
+  if (C % 8) return false;
+  if (C > 256) return C % 256 == 0;                     // 256-channel slabs along grid.y
+  const int ct = C / 8;
+  return ct >= 1 && (ct & (ct - 1)) == 0;               // C/8 a power of two: one block covers all channels
+}
+template <int MODE>
+static void colred_launch(ColRed p, cudaStream_t s) {
+  const int slabs = p.C > 256 ? p.C / 256 : 1;
+  const int rpi = 256 / ((p.C > 256 ? 256 : p.C) / 8);
+  long long blocks = 8 * 148 / slabs;
+  const long long maxb = (p.P + (long long)rpi * 4 - 1) / ((long long)rpi * 4);
+  if (blocks > maxb) blocks = maxb;
+  if (blocks < 1) blocks = 1;
+  p.rows_per_block = (p.P + blocks - 1) / blocks;
+  p.rows_per_block = (p.rows_per_block + rpi - 1) / rpi * rpi;
+  blocks = (p.P + p.rows_per_block - 1) / p.rows_per_block;
+  colred_v8_kernel<MODE><<<dim3((unsigned)blocks, (unsigned)slabs, 1), 256, 0, s>>>(p);
+}
+
 extern "C" {
 
 int t2v_relu_fwd(const void* x, void* y, int64_t n, void* stream) {
@@ -616,6 +776,35 @@ int t2v_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, void* str
   relu_bwd_kernel<<<blocks_for(n / 8, 256), 256, 0, STREAM>>>(CBF(dy), CBF(ref), BF(dx), n / 8);
   count_launch();
   return check_last("relu_bwd");
+}
+
+int t2v_leaky_relu_fwd(const void* x, void* y, int64_t n, float slope, void* stream) {
+  if (n % 8) return T2V_ERR_ARG;
+  if (n == 0) return T2V_OK;
+  leaky_fwd_kernel<<<blocks_for(n / 8, 256), 256, 0, STREAM>>>(CBF(x), BF(y), slope, n / 8);
+  count_launch();
+  return check_last("leaky_relu_fwd");
+}
+int t2v_leaky_relu_bwd(const void* dy, const void* ref, void* dx, int64_t n, float slope, void* stream) {
+  if (n % 8) return T2V_ERR_ARG;
+  if (n == 0) return T2V_OK;
+  leaky_bwd_kernel<<<blocks_for(n / 8, 256), 256, 0, STREAM>>>(CBF(dy), CBF(ref), BF(dx), slope, n / 8);
+  count_launch();
+  return check_last("leaky_relu_bwd");
+}
+int t2v_tanh_fwd(const void* x, void* y, int64_t n, void* stream) {
+  if (n % 8) return T2V_ERR_ARG;
+  if (n == 0) return T2V_OK;
+  tanh_fwd_kernel<<<blocks_for(n / 8, 256), 256, 0, STREAM>>>(CBF(x), BF(y), n / 8);
+  count_launch();
+  return check_last("tanh_fwd");
+}
+int t2v_tanh_bwd(const void* dy, const void* y, void* dx, int64_t n, void* stream) {
+  if (n % 8) return T2V_ERR_ARG;
+  if (n == 0) return T2V_OK;
+  tanh_bwd_kernel<<<blocks_for(n / 8, 256), 256, 0, STREAM>>>(CBF(dy), CBF(y), BF(dx), n / 8);
+  count_launch();
+  return check_last("tanh_bwd");
 }
 
 static int pool_params(PoolParams& p, const int32_t* shape, const int32_t* k, const int32_t* s, const int32_t* pad) {
@@ -685,9 +874,15 @@ int t2v_cl_to_nchw(const void* x, float* y, int64_t N, int32_t C, int64_t S, int
 int t2v_im2col3(const float* x, void* col, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
                 void* stream) {
   if (C < 1 || C > 4 || Kp % 8 || Kp < 27 * C) return T2V_ERR_ARG;
-  const long long total = N * D * H * W * (Kp / 8);
+  const long long total = N * D * H * W;
   if (total == 0) return T2V_OK;
-  im2col3_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, BF(col), C, D, H, W, Kp, total);
+  const unsigned nb = blocks_for(total, 128);
+  switch (C) {
+    case 1: im2col3_kernel<1><<<nb, 128, 0, STREAM>>>(x, BF(col), D, H, W, Kp, total); break;
+    case 2: im2col3_kernel<2><<<nb, 128, 0, STREAM>>>(x, BF(col), D, H, W, Kp, total); break;
+    case 3: im2col3_kernel<3><<<nb, 128, 0, STREAM>>>(x, BF(col), D, H, W, Kp, total); break;
+    default: im2col3_kernel<4><<<nb, 128, 0, STREAM>>>(x, BF(col), D, H, W, Kp, total); break;
+  }
   count_launch();
   return check_last("im2col3");
 }
@@ -696,7 +891,13 @@ int t2v_col2im3(const void* dcol, float* dx, int64_t N, int32_t C, int32_t D, in
   if (C < 1 || C > 4 || Kp < 27 * C) return T2V_ERR_ARG;
   const long long total = N * D * H * W;
   if (total == 0) return T2V_OK;
-  col2im3_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(CBF(dcol), dx, C, D, H, W, Kp, total);
+  const unsigned nb = blocks_for(total, 128);
+  switch (C) {
+    case 1: col2im3_kernel<1><<<nb, 128, 0, STREAM>>>(CBF(dcol), dx, D, H, W, Kp, total); break;
+    case 2: col2im3_kernel<2><<<nb, 128, 0, STREAM>>>(CBF(dcol), dx, D, H, W, Kp, total); break;
+    case 3: col2im3_kernel<3><<<nb, 128, 0, STREAM>>>(CBF(dcol), dx, D, H, W, Kp, total); break;
+    default: col2im3_kernel<4><<<nb, 128, 0, STREAM>>>(CBF(dcol), dx, D, H, W, Kp, total); break;
+  }
   count_launch();
   return check_last("col2im3");
 }
@@ -711,6 +912,13 @@ static void row_split(long long P, int C, dim3* grid, long long* rows_per_block)
 int t2v_sum_rows(const void* x, float* out, int64_t P, int32_t C, void* stream) {
   cudaMemsetAsync(out, 0, sizeof(float) * C, STREAM);
   if (P == 0) return T2V_OK;
+  if (colred_ok(C)) {
+    ColRed cr{};
+    cr.P = P; cr.C = C; cr.x = CBF(x); cr.out = out;
+    colred_launch<0>(cr, STREAM);
+    count_launch();
+    return check_last("sum_rows");
+  }
   dim3 grid;
   long long rpb;
   row_split(P, C, &grid, &rpb);
@@ -734,6 +942,13 @@ int t2v_broadcast_spatial(const float* g, void* y, int64_t N, int64_t S, int32_t
 }
 int t2v_bn_stats(const void* x, float* stats, int64_t P, int32_t C, void* stream) {
   cudaMemsetAsync(stats, 0, sizeof(float) * 2 * C, STREAM);
+  if (colred_ok(C) && P > 0) {
+    ColRed cr{};
+    cr.P = P; cr.C = C; cr.x = CBF(x); cr.out = stats;
+    colred_launch<1>(cr, STREAM);
+    count_launch();
+    return check_last("bn_stats");
+  }
   dim3 grid;
   long long rpb;
   row_split(P, C, &grid, &rpb);
@@ -764,11 +979,18 @@ int t2v_bn_bwd(const void* dy, const void* x, const float* scale_shift, const fl
   const long long P = N * H * W;
   cudaMemsetAsync(red, 0, sizeof(float) * 2 * C, STREAM);
   if (P == 0) return T2V_OK;
-  dim3 grid;
-  long long rpb;
-  row_split(P, C, &grid, &rpb);
-  bn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(CBF(dy), CBF(x), scale_shift, mean_invstd, red, P, H, W, C, relu, up,
-                                                 rpb);
+  if (colred_ok(C)) {
+    ColRed cr{};
+    cr.P = P; cr.C = C; cr.H = H; cr.W = W; cr.act = relu; cr.up = up;
+    cr.x = CBF(x); cr.dy = CBF(dy); cr.scale_shift = scale_shift; cr.mean_invstd = mean_invstd; cr.out = red;
+    colred_launch<2>(cr, STREAM);
+  } else {
+    dim3 grid;
+    long long rpb;
+    row_split(P, C, &grid, &rpb);
+    bn_bwd_reduce_kernel<<<grid, 256, 0, STREAM>>>(CBF(dy), CBF(x), scale_shift, mean_invstd, red, P, H, W, C, relu,
+                                                   up, rpb);
+  }
   const long long total8 = P * C / 8;
   bn_bwd_apply_kernel<<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(dy), CBF(x), scale_shift, mean_invstd, red,
                                                                    BF(dx), P, H, W, C, relu, up, total8);

@@ -586,7 +586,7 @@ int halo_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, cons
   p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
   const size_t smem = 2 * (size_t)p.a_bytes + kWStages * kWTapBytes + 1024 + (8 + 2 * kWStages) * 8 + 16;
   cudaFuncSetAttribute(halo_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  int cs = p.tiles_total >= 592 ? 4 : (p.tiles_total >= 296 ? 2 : 1);
+  int cs = 1;   // measured on B200: cs = 1 and 2 tie (the kernel is not weight-traffic bound), cs = 4 loses SMs
   { const char* e = getenv("T2V_HALO_CLUSTER"); if (e && e[0] >= '1' && e[0] <= '4') cs = e[0] - '0'; if (cs == 3) cs = 2; }
   int ncl = cs > 1 ? max_active_clusters(cs, smem) : 148;
   const int need = (p.tiles_total + cs - 1) / cs;

@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import ConvGeom, check, lib, ptr, require_cuda, stream
+from ._lib import ConvGeom, GconvGeom, check, lib, ptr, require_cuda, stream
 
 BF16 = torch.bfloat16
 F32 = torch.float32
@@ -125,6 +125,92 @@ def unpack_wgrad(dwp, Cout, Cin):
     check(lib().t2v_unpack_wgrad_padded(ptr(dwp), ptr(dst), Cout, taps, Cin, CinP, stream()),
           "t2v_unpack_wgrad_padded")
     return dst
+
+
+# ------------------------------------------------------------------------------------- general conv (TGAN / TCWYT)
+def gconv_out_extent(i, k, s, p):
+    return (i + 2 * p - k) // s + 1
+
+
+def _ggeom(N, in_sp, Cin, Cout, k, s, p):
+    out_sp = [gconv_out_extent(i, kk, ss, pp) for i, kk, ss, pp in zip(in_sp, k, s, p)]
+    return GconvGeom(N, in_sp[0], in_sp[1], in_sp[2], out_sp[0], out_sp[1], out_sp[2], Cin, Cout, k[0], k[1], k[2],
+                     s[0], s[1], s[2], p[0], p[1], p[2]), out_sp
+
+
+def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
+    """Strided convolution: x (N,Di,Hi,Wi,Cin) bf16, w (Cout,taps,Cin) bf16 -> y (N,Do,Ho,Wo,Cout)."""
+    require_cuda(x, w, bias)
+    N, Di, Hi, Wi, Cin = x.shape
+    Cout = w.shape[0]
+    assert x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
+    g, osp = _ggeom(N, (Di, Hi, Wi), Cin, Cout, k, s, p)
+    y = torch.empty((N, osp[0], osp[1], osp[2], Cout), device=x.device, dtype=F32 if out_f32 else BF16)
+    check(lib().t2v_gconv_fprop(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), 1 if out_f32 else 0, stream()),
+          "t2v_gconv_fprop")
+    return y
+
+
+def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
+    """Data gradient of gconv_fprop == forward of a transposed convolution: dy (N,Do,Ho,Wo,Cout) bf16,
+    w (Cout,taps,Cin) bf16 -> dx (N,Di,Hi,Wi,Cin); in_sp = (Di,Hi,Wi); bias fp32 (Cin,) or None."""
+    require_cuda(dy, w, bias)
+    N, Cout = dy.shape[0], dy.shape[-1]
+    Cin = w.shape[2]
+    assert dy.dtype == BF16 and w.dtype == BF16 and dy.is_contiguous() and w.is_contiguous() and w.shape[0] == Cout
+    g, osp = _ggeom(N, tuple(in_sp), Cin, Cout, k, s, p)
+    assert tuple(osp) == tuple(dy.shape[1:4]), (osp, dy.shape)
+    dx = torch.empty((N, in_sp[0], in_sp[1], in_sp[2], Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
+    check(lib().t2v_gconv_dgrad(ctypes.byref(g), ptr(dy), ptr(w), ptr(bias), ptr(dx), 1 if out_f32 else 0, stream()),
+          "t2v_gconv_dgrad")
+    return dx
+
+
+def gconv_wgrad(dy, x, k, s, p):
+    """dw (Cout,taps,Cin) fp32 = sum_pos dy[pos,co] * x[in(pos,tap),ci]."""
+    require_cuda(dy, x)
+    N, Di, Hi, Wi, Cin = x.shape
+    Cout = dy.shape[-1]
+    assert dy.dtype == BF16 and x.dtype == BF16 and dy.is_contiguous() and x.is_contiguous()
+    g, osp = _ggeom(N, (Di, Hi, Wi), Cin, Cout, k, s, p)
+    assert tuple(osp) == tuple(dy.shape[1:4]), (osp, dy.shape)
+    dw = torch.empty((Cout, k[0] * k[1] * k[2], Cin), device=x.device, dtype=F32)
+    check(lib().t2v_gconv_wgrad(ctypes.byref(g), ptr(dy), ptr(x), ptr(dw), 0, stream()), "t2v_gconv_wgrad")
+    return dw
+
+
+def leaky_relu_fwd(x, slope):
+    require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().t2v_leaky_relu_fwd(ptr(x), ptr(y), x.numel(), float(slope), stream()), "t2v_leaky_relu_fwd")
+    return y
+
+
+def leaky_relu_bwd(dy, ref, slope):
+    require_cuda(dy, ref)
+    assert dy.dtype == BF16 and ref.dtype == BF16 and dy.is_contiguous() and ref.is_contiguous()
+    dx = torch.empty_like(dy)
+    check(lib().t2v_leaky_relu_bwd(ptr(dy), ptr(ref), ptr(dx), dy.numel(), float(slope), stream()),
+          "t2v_leaky_relu_bwd")
+    return dx
+
+
+def tanh_fwd(x):
+    require_cuda(x)
+    assert x.dtype == BF16 and x.is_contiguous()
+    y = torch.empty_like(x)
+    check(lib().t2v_tanh_fwd(ptr(x), ptr(y), x.numel(), stream()), "t2v_tanh_fwd")
+    return y
+
+
+def tanh_bwd(dy, y):
+    require_cuda(dy, y)
+    assert dy.dtype == BF16 and y.dtype == BF16 and dy.is_contiguous() and y.is_contiguous()
+    dx = torch.empty_like(dy)
+    check(lib().t2v_tanh_bwd(ptr(dy), ptr(y), ptr(dx), dy.numel(), stream()), "t2v_tanh_bwd")
+    return dx
 
 
 # ------------------------------------------------------------------------------------- pointwise / pooling
@@ -262,8 +348,13 @@ def broadcast_spatial(g, shape):
 # ------------------------------------------------------------------------------------- BatchNorm (train)
 def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, momentum=0.1, training=True):
     """x (N,1,H,W,C) bf16 -> y (N,1,up*H,up*W,C), plus (mean_invstd, scale_shift) fp32 [2C] for backward.
-    training=False normalises with the running statistics (no update)."""
+    training=False normalises with the running statistics (no update).  `relu` is the fused activation code:
+    0/False none, 1/True ReLU, 2 LeakyReLU(0.2).  With up == 1 any CL shape is accepted (statistics over all
+    leading dims: BatchNorm1d/2d/3d)."""
     require_cuda(x, gamma, beta)
+    shape0 = tuple(x.shape)
+    if up == 1 and x.shape[1] != 1:
+        x = x.reshape(-1, 1, 1, 1, x.shape[-1])
     N, D, H, W, C = x.shape
     assert D == 1 and x.dtype == BF16 and x.is_contiguous()
     dev = x.device
@@ -282,21 +373,27 @@ def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, mo
         check(lib().t2v_bn_finalize(ptr(stats), ptr(gamma), ptr(beta), None, None, ptr(mean_invstd),
                                     ptr(scale_shift), C, 1, eps, momentum, stream()), "t2v_bn_finalize")
     y = torch.empty((N, 1, up * H, up * W, C), device=dev, dtype=BF16)
-    check(lib().t2v_bn_apply(ptr(x), ptr(scale_shift), ptr(y), N, H, W, C, 1 if relu else 0, up, stream()),
+    check(lib().t2v_bn_apply(ptr(x), ptr(scale_shift), ptr(y), N, H, W, C, int(relu), up, stream()),
           "t2v_bn_apply")
+    if up == 1:
+        y = y.view(shape0)
     return y, mean_invstd, scale_shift
 
 
 def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
     """-> dx (x-shaped bf16), dgamma fp32 [C], dbeta fp32 [C]."""
     require_cuda(dy, x)
+    shape0 = tuple(x.shape)
+    if up == 1 and x.shape[1] != 1:
+        x = x.reshape(-1, 1, 1, 1, x.shape[-1])
+        dy = dy.reshape(x.shape)
     N, D, H, W, C = x.shape
     assert dy.is_contiguous() and dy.dtype == BF16 and tuple(dy.shape) == (N, 1, up * H, up * W, C)
     red = torch.empty((2 * C,), device=x.device, dtype=F32)
     dx = torch.empty_like(x)
     check(lib().t2v_bn_bwd(ptr(dy), ptr(x), ptr(scale_shift), ptr(mean_invstd), ptr(red), ptr(dx), N, H, W, C,
-                           1 if relu else 0, up, stream()), "t2v_bn_bwd")
-    return dx, red[C:], red[:C]
+                           int(relu), up, stream()), "t2v_bn_bwd")
+    return dx.view(shape0), red[C:], red[:C]
 
 
 # ------------------------------------------------------------------------------------- render / index

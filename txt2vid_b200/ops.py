@@ -36,6 +36,8 @@ def kernel_of(weight):
     """(kd,kh,kw) of a Linear / Conv2d / Conv3d weight."""
     if weight.dim() == 2:
         return (1, 1, 1)
+    if weight.dim() == 3:
+        return (1, 1, weight.shape[2])
     if weight.dim() == 4:
         return (1, weight.shape[2], weight.shape[3])
     return tuple(weight.shape[2:])
@@ -46,19 +48,20 @@ def w3_view(weight):
     if weight.dim() == 2:
         assert weight.is_contiguous()
         return weight.view(weight.shape[0], 1, weight.shape[1])
-    fmt = torch.channels_last_3d if weight.dim() == 5 else torch.channels_last
-    if not weight.is_contiguous(memory_format=fmt) or (weight.numel() and weight.stride(1) != 1):
+    perm = _CL_PERM[weight.dim()]
+    if not weight.permute(*perm).is_contiguous():
         with torch.no_grad():
             weight.data = _to_cl_memory(weight.data)
-    perm = (0, 2, 3, 4, 1) if weight.dim() == 5 else (0, 2, 3, 1)
     wp = weight.permute(*perm)
     return wp.reshape(weight.shape[0], -1, weight.shape[1])
 
 
+_CL_PERM = {3: (0, 2, 1), 4: (0, 2, 3, 1), 5: (0, 2, 3, 4, 1)}
+_CL_INV = {3: (0, 2, 1), 4: (0, 3, 1, 2), 5: (0, 4, 1, 2, 3)}
+
+
 def _to_cl_memory(t):
-    perm = (0, 2, 3, 4, 1) if t.dim() == 5 else (0, 2, 3, 1)
-    inv = (0, 4, 1, 2, 3) if t.dim() == 5 else (0, 3, 1, 2)
-    return t.permute(*perm).contiguous().permute(*inv)
+    return t.permute(*_CL_PERM[t.dim()]).contiguous().permute(*_CL_INV[t.dim()])
 
 
 def grad_like_weight(dw3, weight):
@@ -66,6 +69,8 @@ def grad_like_weight(dw3, weight):
     if weight.dim() == 2:
         return dw3.view(weight.shape)
     Cout, Cin = weight.shape[0], weight.shape[1]
+    if weight.dim() == 3:
+        return dw3.view(Cout, weight.shape[2], Cin).permute(0, 2, 1)
     if weight.dim() == 4:
         return dw3.view(Cout, weight.shape[2], weight.shape[3], Cin).permute(0, 3, 1, 2)
     return dw3.view(Cout, weight.shape[2], weight.shape[3], weight.shape[4], Cin).permute(0, 4, 1, 2, 3)
@@ -219,6 +224,169 @@ class SumRowsF(Function):
 
 def conv(x, weight, bias=None, residual=None, relu=False):
     return ConvF.apply(x, weight, bias, residual, relu)
+
+
+# ------------------------------------------------------------------------------------- general conv (TGAN / TCWYT)
+def _t3(v):
+    """int | 1/2/3-tuple -> (d, h, w) triple padded on the left with `fill` semantics of the caller."""
+    return tuple(v)
+
+
+def conv_args(module):
+    """(k, s, p) triples of an nn.Conv{1,2,3}d / nn.ConvTranspose{1,2,3}d container (unit extents on the left)."""
+    nd = len(module.kernel_size)
+    k = (1,) * (3 - nd) + tuple(module.kernel_size)
+    s = (1,) * (3 - nd) + tuple(module.stride)
+    p = (0,) * (3 - nd) + tuple(module.padding)
+    return k, s, p
+
+
+class GConvF(Function):
+    """Strided / padded convolution on a CL tensor (first-order): the k4 s2 p1 and head convolutions of
+    models/tcwyt/video_discrim.py:12-46, frame_discrim.py:8-49, motion_discrim.py:8-19."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, s, p):
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        CinP, CoutP = x.shape[-1], round16(Cout)
+        wp = PACKS.get(weight, "fprop", CoutP, CinP)
+        y = K.gconv_fprop(x, wp, _pad_bias(bias, CoutP), k, s, p)
+        ctx.cfg = (k, s, p, bias is not None)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        k, s, p, has_bias = ctx.cfg
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        Cout, Cin = weight.shape[0], weight.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = PACKS.get(weight, "fprop", dy.shape[-1], x.shape[-1])
+            dx = K.gconv_dgrad(dy, wp, None, tuple(x.shape[1:4]), k, s, p)
+        if ctx.needs_input_grad[1]:
+            dw3 = K.unpack_wgrad(K.gconv_wgrad(dy, x, k, s, p), Cout, Cin)
+            dw = grad_like_weight(dw3, weight)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = K.sum_rows(dy)[:Cout]
+        return dx, dw, db, None, None, None
+
+
+class GConvTF(Function):
+    """Transposed convolution (first-order) = the data-gradient kernel of the convolution that shares its weight
+    tensor: weight (Cin_t, Cout_t, k...) is that convolution's (Cout, Cin, k...).  models/tgan/gen.py:21-25,
+    tgan/temporal_gen.py:16-20, tcwyt/gen.py:14-30."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias, k, s, p):
+        Cin_t, Cout_t = weight.shape[0], weight.shape[1]
+        CinP, CoutP = x.shape[-1], round16(Cout_t)
+        wp = PACKS.get(weight, "fprop", CinP, CoutP)                       # [Cin_t p][taps][Cout_t p]
+        out_sp = tuple((i - 1) * ss - 2 * pp + kk for i, ss, pp, kk in zip(x.shape[1:4], s, p, k))
+        y = K.gconv_dgrad(x, wp, _pad_bias(bias, CoutP), out_sp, k, s, p)
+        ctx.cfg = (k, s, p, bias is not None)
+        ctx.save_for_backward(x, weight)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        k, s, p, has_bias = ctx.cfg
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        Cin_t, Cout_t = weight.shape[0], weight.shape[1]
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            wp = PACKS.get(weight, "fprop", x.shape[-1], dy.shape[-1])
+            dx = K.gconv_fprop(dy, wp, None, k, s, p)
+        if ctx.needs_input_grad[1]:
+            dw3 = K.unpack_wgrad(K.gconv_wgrad(x, dy, k, s, p), Cin_t, Cout_t)
+            dw = grad_like_weight(dw3, weight)
+        if has_bias and ctx.needs_input_grad[2]:
+            db = K.sum_rows(dy)[:Cout_t]
+        return dx, dw, db, None, None, None
+
+
+def gconv(x, module):
+    """nn.Conv{1,2,3}d container applied to a CL tensor (any stride / padding)."""
+    k, s, p = conv_args(module)
+    return GConvF.apply(x, module.weight, module.bias, k, s, p)
+
+
+def gconv_transpose(x, module):
+    """nn.ConvTranspose{1,2,3}d container applied to a CL tensor (output_padding 0)."""
+    k, s, p = conv_args(module)
+    return GConvTF.apply(x, module.weight, module.bias, k, s, p)
+
+
+class LeakyF(Function):
+    @staticmethod
+    def forward(ctx, x, slope):
+        y = K.leaky_relu_fwd(x, slope)
+        ctx.slope = slope
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.leaky_relu_bwd(dy.contiguous(), y, ctx.slope), None
+
+
+def leaky_relu(x, slope=0.2):
+    return LeakyF.apply(x, slope)
+
+
+class TanhF(Function):
+    @staticmethod
+    def forward(ctx, x):
+        y = K.tanh_fwd(x)
+        ctx.save_for_backward(y)
+        return y
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dy):
+        (y,) = ctx.saved_tensors
+        return K.tanh_bwd(dy.contiguous(), y)
+
+
+def tanh(x):
+    return TanhF.apply(x)
+
+
+def bn_act(x, bn, act=0):
+    """BatchNorm1d/2d/3d (batch statistics in train()) + fused activation on a CL tensor of any rank-5 shape:
+    act 0 none, 1 ReLU, 2 LeakyReLU(0.2).  Channel counts that are not a multiple of 16 (BatchNorm1d(356) of
+    models/tcwyt/gen.py:37) run on zero/one-padded parameter copies."""
+    C, Cp = bn.num_features, x.shape[-1]
+    if Cp == C:
+        return BnReluUpF.apply(x, bn.weight, bn.bias, bn.running_mean, bn.running_var, act, 1, bn.training, bn.eps,
+                               bn.momentum)
+    import torch.nn.functional as Fnn
+    gamma = Fnn.pad(bn.weight, (0, Cp - C), value=1.0)
+    beta = Fnn.pad(bn.bias, (0, Cp - C))
+    rm = Fnn.pad(bn.running_mean, (0, Cp - C))
+    rv = Fnn.pad(bn.running_var, (0, Cp - C), value=1.0)
+    y = BnReluUpF.apply(x, gamma, beta, rm, rv, act, 1, bn.training, bn.eps, bn.momentum)
+    if bn.training:
+        bn.running_mean.copy_(rm[:C])
+        bn.running_var.copy_(rv[:C])
+    return y
+
+
+def linear_cl(x, module):
+    """nn.Linear container on a CL tensor (..., CinP) -> (..., CoutP) through the 1x1x1 conv engine."""
+    return conv(x, module.weight, module.bias)
+
+
+def vec_to_cl(v, Cp=None):
+    """fp32 (B, C) -> CL bf16 (B,1,1,1,Cp) (zero channel padding)."""
+    B, C = v.shape
+    return to_cl(v.reshape(B, C, 1, 1, 1), Cp)
 
 
 # ------------------------------------------------------------------------------------- ReLU
