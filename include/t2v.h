@@ -59,6 +59,9 @@ unsigned long long t2v_launch_count(void);
  * host_out6 = {fprop+dgrad ms, useful FLOPs, launches, wgrad ms, useful FLOPs, launches} and resets */
 int t2v_profile_enable(int on);
 int t2v_profile_read(double* host_out6);
+/* same, split by kernel: {generic fprop/dgrad, generic wgrad, halo-resident fprop/dgrad, halo-resident wgrad} x
+ * {ms, useful FLOPs, launches} */
+int t2v_profile_read4(double* host_out12);
 
 /* convolution engine (tcgen05 implicit GEMM; replaces F.conv2d/conv3d/linear = cuDNN/cuBLAS)  */
 /* y[n,d,h,w,co] = sum_{taps,ci} x[n,d+a-pd,h+b-ph,w+c-pw,ci] * w[co,a,b,c,ci] + bias[co] (+ residual)

@@ -1,0 +1,65 @@
+"""Times the conv engine (fprop + wgrad, CUDA events, 20 launches after 3 warm-ups) on the TGANv2 shapes that
+carry the step at batch 1024 / GPU.  Usage: python scripts/perf_shapes.py [tag]  (env knobs select variants)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch
+from txt2vid_b200 import kernels as K
+
+SHAPES = [
+    ("G0 128->128 @8x8", (16384, 1, 8, 8, 128, 128, (1, 3, 3))),
+    ("G0 256->256 @4x4", (16384, 1, 4, 4, 256, 256, (1, 3, 3))),
+    ("G0 512->512 @2x2", (16384, 1, 2, 2, 512, 512, (1, 3, 3))),
+    ("G0 1024->512 @2x2", (16384, 1, 2, 2, 1024, 512, (1, 3, 3))),
+    ("G0 256->128 @8x8", (16384, 1, 8, 8, 256, 128, (1, 3, 3))),
+    ("D 64->64 (512,4,8,8)", (512, 4, 8, 8, 64, 64, (3, 3, 3))),
+    ("D 64->64 (1024,8,4,4)", (1024, 8, 4, 4, 64, 64, (3, 3, 3))),
+    ("D 128->64 (512,4,8,8)", (512, 4, 8, 8, 128, 64, (3, 3, 3))),
+    ("D 64->128 (1024,8,4,4)", (1024, 8, 4, 4, 64, 128, (3, 3, 3))),
+    ("D 128->128 (512,2,4,4)", (512, 2, 4, 4, 128, 128, (3, 3, 3))),
+    ("D 128->256 (1024,4,2,2)", (1024, 4, 2, 2, 128, 256, (3, 3, 3))),
+    ("D 256->256 (256,1,4,4)", (256, 1, 4, 4, 256, 256, (3, 3, 3))),
+    ("D 512->512 (256,1,2,2)", (256, 1, 2, 2, 512, 512, (3, 3, 3))),
+    ("D 512->1024 (128,1,4,4)", (128, 1, 4, 4, 512, 1024, (3, 3, 3))),
+    ("G 32->32 @64x64", (256, 1, 64, 64, 32, 32, (1, 3, 3))),
+    ("G 64->32 @32x32", (1024, 1, 32, 32, 64, 32, (1, 3, 3))),
+    ("G 128->64 @16x16", (4096, 1, 16, 16, 128, 64, (1, 3, 3))),
+    ("G render 128->16 @8x8", (16384, 1, 8, 8, 128, 16, (1, 3, 3))),
+    ("stem1 96->64 1x1 L0", (1024, 16, 8, 8, 96, 64, (1, 1, 1))),
+    ("LSTM 1024->4096", (1024, 1, 1, 1, 1024, 4096, (1, 1, 1))),
+]
+
+
+def mk(N, D, H, W, Cin, Cout, k, seed=0):
+    g = torch.Generator(device="cuda").manual_seed(seed)
+    x = torch.randn((N, D, H, W, Cin), device="cuda", generator=g).to(torch.bfloat16)
+    taps = k[0] * k[1] * k[2]
+    w = (torch.randn((Cout, taps, Cin), device="cuda", generator=g) / (taps * Cin) ** 0.5).to(torch.bfloat16)
+    dy = torch.randn((N, D, H, W, Cout), device="cuda", generator=g).to(torch.bfloat16)
+    return x, w, dy
+
+
+def t(fn, n=20):
+    for _ in range(3):
+        fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(n):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / n
+
+
+tag = sys.argv[1] if len(sys.argv) > 1 else ""
+tot_f = tot_w = 0.0
+for name, case in SHAPES:
+    N, D, H, W, Cin, Cout, k = case
+    x, w, dy = mk(*case)
+    live = [kk if ext > 1 else 1 for kk, ext in zip(k, (D, H, W))]
+    fl = 2.0 * N * D * H * W * Cin * Cout * live[0] * live[1] * live[2]
+    tf = t(lambda: K.conv_fprop(x, w, k=k))
+    tw = t(lambda: K.conv_wgrad(dy, x, k=k))
+    tot_f += tf; tot_w += tw
+    print("%-6s %-26s fprop %.3f ms %6.0f TF/s | wgrad %.3f ms %6.0f TF/s" % (tag, name, tf, fl / tf / 1e9, tw, fl / tw / 1e9), flush=True)
+    del x, w, dy
+print("%-6s TOTAL fprop %.3f ms wgrad %.3f ms" % (tag, tot_f, tot_w))

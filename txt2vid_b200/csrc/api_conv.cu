@@ -18,7 +18,7 @@ int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const floa
                       uint32_t, cudaStream_t);
 int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
 void prof_enable(int on);
-void prof_read(double* out);
+void prof_read(double* out, int nkinds);
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -80,7 +80,8 @@ extern "C" {
 int t2v_version(void) { return 100; }
 unsigned long long t2v_launch_count(void) { return g_launch_count; }
 int t2v_profile_enable(int on) { prof_enable(on); return T2V_OK; }
-int t2v_profile_read(double* host_out6) { prof_read(host_out6); return T2V_OK; }
+int t2v_profile_read(double* host_out6) { prof_read(host_out6, 2); return T2V_OK; }
+int t2v_profile_read4(double* host_out12) { prof_read(host_out12, 4); return T2V_OK; }
 
 int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                    const void* residual, void* y, uint32_t epi_flags, int algo, void* stream) {

@@ -266,7 +266,7 @@ int halo_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, flo
   cudaFuncSetAttribute(halo_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   ProfRec rec;
   if (g_prof_on)
-    prof_begin(stream, &rec, 1, 2.0 * g->N * g->D * g->H * g->W * 64.0 * g->Cout * p.ntaps, g,
+    prof_begin(stream, &rec, 3, 2.0 * g->N * g->D * g->H * g->W * 64.0 * g->Cout * p.ntaps, g,
                (int)(grid.x * grid.y));
   halo_wgrad_kernel<<<grid, kHaloThreads, smem, stream>>>(tmDy, tmX, p);
   if (g_prof_on) prof_end(stream, &rec);
@@ -617,7 +617,7 @@ int halo_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, cons
   cfg.attrs = attr; cfg.numAttrs = 1;
   ProfRec rec;
   if (g_prof_on)
-    prof_begin(stream, &rec, 0, 2.0 * g->N * g->D * g->H * g->W * 64.0 * 64.0 * p.ntaps, g, ncl * cs);
+    prof_begin(stream, &rec, 2, 2.0 * g->N * g->D * g->H * g->W * 64.0 * 64.0 * p.ntaps, g, ncl * cs);
   cudaError_t e = cudaLaunchKernelEx(&cfg, halo_fprop_kernel, tmA, tmW, p);
   if (g_prof_on) prof_end(stream, &rec);
   count_launch();

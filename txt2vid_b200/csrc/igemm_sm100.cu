@@ -57,7 +57,7 @@ struct SwizzleOf {
 
 // ------------------------------------------------------------------------------------ fprop
 template <int BLOCK_K>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -217,7 +217,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
 // boxes (64 positions per k-block).  dy box -> A (MN-major, two 64-channel atoms), shifted x box -> B.
 static constexpr int kWgradPos = 64;
 
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(kThreads, 2)
 igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constant__ CUtensorMap tmX,
                    const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -361,9 +361,10 @@ void prof_begin(cudaStream_t s, ProfRec* r, int kind, double flops, const t2v_co
   cudaEventRecord(r->a, s);
 }
 void prof_end(cudaStream_t s, ProfRec* r) { cudaEventRecord(r->b, s); g_prof.push_back(*r); }
-// out[kind*3 + {0,1,2}] = {milliseconds, flops, launches}, kind 0 = fprop/dgrad, 1 = wgrad
-void prof_read(double* out) {
-  for (int i = 0; i < 6; ++i) out[i] = 0.0;
+// out[kind*3 + {0,1,2}] = {milliseconds, flops, launches}; kind 0 = generic fprop/dgrad, 1 = generic wgrad,
+// 2 = halo-resident fprop/dgrad, 3 = halo-resident wgrad.  nkinds = 2 folds the halo kernels into 0 / 1.
+void prof_read(double* out, int nkinds) {
+  for (int i = 0; i < 3 * nkinds; ++i) out[i] = 0.0;
   const char* dump = getenv("T2V_PROFILE_DUMP");
   FILE* f = dump ? fopen(dump, "a") : nullptr;
   for (auto& r : g_prof) {
@@ -371,15 +372,20 @@ void prof_read(double* out) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);
     if (f)
-      fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.0f\n", r.kind, r.g.N, r.g.D, r.g.H, r.g.W, r.g.Cin, r.g.Cout,
+      fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.0f\n", r.kind % 2, r.g.N, r.g.D, r.g.H, r.g.W, r.g.Cin, r.g.Cout,
               r.g.kd, r.g.kh, r.g.kw, r.ctas, ms, r.flops);
-    out[r.kind * 3 + 0] += ms; out[r.kind * 3 + 1] += r.flops; out[r.kind * 3 + 2] += 1.0;
+    const int kk = r.kind % nkinds;
+    out[kk * 3 + 0] += ms; out[kk * 3 + 1] += r.flops; out[kk * 3 + 2] += 1.0;
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }
   if (f) fclose(f);
   g_prof.clear();
 }
 
+static int env_int(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
 static int pow2_floor(int v) {
   int r = 1;
   while (r * 2 <= v) r *= 2;
@@ -440,12 +446,22 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
   p.tn = (g->N + p.bn - 1) / p.bn; p.td = (g->D + p.bd - 1) / p.bd;
   p.th = (g->H + p.bh - 1) / p.bh; p.tw = (g->W + p.bw - 1) / p.bw;
   p.BN = g->Cout >= 128 ? 128 : g->Cout;
+  const int mtiles_total = p.tn * p.td * p.th * p.tw;
+  static const int adapt_bn = env_int("T2V_FPROP_ADAPT_BN", 1), two_cta = env_int("T2V_FPROP_2CTA", 1);
+  // small problems: narrower N tiles -> more CTAs (the kernel is load-latency bound there, not tensor bound)
+  if (adapt_bn)
+    while (p.BN > 64 && p.BN % 32 == 0 && mtiles_total * ((g->Cout + p.BN - 1) / p.BN) < 120) p.BN /= 2;
   p.cblocks = g->Cin / BLOCK_K;
   p.num_k_blocks = ntaps * p.cblocks;
   p.a_bytes = 128u * BLOCK_K * 2u;
   p.b_bytes = (uint32_t)p.BN * BLOCK_K * 2u;
   p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
-  int stages = (int)(196608u / p.stage_bytes);
+  // many CTAs: cap shared memory at half an SM so that two CTAs are co-resident and one CTA's prologue /
+  // epilogue overlaps the other's main loop (TMEM: 2 x BN <= 512 columns)
+  const int total_ctas = mtiles_total * ((g->Cout + p.BN - 1) / p.BN);
+  const uint32_t budget = (two_cta && total_ctas > 222) ? 106496u : 196608u;
+  int stages = (int)(budget / p.stage_bytes);
+  if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
   if (stages > p.num_k_blocks) stages = p.num_k_blocks < 2 ? 2 : p.num_k_blocks;
   p.stages = stages;
@@ -493,8 +509,14 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   p.BN = g->Cin >= 128 ? 128 : 64;
   const int mtiles = (g->Cout + 127) / 128, ntiles = (g->Cin + p.BN - 1) / p.BN;
   const int base_ctas = mtiles * ntiles * ntaps;
-  // one CTA per SM (smem-bound): fill at most two FULL waves of 148 so that no third, nearly empty wave runs
-  int splits = (2 * 148) / base_ctas;
+  // two CTAs per SM (shared memory capped at half an SM: one CTA's prologue / atomics epilogue overlaps the
+  // other's main loop): fill at most two FULL waves of 2 x 148 so that no nearly empty extra wave runs
+  static const int two_cta = env_int("T2V_WGRAD_2CTA", 1);
+  const int slots = two_cta ? 2 * 148 : 148;
+  int splits = (2 * slots) / base_ctas;
+  // every split adds a full Cout x taps x Cin round of fp32 atomics: only go beyond two waves of 148 when each
+  // CTA still sums >= 32 position boxes (position-heavy layers), else the atomics of weight-heavy layers dominate
+  if (splits < 1 || p.tiles_total / (splits < 1 ? 1 : splits) < 32) splits = (2 * 148) / base_ctas;
   const int max_splits = (p.tiles_total + 3) / 4;  // keep >= 4 k-blocks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
@@ -502,7 +524,7 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   p.a_bytes = 2u * kWgradPos * 128u;
   p.b_bytes = (uint32_t)(p.BN / 64) * kWgradPos * 128u;
   p.stage_bytes = p.a_bytes + p.b_bytes;
-  int stages = (int)(196608u / p.stage_bytes);
+  int stages = (int)((two_cta ? 106496u : 196608u) / p.stage_bytes);
   if (stages > 8) stages = 8;
   p.stages = stages;
   p.idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
