@@ -205,16 +205,28 @@ def run_b200(args):
         x, t, l = dev[i % nb]
         return run_step(x, t, l)
 
+    # end-to-end leg: the public loop of gan/trainer.py:176-267 -- batches come from pinned HOST memory through
+    # data_prefetcher (data/__init__.py:131-156: next batch copied on a side stream while the current one trains),
+    # every step's H2D copy happens inside the timed region, and both losses are read back on the host each step.
+    from txt2vid_b200.data import data_prefetcher
+    e2e_state = {}
+
+    def e2e_begin(n):
+        e2e_state["pf"] = data_prefetcher(((host[i % nb][0], host[i % nb][1], host[i % nb][2]) for i in range(n)),
+                                          device=device)
+
     def step_e2e(i):
-        x, t, l = host[i % nb]                                   # pinned host memory -> H2D inside the timed region
-        ld, lg = run_step(x.to(device, non_blocking=True), t.to(device, non_blocking=True), l)
+        x, y = e2e_state["pf"].next()
+        ld, lg = run_step(x, y[0], y[1])
         return float(ld), float(lg)                               # the device->host read of the step's result
 
-    def timed(fn, n):
+    def timed(fn, n, begin=None):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
+        if begin is not None:
+            begin(n)                                              # first H2D copy is issued inside the timed region
         for i in range(n):
             fn(i)
         e1.record()
@@ -236,7 +248,7 @@ def run_b200(args):
     t_res = timed(step_resident, args.steps)
     launches = launches_per_step * args.steps
     clk = clocks.stop() if rank == 0 else None
-    t_e2e = timed(step_e2e, args.steps)
+    t_e2e = timed(step_e2e, args.steps, begin=e2e_begin)
 
     # ---- roofline pass: per-launch CUDA-event timing of the conv engine over the same step, run eagerly
     # (events cannot be read back from inside a replayed graph; kernels, shapes and launch order are the same)
@@ -250,9 +262,9 @@ def run_b200(args):
     lib.t2v_profile_enable(1)
     timed(step_eager, prof_steps)
     lib.t2v_profile_enable(0)
-    buf = (ctypes.c_double * 6)()
-    lib.t2v_profile_read(buf)
-    fp_ms, fp_fl, fp_n, wg_ms, wg_fl, wg_n = list(buf)
+    buf = (ctypes.c_double * 12)()
+    lib.t2v_profile_read4(buf)
+    prof = list(buf)
     t_prof = t_res / args.steps * prof_steps                       # share is quoted against the timed step
     mem_gb = torch.cuda.max_memory_allocated() / 1e9
 
@@ -265,16 +277,32 @@ def run_b200(args):
     x0, t0_, _ = host[0]
     h2d = x0.numel() * x0.element_size() + t0_.numel() * t0_.element_size()
     step_ms_prof = t_prof / prof_steps * 1e3
-    roof = {"bound": "tensor", "kernel": "igemm_fprop_kernel (tcgen05 implicit GEMM: conv fprop + dgrad)",
-            "achieved": fp_fl / (fp_ms * 1e-3) / 1e12 if fp_ms > 0 else None, "peak": pk["bf16_tflops_sustained"],
+    names = ["igemm_fprop_kernel (generic tcgen05 implicit GEMM: conv fprop + dgrad, Linear, ConvLSTM gates)",
+             "igemm_wgrad_kernel (generic tcgen05 weight gradient)",
+             "halo_fprop_kernel (halo-resident tcgen05 fprop + dgrad of the 64-channel 3x3x3 stem convs)",
+             "halo_wgrad_kernel (halo-resident tcgen05 weight gradient, two taps stacked per MMA)"]
+    kern = {}
+    for i, nm in enumerate(names):
+        ms, fl, n = prof[3 * i:3 * i + 3]
+        kern[nm.split(" ")[0]] = {"achieved": fl / (ms * 1e-3) / 1e12 if ms > 0 else None,
+                                  "launches_per_step": n / prof_steps, "ms_per_step_in_kernel": ms / prof_steps,
+                                  "share_of_step": ms / prof_steps / step_ms_prof if step_ms_prof > 0 else None}
+    top = max(range(4), key=lambda i: prof[3 * i])
+    tk = kern[names[top].split(" ")[0]]
+    conv_ms = sum(prof[3 * i] for i in range(4)) / prof_steps
+    conv_fl = sum(prof[3 * i + 1] for i in range(4)) / prof_steps
+    roof = {"bound": "tensor", "kernel": names[top], "achieved": tk["achieved"], "peak": pk["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "traffic": None,
+            "traffic_note": "per-launch DRAM bytes of these kernels on the hot shapes are in profiles/ "
+                            "(ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum); the step-level kernel mixes "
+                            "~60 shapes, so no single per-launch figure applies",
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), %s" % pk["source"],
-            "launches_per_step": fp_n / prof_steps, "ms_per_step_in_kernel": fp_ms / prof_steps,
-            "share_of_step": fp_ms / prof_steps / step_ms_prof if step_ms_prof > 0 else None,
+            "launches_per_step": tk["launches_per_step"], "ms_per_step_in_kernel": tk["ms_per_step_in_kernel"],
+            "share_of_step": tk["share_of_step"],
             "flops_counted": "useful MACs x2 (live taps only, padded channels included)",
-            "wgrad_kernel": {"achieved": wg_fl / (wg_ms * 1e-3) / 1e12 if wg_ms > 0 else None,
-                             "launches_per_step": wg_n / prof_steps, "ms_per_step_in_kernel": wg_ms / prof_steps,
-                             "share_of_step": wg_ms / prof_steps / step_ms_prof if step_ms_prof > 0 else None},
+            "kernels": kern,
+            "conv_engine_all": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None,
+                                "ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms_prof if step_ms_prof else None},
             "step_nominal_tflops_per_gpu": value / world * GFLOP_PER_VIDEO_NOMINAL / 1e3,
             "step_nominal_frac_of_sustained_peak": value / world * GFLOP_PER_VIDEO_NOMINAL / 1e3 / pk["bf16_tflops_sustained"]}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
