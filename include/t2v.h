@@ -161,6 +161,16 @@ int t2v_bn_apply(const void* x, const float* scale_shift, void* y, int64_t N, in
 int t2v_bn_bwd(const void* dy, const void* x, const float* scale_shift, const float* mean_invstd, float* red,
                void* dx, int64_t N, int32_t H, int32_t W, int32_t C, int32_t relu, int32_t up, void* stream);
 
+/* Fused core of the non-local block (models/layers.py:23-36,52-68): o = softmax(theta . maxpool(phi)^T) . maxpool(g)
+ * per map, max-pool (1,2,2); theta/phi (N,D,H,W,C8p) and g/o (N,D,H,W,C2p) bf16 CL with c8 <= 8, c2 <= 16 real
+ * channels (the rest zero padding); H, W even.  The attention matrix is never materialised.  bwd writes
+ * d theta, d phi, d g (full resolution: the pooled gradients land on the arg-max voxel of each window).   */
+int t2v_attention_fwd(const void* theta, const void* phi, const void* g, void* o, int64_t N, int32_t D, int32_t H,
+                      int32_t W, int32_t c8, int32_t c2, int32_t C8p, int32_t C2p, void* stream);
+int t2v_attention_bwd(const void* theta, const void* phi, const void* g, const void* dout, void* dtheta, void* dphi,
+                      void* dg, int64_t N, int32_t D, int32_t H, int32_t W, int32_t c8, int32_t c2, int32_t C8p,
+                      int32_t C2p, void* stream);
+
 /* RenderBlock tail: tanh + (B*T,H,W,Cp) bf16 -> (B,C,T,H,W) fp32 (layers.py:252, gen.py:116-119)  */
 int t2v_render_fwd(const void* pre, float* y, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, int32_t Cp,
                    void* stream);

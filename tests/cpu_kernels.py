@@ -261,6 +261,36 @@ def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
     return dx.to(STORE), dgamma, dbeta
 
 
+def _attn_parts(theta, phi, g, c8, c2):
+    N, D, H, W, _ = theta.shape
+    th = theta.float()[..., :c8].reshape(N, D * H * W, c8)
+
+    def mp(t, c):
+        tt = t.float()[..., :c].permute(0, 4, 1, 2, 3)
+        return F.max_pool3d(tt, [1, 2, 2]).permute(0, 2, 3, 4, 1).reshape(N, -1, c)
+    return th, mp(phi, c8), mp(g, c2)
+
+
+def attention_fwd(theta, phi, g, c8, c2):
+    N, D, H, W, _ = theta.shape
+    th, ph, gp = _attn_parts(theta, phi, g, c8, c2)
+    beta = torch.softmax(torch.bmm(th, ph.transpose(1, 2)), -1)
+    o = torch.zeros((N, D, H, W, g.shape[-1]), dtype=F32, device=theta.device)
+    o[..., :c2] = torch.bmm(beta, gp).reshape(N, D, H, W, c2)
+    return o.to(STORE)
+
+
+def attention_bwd(theta, phi, g, dout, c8, c2):
+    th_, ph_, g_ = (t.detach().float().requires_grad_(True) for t in (theta, phi, g))
+    with torch.enable_grad():
+        N, D, H, W, _ = theta.shape
+        th, ph, gp = _attn_parts(th_, ph_, g_, c8, c2)
+        beta = torch.softmax(torch.bmm(th, ph.transpose(1, 2)), -1)
+        o = torch.bmm(beta, gp).reshape(N, D, H, W, c2)
+        grads = torch.autograd.grad(o, (th_, ph_, g_), dout.float()[..., :c2])
+    return tuple(x.to(STORE) for x in grads)
+
+
 def render_fwd(pre, B, T, C):
     BT, D, H, W, Cp = pre.shape
     return torch.tanh(pre.float()[..., :C]).view(B, T, H, W, C).permute(0, 4, 1, 2, 3).contiguous()

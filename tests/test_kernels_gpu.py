@@ -68,6 +68,26 @@ def test_im2col3_and_adjoint(shape):
     assert abs(lhs - rhs) <= 1e-3 * max(1.0, abs(lhs)), (lhs, rhs)
 
 
+@pytest.mark.parametrize("shape,c8,c2", [((5, 1, 32, 32), 4, 16), ((3, 1, 8, 12), 4, 16), ((2, 2, 4, 6), 8, 16),
+                                         ((4, 1, 16, 16), 2, 8)])
+def test_attention_core(shape, c8, c2):
+    """fused non-local core (max-pool + QK^T + softmax + beta.g) and its gradient vs the composite torch formulation"""
+    N, D, H, W = shape
+    def padded(c, scale):
+        t = torch.zeros(N, D, H, W, 16, device="cuda")
+        t[..., :c] = torch.randn(N, D, H, W, c, device="cuda") * scale
+        return t.to(BF)
+    theta, phi, g = padded(c8, 1.0), padded(c8, 1.0), padded(c2, 1.0)
+    o = K().attention_fwd(theta, phi, g, c8, c2)
+    close(o, C.attention_fwd(theta, phi, g, c8, c2), 1e-2)
+    assert float(o[..., c2:].abs().max()) == 0.0 if c2 < 16 else True
+    do = padded(c2, 1.0)
+    got = K().attention_bwd(theta, phi, g, do, c8, c2)
+    ref = C.attention_bwd(theta, phi, g, do, c8, c2)
+    for a, b in zip(got, ref):
+        close(a, b, 2e-2)
+
+
 def test_layout_roundtrip():
     x = torch.randn(3, 3, 4, 5, 6, device="cuda")
     y = K().nchw_to_cl(x, 16)

@@ -396,6 +396,30 @@ def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
     return dx.view(shape0), red[C:], red[:C]
 
 
+# ------------------------------------------------------------------------------------- non-local attention core
+def attention_fwd(theta, phi, g, c8, c2):
+    """theta/phi (N,D,H,W,C8p), g (N,D,H,W,C2p) bf16 -> o (N,D,H,W,C2p): softmax(theta . maxpool(phi)^T) . maxpool(g)."""
+    require_cuda(theta, phi, g)
+    N, D, H, W, C8p = theta.shape
+    C2p = g.shape[-1]
+    assert theta.dtype == BF16 and theta.is_contiguous() and phi.is_contiguous() and g.is_contiguous()
+    o = torch.empty((N, D, H, W, C2p), device=theta.device, dtype=BF16)
+    check(lib().t2v_attention_fwd(ptr(theta), ptr(phi), ptr(g), ptr(o), N, D, H, W, c8, c2, C8p, C2p, stream()),
+          "t2v_attention_fwd")
+    return o
+
+
+def attention_bwd(theta, phi, g, dout, c8, c2):
+    require_cuda(theta, phi, g, dout)
+    N, D, H, W, C8p = theta.shape
+    C2p = g.shape[-1]
+    assert dout.dtype == BF16 and dout.is_contiguous()
+    dtheta, dphi, dg = torch.empty_like(theta), torch.empty_like(phi), torch.empty_like(g)
+    check(lib().t2v_attention_bwd(ptr(theta), ptr(phi), ptr(g), ptr(dout), ptr(dtheta), ptr(dphi), ptr(dg), N, D, H, W,
+                                  c8, c2, C8p, C2p, stream()), "t2v_attention_bwd")
+    return dtheta, dphi, dg
+
+
 # ------------------------------------------------------------------------------------- render / index
 def render_fwd(pre, B, T, C):
     """pre (B*T,1,H,W,Cp) bf16 -> tanh -> fp32 (B,C,T,H,W)."""

@@ -740,7 +740,25 @@ class ConvLstmF(Function):
 
 
 # ------------------------------------------------------------------------------------- non-local block
-def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2)):
+class AttentionCoreF(Function):
+    """o = softmax(theta . maxpool(phi)^T) . maxpool(g) per map (t2v_attention_fwd / _bwd), first-order."""
+
+    @staticmethod
+    def forward(ctx, theta, phi, g, c8, c2):
+        ctx.cfg = (c8, c2)
+        ctx.save_for_backward(theta, phi, g)
+        return K.attention_fwd(theta, phi, g, c8, c2)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, do):
+        theta, phi, g = ctx.saved_tensors
+        c8, c2 = ctx.cfg
+        dtheta, dphi, dg = K.attention_bwd(theta, phi, g, do.contiguous(), c8, c2)
+        return dtheta, dphi, dg, None, None
+
+
+def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2), fused=False):
     """SA-GAN / non-local block (models/layers.py:23-36 2-D, :52-68 3-D) on a CL tensor.
 
     The four 1x1(x1) convs run on the tcgen05 engine (channel counts < 16 are zero-padded).  ROUND-1
@@ -750,6 +768,10 @@ def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2)):
     import torch.nn.functional as Fnn
     N, D, H, W, C = x.shape
     c8, c2 = w_theta.shape[0], w_g.shape[0]
+    if fused and c8 <= 8 and c2 <= 16 and H % 2 == 0 and W % 2 == 0 and D * H * W <= 4096:
+        # generator block (first-order autograd is enough): max-pool + QK^T + softmax + beta.g in one kernel
+        o = AttentionCoreF.apply(conv(x, w_theta), conv(x, w_phi), conv(x, w_g), c8, c2)
+        return gamma.to(x.dtype) * conv(o, w_o) + x
     theta = conv(x, w_theta)[..., :c8].float()
     phi = conv(x, w_phi)[..., :c8].float()
     g = conv(x, w_g)[..., :c2].float()
