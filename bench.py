@@ -215,12 +215,34 @@ def run_b200(args):
         e2e_state["pf"] = data_prefetcher(((host[i % nb][0], host[i % nb][1], host[i % nb][2]) for i in range(n)),
                                           device=device)
 
-    def step_e2e(i):
-        x, y = e2e_state["pf"].next()
-        ld, lg = run_step(x, y[0], y[1])
-        return float(ld), float(lg)                               # the device->host read of the step's result
+    loss_host = [torch.zeros(2).pin_memory() for _ in range(2)]
+    loss_evt = [torch.cuda.Event() for _ in range(2)]
 
-    def timed(fn, n, begin=None):
+    variant = os.environ.get("T2V_E2E_VARIANT", "")      # diagnosis only: "nopf" = resident inputs, "noloss" = no read-back
+
+    def step_e2e(i):
+        if variant == "nopf":
+            x, y = dev[i % nb][0], dev[i % nb][1:]
+        else:
+            x, y = e2e_state["pf"].next()
+        ld, lg = run_step(x, y[0], y[1])
+        if variant == "noloss":
+            loss_evt[i % 2].record()
+            return
+        # device->host read of EVERY step's result: asynchronous copy into pinned memory, consumed one step later
+        # (the host logs step i while step i+1 is already enqueued; the last one is drained before the clock stops)
+        loss_host[i % 2].copy_(torch.stack((ld.detach().float().reshape(()), lg.detach().float().reshape(()))),
+                               non_blocking=True)
+        loss_evt[i % 2].record()
+        if i > 0:
+            loss_evt[(i - 1) % 2].synchronize()
+            e2e_state["last"] = (float(loss_host[(i - 1) % 2][0]), float(loss_host[(i - 1) % 2][1]))
+
+    def e2e_end(n):
+        loss_evt[(n - 1) % 2].synchronize()
+        e2e_state["last"] = (float(loss_host[(n - 1) % 2][0]), float(loss_host[(n - 1) % 2][1]))
+
+    def timed(fn, n, begin=None, end=None):
         dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -229,6 +251,8 @@ def run_b200(args):
             begin(n)                                              # first H2D copy is issued inside the timed region
         for i in range(n):
             fn(i)
+        if end is not None:
+            end(n)
         e1.record()
         torch.cuda.synchronize()
         dist.barrier()
@@ -248,7 +272,7 @@ def run_b200(args):
     t_res = timed(step_resident, args.steps)
     launches = launches_per_step * args.steps
     clk = clocks.stop() if rank == 0 else None
-    t_e2e = timed(step_e2e, args.steps, begin=e2e_begin)
+    t_e2e = timed(step_e2e, args.steps, begin=e2e_begin, end=e2e_end)
 
     # ---- roofline pass: per-launch CUDA-event timing of the conv engine over the same step, run eagerly
     # (events cannot be read back from inside a replayed graph; kernels, shapes and launch order are the same)

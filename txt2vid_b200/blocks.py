@@ -325,6 +325,14 @@ class Resnet3D(nn.Module):
             h = d.forward_cl(h)
         return ops.sum_spatial(h)
 
+    def heads(self, feat, cond=None):
+        """(uncond, cond, feat) from trunk features (resnet3d.py:50-57)"""
+        uncond = ops.head_linear(feat, self.fc_uncond.weight, self.fc_uncond.bias)
+        if cond is not None:
+            c = ops.head_linear(torch.cat((feat, cond), dim=1), self.fc.weight, self.fc.bias)
+            return uncond, c, feat
+        return uncond, None, feat
+
     def forward(self, x=None, cond=None, xbar=None, computed_features=None):
         uncond = None
         if computed_features is not None:

@@ -165,6 +165,10 @@ def gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xba
     return torch.stack(total).sum()
 
 
+import os as _os
+PAIR_D_STEP = _os.environ.get("T2V_PAIR_D_STEP", "1") == "1"   # batch the real / fake trunk passes of the D step
+
+
 class CondGan(object):
     """gan/cond_gan.py:7-217."""
 
@@ -197,21 +201,32 @@ class CondGan(object):
         """(x_r,c_r) / (x_r,c_f) / (x_f,c_r) pairs and their per-level loss average (cond_gan.py:34-87)."""
         fake_pred = real_pred = l = None
         if real_cond is not None and fake_cond is not None:
-            real_cc = discrim(x=real, cond=real_cond, xbar=real_mapping)
+            pair = loss is not None and hasattr(discrim, "forward_pair") and real_mapping is None \
+                and fake_mapping is None and PAIR_D_STEP
+            if pair:       # (x_r, c_r) and (x_f, c_r) through the shared trunk in one pass (no normalisation in D)
+                real_cc, fake_cc = discrim.forward_pair(x_a=real, x_b=fake, cond_a=real_cond, cond_b=real_cond)
+            else:
+                real_cc = discrim(x=real, cond=real_cond, xbar=real_mapping)
             real_pred = real_cc
             if loss is not None:
                 real_ic = discrim(x=real, cond=fake_cond, xbar=real_mapping,
                                   computed_features=[t[-1] for t in real_cc])
-                fake_cc = discrim(x=fake, cond=real_cond, xbar=fake_mapping)
+                if not pair:
+                    fake_cc = discrim(x=fake, cond=real_cond, xbar=fake_mapping)
                 l_u = self._mean_over_levels(loss, fake_cc, real_cc, 0)
                 l_c = (self._mean_over_levels(loss, fake_cc, real_cc, 1) +
                        self._mean_over_levels(loss, real_ic, real_cc, 1)) / 2
                 l = (l_u + l_c) / 2.0
         else:
-            if real is not None:
-                real_pred = [r[0] for r in discrim(x=real, cond=None, xbar=real_mapping)]
-            if fake is not None:
-                fake_pred = [f[0] for f in discrim(x=fake, cond=None, xbar=fake_mapping)]
+            if real is not None and fake is not None and loss is not None and hasattr(discrim, "forward_pair") \
+                    and real_mapping is None and fake_mapping is None and PAIR_D_STEP:
+                ra, fa = discrim.forward_pair(x_a=real, x_b=fake)
+                real_pred, fake_pred = [r[0] for r in ra], [f[0] for f in fa]
+            else:
+                if real is not None:
+                    real_pred = [r[0] for r in discrim(x=real, cond=None, xbar=real_mapping)]
+                if fake is not None:
+                    fake_pred = [f[0] for f in discrim(x=fake, cond=None, xbar=fake_mapping)]
             if loss is not None and fake_pred is not None and real_pred is not None:
                 l = torch.stack([loss(fake=f, real=r) for f, r in zip(fake_pred, real_pred)]).mean()
         if l is not None and gp_lambda > 0:

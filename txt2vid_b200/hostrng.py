@@ -50,10 +50,12 @@ class RecordingDraws(EagerDraws):
 
 
 class StaticDraws(EagerDraws):
+    RING = 4      # pinned staging slots: the host may run this many replays ahead of the device
+
     def __init__(self, calls, device):
         self.calls = list(calls)
         self.device = device
-        self.host, self.dev = [], []
+        self.host, self.dev = [[] for _ in range(self.RING)], []
         for kind, n in self.calls:
             if kind == "bt":
                 h = torch.zeros(1, dtype=torch.int32)
@@ -61,14 +63,15 @@ class StaticDraws(EagerDraws):
                 h = torch.zeros(n, dtype=torch.int64)
             else:
                 h = torch.zeros(n, dtype=torch.float32)
-            h = h.pin_memory() if device.type == "cuda" else h
-            self.host.append(h)
+            for r in range(self.RING):
+                self.host[r].append(h.clone().pin_memory() if device.type == "cuda" else h.clone())
             self.dev.append(torch.zeros_like(h, device=device))
         self.i = 0
 
-    def refresh(self):
-        """Draw the next iteration's values in the recorded (= reference) order and stage them on the device."""
-        for (kind, n), h, d in zip(self.calls, self.host, self.dev):
+    def refresh(self, slot=0):
+        """Draw the next iteration's values in the recorded (= reference) order and stage them on the device.
+        The copies are asynchronous: the caller owns `slot` (a pinned staging set nobody is still reading)."""
+        for (kind, n), h, d in zip(self.calls, self.host[slot % self.RING], self.dev):
             if kind == "bt":
                 h[0] = int(torch.randint(n, (1,)))
             elif kind == "perm":

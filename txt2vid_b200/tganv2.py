@@ -160,6 +160,25 @@ class MultiScaleDiscrim(nn.Module):
         return out
 
 
+    def forward_pair(self, x_a=None, x_b=None, cond_a=None, cond_b=None):
+        """Two inputs through the shared trunk in ONE pass per level: D(x_a, cond_a) and D(x_b, cond_b) with the
+        clips concatenated along the batch.  The discriminator has no normalisation layer, so
+        every sample is processed independently and the results equal two separate calls; the D step of
+        cond_gan.py:42-53 (real and fake pair) then launches half as many kernels on twice the positions."""
+        out_a, out_b = [], []
+        for i, (ra, rb) in enumerate(zip(x_a, x_b)):
+            d = self.sub_discrims[i]
+            d = d.module if hasattr(d, "module") else d
+            na = ra.size(0)
+            feat = d.features(torch.cat((ra, rb), dim=0))
+            fa, fb = feat[:na], feat[na:]
+            ca = cond_a[i] if cond_a is not None else None
+            cb = cond_b[i] if cond_b is not None else None
+            out_a.append(d.heads(fa, ca))
+            out_b.append(d.heads(fb, cb))
+        return out_a, out_b
+
+
 class MultiScaleDiscrimUncond(MultiScaleDiscrim):
     """txt2vid.models.tganv2.discrim.MultiScaleDiscrim: no DataParallel wrapper (plain keys); forward
     takes (x, cond=None, xbar=None) and ignores cond (tganv2/discrim.py:23-31)."""

@@ -192,6 +192,11 @@ def train_iteration(gan, x, y, device, optD, optG, params, losses, channel_first
     return total_d, total_g, st["fake"], st["xs"], st["conds"]
 
 
+def hostrng_ring():
+    from . import hostrng
+    return hostrng.StaticDraws.RING
+
+
 class GraphedTrainStep(object):
     """The training iteration as three replayed CUDA graphs (no tracing compiler: the eager iteration above is
     captured as is).  Segments: [pyramid, G fwd, D fwd/bwd incl. gradient penalty] -> (all-reduce D grads) ->
@@ -209,13 +214,19 @@ class GraphedTrainStep(object):
         self.warmup, self.calls, self.graphs = warmup, 0, None
         self.static_x = self.static_cond = self.draws = None
         self.side = torch.cuda.Stream(device=device)
+        # per-replay host values (RNG draws, Adam bias corrections) go through a ring of pinned staging slots: the
+        # H2D copies are asynchronous, so a slot is rewritten only after the copies issued from it have executed
+        self.ring = hostrng_ring()
+        self.stage_evt = [None] * self.ring
+        self.replays = 0
 
     # ---- per-replay host work
-    def _stage_adam(self, opt, step):
+    def _stage_adam(self, opt, step, slot):
         b1, b2 = opt.param_groups[0]["betas"]
-        opt._dyn_host[0] = opt.param_groups[0]["lr"] / (1.0 - b1 ** step)
-        opt._dyn_host[1] = 1.0 / (1.0 - b2 ** step) ** 0.5
-        opt.dyn.copy_(opt._dyn_host, non_blocking=True)
+        h = opt._dyn_host[slot]
+        h[0] = opt.param_groups[0]["lr"] / (1.0 - b1 ** step)
+        h[1] = 1.0 / (1.0 - b2 ** step) ** 0.5
+        opt.dyn.copy_(h, non_blocking=True)
 
     def _capture(self, x, cond):
         """Capture only: nothing executes here.  The caller replays right afterwards."""
@@ -224,7 +235,7 @@ class GraphedTrainStep(object):
         self.static_cond = None if cond is None else cond.clone()
         for opt in (self.optD, self.optG):
             opt.dyn = torch.zeros(2, device=dev, dtype=torch.float32)
-            opt._dyn_host = torch.zeros(2, dtype=torch.float32).pin_memory()
+            opt._dyn_host = [torch.zeros(2, dtype=torch.float32).pin_memory() for _ in range(self.ring)]
             opt._step_count = max([st_["step"] for st_ in opt.state.values()] or [0])
             opt.zero_grad(set_to_none=True)
         torch.cuda.synchronize()
@@ -272,9 +283,15 @@ class GraphedTrainStep(object):
         self.static_x.copy_(x, non_blocking=True)
         if cond is not None:
             self.static_cond.copy_(cond)
-        self.draws.refresh()
-        self._stage_adam(self.optD, self.optD._step_count + 1)
-        self._stage_adam(self.optG, self.optG._step_count + 1)
+        slot = self.replays % self.ring
+        self.replays += 1
+        if self.stage_evt[slot] is not None:
+            self.stage_evt[slot].synchronize()
+        self.draws.refresh(slot)
+        self._stage_adam(self.optD, self.optD._step_count + 1, slot)
+        self._stage_adam(self.optG, self.optG._step_count + 1, slot)
+        self.stage_evt[slot] = torch.cuda.Event()
+        self.stage_evt[slot].record()
         g1, g2, g3 = self.graphs
         g1.replay()
         if self.dist is not None:
