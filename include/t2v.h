@@ -76,6 +76,18 @@ int t2v_conv_dgrad(const t2v_conv_geom* g, const void* dy, const void* wT, const
  * accumulate = 0 overwrites dw, 1 adds into it.                                              */
 int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float* dw,
                    int accumulate, int algo, void* stream);
+/* Convolution with stride (2,1,1), kernel 3x3x3, padding 1, 64 -> 64 channels: the second convolution of the
+ * discriminator stem (models/resnet3d.py:15) is followed by AvgPool3d((1,2,2), 2) (resnet3d.py:16: kernel 1,
+ * stride 2 along d), which never reads its odd output planes; computing only the even planes is the same
+ * function at half the MACs.  g = geometry of x (D even, H >= 16, W >= 8); y / dy are (N, D/2, H, W, 64).
+ * dgrad takes the flipped pack of t2v_pack_dgrad_weight; wgrad writes [Cout][27][Cin] fp32 like t2v_conv_wgrad. */
+int t2v_conv_sd2_supported(const t2v_conv_geom* g);
+int t2v_conv_fprop_sd2(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                       uint32_t epi_flags, void* stream);
+int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, void* dx, uint32_t epi_flags,
+                       void* stream);
+int t2v_conv_wgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
+                       void* stream);
 /* General convolution geometry (any kernel / stride / zero padding; 1-D and 2-D use unit extents):
  * the TGAN / TCWYT layers that are not stride-1 "same" convolutions -- Conv3d/Conv2d k4 s2 p1
  * (models/tcwyt/video_discrim.py:12-27, frame_discrim.py:8-19), k(1,3,3) and k2 s2 heads

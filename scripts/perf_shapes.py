@@ -63,3 +63,16 @@ for name, case in SHAPES:
     print("%-6s %-26s fprop %.3f ms %6.0f TF/s | wgrad %.3f ms %6.0f TF/s" % (tag, name, tf, fl / tf / 1e9, tw, fl / tw / 1e9), flush=True)
     del x, w, dy
 print("%-6s TOTAL fprop %.3f ms wgrad %.3f ms" % (tag, tot_f, tot_w))
+
+# stride-(2,1,1) stem convolution vs the stride-1 kernels on the same input (levels 1-3 at batch 1024)
+for shp in [(512, 8, 16, 16), (256, 4, 32, 32), (128, 2, 64, 64)]:
+    x, w, _ = mk(*shp, 64, 64, (3, 3, 3))
+    dyf = torch.randn(shp + (64,), device="cuda").to(torch.bfloat16)
+    dyh = dyf[:, ::2].contiguous()
+    wT = K.pack_dgrad_weight(w.float())
+    fl = 2.0 * x.numel() * 64 * 27
+    r = [t(lambda: K.conv_fprop(x, w, k=(3, 3, 3))), t(lambda: K.conv_fprop_sd2(x, w)),
+         t(lambda: K.conv_dgrad(dyf, wT, k=(3, 3, 3))), t(lambda: K.conv_dgrad_sd2(dyh, wT)),
+         t(lambda: K.conv_wgrad(dyf, x, k=(3, 3, 3))), t(lambda: K.conv_wgrad_sd2(dyh, x))]
+    print("%-6s sd2 %s fprop %.3f -> %.3f ms (%.0f TF/s useful) | dgrad %.3f -> %.3f ms | wgrad %.3f -> %.3f ms"
+          % (tag, shp, r[0], r[1], fl / 2 / r[1] / 1e9, r[2], r[3], r[4], r[5]), flush=True)

@@ -40,6 +40,34 @@ def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=
     return y if out_f32 else y.to(STORE)
 
 
+def conv_sd2_supported(shape, Cin, Cout, k=(3, 3, 3)):
+    N, D, H, W = [int(v) for v in shape[:4]]
+    return Cin == 64 and Cout == 64 and tuple(k) == (3, 3, 3) and D % 2 == 0 and D >= 2 and H >= 16 and W >= 8
+
+
+def conv_fprop_sd2(x, w, bias=None, relu=False):
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), _w5(w, (3, 3, 3)), bias, stride=(2, 1, 1),
+                 padding=1).permute(0, 2, 3, 4, 1)
+    if relu:
+        y = torch.relu(y)
+    return y.contiguous().to(STORE)
+
+
+def conv_dgrad_sd2(dy, wT):
+    # scatter dy onto the even planes of a zero tensor, then the stride-1 adjoint
+    N, Dj, H, W, C = dy.shape
+    full = torch.zeros((N, 2 * Dj, H, W, C), dtype=dy.dtype)
+    full[:, ::2] = dy
+    return conv_fprop(full, wT, None, None, (3, 3, 3))
+
+
+def conv_wgrad_sd2(dy, x):
+    N, Dj, H, W, C = dy.shape
+    full = torch.zeros((N, 2 * Dj, H, W, C), dtype=dy.dtype)
+    full[:, ::2] = dy
+    return conv_wgrad(full, x, (3, 3, 3))
+
+
 def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0):
     # wT (Cin,taps,Cout) with reversed taps == the forward weight of the adjoint convolution
     return conv_fprop(dy, wT, None, residual, k, relu, out_f32)

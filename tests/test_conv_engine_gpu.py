@@ -172,6 +172,50 @@ def test_wgrad(case, algo):
     assert e2 < 2e-3
 
 
+# stride-(2,1,1) stem convolution (even output planes only): levels 1-3 of the pyramid (D = 8, 4, 2), ragged H / W,
+# more tiles than CTAs, odd sample counts for the sample-paired D = 2 case
+SD2_CASES = [(3, 8, 16, 16), (2, 4, 32, 32), (5, 2, 64, 64), (3, 2, 16, 16), (2, 6, 40, 24), (1, 2, 20, 12),
+             (70, 4, 32, 32)]
+
+
+def _ref_sd2(x, w, bias=None):
+    w5 = w.float().view(64, 3, 3, 3, 64).permute(0, 4, 1, 2, 3).contiguous()
+    y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), w5, bias, stride=(2, 1, 1), padding=1)
+    return y.permute(0, 2, 3, 4, 1).contiguous()
+
+
+@pytest.mark.parametrize("shape", SD2_CASES)
+def test_sd2_conv(shape):
+    """fprop / dgrad / wgrad of Conv3d(64,64,3,stride=(2,1,1),padding=1) against torch fp32 autograd."""
+    from txt2vid_b200 import kernels as K
+    N, D, H, W = shape
+    assert K.conv_sd2_supported((N, D, H, W), 64, 64)
+    x, w = _mk(N, D, H, W, 64, 64, (3, 3, 3), seed=7)
+    bias = torch.randn(64, device="cuda")
+    y = K.conv_fprop_sd2(x, w, bias)
+    assert tuple(y.shape) == (N, D // 2, H, W, 64)
+    ref = _ref_sd2(x, w, bias)
+    e = _rel(y, ref)
+    # identical to the even planes of the stride-1 kernel
+    full = K.conv_fprop(x, w, bias=bias, k=(3, 3, 3))
+    e_same = _rel(y, full[:, ::2])
+    dy = torch.randn((N, D // 2, H, W, 64), device="cuda").to(torch.bfloat16)
+    xr, wr = x.float().requires_grad_(True), w.float().requires_grad_(True)
+    gx, gw = torch.autograd.grad(_ref_sd2(xr, wr), (xr, wr), dy.float())
+    dx = K.conv_dgrad_sd2(dy, K.pack_dgrad_weight(w.float()))
+    dw = K.conv_wgrad_sd2(dy, x)
+    e_dx, e_dw = _rel(dx, gx), _rel(dw, gw)
+    _log("sd2 %s fprop %.3e (vs stride-1 kernel %.3e) dgrad %.3e wgrad %.3e" % (shape, e, e_same, e_dx, e_dw))
+    assert e < 1.5e-2 and e_same < 1e-6 and e_dx < 1.5e-2 and e_dw < 2e-3
+
+
+def test_sd2_unsupported_shapes():
+    from txt2vid_b200 import kernels as K
+    assert not K.conv_sd2_supported((4, 16, 8, 8), 64, 64)      # level 0: 8x8 planes stay on the stride-1 kernel
+    assert not K.conv_sd2_supported((4, 3, 16, 16), 64, 64)     # odd D
+    assert not K.conv_sd2_supported((4, 4, 16, 16), 64, 128)
+
+
 def test_simt_odd_channels():
     from txt2vid_b200 import kernels as K
     case = (4, 2, 4, 4, 3, 5, (3, 3, 3))

@@ -64,6 +64,10 @@ SIGNATURES = {
     "t2v_conv_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],
+    "t2v_conv_sd2_supported": [ctypes.POINTER(ConvGeom)],
+    "t2v_conv_fprop_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, _P],
+    "t2v_conv_dgrad_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_u32, _P],
+    "t2v_conv_wgrad_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, _P],
     "t2v_gconv_fprop": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_dgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_wgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, c_i32, _P],

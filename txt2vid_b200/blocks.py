@@ -10,6 +10,8 @@ never called.  Every block has two entry points:
   forward_cl(x)  channels-last bf16 tensors (N, D, H, W, C) -- used between blocks;
   forward(x)     the reference's signature (fp32, channel-first) -- converts at the boundary.
 """
+import os
+
 import torch
 import torch.nn as nn
 from torch.nn import Parameter as P
@@ -286,6 +288,9 @@ class ConvLSTM(nn.Module):
         return outputs, (outputs[-1], None)
 
 
+STEM_SD2 = os.environ.get("T2V_STEM_SD2", "1") == "1"
+
+
 class Resnet3D(nn.Module):
     """ResNet-3D discriminator trunk + unconditional / conditional heads (resnet3d.py:6-57)."""
 
@@ -316,11 +321,16 @@ class Resnet3D(nn.Module):
         xc = ops.to_cl(x)                                             # RGB padded to 16 channels (skip path)
         # first conv (K = 27*3 = 81): im2col once, then a 1x1x1 GEMM on the tensor cores
         h = ops.conv(ops.im2col3(x), ops.stem_weight_2d(m[0].weight), m[0].bias, relu=True)
-        h = ops.conv(h, m[2].weight, m[2].bias)
         c1 = self.res_block.identity_map[1]
         pk, ps = (1, 2, 2), (2, 2, 2)                                 # AvgPool3d((1,2,2), 2): stride 2 in ALL dims
         skip = ops.conv(ops.avg_pool(xc, pk, ps), c1.weight, c1.bias)
-        h = ops.avg_pool(h, pk, ps, residual=skip)
+        if STEM_SD2 and ops.K.conv_sd2_supported(h.shape, h.shape[-1], m[2].weight.shape[0], tuple(m[2].weight.shape[2:])):
+            # the pool keeps only the even d planes of this convolution (kernel 1, stride 2 along d): compute only those
+            h = ops.conv_sd2(h, m[2].weight, m[2].bias)
+            h = ops.avg_pool(h, pk, (1, 2, 2), residual=skip)
+        else:
+            h = ops.conv(h, m[2].weight, m[2].bias)
+            h = ops.avg_pool(h, pk, ps, residual=skip)
         for d in self.down:
             h = d.forward_cl(h)
         return ops.sum_spatial(h)

@@ -13,7 +13,10 @@ bool halo_wgrad_supported(const t2v_conv_geom* g);
 bool halo_fprop_supported(const t2v_conv_geom* g);
 int halo_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                       uint32_t, cudaStream_t);
-int halo_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+int halo_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t, int sd2);
+bool halo_sd2_supported(const t2v_conv_geom* g);
+int halo_fprop_sd2_launch(const t2v_conv_geom*, const void*, const void*, const float*, void*, uint32_t, cudaStream_t);
+int halo_dgrad_sd2_launch(const t2v_conv_geom*, const void*, const void*, void*, uint32_t, cudaStream_t);
 int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                       uint32_t, cudaStream_t);
 int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
@@ -110,8 +113,28 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
   const bool tc_ok = igemm_wgrad_supported(g);
   if ((algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) && !tc_ok) return T2V_ERR_ARG;
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_wgrad_launch(g, dy, x, dw, accumulate, s);
-  if (algo != T2V_ALGO_TC_GENERIC && halo_wgrad_supported(g)) return halo_wgrad_launch(g, dy, x, dw, accumulate, s);
+  if (algo != T2V_ALGO_TC_GENERIC && halo_wgrad_supported(g)) return halo_wgrad_launch(g, dy, x, dw, accumulate, s, 0);
   return igemm_wgrad_launch(g, dy, x, dw, accumulate, s);
+}
+
+int t2v_conv_sd2_supported(const t2v_conv_geom* g) { return (g && halo_sd2_supported(g)) ? 1 : 0; }
+
+int t2v_conv_fprop_sd2(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                       uint32_t epi_flags, void* stream) {
+  if (!g || !x || !w || !y) return T2V_ERR_ARG;
+  return halo_fprop_sd2_launch(g, x, w, bias, y, epi_flags, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, void* dx, uint32_t epi_flags,
+                       void* stream) {
+  if (!g || !dy || !wT || !dx) return T2V_ERR_ARG;
+  return halo_dgrad_sd2_launch(g, dy, wT, dx, epi_flags, reinterpret_cast<cudaStream_t>(stream));
+}
+
+int t2v_conv_wgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
+                       void* stream) {
+  if (!g || !dy || !x || !dw) return T2V_ERR_ARG;
+  return halo_wgrad_launch(g, dy, x, dw, accumulate, reinterpret_cast<cudaStream_t>(stream), 1);
 }
 
 int t2v_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {

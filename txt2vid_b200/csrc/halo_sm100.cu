@@ -43,6 +43,7 @@ struct HaloWgParams {
   uint32_t stage_bytes, dy_bytes, dy_box_bytes, x_bytes;
   uint32_t tmem_cols, idesc;
   int xpitch_d;            // x-tile rows per d plane = (bh+2)*kXW
+  int xd_mul;              // x plane of dy plane d = xd_mul * d (2: convolution with stride 2 along d)
   float* dw;
   int debug_skip_epi;
 };
@@ -112,7 +113,7 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
           mbar_expect_tx(&full_bar[stage], p.dy_bytes + p.x_bytes);
           for (int j = 0; j < nboxes; ++j)
             tma_load_5d(sdy + (size_t)j * p.dy_box_bytes, &tmDy, &full_bar[stage], 64 * j, w0, h0, d0, n);
-          tma_load_5d(sx, &tmX, &full_bar[stage], 0, w0 - 1, h0 - 1, d0 - (p.kd3 ? 1 : 0), n);
+          tma_load_5d(sx, &tmX, &full_bar[stage], 0, w0 - 1, h0 - 1, p.xd_mul * d0 - (p.kd3 ? 1 : 0), n);
           if (++stage == p.stages) { stage = 0; phase ^= 1u; }
         }
       }
@@ -140,7 +141,7 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
         const uint32_t sx16 = (sdy + p.dy_bytes) >> 4;
         int d = 0, h = 0;
         for (int j = 0; j < ksteps; ++j) {
-          const uint32_t line16 = sx16 + (uint32_t)(d * p.xpitch_d + h * kXW) * 8u;
+          const uint32_t line16 = sx16 + (uint32_t)(d * p.xd_mul * p.xpitch_d + h * kXW) * 8u;
           const uint32_t b_lo = desc_lo((sdy >> 4) + 128u * (uint32_t)j, p.dy_box_bytes);
           const uint32_t acc = (it | j) != 0 ? 1u : 0u;
 #pragma unroll
@@ -193,26 +194,31 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
 // ------------------------------------------------------------------------------------ host side
 static constexpr uint32_t kSmemBudget = 227u * 1024u - 2048u;
 
-static bool halo_wgrad_plan(const t2v_conv_geom* g, HaloWgParams* p) {
+// g describes the dy grid (for sd2: D = the number of OUTPUT planes, x has 2*D planes)
+static bool halo_wgrad_plan(const t2v_conv_geom* g, HaloWgParams* p, int sd2 = 0) {
   if (g->Cin != 64 || (g->Cout != 64 && g->Cout != 128)) return false;
   if (g->kh != 3 || g->kw != 3 || (g->kd != 1 && g->kd != 3)) return false;
   if (g->W < 8 || g->H < 4) return false;
-  if (g->kd == 3 && g->D < 2) return false;     // dead taps: the generic kernel skips them
+  if (g->kd == 3 && g->D < 2 && !sd2) return false;     // dead taps: the generic kernel skips them
   if (g->kd == 1 && g->D != 1) return false;
+  if (sd2 && g->kd != 3) return false;
   p->N = g->N; p->D = g->D; p->H = g->H; p->W = g->W; p->Cout = g->Cout;
   p->kd3 = g->kd == 3;
   p->ntaps = g->kd * 9;
+  p->xd_mul = sd2 ? 2 : 1;
   // candidate interior tiles, largest first (more reuse of the halo); need >= 2 pipeline stages
-  const int cand3[][2] = {{4, 8}, {2, 8}, {2, 4}};
-  const int cand1[][2] = {{1, 32}, {1, 16}, {1, 8}, {1, 4}};
+  const int cand3[][2] = {{4, 8}, {2, 8}, {2, 4}, {1, 16}, {1, 8}};
+  const int cand1[][2] = {{1, 32}, {1, 16}, {1, 8}, {1, 4}, {1, 4}};
   bool ok = false;
-  for (int i = 0; i < (p->kd3 ? 3 : 4) && !ok; ++i) {
+  for (int i = 0; i < 5 && !ok; ++i) {
     const int bd = p->kd3 ? cand3[i][0] : cand1[i][0], bh = p->kd3 ? cand3[i][1] : cand1[i][1];
     if (bd > 2 && bd > g->D) continue;
+    if (bd == 2 && g->D < 2) continue;
+    if (bd == 1 && p->kd3 && g->D >= 2) continue;
     if (bh > 4 && bh > g->H) continue;
     const uint32_t dy_box = (uint32_t)bd * bh * 1024u;
     const uint32_t dyb = dy_box * (uint32_t)(g->Cout / 64);
-    const uint32_t xb = (uint32_t)((p->kd3 ? bd + 2 : bd) * (bh + 2) * kXW) * 128u;
+    const uint32_t xb = (uint32_t)((p->kd3 ? p->xd_mul * (bd - 1) + 3 : bd) * (bh + 2) * kXW) * 128u;
     const uint32_t stage = (dyb + xb + 1023u) & ~1023u;
     const int stages = (int)(kSmemBudget / stage);
     if (stages < 2) continue;
@@ -248,17 +254,27 @@ bool halo_wgrad_supported(const t2v_conv_geom* g) {
   return halo_wgrad_plan(g, &p);
 }
 
-int halo_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
-                      cudaStream_t stream) {
+bool halo_sd2_supported(const t2v_conv_geom* g);
+
+// sd2 = 1: the convolution has stride 2 along d: g is the geometry of x (D planes), dy has D/2 planes
+int halo_wgrad_launch(const t2v_conv_geom* g_in, const void* dy, const void* x, float* dw, int accumulate,
+                      cudaStream_t stream, int sd2) {
   HaloWgParams p{};
-  if (!halo_wgrad_plan(g, &p)) return T2V_ERR_ARG;
+  t2v_conv_geom gg = *g_in;
+  if (sd2) {
+    if (!halo_sd2_supported(g_in)) return T2V_ERR_ARG;
+    gg.D = g_in->D / 2;
+  }
+  const t2v_conv_geom* g = &gg;
+  if (!halo_wgrad_plan(g, &p, sd2)) return T2V_ERR_ARG;
   p.dw = dw;
   { const char* e = getenv("T2V_HALO_SKIP_EPI"); p.debug_skip_epi = (e && e[0] == '1') ? 1 : 0; }
   if (!accumulate) cudaMemsetAsync(dw, 0, (size_t)g->Cout * p.ntaps * 64 * sizeof(float), stream);
   CUtensorMap tmDy, tmX;
   int rc = make_act_map(&tmDy, dy, g->N, g->D, g->H, g->W, g->Cout, 64, 8, p.bh, p.bd, 1);
   if (rc) return rc;
-  rc = make_act_map(&tmX, x, g->N, g->D, g->H, g->W, 64, 64, kXW, p.bh + 2, p.kd3 ? p.bd + 2 : p.bd, 1);
+  rc = make_act_map(&tmX, x, g->N, g_in->D, g->H, g->W, 64, 64, kXW, p.bh + 2,
+                    p.kd3 ? p.xd_mul * (p.bd - 1) + 3 : p.bd, 1);
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
   const int classes = (p.ntaps + p.taps_per_cta - 1) / p.taps_per_cta;
@@ -276,16 +292,28 @@ int halo_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, flo
 
 // ==================================================================================== fprop / dgrad
 static constexpr int kFpThreads = 224;     // warp 0: A tiles, 1: MMA, 2-5: epilogue, 6: weight ring
-static constexpr int kWStages = 4;
+static constexpr int kWStagesMax = 8;
 static constexpr uint32_t kWTapBytes = 64u * 128u;
 
+// One kernel, four uses (mode):
+//   0  stride-1 "same" convolution (fprop, or dgrad with the flipped pack)
+//   1  fprop with stride 2 along d: output plane j reads input planes 2j-1, 2j, 2j+1
+//   2  dgrad of (1), ODD  dx planes: dx[2j+1] = Wflip[0] * dy[j] + Wflip[2] * dy[j+1]
+//   3  dgrad of (1), EVEN dx planes: dx[2j]   = Wflip[1] * dy[j]   (a 2-D convolution over merged (n, j))
+// expressed through: the d taps of the tile (nd consecutive smem planes, weight d index wd[t]), the first input
+// plane of a tile (in_dmul * d0 + in_dadd) and the output plane number q = n * oq_n + d * oq_d + oq_0.
 struct HaloFpParams {
-  int N, D, H, W;
+  int N, D, H, W;          // OUTPUT iteration extents (samples, planes) and the plane size
   int kd3, np, ntaps;
+  int nd, wd[3];           // d taps per tile and their weight d index
+  int in_dmul, in_dadd;    // TMA d coordinate of a tile = in_dmul * d0 + in_dadd
+  int oq_n, oq_d, oq_0;    // output plane number of (n, d)
+  int wstages;
   int t_w, t_h, t_d, tiles_total, iters, cs;
   int th_step, td_step, tn_step;   // tile origin steps along h, d, n
   int mn, md, mh, ld, lh;          // voxel of (M tile m, line l): n0 + m*mn, d0 + m*md + l*ld, h0 + m*mh + l*lh
   int Pd, MS, LS;                  // rows per d plane, rows between M tiles, rows between lines
+  int box_d, box_n, box_h;         // TMA box extents of the halo tile
   uint32_t a_bytes, a_tx, tmem_cols, idesc;
   const float* bias;
   const __nv_bfloat16* residual;
@@ -311,13 +339,14 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
+  const int kWStages = p.wstages;
   uint8_t* sA = smem;
   uint8_t* sW = smem + 2 * (size_t)p.a_bytes;
   uint64_t* a_full = reinterpret_cast<uint64_t*>(sW + kWStages * kWTapBytes);
   uint64_t* a_empty = a_full + 2;
   uint64_t* w_full = a_empty + 2;
-  uint64_t* w_empty = w_full + kWStages;
-  uint64_t* acc_full = w_empty + kWStages;
+  uint64_t* w_empty = w_full + kWStagesMax;
+  uint64_t* acc_full = w_empty + kWStagesMax;
   uint64_t* acc_empty = acc_full + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
@@ -362,7 +391,7 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const FpTile t = fp_tile(p, (it * ncl + cl) * cs + rank);
         mbar_expect_tx(&a_full[buf], p.a_tx);
         tma_load_5d(sA + (size_t)buf * p.a_bytes, &tmA, &a_full[buf], 0, t.w0 - 1, t.h0 - 1,
-                    p.kd3 ? t.d0 - 1 : 0, t.n0);
+                    p.in_dmul * t.d0 + p.in_dadd, t.n0);
       }
     }
   } else if (warp == 6) {
@@ -372,13 +401,16 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
       uint32_t ph = 0;
       const int rows = 64 / cs;
       for (int it = 0; it < p.iters; ++it) {
+        int t9 = 0, a_d = 0;
         for (int tap = 0; tap < p.ntaps; ++tap) {
           mbar_wait(&w_empty[st], ph ^ 1u);
           mbar_expect_tx(&w_full[st], kWTapBytes);
           uint8_t* dst = sW + (size_t)st * kWTapBytes + (size_t)rank * rows * 128;
-          if (cs > 1) tma_load_2d_mc(dst, &tmW, &w_full[st], tap * 64, rank * rows, mask);
-          else tma_load_2d(dst, &tmW, &w_full[st], tap * 64, 0);
+          const int wtap = p.wd[a_d] * 9 + t9;
+          if (cs > 1) tma_load_2d_mc(dst, &tmW, &w_full[st], wtap * 64, rank * rows, mask);
+          else tma_load_2d(dst, &tmW, &w_full[st], wtap * 64, 0);
           if (++st == kWStages) { st = 0; ph ^= 1u; }
+          if (++t9 == 9) { t9 = 0; ++a_d; }
         }
       }
     }
@@ -443,7 +475,7 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         const int n = t.n0 + m * p.mn, d = t.d0 + m * p.md + l * p.ld, h = t.h0 + m * p.mh + l * p.lh;
         const int w = t.w0 + wv;
         const bool row_ok = (n < p.N) && (d < p.D) && (h < p.H) && (w < p.W);
-        const size_t pos = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
+        const size_t pos = (((size_t)n * p.oq_n + (size_t)(d * p.oq_d + p.oq_0)) * p.H + h) * p.W + w;
 #pragma unroll
         for (int c = 0; c < 64; c += 16) {
           uint32_t v[16];
@@ -502,51 +534,102 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
   }
 }
 
-static bool halo_fprop_plan(const t2v_conv_geom* g, HaloFpParams* p) {
+// g: geometry of the tensor the kernel READS (x for modes 0/1, dy for modes 2/3); see HaloFpParams for the modes
+static bool halo_fprop_plan(const t2v_conv_geom* g, HaloFpParams* p, int mode = 0) {
   if (g->Cin != 64 || g->Cout != 64) return false;
   if (g->kh != 3 || g->kw != 3 || (g->kd != 1 && g->kd != 3)) return false;
   if (g->W < 8) return false;
+  if (mode != 0 && (g->kd != 3 || g->H < 16)) return false;
   p->N = g->N; p->D = g->D; p->H = g->H; p->W = g->W;
   p->kd3 = g->kd == 3;
-  p->ntaps = g->kd * 9;
   p->mn = p->md = p->mh = p->ld = p->lh = 0;
   p->t_w = (g->W + 7) / 8;
-  int rows;
-  if (p->kd3) {
-    if (g->D < 2) return false;
+  p->nd = p->kd3 ? 3 : 1;
+  p->wd[0] = 0; p->wd[1] = 1; p->wd[2] = 2;
+  p->in_dmul = 1; p->in_dadd = p->kd3 ? -1 : 0;
+  p->oq_n = g->D; p->oq_d = 1; p->oq_0 = 0;
+  int planes_d = 1, planes_n = 1;          // TMA box extents along d and n
+  bool merged2d = !p->kd3;                 // 16 lines along h, np consecutive SAMPLES per tile
+  if (mode == 1) {                         // g = x geometry (D planes, even): output has D/2 planes
+    if (g->D < 2 || (g->D & 1)) return false;
+    p->D = g->D / 2;
+    p->oq_n = p->D;
+    if (p->D == 1) {                       // only output plane 0: reads planes 0, 1 (plane -1 is padding): 18 taps,
+      p->nd = 2; p->wd[0] = 1; p->wd[1] = 2;   // M tiles = np samples (box: 2 planes x np samples)
+      p->in_dmul = 0; p->in_dadd = 0;
+      p->np = 2; p->mn = 1; p->lh = 1;
+      p->Pd = 18 * kXW; p->MS = 2 * p->Pd; p->LS = kXW;
+      p->th_step = 16; p->td_step = 1; p->tn_step = p->np;
+      planes_d = 2; planes_n = p->np;
+      p->t_h = (g->H + 15) / 16; p->t_d = 1;
+      p->tiles_total = ((g->N + p->np - 1) / p->np) * p->t_h * p->t_w;
+      merged2d = false;
+      goto done;
+    }
+    p->in_dmul = 2; p->in_dadd = -1;
+  } else if (mode == 2) {                  // g = dy geometry (D = output planes of the forward conv)
+    if (g->D < 2) return false;            // D == 1: only tap 0 is live -> the caller uses mode 3 with wd = 0
+    p->nd = 2; p->wd[0] = 0; p->wd[1] = 2;
+    p->in_dmul = 1; p->in_dadd = 0;
+    p->oq_n = 2 * g->D; p->oq_d = 2; p->oq_0 = 1;
+  } else if (mode == 3 || mode == 4) {     // 2-D over merged (n, j); mode 4: the odd plane of a one-plane dy
+    p->N = g->N * g->D; p->D = 1;
+    p->kd3 = 0; p->nd = 1; p->wd[0] = mode == 3 ? 1 : 0;
+    p->in_dmul = 0; p->in_dadd = 0;
+    p->oq_n = 2; p->oq_d = 0; p->oq_0 = mode == 3 ? 0 : 1;
+    merged2d = true;
+  }
+  if (!merged2d) {
+    if (g->D < 2 && mode == 0) return false;
     if (g->H >= 16) {                 // 16 lines along h inside one d plane; a tile = np planes
-      p->np = 2;
-      p->Pd = 18 * kXW; p->MS = p->Pd; p->LS = kXW;
+      p->np = mode == 1 ? 1 : 2;
+      { const char* e = getenv("T2V_HALO_NP"); if (e && e[0] == '1') p->np = 1; }
+      p->Pd = 18 * kXW; p->MS = (p->in_dmul ? p->in_dmul : 1) * p->Pd; p->LS = kXW;
       p->th_step = 16; p->td_step = p->np; p->tn_step = 1;
       p->md = 1; p->lh = 1;
-      rows = (p->np + 2) * p->Pd;
-    } else if (g->D >= 16 && g->H >= 2) {   // 16 lines along d; a tile = np h rows
+      planes_d = (p->in_dmul ? p->in_dmul : 1) * (p->np - 1) + p->nd;
+    } else if (mode == 0 && g->D >= 16 && g->H >= 2) {   // 16 lines along d; a tile = np h rows
       p->np = 2;
       p->Pd = (p->np + 2) * kXW; p->MS = kXW; p->LS = p->Pd;
       p->th_step = p->np; p->td_step = 16; p->tn_step = 1;
       p->mh = 1; p->ld = 1;
-      rows = 18 * p->Pd;
+      planes_d = 18;
     } else {
       return false;
     }
-    p->t_h = (g->H + p->th_step - 1) / p->th_step;
-    p->t_d = (g->D + p->td_step - 1) / p->td_step;
-    p->tiles_total = g->N * p->t_d * p->t_h * p->t_w;
+    p->t_h = (p->H + p->th_step - 1) / p->th_step;
+    p->t_d = (p->D + p->td_step - 1) / p->td_step;
+    p->tiles_total = p->N * p->t_d * p->t_h * p->t_w;
   } else {
-    if (g->D != 1 || g->H < 16) return false;   // 2-D maps: a tile = 16 lines of np consecutive samples
+    if ((mode == 0 && g->D != 1) || g->H < 16) return false;   // 2-D maps: a tile = 16 lines of np consecutive samples
     p->np = 4;
     p->Pd = 18 * kXW; p->MS = p->Pd; p->LS = kXW;
     p->th_step = 16; p->td_step = 1; p->tn_step = p->np;
     p->mn = 1; p->lh = 1;
-    rows = p->np * p->Pd;
+    planes_d = 1; planes_n = p->np;
     p->t_h = (g->H + 15) / 16;
     p->t_d = 1;
-    p->tiles_total = ((g->N + p->np - 1) / p->np) * p->t_h * p->t_w;
+    p->tiles_total = ((p->N + p->np - 1) / p->np) * p->t_h * p->t_w;
   }
-  p->a_tx = (uint32_t)rows * 128u;
+done:
+  p->box_d = planes_d; p->box_n = planes_n;
+  p->box_h = (p->lh ? 18 : p->np + 2);
+  p->ntaps = p->nd * 9;
+  {
+    const int rows = planes_d * planes_n * (p->lh ? 18 * kXW : p->Pd);
+    p->a_tx = (uint32_t)rows * 128u;
+  }
   p->a_bytes = (p->a_tx + 1023u) & ~1023u;
   p->tmem_cols = (uint32_t)(2 * p->np * 64);
+  if (p->tmem_cols < 32) p->tmem_cols = 32;
+  { uint32_t tc = 32; while (tc < p->tmem_cols) tc *= 2; p->tmem_cols = tc; }
   p->idesc = make_idesc_bf16(128, 64, 0, 0);
+  {
+    int ws = (int)((kSmemBudget - 2u * p->a_bytes - 1024u) / kWTapBytes);
+    if (ws > kWStagesMax) ws = kWStagesMax;
+    if (ws < 2) return false;
+    p->wstages = ws;
+  }
   return true;
 }
 
@@ -575,16 +658,17 @@ static int max_active_clusters(int cs, size_t smem) {
   return n;
 }
 
-int halo_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
-                      const void* residual, void* y, uint32_t flags, cudaStream_t stream) {
+static int halo_fprop_launch_mode(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
+                                  const void* residual, void* y, uint32_t flags, cudaStream_t stream, int mode) {
   HaloFpParams p{};
-  if (!halo_fprop_plan(g, &p)) return T2V_ERR_ARG;
+  if (!halo_fprop_plan(g, &p, mode)) return T2V_ERR_ARG;
+  if (mode != 0 && residual != nullptr) return T2V_ERR_ARG;
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = y;
   p.out_f32 = (flags & T2V_EPI_OUT_F32) ? 1 : 0;
   p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
-  const size_t smem = 2 * (size_t)p.a_bytes + kWStages * kWTapBytes + 1024 + (8 + 2 * kWStages) * 8 + 16;
+  const size_t smem = 2 * (size_t)p.a_bytes + p.wstages * kWTapBytes + 1024 + (8 + 2 * kWStagesMax) * 8 + 16;
   cudaFuncSetAttribute(halo_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int cs = 1;   // measured on B200: cs = 1 and 2 tie (the kernel is not weight-traffic bound), cs = 4 loses SMs
   { const char* e = getenv("T2V_HALO_CLUSTER"); if (e && e[0] >= '1' && e[0] <= '4') cs = e[0] - '0'; if (cs == 3) cs = 2; }
@@ -596,14 +680,12 @@ int halo_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, cons
 
   CUtensorMap tmA, tmW;
   int rc;
-  if (p.kd3) {
-    const int bh = p.lh ? 18 : p.np + 2, bd = p.lh ? p.np + 2 : 18;
-    rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, 64, 64, kXW, bh, bd, 1);
-  } else {
-    rc = make_act_map(&tmA, x, g->N, 1, g->H, g->W, 64, 64, kXW, 18, 1, p.np);
-  }
+  if (mode == 3 || mode == 4)      // merged (n, j) samples of single planes
+    rc = make_act_map(&tmA, x, g->N * g->D, 1, g->H, g->W, 64, 64, kXW, p.box_h, p.box_d, p.box_n);
+  else
+    rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, 64, 64, kXW, p.box_h, p.box_d, p.box_n);
   if (rc) return rc;
-  rc = make_w_map(&tmW, w, 64, p.ntaps * 64, 64, 64 / cs);
+  rc = make_w_map(&tmW, w, 64, g->kd * 9 * 64, 64, 64 / cs);
   if (rc) return rc;
 
   cudaLaunchConfig_t cfg = {};
@@ -616,13 +698,45 @@ int halo_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, cons
   attr[0].val.clusterDim.x = (unsigned)cs; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   ProfRec rec;
-  if (g_prof_on)
-    prof_begin(stream, &rec, 2, 2.0 * g->N * g->D * g->H * g->W * 64.0 * 64.0 * p.ntaps, g, ncl * cs);
+  if (g_prof_on)     // useful MACs: output voxels x live taps
+    prof_begin(stream, &rec, 2, 2.0 * p.N * p.D * g->H * g->W * 64.0 * 64.0 * p.ntaps, g, ncl * cs);
   cudaError_t e = cudaLaunchKernelEx(&cfg, halo_fprop_kernel, tmA, tmW, p);
   if (g_prof_on) prof_end(stream, &rec);
   count_launch();
   if (e != cudaSuccess) { cudaGetLastError(); return T2V_ERR_LAUNCH; }
   return check_last("halo_fprop");
+}
+
+int halo_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
+                      const void* residual, void* y, uint32_t flags, cudaStream_t stream) {
+  return halo_fprop_launch_mode(g, x, w, bias, residual, y, flags, stream, 0);
+}
+
+// ---- convolution with stride (2,1,1): Conv3d(64 -> 64, 3, padding 1) of which only the even output planes are
+// used (the discriminator stem: txt2vid/models/resnet3d.py:15-16, AvgPool3d((1,2,2), 2) has stride 2 along d
+// with kernel 1, so the odd planes of the second conv are never read).  g = geometry of x (D even).
+bool halo_sd2_supported(const t2v_conv_geom* g) {
+  HaloFpParams p{};
+  if (g->Cin != 64 || g->Cout != 64 || g->kd != 3 || g->kh != 3 || g->kw != 3) return false;
+  return halo_fprop_plan(g, &p, 1);
+}
+
+int halo_fprop_sd2_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                          uint32_t flags, cudaStream_t stream) {
+  if (!halo_sd2_supported(g)) return T2V_ERR_ARG;
+  return halo_fprop_launch_mode(g, x, w, bias, nullptr, y, flags, stream, 1);
+}
+
+// dx (N, D, H, W, 64) = conv_transpose(dy (N, D/2, H, W, 64), w) with the flipped pack: even and odd planes of dx are
+// two different sub-convolutions of dy (27 taps per TWO dx planes).  g = geometry of x / dx.
+int halo_dgrad_sd2_launch(const t2v_conv_geom* g, const void* dy, const void* wT, void* dx, uint32_t flags,
+                          cudaStream_t stream) {
+  if (!halo_sd2_supported(g)) return T2V_ERR_ARG;
+  t2v_conv_geom gd = *g;
+  gd.D = g->D / 2;
+  int rc = halo_fprop_launch_mode(&gd, dy, wT, nullptr, nullptr, dx, flags, stream, 3);
+  if (rc) return rc;
+  return halo_fprop_launch_mode(&gd, dy, wT, nullptr, nullptr, dx, flags, stream, gd.D >= 2 ? 2 : 4);
 }
 
 }  // namespace t2v

@@ -459,7 +459,11 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
   // many CTAs: cap shared memory at half an SM so that two CTAs are co-resident and one CTA's prologue /
   // epilogue overlaps the other's main loop (TMEM: 2 x BN <= 512 columns)
   const int total_ctas = mtiles_total * ((g->Cout + p.BN - 1) / p.BN);
-  const uint32_t budget = (two_cta && total_ctas > 222) ? 106496u : 196608u;
+  uint32_t budget = (two_cta && total_ctas > 222) ? 106496u : 196608u;
+  // short K loops over small tiles are latency bound per CTA: trade pipeline depth for residency (measured:
+  // 32->32 channels at 64x64, 9 k-blocks of 10 KB: 0.166 -> 0.082 ms with 3 stages and 6 CTAs per SM)
+  static const int small_kb = env_int("T2V_FPROP_SMALL_SMEM_KB", 32);
+  if (small_kb > 0 && p.stage_bytes <= 12288u && total_ctas > 4 * 148) budget = (uint32_t)small_kb * 1024u;
   int stages = (int)(budget / p.stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;

@@ -74,6 +74,53 @@ def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
     return out
 
 
+def conv_sd2_supported(shape, Cin, Cout, k=(3, 3, 3)):
+    """Can the stride-(2,1,1) kernels take an input of CL shape (N, D, H, W, C)?  (no GPU work)"""
+    N, D, H, W = [int(v) for v in shape[:4]]
+    g = _geom(N, D, H, W, Cin, Cout, k)
+    return bool(lib().t2v_conv_sd2_supported(ctypes.byref(g)))
+
+
+def conv_fprop_sd2(x, w, bias=None, relu=False):
+    """Conv3d(64 -> 64, 3, stride (2,1,1), padding 1): x (N,D,H,W,64) bf16 -> y (N,D/2,H,W,64) bf16
+    (= the even output planes of the stride-1 convolution)."""
+    require_cuda(x, w, bias)
+    N, D, H, W, Cin = x.shape
+    Cout = w.shape[0]
+    assert w.shape[1] == 27 and w.shape[2] == Cin and x.is_contiguous() and w.is_contiguous()
+    assert x.dtype == BF16 and w.dtype == BF16 and (bias is None or (bias.dtype == F32 and bias.numel() == Cout))
+    y = torch.empty((N, D // 2, H, W, Cout), device=x.device, dtype=BF16)
+    g = _geom(N, D, H, W, Cin, Cout, (3, 3, 3))
+    check(lib().t2v_conv_fprop_sd2(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y),
+                                   _lib.EPI_RELU if relu else 0, stream()), "t2v_conv_fprop_sd2")
+    return y
+
+
+def conv_dgrad_sd2(dy, wT):
+    """dy (N,D/2,H,W,Cout) bf16, wT (Cin,27,Cout) flipped pack -> dx (N,D,H,W,Cin) bf16."""
+    require_cuda(dy, wT)
+    N, Dj, H, W, Cout = dy.shape
+    Cin = wT.shape[0]
+    assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and dy.dtype == BF16
+    dx = torch.empty((N, 2 * Dj, H, W, Cin), device=dy.device, dtype=BF16)
+    g = _geom(N, 2 * Dj, H, W, Cin, Cout, (3, 3, 3))
+    check(lib().t2v_conv_dgrad_sd2(ctypes.byref(g), ptr(dy), ptr(wT), ptr(dx), 0, stream()), "t2v_conv_dgrad_sd2")
+    return dx
+
+
+def conv_wgrad_sd2(dy, x):
+    """dw (Cout,27,Cin) fp32 = sum over the even output planes of dy[pos,co] x[pos+tap,ci]."""
+    require_cuda(dy, x)
+    N, D, H, W, Cin = x.shape
+    Cout = dy.shape[-1]
+    assert tuple(dy.shape[:4]) == (N, D // 2, H, W) and dy.is_contiguous() and x.is_contiguous()
+    assert dy.dtype == BF16 and x.dtype == BF16
+    out = torch.empty((Cout, 27, Cin), device=x.device, dtype=F32)
+    g = _geom(N, D, H, W, Cin, Cout, (3, 3, 3))
+    check(lib().t2v_conv_wgrad_sd2(ctypes.byref(g), ptr(dy), ptr(x), ptr(out), 0, stream()), "t2v_conv_wgrad_sd2")
+    return out
+
+
 def cast_bf16(src):
     require_cuda(src)
     assert src.dtype == F32 and src.is_contiguous()

@@ -207,6 +207,66 @@ class ConvWgradF(Function):
         return g_dy, g_x, None
 
 
+class ConvSd2F(Function):
+    """y = conv3d(x, w, stride (2,1,1), padding 1) + b: the even output planes of the stride-1 convolution.
+    The discriminator stem (resnet3d.py:15-16) pools its second convolution with AvgPool3d((1,2,2), 2) -- kernel 1,
+    stride 2 along d -- so the odd planes are never read; results are identical at half the MACs."""
+
+    @staticmethod
+    def forward(ctx, x, weight, bias):
+        wp = PACKS.get(weight, "fprop", weight.shape[0], x.shape[-1])
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(x, weight)
+        return K.conv_fprop_sd2(x, wp, _pad_bias(bias, weight.shape[0]))
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            dx = ConvSd2DgradF.apply(dy, weight)
+        if ctx.needs_input_grad[1]:
+            dw = ConvSd2WgradF.apply(dy, x, weight)
+        if ctx.has_bias and ctx.needs_input_grad[2]:
+            db = SumRowsF.apply(dy)[:weight.shape[0]]
+        return dx, dw, db
+
+
+class ConvSd2DgradF(Function):
+    @staticmethod
+    def forward(ctx, dy, weight):
+        wT = PACKS.get(weight, "dgrad", dy.shape[-1], weight.shape[1])
+        ctx.save_for_backward(dy, weight)
+        return K.conv_dgrad_sd2(dy, wT)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        dy, weight = ctx.saved_tensors
+        ddx = ddx.contiguous()
+        g_dy = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_dy = ConvSd2F.apply(ddx, weight, None)
+        if ctx.needs_input_grad[1]:
+            g_w = ConvSd2WgradF.apply(dy, ddx, weight)
+        return g_dy, g_w
+
+
+class ConvSd2WgradF(Function):
+    @staticmethod
+    def forward(ctx, dy, x, weight):
+        return grad_like_weight(K.conv_wgrad_sd2(dy, x), weight)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ddw):
+        raise NotImplementedError("third-order graph through the stride-(2,1,1) weight gradient")
+
+
+def conv_sd2(x, weight, bias=None):
+    return ConvSd2F.apply(x, weight, bias)
+
+
 class SumRowsF(Function):
     """fp32 (C,) = sum over positions (bias gradient)."""
 
