@@ -41,6 +41,9 @@ extern "C" {
 /* epilogue flags of t2v_conv_fprop */
 #define T2V_EPI_RELU 1u       /* y = max(y, 0) after bias/residual */
 #define T2V_EPI_OUT_F32 2u    /* y is fp32 CL instead of bf16 CL */
+#define T2V_EPI_RELU_MASK 4u  /* the `residual` pointer is a ReLU reference r (bf16 CL, output-shaped): instead of
+                               * adding it, zero the output where r <= 0 -- the backward of the ReLU that produced the
+                               * convolution's input, fused into the data-gradient epilogue (layers.py:230-232) */
 
 /* Stride-1, "same"-padded convolution geometry (every conv on the TGANv2 path:
  * models/layers.py:174,177,183,231,233,237,251; models/resnet3d.py:12-17; 1x1(x1) convs of the
@@ -80,12 +83,13 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
  * discriminator stem (models/resnet3d.py:15) is followed by AvgPool3d((1,2,2), 2) (resnet3d.py:16: kernel 1,
  * stride 2 along d), which never reads its odd output planes; computing only the even planes is the same
  * function at half the MACs.  g = geometry of x (D even, H >= 16, W >= 8); y / dy are (N, D/2, H, W, 64).
- * dgrad takes the flipped pack of t2v_pack_dgrad_weight; wgrad writes [Cout][27][Cin] fp32 like t2v_conv_wgrad. */
+ * dgrad takes the flipped pack of t2v_pack_dgrad_weight and an optional ReLU reference (NULL or x-shaped, see
+ * T2V_EPI_RELU_MASK); wgrad writes [Cout][27][Cin] fp32 like t2v_conv_wgrad. */
 int t2v_conv_sd2_supported(const t2v_conv_geom* g);
 int t2v_conv_fprop_sd2(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, void* y,
                        uint32_t epi_flags, void* stream);
-int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, void* dx, uint32_t epi_flags,
-                       void* stream);
+int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, const void* relu_ref, void* dx,
+                       uint32_t epi_flags, void* stream);
 int t2v_conv_wgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
                        void* stream);
 /* General convolution geometry (any kernel / stride / zero padding; 1-D and 2-D use unit extents):

@@ -53,24 +53,27 @@ def conv_fprop_sd2(x, w, bias=None, relu=False):
     return y.contiguous().to(STORE)
 
 
-def conv_dgrad_sd2(dy, wT):
+def conv_dgrad_sd2(dy, wT, relu_ref=None):
     # scatter dy onto the even planes of a zero tensor, then the stride-1 adjoint
     N, Dj, H, W, C = dy.shape
     full = torch.zeros((N, 2 * Dj, H, W, C), dtype=dy.dtype)
     full[:, ::2] = dy
-    return conv_fprop(full, wT, None, None, (3, 3, 3))
+    return conv_dgrad(full, wT, (3, 3, 3), relu_ref=relu_ref)
 
 
-def conv_wgrad_sd2(dy, x):
+def conv_wgrad_sd2(dy, x, out=None, accumulate=False):
     N, Dj, H, W, C = dy.shape
     full = torch.zeros((N, 2 * Dj, H, W, C), dtype=dy.dtype)
     full[:, ::2] = dy
-    return conv_wgrad(full, x, (3, 3, 3))
+    return conv_wgrad(full, x, (3, 3, 3), out=out, accumulate=accumulate)
 
 
-def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0):
+def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0, relu_ref=None):
     # wT (Cin,taps,Cout) with reversed taps == the forward weight of the adjoint convolution
-    return conv_fprop(dy, wT, None, residual, k, relu, out_f32)
+    if relu_ref is None:
+        return conv_fprop(dy, wT, None, residual, k, relu, out_f32)
+    dx = conv_fprop(dy, wT, None, None, k, False, True) * (relu_ref.float() > 0).float()
+    return dx if out_f32 else dx.to(STORE)
 
 
 def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):

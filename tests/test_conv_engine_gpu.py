@@ -209,6 +209,25 @@ def test_sd2_conv(shape):
     assert e < 1.5e-2 and e_same < 1e-6 and e_dx < 1.5e-2 and e_dw < 2e-3
 
 
+@pytest.mark.parametrize("case", [(2, 4, 8, 8, 64, 128, (3, 3, 3)), (3, 4, 16, 16, 64, 64, (3, 3, 3)),
+                                  (4, 1, 4, 4, 256, 256, (3, 3, 3)), (2, 4, 32, 32, 64, 64, (3, 3, 3))])
+def test_dgrad_relu_mask_epilogue(case):
+    """dx = dgrad(dy) * (ref > 0) in the epilogue (T2V_EPI_RELU_MASK) == the unfused composite, bit for bit."""
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k = case
+    x, w = _mk(*case, seed=11)
+    ref = torch.relu(x)
+    dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
+    wT = K.pack_dgrad_weight(w.float())
+    fused = K.conv_dgrad(dy, wT, k=k, relu_ref=ref)
+    comp = K.relu_bwd(K.conv_dgrad(dy, wT, k=k), ref)
+    assert torch.equal(fused, comp)
+    assert float((fused != 0).float().mean()) > 0.2
+    if K.conv_sd2_supported((N, D, H, W), Cin, Cout, k):
+        dyh = dy[:, ::2].contiguous()
+        assert torch.equal(K.conv_dgrad_sd2(dyh, wT, relu_ref=ref), K.relu_bwd(K.conv_dgrad_sd2(dyh, wT), ref))
+
+
 def test_sd2_unsupported_shapes():
     from txt2vid_b200 import kernels as K
     assert not K.conv_sd2_supported((4, 16, 8, 8), 64, 64)      # level 0: 8x8 planes stay on the stride-1 kernel

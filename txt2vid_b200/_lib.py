@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libt2v_b200.so")
 
 T2V_OK = 0
 ALGO_AUTO, ALGO_TC, ALGO_SIMT, ALGO_TC_GENERIC = 0, 1, 2, 3
-EPI_RELU, EPI_OUT_F32 = 1, 2
+EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK = 1, 2, 4
 
 
 class ConvGeom(ctypes.Structure):
@@ -66,7 +66,7 @@ SIGNATURES = {
     "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],
     "t2v_conv_sd2_supported": [ctypes.POINTER(ConvGeom)],
     "t2v_conv_fprop_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, _P],
-    "t2v_conv_dgrad_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_u32, _P],
+    "t2v_conv_dgrad_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, _P],
     "t2v_conv_wgrad_sd2": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, _P],
     "t2v_gconv_fprop": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_dgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],

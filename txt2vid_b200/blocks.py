@@ -191,8 +191,9 @@ class DownBlock(nn.Module):
         m = self.main.inner_module
         c1 = self.main.identity_map[0]
         skip = ops.conv(x, c1.weight, c1.bias)
-        h = ops.conv(ops.relu(x), m[1].weight, m[1].bias, relu=True)
-        h = ops.conv(h, m[3].weight, m[3].bias, residual=skip)
+        # both ReLU backward masks ride in the data-gradient epilogues of their (single) consumers
+        h = ops.conv(ops.relu(x, later=True), m[1].weight, m[1].bias, relu=True, x_relu=True, relu_later=True)
+        h = ops.conv(h, m[3].weight, m[3].bias, residual=skip, x_relu=True)
         k, s, p = ops.down_sample_cfg(h.shape)
         return ops.avg_pool(h, k, s, p)
 
@@ -320,16 +321,16 @@ class Resnet3D(nn.Module):
         m = self.res_block.inner_module
         xc = ops.to_cl(x)                                             # RGB padded to 16 channels (skip path)
         # first conv (K = 27*3 = 81): im2col once, then a 1x1x1 GEMM on the tensor cores
-        h = ops.conv(ops.im2col3(x), ops.stem_weight_2d(m[0].weight), m[0].bias, relu=True)
+        h = ops.conv(ops.im2col3(x), ops.stem_weight_2d(m[0].weight), m[0].bias, relu=True, relu_later=True)
         c1 = self.res_block.identity_map[1]
         pk, ps = (1, 2, 2), (2, 2, 2)                                 # AvgPool3d((1,2,2), 2): stride 2 in ALL dims
         skip = ops.conv(ops.avg_pool(xc, pk, ps), c1.weight, c1.bias)
         if STEM_SD2 and ops.K.conv_sd2_supported(h.shape, h.shape[-1], m[2].weight.shape[0], tuple(m[2].weight.shape[2:])):
             # the pool keeps only the even d planes of this convolution (kernel 1, stride 2 along d): compute only those
-            h = ops.conv_sd2(h, m[2].weight, m[2].bias)
+            h = ops.conv_sd2(h, m[2].weight, m[2].bias, x_relu=True)
             h = ops.avg_pool(h, pk, (1, 2, 2), residual=skip)
         else:
-            h = ops.conv(h, m[2].weight, m[2].bias)
+            h = ops.conv(h, m[2].weight, m[2].bias, x_relu=True)
             h = ops.avg_pool(h, pk, ps, residual=skip)
         for d in self.down:
             h = d.forward_cl(h)

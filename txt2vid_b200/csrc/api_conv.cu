@@ -16,7 +16,7 @@ int halo_fprop_launch(const t2v_conv_geom*, const void*, const void*, const floa
 int halo_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t, int sd2);
 bool halo_sd2_supported(const t2v_conv_geom* g);
 int halo_fprop_sd2_launch(const t2v_conv_geom*, const void*, const void*, const float*, void*, uint32_t, cudaStream_t);
-int halo_dgrad_sd2_launch(const t2v_conv_geom*, const void*, const void*, void*, uint32_t, cudaStream_t);
+int halo_dgrad_sd2_launch(const t2v_conv_geom*, const void*, const void*, const void*, void*, uint32_t, cudaStream_t);
 int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                       uint32_t, cudaStream_t);
 int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
@@ -92,6 +92,7 @@ int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const f
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
   const bool tc_ok = igemm_fprop_supported(g);
   if ((algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) && !tc_ok) return T2V_ERR_ARG;
+  if ((epi_flags & T2V_EPI_RELU_MASK) && (algo == T2V_ALGO_SIMT || !tc_ok || !residual)) return T2V_ERR_ARG;
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
   if (algo != T2V_ALGO_TC_GENERIC && halo_fprop_supported(g)) return halo_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
   return igemm_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
@@ -125,10 +126,10 @@ int t2v_conv_fprop_sd2(const t2v_conv_geom* g, const void* x, const void* w, con
   return halo_fprop_sd2_launch(g, x, w, bias, y, epi_flags, reinterpret_cast<cudaStream_t>(stream));
 }
 
-int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, void* dx, uint32_t epi_flags,
-                       void* stream) {
+int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, const void* relu_ref, void* dx,
+                       uint32_t epi_flags, void* stream) {
   if (!g || !dy || !wT || !dx) return T2V_ERR_ARG;
-  return halo_dgrad_sd2_launch(g, dy, wT, dx, epi_flags, reinterpret_cast<cudaStream_t>(stream));
+  return halo_dgrad_sd2_launch(g, dy, wT, relu_ref, dx, epi_flags, reinterpret_cast<cudaStream_t>(stream));
 }
 
 int t2v_conv_wgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,

@@ -318,7 +318,7 @@ struct HaloFpParams {
   const float* bias;
   const __nv_bfloat16* residual;
   void* out;
-  int out_f32, relu;
+  int out_f32, relu, relu_mask;
 };
 
 struct FpTile { int n0, d0, h0, w0; };
@@ -499,8 +499,15 @@ halo_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 const uint4 u = rp[j];
                 const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z),
                              dd = unpack_bf16x2(u.w);
-                f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-                f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += dd.x; f[8 * j + 7] += dd.y;
+                if (p.relu_mask) {      // the pointer is a ReLU reference: dx = dgrad(dy) * (ref > 0)
+                  f[8 * j + 0] = a.x > 0.f ? f[8 * j + 0] : 0.f; f[8 * j + 1] = a.y > 0.f ? f[8 * j + 1] : 0.f;
+                  f[8 * j + 2] = b.x > 0.f ? f[8 * j + 2] : 0.f; f[8 * j + 3] = b.y > 0.f ? f[8 * j + 3] : 0.f;
+                  f[8 * j + 4] = cc.x > 0.f ? f[8 * j + 4] : 0.f; f[8 * j + 5] = cc.y > 0.f ? f[8 * j + 5] : 0.f;
+                  f[8 * j + 6] = dd.x > 0.f ? f[8 * j + 6] : 0.f; f[8 * j + 7] = dd.y > 0.f ? f[8 * j + 7] : 0.f;
+                } else {
+                  f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+                  f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += dd.x; f[8 * j + 7] += dd.y;
+                }
               }
             }
             if (p.relu) {
@@ -662,12 +669,13 @@ static int halo_fprop_launch_mode(const t2v_conv_geom* g, const void* x, const v
                                   const void* residual, void* y, uint32_t flags, cudaStream_t stream, int mode) {
   HaloFpParams p{};
   if (!halo_fprop_plan(g, &p, mode)) return T2V_ERR_ARG;
-  if (mode != 0 && residual != nullptr) return T2V_ERR_ARG;
+  if (mode != 0 && residual != nullptr && !(flags & T2V_EPI_RELU_MASK)) return T2V_ERR_ARG;
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = y;
   p.out_f32 = (flags & T2V_EPI_OUT_F32) ? 1 : 0;
   p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
+  p.relu_mask = (flags & T2V_EPI_RELU_MASK) ? 1 : 0;
   const size_t smem = 2 * (size_t)p.a_bytes + p.wstages * kWTapBytes + 1024 + (8 + 2 * kWStagesMax) * 8 + 16;
   cudaFuncSetAttribute(halo_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
   int cs = 1;   // measured on B200: cs = 1 and 2 tie (the kernel is not weight-traffic bound), cs = 4 loses SMs
@@ -729,14 +737,15 @@ int halo_fprop_sd2_launch(const t2v_conv_geom* g, const void* x, const void* w, 
 
 // dx (N, D, H, W, 64) = conv_transpose(dy (N, D/2, H, W, 64), w) with the flipped pack: even and odd planes of dx are
 // two different sub-convolutions of dy (27 taps per TWO dx planes).  g = geometry of x / dx.
-int halo_dgrad_sd2_launch(const t2v_conv_geom* g, const void* dy, const void* wT, void* dx, uint32_t flags,
-                          cudaStream_t stream) {
+int halo_dgrad_sd2_launch(const t2v_conv_geom* g, const void* dy, const void* wT, const void* relu_ref, void* dx,
+                          uint32_t flags, cudaStream_t stream) {
   if (!halo_sd2_supported(g)) return T2V_ERR_ARG;
   t2v_conv_geom gd = *g;
   gd.D = g->D / 2;
-  int rc = halo_fprop_launch_mode(&gd, dy, wT, nullptr, nullptr, dx, flags, stream, 3);
+  flags = relu_ref ? (flags | T2V_EPI_RELU_MASK) : (flags & ~T2V_EPI_RELU_MASK);
+  int rc = halo_fprop_launch_mode(&gd, dy, wT, nullptr, relu_ref, dx, flags, stream, 3);
   if (rc) return rc;
-  return halo_fprop_launch_mode(&gd, dy, wT, nullptr, nullptr, dx, flags, stream, gd.D >= 2 ? 2 : 4);
+  return halo_fprop_launch_mode(&gd, dy, wT, nullptr, relu_ref, dx, flags, stream, gd.D >= 2 ? 2 : 4);
 }
 
 }  // namespace t2v

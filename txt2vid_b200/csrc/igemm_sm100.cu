@@ -41,7 +41,7 @@ struct IgemmParams {
   const float* bias;
   const __nv_bfloat16* residual;
   void* out;
-  int out_f32, relu;
+  int out_f32, relu, relu_mask;
   // wgrad only
   float* dw;
   int taps_total, splits, tiles_total, atomic_out;
@@ -182,8 +182,15 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             const uint4 u = rp[j];
             const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z),
                          dd = unpack_bf16x2(u.w);
-            f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
-            f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += dd.x; f[8 * j + 7] += dd.y;
+            if (p.relu_mask) {      // the pointer is a ReLU reference: dx = dgrad(dy) * (ref > 0)
+              f[8 * j + 0] = a.x > 0.f ? f[8 * j + 0] : 0.f; f[8 * j + 1] = a.y > 0.f ? f[8 * j + 1] : 0.f;
+              f[8 * j + 2] = b.x > 0.f ? f[8 * j + 2] : 0.f; f[8 * j + 3] = b.y > 0.f ? f[8 * j + 3] : 0.f;
+              f[8 * j + 4] = cc.x > 0.f ? f[8 * j + 4] : 0.f; f[8 * j + 5] = cc.y > 0.f ? f[8 * j + 5] : 0.f;
+              f[8 * j + 6] = dd.x > 0.f ? f[8 * j + 6] : 0.f; f[8 * j + 7] = dd.y > 0.f ? f[8 * j + 7] : 0.f;
+            } else {
+              f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+              f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += dd.x; f[8 * j + 7] += dd.y;
+            }
           }
         }
         if (p.relu) {
@@ -329,7 +336,9 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
           float* dst = p.dw + ((size_t)co * p.taps_total + tap) * p.Cin + ci;
           if (p.atomic_out) {
 #pragma unroll
-            for (int j = 0; j < 16; ++j) atomicAdd(dst + j, __uint_as_float(v[j]));
+            for (int j = 0; j < 16; j += 4)
+              red_add_v4(dst + j, __uint_as_float(v[j]), __uint_as_float(v[j + 1]), __uint_as_float(v[j + 2]),
+                         __uint_as_float(v[j + 3]));
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
@@ -476,6 +485,7 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
   p.out = y;
   p.out_f32 = (flags & T2V_EPI_OUT_F32) ? 1 : 0;
   p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
+  p.relu_mask = (flags & T2V_EPI_RELU_MASK) ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   int rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, g->Cin, BLOCK_K, p.bw, p.bh, p.bd, p.bn);

@@ -169,6 +169,13 @@ import os as _os
 PAIR_D_STEP = _os.environ.get("T2V_PAIR_D_STEP", "1") == "1"   # batch the real / fake trunk passes of the D step
 
 
+def _zero_grad(module):
+    """module.zero_grad() of cond_gan.py:91,157; the product modules' conv weights keep persistent gradient buffers
+    that the weight-gradient kernels accumulate into (ops.zero_grads)."""
+    from . import ops
+    ops.zero_grads(module)
+
+
 class CondGan(object):
     """gan/cond_gan.py:7-217."""
 
@@ -237,7 +244,7 @@ class CondGan(object):
     def gen_step(self, fake=None, real_pred=None, cond=None, loss=None):
         """cond_gan.py:90-118 (unconditional branch: element [0] of each tuple -- the reference passes the
         tuples themselves and raises, cond_gan.py:102-106; documented adapter)."""
-        self.gen.zero_grad()
+        _zero_grad(self.gen)
         if self.cond_encoder is not None:
             self.cond_encoder.zero_grad()
         fake_mapping = self._map_input(fake)
@@ -274,7 +281,7 @@ class CondGan(object):
 
     def discrim_step(self, real=None, fake=None, cond=None, loss=None, gp_lambda=-1):
         for discrim in self.discrims:
-            discrim.zero_grad()
+            _zero_grad(discrim)
         if self.cond_encoder is not None:
             self.cond_encoder.zero_grad()
         losses, _, _ = self.all_discrim_forward(real=real, fake=fake, cond=cond, loss=loss, gp_lambda=gp_lambda)

@@ -43,15 +43,21 @@ def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=
     return y
 
 
-def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0):
-    """dy (N,D,H,W,Cout) bf16, wT (Cin,taps,Cout) bf16 (from pack_dgrad_weight) -> dx (N,D,H,W,Cin)."""
-    require_cuda(dy, wT, residual)
+def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0, relu_ref=None):
+    """dy (N,D,H,W,Cout) bf16, wT (Cin,taps,Cout) bf16 (from pack_dgrad_weight) -> dx (N,D,H,W,Cin).
+    relu_ref (dx-shaped bf16): dx is zeroed where relu_ref <= 0 (the ReLU in front of the convolution, fused)."""
+    require_cuda(dy, wT, residual, relu_ref)
+    if relu_ref is not None:
+        assert residual is None and relu_ref.is_contiguous() and relu_ref.dtype == BF16
+        assert tuple(relu_ref.shape) == tuple(dy.shape[:4]) + (wT.shape[0],)
+        residual = relu_ref
     N, D, H, W, Cout = dy.shape
     Cin = wT.shape[0]
     assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and dy.dtype == BF16
     dx = torch.empty((N, D, H, W, Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
-    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0)
+    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0) | \
+        (_lib.EPI_RELU_MASK if relu_ref is not None else 0)
     check(lib().t2v_conv_dgrad(ctypes.byref(g), ptr(dy), ptr(wT), ptr(residual), ptr(dx), flags, algo, stream()),
           "t2v_conv_dgrad")
     return dx
@@ -96,28 +102,35 @@ def conv_fprop_sd2(x, w, bias=None, relu=False):
     return y
 
 
-def conv_dgrad_sd2(dy, wT):
-    """dy (N,D/2,H,W,Cout) bf16, wT (Cin,27,Cout) flipped pack -> dx (N,D,H,W,Cin) bf16."""
-    require_cuda(dy, wT)
+def conv_dgrad_sd2(dy, wT, relu_ref=None):
+    """dy (N,D/2,H,W,Cout) bf16, wT (Cin,27,Cout) flipped pack -> dx (N,D,H,W,Cin) bf16 (zeroed where the dx-shaped
+    relu_ref <= 0, if given)."""
+    require_cuda(dy, wT, relu_ref)
+    assert relu_ref is None or (relu_ref.is_contiguous() and relu_ref.dtype == BF16)
     N, Dj, H, W, Cout = dy.shape
     Cin = wT.shape[0]
     assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and dy.dtype == BF16
     dx = torch.empty((N, 2 * Dj, H, W, Cin), device=dy.device, dtype=BF16)
     g = _geom(N, 2 * Dj, H, W, Cin, Cout, (3, 3, 3))
-    check(lib().t2v_conv_dgrad_sd2(ctypes.byref(g), ptr(dy), ptr(wT), ptr(dx), 0, stream()), "t2v_conv_dgrad_sd2")
+    assert relu_ref is None or tuple(relu_ref.shape) == tuple(dx.shape)
+    check(lib().t2v_conv_dgrad_sd2(ctypes.byref(g), ptr(dy), ptr(wT), ptr(relu_ref), ptr(dx), 0, stream()),
+          "t2v_conv_dgrad_sd2")
     return dx
 
 
-def conv_wgrad_sd2(dy, x):
+def conv_wgrad_sd2(dy, x, out=None, accumulate=False):
     """dw (Cout,27,Cin) fp32 = sum over the even output planes of dy[pos,co] x[pos+tap,ci]."""
     require_cuda(dy, x)
     N, D, H, W, Cin = x.shape
     Cout = dy.shape[-1]
     assert tuple(dy.shape[:4]) == (N, D // 2, H, W) and dy.is_contiguous() and x.is_contiguous()
     assert dy.dtype == BF16 and x.dtype == BF16
-    out = torch.empty((Cout, 27, Cin), device=x.device, dtype=F32)
+    if out is None:
+        assert not accumulate
+        out = torch.empty((Cout, 27, Cin), device=x.device, dtype=F32)
     g = _geom(N, D, H, W, Cin, Cout, (3, 3, 3))
-    check(lib().t2v_conv_wgrad_sd2(ctypes.byref(g), ptr(dy), ptr(x), ptr(out), 0, stream()), "t2v_conv_wgrad_sd2")
+    check(lib().t2v_conv_wgrad_sd2(ctypes.byref(g), ptr(dy), ptr(x), ptr(out), 1 if accumulate else 0, stream()),
+          "t2v_conv_wgrad_sd2")
     return out
 
 

@@ -10,6 +10,8 @@ fp32 `nn.Parameter`s with the reference's logical shapes; conv weights are re-ho
 channels-last memory ([Cout][taps][Cin]) so that packing is a cast and the weight gradient the
 kernels write is the parameter gradient's memory.
 """
+import os
+
 import torch
 from torch.autograd import Function
 from torch.autograd.function import once_differentiable
@@ -110,6 +112,69 @@ class _PackCache(object):
 PACKS = _PackCache()
 
 
+# ------------------------------------------------------------------------------------- gradient sinks
+# The discriminator's weights are shared by the four pyramid levels and by the loss and penalty graphs, so one
+# backward pass produces ~11 partial weight gradients per tensor; summed by autograd that is ~440 fp32 add kernels per
+# iteration.  Instead every unpadded conv weight owns one persistent fp32 buffer [Cout][taps][Cin] (= p.grad's memory,
+# zeroed by zero_grads) and the weight-gradient kernels accumulate into it directly (fp32 red.add, as they already
+# do between their own position splits).  Second-order graphs (create_graph=True) keep the functional path.
+GRAD_SINKS = os.environ.get("T2V_GRAD_SINKS", "1") == "1"
+
+
+def _sinkable(p):
+    # only weights that ConvF / ConvSd2F have consumed (marked at their first forward) and that need no channel padding
+    return getattr(p, "_t2v_conv", False) and p.dim() >= 2 and p.shape[0] % 16 == 0 and p.shape[1] % 16 == 0
+
+
+def mark_conv_weights(module):
+    """Flag the Conv2d / Conv3d / Linear weights of a product module as consumed by the conv engine (ConvLSTM cells
+    excluded: their eight kernels are stacked into one gate GEMM and receive their gradient through torch.cat)."""
+    skip = set()
+    for name, m in module.named_modules():
+        if type(m).__name__ == "ConvLSTMCell":
+            skip.update(id(c) for c in m.modules())
+    for m in module.modules():
+        if id(m) not in skip and isinstance(m, (torch.nn.Conv2d, torch.nn.Conv3d, torch.nn.Linear)):
+            m.weight._t2v_conv = True
+    module._t2v_marked = True
+
+
+def zero_grads(module):
+    """module.zero_grad() (gan/cond_gan.py:91-94,157-161): gradients of sink-owning weights become zeroed persistent
+    buffers, all others None (filled by autograd)."""
+    if not getattr(module, "_t2v_marked", False):
+        mark_conv_weights(module)
+    bufs = []
+    for p in module.parameters():
+        if not (GRAD_SINKS and p.requires_grad and _sinkable(p)):
+            p.grad = None
+            continue
+        w3 = w3_view(p)                                  # re-homes the parameter to channels-last memory if needed
+        sink = getattr(p, "_t2v_sink", None)
+        if sink is None or sink.shape != w3.shape or sink.device != p.device:
+            sink = torch.empty(w3.shape, device=p.device, dtype=F32)
+            p._t2v_sink = sink
+        bufs.append(sink)
+        if p.grad is None or p.grad.data_ptr() != sink.data_ptr():
+            p.grad = grad_like_weight(sink, p)
+    if bufs:
+        torch._foreach_zero_(bufs)
+
+
+def _wgrad(dy, x, weight, sd2=False):
+    """Weight gradient of a convolution: into the parameter's sink when this is a first-order backward pass."""
+    sink = getattr(weight, "_t2v_sink", None)
+    if (sink is not None and not torch.is_grad_enabled() and weight.grad is not None
+            and weight.grad.data_ptr() == sink.data_ptr() and dy.shape[-1] == weight.shape[0]
+            and x.shape[-1] == weight.shape[1]):
+        if sd2:
+            K.conv_wgrad_sd2(dy, x, out=sink, accumulate=True)
+        else:
+            K.conv_wgrad(dy, x, kernel_of(weight), out=sink, accumulate=True)
+        return None
+    return (ConvSd2WgradF if sd2 else ConvWgradF).apply(dy, x, weight)
+
+
 def _pad_bias(bias, CoutP):
     if bias is None:
         return None
@@ -122,21 +187,32 @@ def _pad_bias(bias, CoutP):
 
 
 # ------------------------------------------------------------------------------------- convolution
+FUSE_RELU_BWD = os.environ.get("T2V_FUSE_RELU_BWD", "1") == "1"
+
+
 class ConvF(Function):
-    """y = [relu](conv(x, w) + b [+ residual]);  x CL (.., CinP) -> y CL (.., CoutP)."""
+    """y = [relu](conv(x, w) + b [+ residual]);  x CL (.., CinP) -> y CL (.., CoutP).
+
+    ReLU-backward fusion (the discriminator's ReLU -> conv chains, layers.py:229-235, resnet3d.py:12-15):
+      x_relu      x is the output of a ReLU whose backward THIS op applies: dx = dgrad(dy) * (x > 0), in the
+                  data-gradient kernel's epilogue on first-order passes (a separate mask op under create_graph);
+      relu_later  the consumer of y applies this op's own ReLU mask (it was built with x_relu): backward does not
+                  mask dy again.  Masks are idempotent, so a y with several consumers needs all of them to mask."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, residual, relu):
+    def forward(ctx, x, weight, bias, residual, relu, x_relu=False, relu_later=False):
         k = kernel_of(weight)
         Cout, Cin = weight.shape[0], weight.shape[1]
         CinP, CoutP = x.shape[-1], round16(Cout)
         assert CinP >= Cin and CinP % 16 == 0, (CinP, Cin)
         wp = PACKS.get(weight, "fprop", CoutP, CinP)
+        weight._t2v_conv = True
         y = K.conv_fprop(x, wp, _pad_bias(bias, CoutP), residual, k, relu)
-        ctx.relu = relu
+        ctx.relu = relu and not relu_later
+        ctx.x_relu = x_relu
         ctx.has_bias = bias is not None
         ctx.has_res = residual is not None
-        ctx.save_for_backward(x, weight, y if relu else None)
+        ctx.save_for_backward(x, weight, y if ctx.relu else None)
         return y
 
     @staticmethod
@@ -147,14 +223,20 @@ class ConvF(Function):
             dy = ReluBwdF.apply(dy, y)
         dx = dw = db = dres = None
         if ctx.needs_input_grad[0]:
-            dx = ConvDgradF.apply(dy, weight, x.shape[-1])
+            if not ctx.x_relu:
+                dx = ConvDgradF.apply(dy, weight, x.shape[-1])
+            elif torch.is_grad_enabled() or x.shape[-1] % 16 or dy.shape[-1] % 16:
+                dx = ReluBwdF.apply(ConvDgradF.apply(dy, weight, x.shape[-1]), x)
+            else:
+                dx = K.conv_dgrad(dy, PACKS.get(weight, "dgrad", dy.shape[-1], x.shape[-1]), kernel_of(weight),
+                                  relu_ref=x)
         if ctx.needs_input_grad[1]:
-            dw = ConvWgradF.apply(dy, x, weight)
+            dw = _wgrad(dy, x, weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = SumRowsF.apply(dy)[:weight.shape[0]]
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
-        return dx, dw, db, dres, None
+        return dx, dw, db, dres, None, None, None
 
 
 class ConvDgradF(Function):
@@ -173,9 +255,9 @@ class ConvDgradF(Function):
         ddx = ddx.contiguous()
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
-            g_dy = ConvF.apply(ddx, weight, None, None, False)
+            g_dy = ConvF.apply(ddx, weight, None, None, False, False, False)
         if ctx.needs_input_grad[1]:
-            g_w = ConvWgradF.apply(dy, ddx, weight)
+            g_w = _wgrad(dy, ddx, weight)
         return g_dy, g_w, None
 
 
@@ -213,9 +295,11 @@ class ConvSd2F(Function):
     stride 2 along d -- so the odd planes are never read; results are identical at half the MACs."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias):
+    def forward(ctx, x, weight, bias, x_relu=False):
         wp = PACKS.get(weight, "fprop", weight.shape[0], x.shape[-1])
+        weight._t2v_conv = True
         ctx.has_bias = bias is not None
+        ctx.x_relu = x_relu
         ctx.save_for_backward(x, weight)
         return K.conv_fprop_sd2(x, wp, _pad_bias(bias, weight.shape[0]))
 
@@ -225,12 +309,17 @@ class ConvSd2F(Function):
         dy = dy.contiguous()
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            dx = ConvSd2DgradF.apply(dy, weight)
+            if not ctx.x_relu:
+                dx = ConvSd2DgradF.apply(dy, weight)
+            elif torch.is_grad_enabled():
+                dx = ReluBwdF.apply(ConvSd2DgradF.apply(dy, weight), x)
+            else:
+                dx = K.conv_dgrad_sd2(dy, PACKS.get(weight, "dgrad", dy.shape[-1], weight.shape[1]), relu_ref=x)
         if ctx.needs_input_grad[1]:
-            dw = ConvSd2WgradF.apply(dy, x, weight)
+            dw = _wgrad(dy, x, weight, sd2=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
             db = SumRowsF.apply(dy)[:weight.shape[0]]
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 class ConvSd2DgradF(Function):
@@ -246,9 +335,9 @@ class ConvSd2DgradF(Function):
         ddx = ddx.contiguous()
         g_dy = g_w = None
         if ctx.needs_input_grad[0]:
-            g_dy = ConvSd2F.apply(ddx, weight, None)
+            g_dy = ConvSd2F.apply(ddx, weight, None, False)
         if ctx.needs_input_grad[1]:
-            g_w = ConvSd2WgradF.apply(dy, ddx, weight)
+            g_w = _wgrad(dy, ddx, weight, sd2=True)
         return g_dy, g_w
 
 
@@ -263,8 +352,8 @@ class ConvSd2WgradF(Function):
         raise NotImplementedError("third-order graph through the stride-(2,1,1) weight gradient")
 
 
-def conv_sd2(x, weight, bias=None):
-    return ConvSd2F.apply(x, weight, bias)
+def conv_sd2(x, weight, bias=None, x_relu=False):
+    return ConvSd2F.apply(x, weight, bias, x_relu and FUSE_RELU_BWD)
 
 
 class SumRowsF(Function):
@@ -282,8 +371,9 @@ class SumRowsF(Function):
         return K.broadcast_spatial(g.view(1, -1).expand(N, -1).contiguous(), ctx.shape)
 
 
-def conv(x, weight, bias=None, residual=None, relu=False):
-    return ConvF.apply(x, weight, bias, residual, relu)
+def conv(x, weight, bias=None, residual=None, relu=False, x_relu=False, relu_later=False):
+    """x_relu / relu_later: see ConvF (both must be set consistently by the block that wires producer and consumer)."""
+    return ConvF.apply(x, weight, bias, residual, relu, x_relu and FUSE_RELU_BWD, relu_later and FUSE_RELU_BWD)
 
 
 # ------------------------------------------------------------------------------------- general conv (TGAN / TCWYT)
@@ -452,15 +542,19 @@ def vec_to_cl(v, Cp=None):
 # ------------------------------------------------------------------------------------- ReLU
 class ReluF(Function):
     @staticmethod
-    def forward(ctx, x):
+    def forward(ctx, x, later=False):
         y = K.relu_fwd(x)
-        ctx.save_for_backward(y)
+        ctx.later = later
+        if not later:
+            ctx.save_for_backward(y)
         return y
 
     @staticmethod
     def backward(ctx, dy):
+        if ctx.later:                   # every consumer of y masks its own data gradient (ConvF x_relu)
+            return dy, None
         (y,) = ctx.saved_tensors
-        return ReluBwdF.apply(dy.contiguous(), y)
+        return ReluBwdF.apply(dy.contiguous(), y), None
 
 
 class ReluBwdF(Function):
@@ -477,8 +571,9 @@ class ReluBwdF(Function):
         return ReluBwdF.apply(ddx.contiguous(), ref), None
 
 
-def relu(x):
-    return ReluF.apply(x)
+def relu(x, later=False):
+    """later=True: the consumers apply the backward mask (ops.conv(..., x_relu=True))."""
+    return ReluF.apply(x, later and FUSE_RELU_BWD)
 
 
 # ------------------------------------------------------------------------------------- avg-pool

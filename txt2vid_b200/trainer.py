@@ -280,7 +280,12 @@ class GraphedTrainStep(object):
                 self._capture(x, cond)
             finally:
                 hostrng.set_current(hostrng.EagerDraws())
-        self.static_x.copy_(x, non_blocking=True)
+        if x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and self.static_x.is_contiguous():
+            # an SM copy kernel, not cudaMemcpyAsync: a copy-engine D2D copy would queue behind the prefetcher's
+            # H2D chunks of the NEXT batch (data.data_prefetcher) and delay this step by the whole transfer
+            K.multi_copy([x], [self.static_x])
+        else:
+            self.static_x.copy_(x, non_blocking=True)
         if cond is not None:
             self.static_cond.copy_(cond)
         slot = self.replays % self.ring
