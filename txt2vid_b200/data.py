@@ -79,17 +79,28 @@ def collate_fn(data):
 
 class data_prefetcher(object):
     """`x, y = prefetcher.next()` with y = [tokens, lengths] (or []); None, None at the end.  The next
-    batch is staged through pinned memory and copied on a side stream while the current one trains."""
+    batch is staged through pinned memory and copied on a side stream while the current one trains.
+
+    Four persistent device staging slots per batch field (a fresh 0.8 GB allocation per step would make the caching
+    allocator fall back to cudaMalloc, a device-wide sync).  Slot reuse is guarded on the HOST: before batch i+1 is
+    copied into the slot batch i-3 lived in, the host waits for an event recorded when batch i-2 was handed out (it
+    fires once everything enqueued for batch i-3 has run).  [measured on B200, scripts/h2d_probe.py; step 86.5 ms
+    with resident inputs] a device-side `copy_stream.wait_stream(compute_stream)` in front of the copies serialises
+    them with the graph replay that follows (100-115 ms); a host-side wait on the PREVIOUS step's event stalls the
+    host, which must stay more than one step ahead of the device for back-to-back graph launches (100 ms); with the
+    guard two steps back the event has always fired and the copies overlap (91 ms)."""
     CHUNK_BYTES = 48 << 20
+    SLOTS = 4
+    GUARD = "host"
 
     def __init__(self, loader, device=None):
         self.loader = iter(loader)
         self.device = torch.device(device if device is not None else
                                    ('cuda' if torch.cuda.is_available() else 'cpu'))
         self.stream = torch.cuda.Stream() if self.device.type == 'cuda' else None
-        # two persistent device staging slots per batch field: a fresh 0.8 GB allocation per step on the side stream
-        # makes the caching allocator fall back to cudaMalloc (a device-wide sync) and serialises the pipeline
-        self._slots, self._slot = ({}, {}), 0
+        self._slots, self._slot = tuple({} for _ in range(self.SLOTS)), 0
+        self._handed = [None] * self.SLOTS      # event recorded when the slot's batch was handed to the consumer
+        self._prev_event = None
         self._preload()
 
     def _to_dev(self, t, key):
@@ -120,9 +131,13 @@ class data_prefetcher(object):
             self.next_x = self.next_y = None
             return
         if self.stream is not None:
-            self._slot ^= 1
-            # the slot being overwritten was consumed two batches ago on the compute stream
-            self.stream.wait_stream(torch.cuda.current_stream())
+            self._slot = (self._slot + 1) % self.SLOTS
+            free = self._handed[self._slot]
+            if free is not None:                 # host-side guard (see class docstring); normally already fired
+                if self.GUARD == "host":
+                    free.synchronize()
+                elif self.GUARD == "device":
+                    self.stream.wait_event(free)
             with torch.cuda.stream(self.stream):
                 self.next_x = self._to_dev(batch[0], 0)
                 self.next_y = [self._to_dev(a, 1 + i) for i, a in enumerate(batch[1:])]
@@ -134,6 +149,13 @@ class data_prefetcher(object):
             torch.cuda.current_stream().wait_stream(self.stream)
         x, y = self.next_x, self.next_y
         if x is not None:
+            if self.stream is not None:
+                # fires when everything enqueued so far (the step of the PREVIOUS batch) has run; it guards the slot
+                # of the previous batch: by then its consumer has finished with it
+                ev = torch.cuda.Event()
+                ev.record()
+                prev = (self._slot - 1) % self.SLOTS
+                self._handed[prev] = ev
             self._preload()
         return x, y
 
