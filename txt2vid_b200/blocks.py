@@ -83,13 +83,13 @@ class Attention(nn.Module):
         self.o = which_conv(ch // 2, ch, kernel_size=1, padding=0, bias=False)
         self.gamma = P(torch.tensor(0.), requires_grad=True)
         self.pool = (1, 2, 2)
-        # The 2-D block lives in the generator (never differentiated twice) and can run on the fused attention-core
-        # kernel (t2v_attention_fwd/_bwd, parity-tested).  Measured on B200 at batch 1024 the CUDA-core kernel is
-        # still slower than the cuBLAS/ATen composite (step 110.1 vs 106.3 ms: its 35 GMAC per step want the tensor
-        # cores), so it is opt-in (T2V_FUSED_ATTENTION=1) until the mma version lands.  The discriminator's 3-D
-        # block is on the gradient-penalty path (double backward) and keeps the composite formulation.
+        # The 2-D block lives in the generator (never differentiated twice) and runs on the fused attention-core
+        # kernels (t2v_attention_fwd/_bwd, parity-tested): the (P x P/4) attention matrix -- 1 GB fp32 per step at batch
+        # 1024 -- never exists.  Measured on B200 (scripts/attn_probe.py, 1024 maps of 32x32): fused bwd 1.49 ms against
+        # 3.84 ms for the ATen composite's forward + backward.  T2V_FUSED_ATTENTION=0 selects the composite.  The
+        # discriminator's 3-D block is on the gradient-penalty path (double backward) and keeps the composite.
         import os
-        self.fused_core = which_conv is nn.Conv2d and os.environ.get("T2V_FUSED_ATTENTION", "0") == "1"
+        self.fused_core = which_conv is nn.Conv2d and os.environ.get("T2V_FUSED_ATTENTION", "1") == "1"
 
     def forward_cl(self, x):
         return ops.nonlocal_block(x, self.theta.weight, self.phi.weight, self.g.weight, self.o.weight, self.gamma,

@@ -12,6 +12,8 @@
 //           2x2 pooling window (the other three voxels get zeros).
 // First-order only: the discriminator's block sits on the gradient-penalty path (double backward) and keeps the
 // composite formulation of ops.nonlocal_block.
+#include <cstdlib>
+
 #include "t2v_common.cuh"
 
 namespace t2v {
@@ -193,6 +195,242 @@ __global__ void __launch_bounds__(256) attn_bwd_kernel(const AttnParams p) {
   }
 }
 
+
+// ------------------------------------------------------------------------------------------------------------
+// Fast path for the generator's block (C = 32: 4 query/key channels, 16 value channels, rows padded to 16 bf16):
+// compile-time channel counts, keys / values in shared memory as float4 (every inner-loop load is one broadcast
+// LDS.128), two queries per thread so that each key row feeds two dot products.  Same math as the generic kernels.
+struct Key4 { float4 v; };
+
+__device__ __forceinline__ float4 ld4_bf16(const __nv_bfloat16* p) {
+  const uint2 u = *reinterpret_cast<const uint2*>(p);
+  const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y);
+  return make_float4(a.x, a.y, b.x, b.y);
+}
+__device__ __forceinline__ void ld16_bf16(const __nv_bfloat16* p, float4* out) {
+  const uint4 u0 = reinterpret_cast<const uint4*>(p)[0], u1 = reinterpret_cast<const uint4*>(p)[1];
+  float2 a = unpack_bf16x2(u0.x), b = unpack_bf16x2(u0.y), c = unpack_bf16x2(u0.z), d = unpack_bf16x2(u0.w);
+  out[0] = make_float4(a.x, a.y, b.x, b.y); out[1] = make_float4(c.x, c.y, d.x, d.y);
+  a = unpack_bf16x2(u1.x); b = unpack_bf16x2(u1.y); c = unpack_bf16x2(u1.z); d = unpack_bf16x2(u1.w);
+  out[2] = make_float4(a.x, a.y, b.x, b.y); out[3] = make_float4(c.x, c.y, d.x, d.y);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+  return fmaf(a.x, b.x, fmaf(a.y, b.y, fmaf(a.z, b.z, a.w * b.w)));
+}
+__device__ __forceinline__ float dot16(const float4* a, const float4* b) {
+  return dot4(a[0], b[0]) + dot4(a[1], b[1]) + dot4(a[2], b[2]) + dot4(a[3], b[3]);
+}
+__device__ __forceinline__ void fma4(float4& acc, float s, const float4& v) {
+  acc.x = fmaf(s, v.x, acc.x); acc.y = fmaf(s, v.y, acc.y); acc.z = fmaf(s, v.z, acc.z); acc.w = fmaf(s, v.w, acc.w);
+}
+__device__ __forceinline__ void st16_bf16(__nv_bfloat16* p, const float4* v, float scale) {
+  uint4 u0, u1;
+  u0.x = pack_bf16x2(v[0].x * scale, v[0].y * scale); u0.y = pack_bf16x2(v[0].z * scale, v[0].w * scale);
+  u0.z = pack_bf16x2(v[1].x * scale, v[1].y * scale); u0.w = pack_bf16x2(v[1].z * scale, v[1].w * scale);
+  u1.x = pack_bf16x2(v[2].x * scale, v[2].y * scale); u1.y = pack_bf16x2(v[2].z * scale, v[2].w * scale);
+  u1.z = pack_bf16x2(v[3].x * scale, v[3].y * scale); u1.w = pack_bf16x2(v[3].z * scale, v[3].w * scale);
+  reinterpret_cast<uint4*>(p)[0] = u0; reinterpret_cast<uint4*>(p)[1] = u1;
+}
+
+// pooled keys / values of one map -> shared memory (+ arg-max of every channel for the backward pass)
+__device__ __forceinline__ void build_keys_fast(const AttnParams& p, long long map0, float4* s_phi, float4* s_g,
+                                                unsigned char* s_aphi, unsigned char* s_ag) {
+  for (int k = threadIdx.x; k < p.Kp; k += blockDim.x) {
+    int pos4[4];
+    pooled_window(p, k, pos4);
+    float4 bp = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+    float4 bg[4];
+    unsigned char ap[4] = {0, 0, 0, 0}, ag[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) bg[i] = bp;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) ag[i] = 0;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 v = ld4_bf16(p.phi + (map0 + pos4[j]) * 16);
+      if (v.x > bp.x) { bp.x = v.x; ap[0] = j; }
+      if (v.y > bp.y) { bp.y = v.y; ap[1] = j; }
+      if (v.z > bp.z) { bp.z = v.z; ap[2] = j; }
+      if (v.w > bp.w) { bp.w = v.w; ap[3] = j; }
+      float4 gv[4];
+      ld16_bf16(p.g + (map0 + pos4[j]) * 16, gv);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        if (gv[i].x > bg[i].x) { bg[i].x = gv[i].x; ag[4 * i + 0] = j; }
+        if (gv[i].y > bg[i].y) { bg[i].y = gv[i].y; ag[4 * i + 1] = j; }
+        if (gv[i].z > bg[i].z) { bg[i].z = gv[i].z; ag[4 * i + 2] = j; }
+        if (gv[i].w > bg[i].w) { bg[i].w = gv[i].w; ag[4 * i + 3] = j; }
+      }
+    }
+    s_phi[k] = bp;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s_g[k * 4 + i] = bg[i];
+    if (s_aphi) {
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_aphi[k * 4 + i] = ap[i];
+#pragma unroll
+      for (int i = 0; i < 16; ++i) s_ag[k * 16 + i] = ag[i];
+    }
+  }
+}
+
+// grid (maps, ceil(P / 512)); 256 threads, two queries per thread
+__global__ void __launch_bounds__(256) attn_fwd_fast_kernel(const AttnParams p) {
+  extern __shared__ float4 smem_v[];
+  float4* s_phi = smem_v;              // [Kp]
+  float4* s_g = s_phi + p.Kp;          // [Kp][4]
+  const long long map0 = (long long)blockIdx.x * p.P;
+  build_keys_fast(p, map0, s_phi, s_g, nullptr, nullptr);
+  __syncthreads();
+  const int q0 = blockIdx.y * 512 + threadIdx.x, q1 = q0 + 256;
+  const bool ok0 = q0 < p.P, ok1 = q1 < p.P;
+  if (!ok0) return;
+  const float4 t0 = ld4_bf16(p.theta + (map0 + q0) * 16);
+  const float4 t1 = ok1 ? ld4_bf16(p.theta + (map0 + q1) * 16) : t0;
+  float m0 = -INFINITY, m1 = -INFINITY;
+  for (int k = 0; k < p.Kp; ++k) {
+    const float4 ph = s_phi[k];
+    m0 = fmaxf(m0, dot4(t0, ph));
+    m1 = fmaxf(m1, dot4(t1, ph));
+  }
+  float l0 = 0.f, l1 = 0.f;
+  float4 a0[4], a1[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) a0[i] = a1[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < p.Kp; ++k) {
+    const float4 ph = s_phi[k];
+    const float e0 = __expf(dot4(t0, ph) - m0), e1 = __expf(dot4(t1, ph) - m1);
+    l0 += e0; l1 += e1;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 gv = s_g[k * 4 + i];
+      fma4(a0[i], e0, gv);
+      fma4(a1[i], e1, gv);
+    }
+  }
+  st16_bf16(p.o + (map0 + q0) * 16, a0, 1.f / l0);
+  if (ok1) st16_bf16(p.o + (map0 + q1) * 16, a1, 1.f / l1);
+}
+
+// one CTA (512 threads) per map
+__global__ void __launch_bounds__(512) attn_bwd_fast_kernel(const AttnParams p) {
+  extern __shared__ float4 smem_v[];
+  float4* s_phi = smem_v;                         // [Kp]
+  float4* s_g = s_phi + p.Kp;                     // [Kp][4]
+  float4* s_th = s_g + 4 * p.Kp;                  // [P]
+  float4* s_do = s_th + p.P;                      // [P][4]
+  float4* s_part = s_do + 4 * p.P;                // [Kp][5] partial sums of the second query half
+  float* s_m = reinterpret_cast<float*>(s_part + 5 * p.Kp);   // [P]
+  float* s_il = s_m + p.P;                        // [P]
+  float* s_dq = s_il + p.P;                       // [P]
+  unsigned char* s_aphi = reinterpret_cast<unsigned char*>(s_dq + p.P);   // [Kp][4]
+  unsigned char* s_ag = s_aphi + 4 * p.Kp;                                 // [Kp][16]
+  const long long map0 = (long long)blockIdx.x * p.P;
+  build_keys_fast(p, map0, s_phi, s_g, s_aphi, s_ag);
+  for (int q = threadIdx.x; q < p.P; q += blockDim.x) {
+    s_th[q] = ld4_bf16(p.theta + (map0 + q) * 16);
+    ld16_bf16(p.dout + (map0 + q) * 16, s_do + 4 * q);
+  }
+  __syncthreads();
+  // ---- phase A (thread = query): softmax statistics, D_q = sum_k beta_k (dy . g_k), d theta
+  for (int q = threadIdx.x; q < p.P; q += blockDim.x) {
+    const float4 th = s_th[q];
+    float4 dy[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dy[i] = s_do[4 * q + i];
+    float m = -INFINITY;
+    for (int k = 0; k < p.Kp; ++k) m = fmaxf(m, dot4(th, s_phi[k]));
+    float l = 0.f, ws = 0.f;
+    for (int k = 0; k < p.Kp; ++k) {
+      const float e = __expf(dot4(th, s_phi[k]) - m);
+      l += e;
+      ws = fmaf(e, dot16(dy, s_g + 4 * k), ws);
+    }
+    const float il = 1.f / l, dq = ws * il;
+    float4 dth = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int k = 0; k < p.Kp; ++k) {
+      const float4 ph = s_phi[k];
+      const float ds = __expf(dot4(th, ph) - m) * il * (dot16(dy, s_g + 4 * k) - dq);
+      fma4(dth, ds, ph);
+    }
+    s_m[q] = m; s_il[q] = il; s_dq[q] = dq;
+    uint4 u0 = make_uint4(pack_bf16x2(dth.x, dth.y), pack_bf16x2(dth.z, dth.w), 0u, 0u);
+    reinterpret_cast<uint4*>(p.dtheta + (map0 + q) * 16)[0] = u0;
+    reinterpret_cast<uint4*>(p.dtheta + (map0 + q) * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+  __syncthreads();
+  // ---- phase B (thread = key x query half): d phi_p, d g_p, routed to the arg-max voxel of the pooling window
+  // (2 * Kp <= blockDim.x: every (key, half) item has its own thread, one sweep)
+  const int nk = p.Kp;
+  const int kk = threadIdx.x;
+  const bool active = kk < 2 * nk;
+  const int k = active ? kk % nk : 0, half = active ? kk / nk : 0;
+  float4 dph = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dgk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dgk[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (active) {
+    const float4 ph = s_phi[k];
+    float4 gk[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) gk[i] = s_g[4 * k + i];
+    const int qh = (p.P + 1) / 2;
+    const int qb = half * qh, qe = min(p.P, qb + qh);
+    for (int q = qb; q < qe; ++q) {
+      const float4 th = s_th[q];
+      float4 dy[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) dy[i] = s_do[4 * q + i];
+      const float beta = __expf(dot4(th, ph) - s_m[q]) * s_il[q];
+      const float ds = beta * (dot16(dy, gk) - s_dq[q]);
+      fma4(dph, ds, th);
+#pragma unroll
+      for (int i = 0; i < 4; ++i) fma4(dgk[i], beta, dy[i]);
+    }
+    if (half == 1) {
+      s_part[5 * k] = dph;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s_part[5 * k + 1 + i] = dgk[i];
+    }
+  }
+  __syncthreads();
+  if (active && half == 0) {
+    const float4 o = s_part[5 * k];
+    dph.x += o.x; dph.y += o.y; dph.z += o.z; dph.w += o.w;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 t = s_part[5 * k + 1 + i];
+      dgk[i].x += t.x; dgk[i].y += t.y; dgk[i].z += t.z; dgk[i].w += t.w;
+    }
+    int pos4[4];
+    pooled_window(p, k, pos4);
+    const float dp[4] = {dph.x, dph.y, dph.z, dph.w};
+    const float* dgf = reinterpret_cast<const float*>(dgk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = s_aphi[4 * k + c] == j ? dp[c] : 0.f;
+      uint4 u0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
+      reinterpret_cast<uint4*>(p.dphi + (map0 + pos4[j]) * 16)[0] = u0;
+      reinterpret_cast<uint4*>(p.dphi + (map0 + pos4[j]) * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = s_ag[16 * k + c] == j ? dgf[c] : 0.f;
+      uint4 g0 = make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]),
+                            pack_bf16x2(v[6], v[7]));
+      uint4 g1 = make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                            pack_bf16x2(v[14], v[15]));
+      reinterpret_cast<uint4*>(p.dg + (map0 + pos4[j]) * 16)[0] = g0;
+      reinterpret_cast<uint4*>(p.dg + (map0 + pos4[j]) * 16)[1] = g1;
+    }
+  }
+}
+
+static bool attn_fast_ok(const AttnParams& p) {
+  // phase B of the backward kernel needs both halves of a key in the same sweep (see the kernel)
+  return p.c8 == 4 && p.c2 == 16 && p.C8p == 16 && p.C2p == 16 && 2 * p.Kp <= 512;
+}
+
 static int attn_fill(AttnParams& p, int64_t N, int D, int H, int W, int c8, int c2, int C8p, int C2p) {
   if (c8 < 1 || c8 > kMaxC8 || c2 < 1 || c2 > kMaxC2 || C8p < c8 || C2p < c2) return T2V_ERR_ARG;
   if ((H & 1) || (W & 1) || N <= 0 || N > 0x7fffffffLL) return T2V_ERR_ARG;
@@ -216,6 +454,17 @@ int t2v_attention_fwd(const void* theta, const void* phi, const void* g, void* o
   p.phi = reinterpret_cast<const __nv_bfloat16*>(phi);
   p.g = reinterpret_cast<const __nv_bfloat16*>(g);
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
+  static const bool fast_off = getenv("T2V_ATTN_GENERIC") != nullptr;
+  if (!fast_off && attn_fast_ok(p)) {
+    const size_t sm = sizeof(float4) * (size_t)p.Kp * 5;
+    if (sm <= 200 * 1024) {
+      cudaFuncSetAttribute(attn_fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      dim3 grid((unsigned)N, (unsigned)((p.P + 511) / 512), 1);
+      attn_fwd_fast_kernel<<<grid, 256, sm, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+      count_launch();
+      return check_last("attention_fwd_fast");
+    }
+  }
   const size_t smem = sizeof(float) * (size_t)p.Kp * (c8 + c2);
   if (smem > 200 * 1024) return T2V_ERR_ARG;
   cudaFuncSetAttribute(attn_fwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
@@ -238,6 +487,17 @@ int t2v_attention_bwd(const void* theta, const void* phi, const void* g, const v
   p.dtheta = reinterpret_cast<__nv_bfloat16*>(dtheta);
   p.dphi = reinterpret_cast<__nv_bfloat16*>(dphi);
   p.dg = reinterpret_cast<__nv_bfloat16*>(dg);
+  static const bool fast_off = getenv("T2V_ATTN_GENERIC") != nullptr;
+  if (!fast_off && attn_fast_ok(p)) {
+    const size_t sm = sizeof(float4) * ((size_t)p.Kp * 10 + (size_t)p.P * 5) + sizeof(float) * 3 * (size_t)p.P +
+                      (size_t)p.Kp * 20 + 16;
+    if (sm <= 220 * 1024) {
+      cudaFuncSetAttribute(attn_bwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+      attn_bwd_fast_kernel<<<(unsigned)N, 512, sm, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+      count_launch();
+      return check_last("attention_bwd_fast");
+    }
+  }
   const size_t smem = sizeof(float) * ((size_t)p.Kp * (c8 + c2) + (size_t)p.P * (c8 + c2 + 3)) + (size_t)p.Kp * (c8 + c2);
   if (smem > 200 * 1024) return T2V_ERR_ARG;
   cudaFuncSetAttribute(attn_bwd_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
