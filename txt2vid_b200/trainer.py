@@ -216,6 +216,8 @@ class GraphedTrainStep(object):
         self.side = torch.cuda.Stream(device=device)
         # per-replay host values (RNG draws, Adam bias corrections) go through a ring of pinned staging slots: the
         # H2D copies are asynchronous, so a slot is rewritten only after the copies issued from it have executed
+        import os
+        self.single_graph = os.environ.get("T2V_SINGLE_GRAPH", "1") == "1"
         self.ring = hostrng_ring()
         self.stage_evt = [None] * self.ring
         self.replays = 0
@@ -239,9 +241,28 @@ class GraphedTrainStep(object):
             opt._step_count = max([st_["step"] for st_ in opt.state.values()] or [0])
             opt.zero_grad(set_to_none=True)
         torch.cuda.synchronize()
-        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         pool = torch.cuda.graph_pool_handle()
         self.draws.begin_iteration()
+        if self.single_graph:
+            # ONE graph for the whole iteration; the two NCCL all-reduces are captured with it (thread-local capture
+            # mode: NCCL's watchdog thread may touch the CUDA API meanwhile).  Separate graphs with eager all-reduces
+            # between them leave cross-stream waits in front of each replay: measured at two GPUs the step then
+            # flips between 90 and 130 ms.
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g, pool=pool, stream=self.side, capture_error_mode="thread_local"):
+                st = _d_phase(self.gan, self.static_x, self.static_cond, dev, self.params, self.losses, None,
+                              self.channel_first, False)
+                if self.dist is not None:
+                    self.dist.reduce_grads(self.optD)
+                self.optD.step()
+                st = _g_phase(self.gan, st, self.params, self.losses)
+                if self.dist is not None:
+                    self.dist.reduce_grads(self.optG)
+                self.optG.step()
+            self.state = st
+            self.graphs = (g,)
+            return
+        g1, g2, g3 = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
         with torch.cuda.graph(g1, pool=pool, stream=self.side):
             st = _d_phase(self.gan, self.static_x, self.static_cond, dev, self.params, self.losses, None,
                           self.channel_first, False)
@@ -297,14 +318,17 @@ class GraphedTrainStep(object):
         self._stage_adam(self.optG, self.optG._step_count + 1, slot)
         self.stage_evt[slot] = torch.cuda.Event()
         self.stage_evt[slot].record()
-        g1, g2, g3 = self.graphs
-        g1.replay()
-        if self.dist is not None:
-            self.dist.reduce_grads(self.optD)
-        g2.replay()
-        if self.dist is not None:
-            self.dist.reduce_grads(self.optG)
-        g3.replay()
+        if len(self.graphs) == 1:
+            self.graphs[0].replay()
+        else:
+            g1, g2, g3 = self.graphs
+            g1.replay()
+            if self.dist is not None:
+                self.dist.reduce_grads(self.optD)
+            g2.replay()
+            if self.dist is not None:
+                self.dist.reduce_grads(self.optG)
+            g3.replay()
         for opt in (self.optD, self.optG):
             opt._step_count += 1
         ops.bump_weight_epoch()          # eager users of the modules must re-pack the updated weights
