@@ -92,6 +92,16 @@ int t2v_conv_dgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* wT, c
                        uint32_t epi_flags, void* stream);
 int t2v_conv_wgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
                        void* stream);
+/* RGB stem of the discriminator on the tensor cores without an im2col tensor in memory
+ * (models/resnet3d.py:12-13: Conv3d(3 -> 64, 3, padding 1) + ReLU): the im2col tile is gathered into shared memory.
+ *   xc  bf16 CL (N, D, H, W, cpv), cpv = 4 or 16 channels per voxel: RGB in channels 0..2, zeros elsewhere
+ *       (t2v_rgb_to_cl; 4-channel rows make the gather's 8-byte loads contiguous across a warp)
+ *   wp  bf16 [64][128]: wp[co][tap*4 + c] = w[co][c][tap] for c < 3, zero elsewhere (tap = (a_d*3 + a_h)*3 + a_w)
+ *   y   bf16 CL (N, D, H, W, 64) = [relu](conv + bias);   dw fp32 [64][27][3] (+)= sum_pos dy[pos,co] x[pos+tap,c] */
+int t2v_stem_fprop(const void* xc, int32_t cpv, const void* wp, const float* bias, void* y, int64_t N, int32_t D,
+                   int32_t H, int32_t W, int32_t relu, void* stream);
+int t2v_stem_wgrad(const void* dy, const void* xc, int32_t cpv, float* dw, int64_t N, int32_t D, int32_t H, int32_t W,
+                   int32_t accumulate, void* stream);
 /* General convolution geometry (any kernel / stride / zero padding; 1-D and 2-D use unit extents):
  * the TGAN / TCWYT layers that are not stride-1 "same" convolutions -- Conv3d/Conv2d k4 s2 p1
  * (models/tcwyt/video_discrim.py:12-27, frame_discrim.py:8-19), k(1,3,3) and k2 s2 heads
@@ -148,6 +158,10 @@ int t2v_upsample2x_fwd(const void* x, void* y, int32_t N, int32_t H, int32_t W, 
 int t2v_upsample2x_bwd(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
 /* fp32 (N,C,S) <-> bf16 (N,S,Cp) with zero channel padding (D input / G output boundary)         */
 int t2v_nchw_to_cl(const float* x, void* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
+/* RGB clip fp32 (N,3,S) -> bf16 (N,S,16) (y16) and bf16 (N,S,4) (y4), zero padded; either output may be NULL.
+ * The discriminator's input boundary: 16-channel rows feed the TMA boxes of the skip path, 4-channel rows the
+ * gather of t2v_stem_fprop / t2v_stem_wgrad.                                                          */
+int t2v_rgb_to_cl(const float* x, void* y16, void* y4, int64_t N, int64_t S, void* stream);
 int t2v_cl_to_nchw(const void* x, float* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
 /* RGB stem of the discriminator (resnet3d.py:12, Conv3d(C<=4 -> 64, 3^3)) as im2col + 1x1x1 GEMM:
  * col bf16 (N,D,H,W,Kp), col[pos][tap*C+c] = x[c][pos+tap-1] (zero padded; Kp >= 27*C, multiple of 8);

@@ -76,3 +76,19 @@ for shp in [(512, 8, 16, 16), (256, 4, 32, 32), (128, 2, 64, 64)]:
          t(lambda: K.conv_wgrad(dyf, x, k=(3, 3, 3))), t(lambda: K.conv_wgrad_sd2(dyh, x))]
     print("%-6s sd2 %s fprop %.3f -> %.3f ms (%.0f TF/s useful) | dgrad %.3f -> %.3f ms | wgrad %.3f -> %.3f ms"
           % (tag, shp, r[0], r[1], fl / 2 / r[1] / 1e9, r[2], r[3], r[4], r[5]), flush=True)
+
+# RGB stem conv: direct kernels vs im2col + 1x1 GEMM (levels 0-3 at batch 1024)
+for shp in [(1024, 16, 8, 8), (512, 8, 16, 16), (256, 4, 32, 32), (128, 2, 64, 64)]:
+    N, D, H, W = shp
+    x = torch.rand((N, 3, D, H, W), device="cuda") * 2 - 1
+    xc16, xc = K.rgb_to_cl(x)
+    w3 = torch.randn((64, 27, 3), device="cuda") / 9
+    wp = K.stem_pack_weight(w3)
+    w96 = torch.zeros((64, 1, 96), device="cuda"); w96[:, 0, :81] = w3.reshape(64, 81); w96 = w96.to(torch.bfloat16)
+    dy = torch.randn((N, D, H, W, 64), device="cuda").to(torch.bfloat16)
+    col = K.im2col3(x, 96)
+    r = [t(lambda: K.stem_fprop(xc, wp)), t(lambda: K.im2col3(x, 96)), t(lambda: K.conv_fprop(col, w96, k=(1, 1, 1), relu=True)),
+         t(lambda: K.stem_wgrad(dy, xc)), t(lambda: K.conv_wgrad(dy, col, k=(1, 1, 1))),
+         t(lambda: K.rgb_to_cl(x)), t(lambda: K.nchw_to_cl(x, 16))]
+    print("%-6s stem %s fprop direct %.3f ms | im2col %.3f + GEMM %.3f ms || wgrad direct %.3f ms | GEMM %.3f ms || rgb_to_cl %.3f vs nchw_to_cl16 %.3f ms"
+          % (tag, shp, r[0], r[1], r[2], r[3], r[4], r[5], r[6]), flush=True)

@@ -40,6 +40,37 @@ def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=
     return y if out_f32 else y.to(STORE)
 
 
+def stem_pack_weight(w3):
+    wp = torch.zeros((64, 32, 4), dtype=torch.float32)
+    wp[:, :27, :3] = w3
+    return wp.reshape(64, 128).to(STORE).contiguous()
+
+
+def _stem_w5(wp):
+    w3 = wp.float()[:, :108].reshape(64, 27, 4)[..., :3]          # (co, tap, c)
+    return w3.reshape(64, 3, 3, 3, 3).permute(0, 4, 1, 2, 3).contiguous()
+
+
+def stem_fprop(xc, wp, bias=None, relu=True):
+    y = F.conv3d(xc.float()[..., :3].permute(0, 4, 1, 2, 3), _stem_w5(wp), bias, padding=1).permute(0, 2, 3, 4, 1)
+    if relu:
+        y = torch.relu(y)
+    return y.contiguous().to(STORE)
+
+
+def stem_wgrad(dy, xc, out=None, accumulate=False):
+    xin = xc.float()[..., :3].permute(0, 4, 1, 2, 3)
+    g = torch.nn.grad.conv3d_weight(xin, (64, 3, 3, 3, 3), dy.float().permute(0, 4, 1, 2, 3), padding=1)
+    g = g.permute(0, 2, 3, 4, 1).reshape(64, 27, 3).contiguous()
+    if out is None:
+        return g
+    if accumulate:
+        out += g
+    else:
+        out.copy_(g)
+    return out
+
+
 def conv_sd2_supported(shape, Cin, Cout, k=(3, 3, 3)):
     N, D, H, W = [int(v) for v in shape[:4]]
     return Cin == 64 and Cout == 64 and tuple(k) == (3, 3, 3) and D % 2 == 0 and D >= 2 and H >= 16 and W >= 8
@@ -209,6 +240,10 @@ def nchw_to_cl(x, Cp):
     y = torch.zeros((N, D, H, W, Cp), dtype=STORE, device=x.device)
     y[..., :C] = x.permute(0, 2, 3, 4, 1).to(STORE)
     return y
+
+
+def rgb_to_cl(x, want4=True):
+    return nchw_to_cl(x, 16), (nchw_to_cl(x, 4) if want4 else None)
 
 
 def cl_to_nchw(x, C):

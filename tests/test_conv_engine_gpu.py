@@ -228,6 +228,37 @@ def test_dgrad_relu_mask_epilogue(case):
         assert torch.equal(K.conv_dgrad_sd2(dyh, wT, relu_ref=ref), K.relu_bwd(K.conv_dgrad_sd2(dyh, wT), ref))
 
 
+@pytest.mark.parametrize("shape", [(2, 4, 8, 8), (3, 2, 16, 16), (1, 2, 64, 64), (5, 3, 6, 10), (1, 1, 5, 7),
+                                   (37, 16, 8, 8)])
+def test_stem_direct(shape):
+    """t2v_stem_fprop / t2v_stem_wgrad (im2col tile in shared memory) against torch conv3d fp32 on the bf16 operands."""
+    from txt2vid_b200 import kernels as K
+    N, D, H, W = shape
+    g = torch.Generator(device="cuda").manual_seed(5)
+    x = torch.rand((N, 3, D, H, W), device="cuda", generator=g) * 2 - 1
+    xc16, xc = K.rgb_to_cl(x)
+    assert torch.equal(xc16, K.nchw_to_cl(x, 16)) and torch.equal(xc, K.nchw_to_cl(x, 4))
+    w3 = torch.randn((64, 27, 3), device="cuda", generator=g) / 9.0
+    bias = torch.randn(64, device="cuda", generator=g)
+    wp = torch.zeros((64, 32, 4), device="cuda")
+    wp[:, :27, :3] = w3
+    wp = wp.reshape(64, 128).to(torch.bfloat16).contiguous()
+    y = K.stem_fprop(xc, wp, bias, relu=True)
+    assert torch.equal(y, K.stem_fprop(xc16, wp, bias, relu=True))
+    w5 = wp.float()[:, :108].reshape(64, 27, 4)[..., :3].reshape(64, 3, 3, 3, 3).permute(0, 4, 1, 2, 3).contiguous()
+    xin = xc.float()[..., :3].permute(0, 4, 1, 2, 3).contiguous()
+    ref = torch.relu(F.conv3d(xin, w5, bias, padding=1)).permute(0, 2, 3, 4, 1)
+    e = _rel(y, ref)
+    dy = torch.randn((N, D, H, W, 64), device="cuda", generator=g).to(torch.bfloat16)
+    dw = K.stem_wgrad(dy, xc)
+    gref = torch.nn.grad.conv3d_weight(xin, (64, 3, 3, 3, 3), dy.float().permute(0, 4, 1, 2, 3), padding=1)
+    gref = gref.permute(0, 2, 3, 4, 1).reshape(64, 27, 3)
+    e_w = _rel(dw, gref)
+    dw2 = K.stem_wgrad(dy, xc, out=dw.clone(), accumulate=True)
+    _log("stem direct %s fprop %.3e wgrad %.3e" % (shape, e, e_w))
+    assert e < 1.5e-2 and e_w < 2e-3 and _rel(dw2, 2 * gref) < 2e-3
+
+
 def test_sd2_unsupported_shapes():
     from txt2vid_b200 import kernels as K
     assert not K.conv_sd2_supported((4, 16, 8, 8), 64, 64)      # level 0: 8x8 planes stay on the stride-1 kernel

@@ -290,6 +290,7 @@ class ConvLSTM(nn.Module):
 
 
 STEM_SD2 = os.environ.get("T2V_STEM_SD2", "1") == "1"
+STEM_DIRECT = os.environ.get("T2V_STEM_DIRECT", "1") == "1"
 
 
 class Resnet3D(nn.Module):
@@ -319,9 +320,15 @@ class Resnet3D(nn.Module):
     def features(self, x):
         """fp32 (B,C,T,H,W) -> fp32 (B, F) sum-pooled trunk features."""
         m = self.res_block.inner_module
-        xc = ops.to_cl(x)                                             # RGB padded to 16 channels (skip path)
-        # first conv (K = 27*3 = 81): im2col once, then a 1x1x1 GEMM on the tensor cores
-        h = ops.conv(ops.im2col3(x), ops.stem_weight_2d(m[0].weight), m[0].bias, relu=True, relu_later=True)
+        if STEM_DIRECT and x.shape[1] == 3 and m[0].weight.shape[0] == 64:
+            # RGB padded to 16 channels (skip path) and to 4 channels (stem gather) in one pass;
+            # first conv (K = 27*3 = 81): im2col tile gathered into shared memory, tensor-core GEMM, bias + ReLU
+            xc, xc4 = ops.rgb_to_cl(x)
+            h = ops.stem_conv(x, xc4, m[0].weight, m[0].bias)
+        else:
+            xc = ops.to_cl(x)                                         # RGB padded to 16 channels (skip path)
+            # im2col once in memory, then a 1x1x1 GEMM on the generic engine
+            h = ops.conv(ops.im2col3(x), ops.stem_weight_2d(m[0].weight), m[0].bias, relu=True, relu_later=True)
         c1 = self.res_block.identity_map[1]
         pk, ps = (1, 2, 2), (2, 2, 2)                                 # AvgPool3d((1,2,2), 2): stride 2 in ALL dims
         skip = ops.conv(ops.avg_pool(xc, pk, ps), c1.weight, c1.bias)

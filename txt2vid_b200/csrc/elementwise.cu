@@ -210,6 +210,22 @@ __global__ void nchw_to_cl_kernel(const float* __restrict__ x, __nv_bfloat16* __
   const long long s = ns % S, n = ns / S;
   y[i] = f2bf(c < C ? x[(n * C + c) * S + s] : 0.f);
 }
+// RGB clip fp32 (N, 3, S) -> bf16 (N, S, 16) and / or bf16 (N, S, 4) (zero padded), one thread per voxel:
+// the discriminator's input conversion (16-channel rows for the TMA-fed skip path, 4-channel rows for the gather of
+// the direct stem kernel); 12 B read, 8 + 32 B written per voxel in 8 / 16-byte stores
+__global__ void rgb_to_cl_kernel(const float* __restrict__ x, uint4* __restrict__ y16, uint2* __restrict__ y4,
+                                 long long S, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const long long n = i / S, s = i - n * S;
+  const float* px = x + n * 3 * S + s;
+  const uint2 v = make_uint2(pack_bf16x2(px[0], px[S]), pack_bf16x2(px[2 * S], 0.f));
+  if (y4 != nullptr) y4[i] = v;
+  if (y16 != nullptr) {
+    y16[2 * i] = make_uint4(v.x, v.y, 0u, 0u);
+    y16[2 * i + 1] = make_uint4(0u, 0u, 0u, 0u);
+  }
+}
 // x bf16 (N, S, Cp) -> y fp32 (N, C, S)
 __global__ void cl_to_nchw_kernel(const __nv_bfloat16* __restrict__ x, float* __restrict__ y, int C, int Cp,
                                   long long S, long long total) {
@@ -863,6 +879,14 @@ int t2v_nchw_to_cl(const float* x, void* y, int64_t N, int32_t C, int64_t S, int
   nchw_to_cl_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, BF(y), C, Cp, S, total);
   count_launch();
   return check_last("nchw_to_cl");
+}
+int t2v_rgb_to_cl(const float* x, void* y16, void* y4, int64_t N, int64_t S, void* stream) {
+  const long long total = N * S;
+  if (total == 0 || (!y16 && !y4)) return T2V_OK;
+  rgb_to_cl_kernel<<<blocks_for(total, 256), 256, 0, STREAM>>>(x, reinterpret_cast<uint4*>(y16),
+                                                               reinterpret_cast<uint2*>(y4), S, total);
+  count_launch();
+  return check_last("rgb_to_cl");
 }
 int t2v_cl_to_nchw(const void* x, float* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream) {
   const long long total = N * S * C;

@@ -134,6 +134,42 @@ def conv_wgrad_sd2(dy, x, out=None, accumulate=False):
     return out
 
 
+def stem_pack_weight(w3):
+    """fp32 (64, 27, 3) -> bf16 (64, 128) operand of t2v_stem_fprop: k = tap * 4 + c, zero padded (once per weight
+    version, ~16 KB: plain tensor ops)."""
+    require_cuda(w3)
+    wp = torch.zeros((64, 32, 4), device=w3.device, dtype=F32)
+    wp[:, :27, :3] = w3
+    return wp.reshape(64, 128).to(BF16).contiguous()
+
+
+def stem_fprop(xc, wp, bias=None, relu=True):
+    """RGB stem conv on the tensor cores: xc (N,D,H,W,16) bf16 (RGB in 0..2), wp (64,128) bf16 (k = tap*4 + c)
+    -> y (N,D,H,W,64) bf16 = [relu](conv3d(x, w, padding 1) + bias)."""
+    require_cuda(xc, wp, bias)
+    N, D, H, W, C = xc.shape
+    assert C in (4, 16) and xc.dtype == BF16 and xc.is_contiguous() and tuple(wp.shape) == (64, 128)
+    assert wp.dtype == BF16 and wp.is_contiguous() and (bias is None or (bias.dtype == F32 and bias.numel() == 64))
+    y = torch.empty((N, D, H, W, 64), device=xc.device, dtype=BF16)
+    check(lib().t2v_stem_fprop(ptr(xc), C, ptr(wp), ptr(bias), ptr(y), N, D, H, W, 1 if relu else 0, stream()),
+          "t2v_stem_fprop")
+    return y
+
+
+def stem_wgrad(dy, xc, out=None, accumulate=False):
+    """dw (64,27,3) fp32 = sum_pos dy[pos,co] x[pos+tap,c] for the RGB stem conv."""
+    require_cuda(dy, xc)
+    N, D, H, W, C = xc.shape
+    assert C in (4, 16) and tuple(dy.shape) == (N, D, H, W, 64) and dy.dtype == BF16 and xc.dtype == BF16
+    assert dy.is_contiguous() and xc.is_contiguous()
+    if out is None:
+        assert not accumulate
+        out = torch.empty((64, 27, 3), device=xc.device, dtype=F32)
+    check(lib().t2v_stem_wgrad(ptr(dy), ptr(xc), C, ptr(out), N, D, H, W, 1 if accumulate else 0, stream()),
+          "t2v_stem_wgrad")
+    return out
+
+
 def cast_bf16(src):
     require_cuda(src)
     assert src.dtype == F32 and src.is_contiguous()
@@ -342,6 +378,17 @@ def nchw_to_cl(x, Cp):
     y = torch.empty((N, D, H, W, Cp), device=x.device, dtype=BF16)
     check(lib().t2v_nchw_to_cl(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_nchw_to_cl")
     return y
+
+
+def rgb_to_cl(x, want4=True):
+    """fp32 (N,3,D,H,W) -> bf16 (N,D,H,W,16) and (optionally) bf16 (N,D,H,W,4), zero padded, in one pass."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5 and x.shape[1] == 3
+    N, C, D, H, W = x.shape
+    y16 = torch.empty((N, D, H, W, 16), device=x.device, dtype=BF16)
+    y4 = torch.empty((N, D, H, W, 4), device=x.device, dtype=BF16) if want4 else None
+    check(lib().t2v_rgb_to_cl(ptr(x), ptr(y16), ptr(y4), N, D * H * W, stream()), "t2v_rgb_to_cl")
+    return y16, y4
 
 
 def cl_to_nchw(x, C):

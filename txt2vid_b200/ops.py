@@ -663,6 +663,24 @@ class ToCLF(Function):
         return FromCLF.apply(dy.contiguous(), ctx.C), None
 
 
+class RgbToCLF(Function):
+    """fp32 (N,3,D,H,W) -> (CL16 bf16, differentiable; CL4 bf16, auxiliary input of the direct stem kernels)."""
+
+    @staticmethod
+    def forward(ctx, x):
+        y16, y4 = K.rgb_to_cl(x.contiguous(), True)
+        ctx.mark_non_differentiable(y4)
+        return y16, y4
+
+    @staticmethod
+    def backward(ctx, dy16, _):
+        return FromCLF.apply(dy16.contiguous(), 3)
+
+
+def rgb_to_cl(x):
+    return RgbToCLF.apply(x)
+
+
 class FromCLF(Function):
     """CL bf16 (N,D,H,W,Cp) -> fp32 (N,C,D,H,W)."""
 
@@ -708,6 +726,62 @@ class Col2im3F(Function):
     @staticmethod
     def backward(ctx, ddx):
         return Im2col3F.apply(ddx.contiguous(), ctx.Kp), None
+
+
+def _stem_pack(weight):
+    """(64, 3, 3,3,3) parameter -> bf16 (64, 128) operand of t2v_stem_fprop: k = tap * 4 + c, zero padded."""
+    ent = PACKS.store.get(("stem", id(weight)))
+    key = PACKS._key(weight)
+    if ent is None or ent[0] != key:
+        with torch.no_grad():
+            wp = K.stem_pack_weight(w3_view(weight).detach())                      # (64, 27, 3) fp32 -> (64, 128)
+        ent = (PACKS._key(weight), wp)
+        PACKS.store[("stem", id(weight))] = ent
+    return ent[1]
+
+
+class StemConvF(Function):
+    """h = relu(conv3d(x, w, padding 1) + b), the RGB stem (resnet3d.py:12-13), on t2v_stem_fprop / _wgrad: the
+    im2col tile lives in shared memory only.  x is given twice: fp32 (N,3,D,H,W) -- the autograd input -- and its
+    bf16 CL16 image xc, which the kernels read.  The ReLU mask of the backward pass is applied by the consumer
+    (ConvF / ConvSd2F with x_relu).  The data gradient (gradient penalty, generator step) keeps the im2col
+    formulation, which is closed under a second differentiation."""
+
+    @staticmethod
+    def forward(ctx, x, xc, weight, bias):
+        weight._t2v_conv = True
+        ctx.has_bias = bias is not None
+        ctx.save_for_backward(xc, weight)
+        return K.stem_fprop(xc, _stem_pack(weight), None if bias is None else bias.detach(), True)
+
+    @staticmethod
+    def backward(ctx, dy):
+        xc, weight = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = dw = db = None
+        if ctx.needs_input_grad[0]:
+            w2d = stem_weight_2d(weight)
+            dx = Col2im3F.apply(ConvDgradF.apply(dy, w2d, stem_k(3)), 3)
+        if ctx.needs_input_grad[2]:
+            dw = StemWgradF.apply(dy, xc, weight)
+        if ctx.has_bias and ctx.needs_input_grad[3]:
+            db = SumRowsF.apply(dy)[:weight.shape[0]]
+        return dx, None, dw, db
+
+
+class StemWgradF(Function):
+    @staticmethod
+    def forward(ctx, dy, xc, weight):
+        return grad_like_weight(K.stem_wgrad(dy, xc), weight)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, ddw):
+        raise NotImplementedError("third-order graph through the stem weight gradient")
+
+
+def stem_conv(x, xc, weight, bias):
+    return StemConvF.apply(x, xc.detach(), weight, bias)
 
 
 def stem_k(C):
