@@ -20,16 +20,17 @@ def emulated(monkeypatch):
     ops.PACKS.clear()
 
 
-def run_product_iteration(conditional, fx, device="cpu"):
+def run_product_iteration(conditional, fx, device="cpu", size=64, frames=16, frame_sizes=(8, 16, 32, 64)):
     import oracle.txt2vid_oracle as O
     from txt2vid_b200.gan import CondGan, MixedGanLoss, RSGANLoss
     from txt2vid_b200.optim import FusedAdam
     from txt2vid_b200.trainer import train_iteration
     B, V = fx["config"]["B"], fx["config"]["V"]
-    txt, gen, dis = build_product_models(conditional, V=V, seed=fx["config"]["seed"])
+    txt, gen, dis = build_product_models(conditional, V=V, seed=fx["config"]["seed"], width=size, height=size,
+                                         num_frames=frames)
     sds = {"gen": state_to_cpu(gen), "dis": state_to_cpu(dis), "txt": None if txt is None else state_to_cpu(txt)}
     rng_t, rng_n = torch.get_rng_state(), np.random.get_state()
-    x, tokens, lengths = synth_batch(B, V, seed=fx["config"]["data_seed"])
+    x, tokens, lengths = synth_batch(B, V, T=frames, S=size, seed=fx["config"]["data_seed"])
 
     # ---- oracle with the reference's draw order
     bt_real = O.draw_real(4, True)
@@ -40,7 +41,8 @@ def run_product_iteration(conditional, fx, device="cpu"):
     sd_t = None if sds["txt"] is None else O.as_leaves(sds["txt"])
     opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
     opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
-    orc = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
+    orc = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d,
+                            frame_sizes=tuple(frame_sizes), num_frames=frames)
 
     # ---- product on the same RNG stream
     torch.set_rng_state(rng_t)
@@ -90,7 +92,8 @@ def run_product_iteration(conditional, fx, device="cpu"):
         return out
     T.multiscale_data = ms
     try:
-        ld, lg, fake, xs, cond = train_iteration(gan, xb, y, torch.device(device), optD, optG, train_params(), losses,
+        ld, lg, fake, xs, cond = train_iteration(gan, xb, y, torch.device(device), optD, optG,
+                                                 train_params(frame_sizes=frame_sizes), losses,
                                                  channel_first=True, end2end=False, z=z_prod.to(device))
     finally:
         T.multiscale_data = real_ms

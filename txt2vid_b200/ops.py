@@ -740,6 +740,23 @@ def _stem_pack(weight):
     return ent[1]
 
 
+_SKIP_LEAF_INPUT_GRADS = [False]
+
+
+class skip_leaf_input_grads(object):
+    """Inside this context a first-order backward pass does not compute d(loss)/d(input clip) when the clip is a LEAF
+    (the gradient penalty's interpolated x_hat, gan/losses.py:140-145): loss.backward() would only deposit it in
+    x_hat.grad, which nobody reads -- the discriminator step updates D's parameters (cond_gan.py:157-164).  The
+    generator step, whose fake clips are non-leaf, is unaffected."""
+
+    def __enter__(self):
+        self.prev = _SKIP_LEAF_INPUT_GRADS[0]
+        _SKIP_LEAF_INPUT_GRADS[0] = True
+
+    def __exit__(self, *a):
+        _SKIP_LEAF_INPUT_GRADS[0] = self.prev
+
+
 class StemConvF(Function):
     """h = relu(conv3d(x, w, padding 1) + b), the RGB stem (resnet3d.py:12-13), on t2v_stem_fprop / _wgrad: the
     im2col tile lives in shared memory only.  x is given twice: fp32 (N,3,D,H,W) -- the autograd input -- and its
@@ -751,6 +768,7 @@ class StemConvF(Function):
     def forward(ctx, x, xc, weight, bias):
         weight._t2v_conv = True
         ctx.has_bias = bias is not None
+        ctx.x_leaf = x.is_leaf
         ctx.save_for_backward(xc, weight)
         return K.stem_fprop(xc, _stem_pack(weight), None if bias is None else bias.detach(), True)
 
@@ -759,7 +777,7 @@ class StemConvF(Function):
         xc, weight = ctx.saved_tensors
         dy = dy.contiguous()
         dx = dw = db = None
-        if ctx.needs_input_grad[0]:
+        if ctx.needs_input_grad[0] and not (ctx.x_leaf and _SKIP_LEAF_INPUT_GRADS[0] and not torch.is_grad_enabled()):
             w2d = stem_weight_2d(weight)
             dx = Col2im3F.apply(ConvDgradF.apply(dy, w2d, stem_k(3)), 3)
         if ctx.needs_input_grad[2]:
@@ -997,7 +1015,7 @@ def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2), fused=Fal
     import torch.nn.functional as Fnn
     N, D, H, W, C = x.shape
     c8, c2 = w_theta.shape[0], w_g.shape[0]
-    if fused and c8 <= 8 and c2 <= 16 and H % 2 == 0 and W % 2 == 0 and D * H * W <= 4096:
+    if fused and c8 <= 8 and c2 <= 16 and H % 2 == 0 and W % 2 == 0 and D * H * W <= 1024:   # kernels' smem bound
         # generator block (first-order autograd is enough): max-pool + QK^T + softmax + beta.g in one kernel
         o = AttentionCoreF.apply(conv(x, w_theta), conv(x, w_phi), conv(x, w_g), c8, c2)
         return gamma.to(x.dtype) * conv(o, w_o) + x

@@ -140,7 +140,9 @@ def _d_phase(gan, x, cond, device, params, losses, z, channel_first, end2end, j=
                             loss=losses.discrim_loss, gp_lambda=params.gp_lambda)
     if not params.no_mean_discrim_loss:
         loss = loss / params.discrim_steps
-    loss.backward(retain_graph=j != params.discrim_steps - 1 or end2end)
+    from . import ops
+    with ops.skip_leaf_input_grads():       # d(loss)/d(x_hat) of the penalty's interpolated clips is never read
+        loss.backward(retain_graph=j != params.discrim_steps - 1 or end2end)
     st["lossD"] = loss.detach()
     return st
 
