@@ -91,8 +91,8 @@ class ClockSampler(object):
                 "samples": len(sm)}
 
 
-def train_params(gp_lambda):
-    return SimpleNamespace(data_is_imgs=False, img_model=False, frame_sizes=[8, 16, 32, 64], subsample_input=True,
+def train_params(gp_lambda, frame_sizes=(8, 16, 32, 64)):
+    return SimpleNamespace(data_is_imgs=False, img_model=False, frame_sizes=list(frame_sizes), subsample_input=True,
                            discrim_steps=1, gen_steps=1, gp_lambda=gp_lambda, no_mean_discrim_loss=False,
                            no_mean_gen_loss=True)
 
@@ -171,8 +171,13 @@ def run_b200(args):
     device = torch.device("cuda", dist.local_rank)
     b = args.batch
     V = 1000
+    # --res 128: BASELINE configs[4] (128x128x32, frame sizes 16..128); default: configs[3] (64x64x16), the metric's
+    res, frames = (128, 32) if args.res == 128 else (64, 16)
+    fsizes = (16, 32, 64, 128) if args.res == 128 else (8, 16, 32, 64)
+    gflop_nominal = 407.3 if args.res == 128 else GFLOP_PER_VIDEO_NOMINAL
+    workload = WORKLOAD if args.res == 64 else WORKLOAD.replace("64x64x16", "128x128x32")
     with contextlib.redirect_stdout(io.StringIO()):
-        txt, gen, dis = build_product_models(True, vocab_size=V, seed=100)
+        txt, gen, dis = build_product_models(True, vocab_size=V, seed=100, width=res, height=res, num_frames=frames)
     txt, gen, dis = txt.to(device), gen.to(device), dis.to(device)
     torch.manual_seed(100)                       # CPU generator: identical frame offsets on every rank
     torch.cuda.manual_seed(100 + rank)
@@ -181,11 +186,11 @@ def run_b200(args):
     losses = MixedGanLoss(g_loss=RSGANLoss(), d_loss=RSGANLoss())
     optD = FusedAdam([{"params": dis.parameters()}], lr=2e-4, betas=(0.5, 0.999))
     optG = FusedAdam([{"params": gen.parameters()}], lr=2e-4, betas=(0.5, 0.999))
-    params = train_params(0.5 * dist.gp_scale)
+    params = train_params(0.5 * dist.gp_scale, fsizes)
     ddp = dist if dist.enabled else None
 
     nb = 4
-    data = SyntheticVideoCaptions(b, nb, vocab_size=V, seed=1234 + 1000 * rank)
+    data = SyntheticVideoCaptions(b, nb, vocab_size=V, seed=1234 + 1000 * rank, frames=frames, size=res)
     host = [data.batch(i) for i in range(nb)]
     host = [(x.contiguous().pin_memory(), t.pin_memory(), l) for x, t, l in host]
     dev = [(x.to(device), t.to(device), l) for x, t, l in host]
@@ -344,8 +349,8 @@ def run_b200(args):
             "kernels": kern,
             "conv_engine_all": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None,
                                 "ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms_prof if step_ms_prof else None},
-            "step_nominal_tflops_per_gpu": value / world * GFLOP_PER_VIDEO_NOMINAL / 1e3,
-            "step_nominal_frac_of_sustained_peak": value / world * GFLOP_PER_VIDEO_NOMINAL / 1e3 / pk["bf16_tflops_sustained"]}
+            "step_nominal_tflops_per_gpu": value / world * gflop_nominal / 1e3,
+            "step_nominal_frac_of_sustained_peak": value / world * gflop_nominal / 1e3 / pk["bf16_tflops_sustained"]}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
     cpu = None
     if not args.no_cpu_baseline:
@@ -354,7 +359,7 @@ def run_b200(args):
     line = {"metric": "TGANv2-cond G+D train videos/sec", "value": value, "unit": "videos/s", "n_gpus": world,
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
-            "config": {"workload": WORKLOAD, "batch_per_gpu": b, "global_batch": world * b,
+            "config": {"workload": workload, "batch_per_gpu": b, "global_batch": world * b,
                        "parallelism": "dp%d" % world, "launch": "eager" if args.eager else "%d CUDA graph(s) per step" % len(graphed.graphs or ()),
                        "l2": "per-step working set (%.1f GB peak allocated) >> 126 MB L2; "
                        "%d distinct resident batches cycled" % (mem_gb, nb)},
@@ -372,6 +377,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=1024, help="videos per GPU per step (multiple of 8)")
+    ap.add_argument("--res", type=int, default=64, choices=[64, 128],
+                    help="64: 64x64x16 clips (the metric's configuration); 128: 128x128x32 (BASELINE configs[4])")
     ap.add_argument("--cpu_batch", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: launch every kernel from Python")

@@ -97,12 +97,15 @@ struct PoolParams {
   float inv;
 };
 // y[n,do,ho,wo,c] = mean over window (zero padding counted) (+ residual)
+// (IDX = unsigned when every element index fits 32 bits: the coordinate decode is a chain of divisions by run-time
+// values, ~5x cheaper in 32-bit arithmetic -- the 64-bit form made these kernels instruction bound)
+template <typename IDX>
 __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __nv_bfloat16* __restrict__ res,
                                    __nv_bfloat16* __restrict__ y, const PoolParams p, long long total8) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
+  const IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (IDX)total8) return;
   const int c8 = p.C / 8;
-  long long t = i;
+  IDX t = i;
   const int c = (int)(t % c8) * 8; t /= c8;
   const int wo = (int)(t % p.Wo); t /= p.Wo;
   const int ho = (int)(t % p.Ho); t /= p.Ho;
@@ -120,7 +123,7 @@ __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __
       for (int e = 0; e < p.kw; ++e) {
         const int w = wo * p.sw - p.pw + e;
         if (w < 0 || w >= p.W) continue;
-        const V8 v = ld8(x + ((((long long)n * p.D + d) * p.H + h) * p.W + w) * p.C + c);
+        const V8 v = ld8(x + ((((IDX)n * p.D + d) * p.H + h) * p.W + w) * p.C + c);
 #pragma unroll
         for (int j = 0; j < 8; ++j) acc.f[j] += v.f[j];
       }
@@ -136,12 +139,13 @@ __global__ void avgpool_fwd_kernel(const __nv_bfloat16* __restrict__ x, const __
   st8(y + i * 8, acc);
 }
 // dx[n,d,h,w,c] = dy[window containing (d,h,w)] * inv   (requires kernel <= stride: at most one window)
+template <typename IDX>
 __global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bfloat16* __restrict__ dx,
                                    const PoolParams p, long long total8) {
-  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (i >= total8) return;
+  const IDX i = (IDX)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= (IDX)total8) return;
   const int c8 = p.C / 8;
-  long long t = i;
+  IDX t = i;
   const int c = (int)(t % c8) * 8; t /= c8;
   const int w = (int)(t % p.W); t /= p.W;
   const int h = (int)(t % p.H); t /= p.H;
@@ -154,7 +158,7 @@ __global__ void avgpool_bwd_kernel(const __nv_bfloat16* __restrict__ dy, __nv_bf
   const int qh = (h + p.ph) / p.sh, rh = (h + p.ph) % p.sh;
   const int qw = (w + p.pw) / p.sw, rw = (w + p.pw) % p.sw;
   if (rd < p.kd && rh < p.kh && rw < p.kw && qd < p.Do && qh < p.Ho && qw < p.Wo) {
-    g = ld8(dy + ((((long long)n * p.Do + qd) * p.Ho + qh) * p.Wo + qw) * p.C + c);
+    g = ld8(dy + ((((IDX)n * p.Do + qd) * p.Ho + qh) * p.Wo + qw) * p.C + c);
 #pragma unroll
     for (int j = 0; j < 8; ++j) g.f[j] *= p.inv;
   }
@@ -842,7 +846,11 @@ int t2v_avgpool_fwd(const void* x, const void* residual, void* y, const int32_t*
   if (rc) return rc;
   const long long total8 = (long long)p.N * p.Do * p.Ho * p.Wo * p.C / 8;
   if (total8 == 0) return T2V_OK;
-  avgpool_fwd_kernel<<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(x), CBF(residual), BF(y), p, total8);
+  const long long in_elems = (long long)p.N * p.D * p.H * p.W * p.C;
+  if (in_elems < 0x7fffffffLL && total8 * 8 < 0x7fffffffLL)
+    avgpool_fwd_kernel<unsigned><<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(x), CBF(residual), BF(y), p, total8);
+  else
+    avgpool_fwd_kernel<long long><<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(x), CBF(residual), BF(y), p, total8);
   count_launch();
   return check_last("avgpool_fwd");
 }
@@ -853,7 +861,10 @@ int t2v_avgpool_bwd(const void* dy, void* dx, const int32_t* in_shape, const int
   if (rc) return rc;
   const long long total8 = (long long)p.N * p.D * p.H * p.W * p.C / 8;
   if (total8 == 0) return T2V_OK;
-  avgpool_bwd_kernel<<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(dy), BF(dx), p, total8);
+  if (total8 * 8 < 0x7fffffffLL)
+    avgpool_bwd_kernel<unsigned><<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(dy), BF(dx), p, total8);
+  else
+    avgpool_bwd_kernel<long long><<<blocks_for(total8, 256), 256, 0, STREAM>>>(CBF(dy), BF(dx), p, total8);
   count_launch();
   return check_last("avgpool_bwd");
 }

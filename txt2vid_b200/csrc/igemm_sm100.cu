@@ -530,7 +530,8 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   int splits = (2 * slots) / base_ctas;
   // every split adds a full Cout x taps x Cin round of fp32 atomics: only go beyond two waves of 148 when each
   // CTA still sums >= 32 position boxes (position-heavy layers), else the atomics of weight-heavy layers dominate
-  if (splits < 1 || p.tiles_total / (splits < 1 ? 1 : splits) < 32) splits = (2 * 148) / base_ctas;
+  static const int min_boxes = env_int("T2V_WGRAD_MIN_BOXES", 32);
+  if (splits < 1 || p.tiles_total / (splits < 1 ? 1 : splits) < min_boxes) splits = (2 * 148) / base_ctas;
   const int max_splits = (p.tiles_total + 3) / 4;  // keep >= 4 k-blocks per CTA
   if (splits > max_splits) splits = max_splits;
   if (splits < 1) splits = 1;
