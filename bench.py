@@ -376,7 +376,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--batch", type=int, default=1024, help="videos per GPU per step (multiple of 8)")
+    ap.add_argument("--batch", type=int, default=2048, help="videos per GPU per step (multiple of 8)")
     ap.add_argument("--res", type=int, default=64, choices=[64, 128],
                     help="64: 64x64x16 clips (the metric's configuration); 128: 128x128x32 (BASELINE configs[4])")
     ap.add_argument("--cpu_batch", type=int, default=8)
