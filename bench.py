@@ -308,8 +308,9 @@ def run_b200(args):
     lib.t2v_profile_enable(1)
     timed(step_eager, prof_steps)
     lib.t2v_profile_enable(0)
-    buf = (ctypes.c_double * 12)()
-    lib.t2v_profile_read4(buf)
+    NK = 6
+    buf = (ctypes.c_double * (3 * NK))()
+    lib.t2v_profile_read6(buf)
     prof = list(buf)
     t_prof = t_res / args.steps * prof_steps                       # share is quoted against the timed step
     mem_gb = torch.cuda.max_memory_allocated() / 1e9
@@ -326,17 +327,19 @@ def run_b200(args):
     names = ["igemm_fprop_kernel (generic tcgen05 implicit GEMM: conv fprop + dgrad, Linear, ConvLSTM gates)",
              "igemm_wgrad_kernel (generic tcgen05 weight gradient)",
              "halo_fprop_kernel (halo-resident tcgen05 fprop + dgrad of the 64-channel 3x3x3 stem convs)",
-             "halo_wgrad_kernel (halo-resident tcgen05 weight gradient, two taps stacked per MMA)"]
+             "halo_wgrad_kernel (halo-resident tcgen05 weight gradient, two taps stacked per MMA)",
+             "stem_fprop_kernel (RGB stem conv, im2col tile gathered into shared memory)",
+             "stem_wgrad_kernel (RGB stem weight gradient, same tile as MN-major operand)"]
     kern = {}
     for i, nm in enumerate(names):
         ms, fl, n = prof[3 * i:3 * i + 3]
         kern[nm.split(" ")[0]] = {"achieved": fl / (ms * 1e-3) / 1e12 if ms > 0 else None,
                                   "launches_per_step": n / prof_steps, "ms_per_step_in_kernel": ms / prof_steps,
                                   "share_of_step": ms / prof_steps / step_ms_prof if step_ms_prof > 0 else None}
-    top = max(range(4), key=lambda i: prof[3 * i])
+    top = max(range(NK), key=lambda i: prof[3 * i])
     tk = kern[names[top].split(" ")[0]]
-    conv_ms = sum(prof[3 * i] for i in range(4)) / prof_steps
-    conv_fl = sum(prof[3 * i + 1] for i in range(4)) / prof_steps
+    conv_ms = sum(prof[3 * i] for i in range(NK)) / prof_steps
+    conv_fl = sum(prof[3 * i + 1] for i in range(NK)) / prof_steps
     roof = {"bound": "tensor", "kernel": names[top], "achieved": tk["achieved"], "peak": pk["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "traffic": None,
             "traffic_note": "per-launch DRAM bytes of these kernels on the hot shapes are in profiles/ "

@@ -65,6 +65,8 @@ int t2v_profile_read(double* host_out6);
 /* same, split by kernel: {generic fprop/dgrad, generic wgrad, halo-resident fprop/dgrad, halo-resident wgrad} x
  * {ms, useful FLOPs, launches} */
 int t2v_profile_read4(double* host_out12);
+/* same with the direct RGB-stem kernels as kinds 4 (fprop) and 5 (wgrad) */
+int t2v_profile_read6(double* host_out18);
 
 /* convolution engine (tcgen05 implicit GEMM; replaces F.conv2d/conv3d/linear = cuDNN/cuBLAS)  */
 /* y[n,d,h,w,co] = sum_{taps,ci} x[n,d+a-pd,h+b-ph,w+c-pw,ci] * w[co,a,b,c,ci] + bias[co] (+ residual)

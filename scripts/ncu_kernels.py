@@ -49,6 +49,18 @@ for shp in [(512, 8, 16, 16), (128, 2, 64, 64)]:
     torch.cuda.synchronize(); torch.cuda.profiler.stop()
     print("ran sd2", shp, "| launches per rep: fprop_sd2, dgrad even planes, dgrad odd planes, wgrad_sd2")
     del x, w, dyh
+# RGB stem conv, direct kernels, level 1 at batch 1024
+x = torch.rand((512, 3, 8, 16, 16), device="cuda") * 2 - 1
+_, xc4 = K.rgb_to_cl(x)
+wp = K.stem_pack_weight(torch.randn((64, 27, 3), device="cuda") / 9)
+dy = torch.randn((512, 8, 16, 16, 64), device="cuda").to(torch.bfloat16)
+for r in range(REPS):
+    if r == REPS - 1:
+        torch.cuda.synchronize(); torch.cuda.profiler.start()
+    K.stem_fprop(xc4, wp)
+    K.stem_wgrad(dy, xc4)
+torch.cuda.synchronize(); torch.cuda.profiler.stop()
+print("ran RGB stem conv (512,8,16,16) | launches per rep: stem_fprop, [memset], stem_wgrad")
 # generator non-local block core, 1024 maps of 32x32
 def padded(c, N=1024):
     t = torch.zeros(N, 1, 32, 32, 16, device="cuda")

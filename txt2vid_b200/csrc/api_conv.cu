@@ -85,6 +85,7 @@ unsigned long long t2v_launch_count(void) { return g_launch_count; }
 int t2v_profile_enable(int on) { prof_enable(on); return T2V_OK; }
 int t2v_profile_read(double* host_out6) { prof_read(host_out6, 2); return T2V_OK; }
 int t2v_profile_read4(double* host_out12) { prof_read(host_out12, 4); return T2V_OK; }
+int t2v_profile_read6(double* host_out18) { prof_read(host_out18, 6); return T2V_OK; }
 
 int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                    const void* residual, void* y, uint32_t epi_flags, int algo, void* stream) {

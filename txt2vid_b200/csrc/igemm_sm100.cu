@@ -381,9 +381,9 @@ void prof_read(double* out, int nkinds) {
     float ms = 0.f;
     cudaEventElapsedTime(&ms, r.a, r.b);
     if (f)
-      fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.0f\n", r.kind % 2, r.g.N, r.g.D, r.g.H, r.g.W, r.g.Cin, r.g.Cout,
+      fprintf(f, "%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%d,%.6f,%.0f\n", r.kind >= 4 ? r.kind - 4 : r.kind % 2, r.g.N, r.g.D, r.g.H, r.g.W, r.g.Cin, r.g.Cout,
               r.g.kd, r.g.kh, r.g.kw, r.ctas, ms, r.flops);
-    const int kk = r.kind % nkinds;
+    const int kk = nkinds >= 6 ? r.kind : (r.kind >= 4 ? (r.kind - 4) % nkinds : r.kind % nkinds);
     out[kk * 3 + 0] += ms; out[kk * 3 + 1] += r.flops; out[kk * 3 + 2] += 1.0;
     cudaEventDestroy(r.a); cudaEventDestroy(r.b);
   }

@@ -67,12 +67,11 @@ __device__ __forceinline__ StemRow stem_row(const StemParams& p, int r, long lon
   return s;
 }
 
-// gather the taps [T0, T1) of the row's voxel into the tile (fully unrolled: tap coordinates, chunk index and
-// block are compile-time; per tap one predicate, one 8-byte load, one 8-byte store)
+// the taps [T0, T1) of the row's voxel: loads (one predicate + one 8-byte load per tap; tap coordinates are compile-time)
+// and stores into the tile (chunk index and K block are compile-time) are separate so that callers can overlap them
 template <int T0, int T1>
-__device__ __forceinline__ void stem_gather(const StemParams& p, uint8_t* tile, uint32_t blk, const StemRow& s) {
+__device__ __forceinline__ void stem_load(const StemParams& p, const StemRow& s, uint2* v) {
   const int sw = 1 << p.cshift, sh = p.W << p.cshift, sd = (p.H * p.W) << p.cshift;
-  uint2 v[T1 - T0];
 #pragma unroll
   for (int tap = T0; tap < T1; ++tap) {
     const int a_w = tap % 3, a_h = (tap / 3) % 3, a_d = tap / 9;
@@ -81,11 +80,20 @@ __device__ __forceinline__ void stem_gather(const StemParams& p, uint8_t* tile, 
     if ((s.vmask & need) == need)
       v[tap - T0] = *reinterpret_cast<const uint2*>(p.xc + s.base + (a_d - 1) * sd + (a_h - 1) * sh + (a_w - 1) * sw);
   }
+}
+template <int T0, int T1>
+__device__ __forceinline__ void stem_store(uint8_t* tile, uint32_t blk, const StemRow& s, const uint2* v) {
 #pragma unroll
   for (int tap = T0; tap < T1; ++tap) {
     const int b = tap >> 4, tt = tap & 15;
     *reinterpret_cast<uint2*>(tile + (uint32_t)b * blk + s.chunk[tt >> 1] + (uint32_t)(tt & 1) * 8u) = v[tap - T0];
   }
+}
+template <int T0, int T1>
+__device__ __forceinline__ void stem_gather(const StemParams& p, uint8_t* tile, uint32_t blk, const StemRow& s) {
+  uint2 v[T1 - T0];
+  stem_load<T0, T1>(p, s, v);
+  stem_store<T0, T1>(tile, blk, s, v);
 }
 __device__ __forceinline__ void stem_pad(uint8_t* tile, uint32_t blk, const StemRow& s) {
 #pragma unroll
@@ -96,40 +104,49 @@ __device__ __forceinline__ void stem_pad(uint8_t* tile, uint32_t blk, const Stem
 }
 
 // ------------------------------------------------------------------------------------ fprop
-static constexpr int kStemFpThreads = 160;   // warps 0-3: gather + epilogue, warp 4: TMEM / weights / MMA
+// Persistent CTAs (two per SM): warps 0-3 gather the A tile of tile i+1 while warp 8 multiplies tile i and warps 4-7
+// drain the accumulator of tile i-1 (two A buffers, two TMEM accumulators); the weights are loaded once per CTA.
+static constexpr int kStemFpThreads = 288;
 
-__global__ void __launch_bounds__(kStemFpThreads, 4)
+__global__ void __launch_bounds__(kStemFpThreads, 2)
 stem_fprop_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
                                              ~static_cast<uintptr_t>(1023));
-  uint8_t* sA = smem;                       // 2 x 16 KB
-  uint8_t* sW = smem + 2 * kBlkA;           // 2 x 8 KB
+  uint8_t* sA = smem;                       // 2 buffers x (2 K blocks x 16 KB)
+  uint8_t* sW = smem + 4 * kBlkA;           // 2 x 8 KB
   uint64_t* w_full = reinterpret_cast<uint64_t*>(sW + 2 * kBlkW);
   uint64_t* a_full = w_full + 1;
-  uint64_t* accum = a_full + 1;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(accum + 1);
+  uint64_t* a_empty = a_full + 2;
+  uint64_t* acc_full = a_empty + 2;
+  uint64_t* acc_empty = acc_full + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 4) {
+  const long long tiles = (p.P + 127) / 128;
+  const int iters = (int)((tiles - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  if (warp == 8) {
     if (lane == 0) {
       tma_prefetch_desc(&tmW);
       mbar_init(w_full, 1);
-      mbar_init(a_full, 128);
-      mbar_init(accum, 1);
+      for (int i = 0; i < 2; ++i) {
+        mbar_init(&a_full[i], 128);
+        mbar_init(&a_empty[i], 1);
+        mbar_init(&acc_full[i], 1);
+        mbar_init(&acc_empty[i], 4);
+      }
       fence_barrier_init();
     }
     __syncwarp();
-    tmem_alloc(tmem_slot, 64);
+    tmem_alloc(tmem_slot, 128);
     tmem_relinquish();
   }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
-  const long long pos0 = (long long)blockIdx.x * 128;
 
-  if (warp == 4) {
+  if (warp == 8) {
     if (lane == 0) {
       mbar_expect_tx(w_full, 2 * kBlkW);
       tma_load_2d(sW, &tmW, w_full, 0, 0);
@@ -138,66 +155,93 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
     const uint32_t d_hi = desc_hi(1024, 2);
     const uint32_t leader = elect_one();
     mbar_wait(w_full, 0);
-    mbar_wait(a_full, 0);
-    tc_fence_after();
-    const uint32_t a16 = smem_u32(sA) >> 4, w16 = smem_u32(sW) >> 4;
+    const uint32_t w16 = smem_u32(sW) >> 4;
+    for (int it = 0; it < iters; ++it) {
+      const int buf = it & 1;
+      const uint32_t par = (uint32_t)(it >> 1) & 1u;
+      mbar_wait(&a_full[buf], par);
+      mbar_wait(&acc_empty[buf], par ^ 1u);
+      tc_fence_after();
+      const uint32_t a16 = smem_u32(sA + (size_t)buf * 2 * kBlkA) >> 4;
 #pragma unroll
-    for (int b = 0; b < 2; ++b) {
+      for (int b = 0; b < 2; ++b) {
 #pragma unroll
-      for (int k = 0; k < 4; ++k) {
-        if (leader)
-          umma_bf16_ss2(tmem_base, desc_lo(a16 + (uint32_t)b * (kBlkA >> 4) + 2u * k, 0), d_hi,
-                        desc_lo(w16 + (uint32_t)b * (kBlkW >> 4) + 2u * k, 0), d_hi, p.idesc, (b | k) != 0 ? 1u : 0u);
+        for (int k = 0; k < 4; ++k) {
+          if (leader)
+            umma_bf16_ss2(tmem_base + (uint32_t)(buf * 64), desc_lo(a16 + (uint32_t)b * (kBlkA >> 4) + 2u * k, 0), d_hi,
+                          desc_lo(w16 + (uint32_t)b * (kBlkW >> 4) + 2u * k, 0), d_hi, p.idesc, (b | k) != 0 ? 1u : 0u);
+        }
       }
+      if (leader) {
+        umma_commit(&a_empty[buf]);
+        umma_commit(&acc_full[buf]);
+      }
+      __syncwarp();
     }
-    if (leader) umma_commit(accum);
-    __syncwarp();
-  } else {
+  } else if (warp < 4) {
     const int r = threadIdx.x;
-    const long long pos = pos0 + r;
-    const StemRow row = stem_row(p, r, pos);
-    stem_gather<0, 14>(p, sA, kBlkA, row);
-    stem_gather<14, 27>(p, sA, kBlkA, row);
-    stem_pad(sA, kBlkA, row);
-    fence_proxy_async();
-    mbar_arrive(a_full);
-    // epilogue: TMEM lane = row
-    mbar_wait(accum, 0);
-    tc_fence_after();
-    const bool ok = pos < p.P;
+    for (int it = 0; it < iters; ++it) {
+      const int buf = it & 1;
+      const long long pos = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r;
+      const StemRow row = stem_row(p, r, pos);
+      uint2 v0[14], v1[13];
+      stem_load<0, 14>(p, row, v0);              // loads are in flight while the buffer is still being multiplied
+      stem_load<14, 27>(p, row, v1);
+      mbar_wait(&a_empty[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);
+      uint8_t* tile = sA + (size_t)buf * 2 * kBlkA;
+      stem_store<0, 14>(tile, kBlkA, row, v0);
+      stem_store<14, 27>(tile, kBlkA, row, v1);
+      stem_pad(tile, kBlkA, row);
+      fence_proxy_async();
+      mbar_arrive(&a_full[buf]);
+    }
+  } else {
+    // epilogue (warps 4-7): TMEM lane = row
+    const int q = warp & 3;
+    const int r = q * 32 + lane;
+    for (int it = 0; it < iters; ++it) {
+      const int buf = it & 1;
+      const long long pos = ((long long)blockIdx.x + (long long)it * gridDim.x) * 128 + r;
+      mbar_wait(&acc_full[buf], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const bool ok = pos < p.P;
 #pragma unroll
-    for (int c = 0; c < 64; c += 16) {
-      uint32_t v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)c, v);
-      tmem_ld_wait();
-      if (ok) {
-        float f[16];
+      for (int c = 0; c < 64; c += 16) {
+        uint32_t v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(buf * 64 + c), v);
+        tmem_ld_wait();
+        if (ok) {
+          float f[16];
 #pragma unroll
-        for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
-        if (p.bias != nullptr) {
+          for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+          if (p.bias != nullptr) {
 #pragma unroll
-          for (int j = 0; j < 16; j += 4) {
-            const float4 b = *reinterpret_cast<const float4*>(p.bias + c + j);
-            f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            for (int j = 0; j < 16; j += 4) {
+              const float4 b = *reinterpret_cast<const float4*>(p.bias + c + j);
+              f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+            }
           }
-        }
-        if (p.relu) {
+          if (p.relu) {
 #pragma unroll
-          for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
-        }
-        uint4* op = reinterpret_cast<uint4*>(p.y + pos * 64 + c);
+            for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+          }
+          uint4* op = reinterpret_cast<uint4*>(p.y + pos * 64 + c);
 #pragma unroll
-        for (int j = 0; j < 2; ++j)
-          op[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                             pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          for (int j = 0; j < 2; ++j)
+            op[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
+                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+        }
       }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&acc_empty[buf]);
     }
   }
   tc_fence_before();
   __syncthreads();
-  if (warp == 4) {
+  if (warp == 8) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, 64);
+    tmem_dealloc(tmem_base, 128);
   }
 }
 
@@ -281,22 +325,33 @@ stem_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const StemParams p) 
       }
     } else {
       // gather: two threads per voxel row (taps 0..13 | 14..26 and the K padding)
+      // (the loads of block i+1 are issued before the stores of block i: their latency overlaps the stores, the
+      // barrier hand-off and the wait for a free stage)
       const int r = threadIdx.x & 63, half = threadIdx.x >> 6;
       int st = 0; uint32_t ph = 0;
+      uint2 cur[14], nxt[14];
+      StemRow row = stem_row(p, r, b0 * 64 + r);
+      if (half == 0) stem_load<0, 14>(p, row, cur); else stem_load<14, 27>(p, row, cur);
       for (int i = 0; i < nb; ++i) {
+        StemRow row_n = row;
+        if (i + 1 < nb) {
+          row_n = stem_row(p, r, (b0 + i + 1) * 64 + r);
+          if (half == 0) stem_load<0, 14>(p, row_n, nxt); else stem_load<14, 27>(p, row_n, nxt);
+        }
         mbar_wait(&empty[st], ph ^ 1u);
         uint8_t* tile = smem + (size_t)st * kWgStage + 2 * kBlkW;
-        const long long pos = (b0 + i) * 64 + r;
-        const StemRow row = stem_row(p, r, pos);
         if (half == 0) {
-          stem_gather<0, 14>(p, tile, kBlkW, row);
+          stem_store<0, 14>(tile, kBlkW, row, cur);
         } else {
-          stem_gather<14, 27>(p, tile, kBlkW, row);
+          stem_store<14, 27>(tile, kBlkW, row, cur);
           stem_pad(tile, kBlkW, row);
         }
         fence_proxy_async();
         mbar_arrive(&full[st]);
         if (++st == kStemWgStages) { st = 0; ph ^= 1u; }
+        row = row_n;
+#pragma unroll
+        for (int j = 0; j < 14; ++j) cur[j] = nxt[j];
       }
       // epilogue: TMEM lane = cout (rows 64..127 are the zero half), column = k = tap * 4 + c
       mbar_wait(accum, 0);
@@ -346,11 +401,16 @@ int t2v_stem_fprop(const void* xc, int32_t cpv, const void* wp, const float* bia
   CUtensorMap tmW;
   int rc = make_w_map(&tmW, wp, 64, 128, 64, 64);
   if (rc) return rc;
-  const size_t smem = 2 * kBlkA + 2 * kBlkW + 1024 + 64;
+  const size_t smem = 4 * kBlkA + 2 * kBlkW + 1024 + 128;
   cudaFuncSetAttribute(stem_fprop_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-  const long long tiles = (p.P + 127) / 128;
-  if (tiles > 0x7fffffffLL) return T2V_ERR_ARG;
-  stem_fprop_kernel<<<(unsigned)tiles, kStemFpThreads, smem, reinterpret_cast<cudaStream_t>(stream)>>>(tmW, p);
+  long long tiles = (p.P + 127) / 128;
+  if (tiles > 2 * 148) tiles = 2 * 148;          // persistent: two CTAs per SM
+  cudaStream_t cs = reinterpret_cast<cudaStream_t>(stream);
+  ProfRec rec;
+  t2v_conv_geom pg = {(int32_t)N, D, H, W, 3, 64, 3, 3, 3};
+  if (g_prof_on) prof_begin(cs, &rec, 4, 2.0 * (double)p.P * 81.0 * 64.0, &pg, (int)tiles);
+  stem_fprop_kernel<<<(unsigned)tiles, kStemFpThreads, smem, cs>>>(tmW, p);
+  if (g_prof_on) prof_end(cs, &rec);
   count_launch();
   return check_last("stem_fprop");
 }
@@ -378,7 +438,11 @@ int t2v_stem_wgrad(const void* dy, const void* xc, int32_t cpv, float* dw, int64
   if (!accumulate) cudaMemsetAsync(dw, 0, 64 * 81 * sizeof(float), s);
   const size_t smem = kStemWgStages * kWgStage + 1024 + (2 * kStemWgStages + 1) * 8 + 16;
   cudaFuncSetAttribute(stem_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+  ProfRec rec;
+  t2v_conv_geom pg = {(int32_t)N, D, H, W, 3, 64, 3, 3, 3};
+  if (g_prof_on) prof_begin(s, &rec, 5, 2.0 * (double)p.P * 81.0 * 64.0, &pg, ctas);
   stem_wgrad_kernel<<<ctas, kStemWgThreads, smem, s>>>(tmDy, p);
+  if (g_prof_on) prof_end(s, &rec);
   count_launch();
   return check_last("stem_wgrad");
 }
