@@ -104,6 +104,10 @@ int t2v_stem_fprop(const void* xc, int32_t cpv, const void* wp, const float* bia
                    int32_t H, int32_t W, int32_t relu, void* stream);
 int t2v_stem_wgrad(const void* dy, const void* xc, int32_t cpv, float* dw, int64_t N, int32_t D, int32_t H, int32_t W,
                    int32_t accumulate, void* stream);
+/* Small-channel (1,3,3) weight gradients on position pairs: run t2v_conv_wgrad on x viewed as (N,1,H,W/2,2*Cin) and
+ * dy as (N,1,H,W/2,2*Cout) (128-byte rows for Cin = 32), then fold dw2 fp32 [2*Cout][9][2*Cin] into
+ * dw fp32 [Cout][9][Cin] (accumulate = 1: dw += ...).  Generator levels 2-3 (models/layers.py:174-183,251).        */
+int t2v_wgrad_fold_pairs(const float* dw2, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream);
 /* General convolution geometry (any kernel / stride / zero padding; 1-D and 2-D use unit extents):
  * the TGAN / TCWYT layers that are not stride-1 "same" convolutions -- Conv3d/Conv2d k4 s2 p1
  * (models/tcwyt/video_discrim.py:12-27, frame_discrim.py:8-19), k(1,3,3) and k2 s2 heads

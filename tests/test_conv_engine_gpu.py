@@ -268,6 +268,27 @@ def test_sd2_unsupported_shapes():
     assert not K.conv_sd2_supported((4, 4, 16, 16), 64, 128)
 
 
+@pytest.mark.parametrize("case", [(6, 1, 32, 32, 32, 32, (1, 3, 3)), (3, 1, 64, 64, 32, 16, (1, 3, 3)),
+                                  (5, 1, 16, 16, 32, 32, (1, 3, 3)), (4, 1, 32, 32, 64, 32, (1, 3, 3)),
+                                  (4, 1, 16, 16, 64, 16, (1, 3, 3)), (2, 4, 8, 8, 64, 32, (3, 3, 3)),
+                                  (3, 1, 20, 24, 32, 32, (1, 3, 3)), (300, 1, 16, 16, 32, 32, (1, 3, 3))])
+def test_wgrad_small_channels_auto(case):
+    """algo = auto on the generator's small-channel layers: Cin = 32 runs on position pairs (64-channel views on the
+    halo-resident kernel + t2v_wgrad_fold_pairs), Cin = 64 with Cout < 64 on the halo kernel with N = Cout."""
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, k = case
+    x, w = _mk(*case, seed=9)
+    dy = torch.randn((N, D, H, W, Cout), device="cuda").to(torch.bfloat16)
+    dw = K.conv_wgrad(dy, x, k=k)
+    wr = w.float().requires_grad_(True)
+    (gr,) = torch.autograd.grad(_ref_conv(x, wr, k), wr, dy.float())
+    e = _rel(dw, gr)
+    dw2 = K.conv_wgrad(dy, x, k=k, out=dw.clone(), accumulate=True)
+    _log("wgrad small-channel auto case=%s rel=%.3e" % (case, e))
+    assert e < 2e-3 and _rel(dw2, 2 * gr) < 2e-3
+    assert _rel(dw, K.conv_wgrad(dy, x, k=k, algo=2)) < 2e-3          # CUDA-core cross-check
+
+
 def test_simt_odd_channels():
     from txt2vid_b200 import kernels as K
     case = (4, 2, 4, 4, 3, 5, (3, 3, 3))

@@ -74,6 +74,28 @@ __global__ void unpack_pad_kernel(const float* __restrict__ src, float* __restri
   const long long r = i / Cin;
   dst[i] = src[r * CinP + ci];
 }
+// Weight gradient of a (1,3,3) convolution computed on position PAIRS (two adjacent w voxels viewed as one voxel
+// with twice the channels: 64-byte rows become 128-byte rows): dw2[(pw,co)][a_h*3 + s + 1][(qw,ci)] holds every
+// product dy[w = 2u + pw] * x[w + 2s + qw - pw]; the real tap a_w (shift a_w - 1 = 2s + qw - pw) collects two of them.
+__global__ void fold_pairs_kernel(const float* __restrict__ dw2, float* __restrict__ dw, int Co, int Ci, int ld2,
+                                  int accumulate, int total) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int ci = i % Ci;
+  int t = i / Ci;
+  const int a_w = t % 3; t /= 3;
+  const int a_h = t % 3;
+  const int co = t / 3;
+  // (s, pw, qw) pairs with 2s + qw - pw == a_w - 1
+  const int s0 = 0, pw0 = a_w == 0 ? 1 : 0, qw0 = a_w == 2 ? 1 : (a_w == 1 ? 0 : 0);
+  int s1, pw1, qw1;
+  if (a_w == 1) { s1 = 0; pw1 = 1; qw1 = 1; }
+  else if (a_w == 2) { s1 = 1; pw1 = 1; qw1 = 0; }
+  else { s1 = -1; pw1 = 0; qw1 = 1; }
+  const float v = dw2[((size_t)(pw0 * Co + co) * 9 + a_h * 3 + s0 + 1) * ld2 + qw0 * Ci + ci] +
+                  dw2[((size_t)(pw1 * Co + co) * 9 + a_h * 3 + s1 + 1) * ld2 + qw1 * Ci + ci];
+  dw[i] = accumulate ? dw[i] + v : v;
+}
 }  // namespace t2v
 
 using namespace t2v;
@@ -137,6 +159,15 @@ int t2v_conv_wgrad_sd2(const t2v_conv_geom* g, const void* dy, const void* x, fl
                        void* stream) {
   if (!g || !dy || !x || !dw) return T2V_ERR_ARG;
   return halo_wgrad_launch(g, dy, x, dw, accumulate, reinterpret_cast<cudaStream_t>(stream), 1);
+}
+
+int t2v_wgrad_fold_pairs(const float* dw2, float* dw, int32_t Cout, int32_t Cin, int32_t accumulate, void* stream) {
+  if (!dw2 || !dw || Cout <= 0 || Cin <= 0) return T2V_ERR_ARG;
+  const int total = Cout * 9 * Cin;
+  fold_pairs_kernel<<<(unsigned)((total + 255) / 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      dw2, dw, Cout, Cin, 2 * Cin, accumulate ? 1 : 0, total);
+  count_launch();
+  return check_last("fold_pairs");
 }
 
 int t2v_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream) {

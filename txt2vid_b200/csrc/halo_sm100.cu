@@ -100,7 +100,7 @@ halo_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_constan
       if (lane == 0) {
         int stage = 0;
         uint32_t phase = 0;
-        const int nboxes = p.Cout >> 6;
+        const int nboxes = p.Cout > 64 ? p.Cout >> 6 : 1;     // Cout < 64: one 64-channel box, upper channels zero filled
         for (int it = 0; it < ntiles; ++it) {
           mbar_wait(&empty_bar[stage], phase ^ 1u);
           int mt = tile_begin + it;
@@ -196,7 +196,9 @@ static constexpr uint32_t kSmemBudget = 227u * 1024u - 2048u;
 
 // g describes the dy grid (for sd2: D = the number of OUTPUT planes, x has 2*D planes)
 static bool halo_wgrad_plan(const t2v_conv_geom* g, HaloWgParams* p, int sd2 = 0) {
-  if (g->Cin != 64 || (g->Cout != 64 && g->Cout != 128)) return false;
+  // Cout 16 / 32 / 48: the MMA's N is the real channel count, read from the first part of the 64-channel dy box
+  if (g->Cin != 64 || (g->Cout != 64 && g->Cout != 128 && !(g->Cout >= 16 && g->Cout < 64 && g->Cout % 16 == 0)))
+    return false;
   if (g->kh != 3 || g->kw != 3 || (g->kd != 1 && g->kd != 3)) return false;
   if (g->W < 8 || g->H < 4) return false;
   if (g->kd == 3 && g->D < 2 && !sd2) return false;     // dead taps: the generic kernel skips them
@@ -217,7 +219,7 @@ static bool halo_wgrad_plan(const t2v_conv_geom* g, HaloWgParams* p, int sd2 = 0
     if (bd == 1 && p->kd3 && g->D >= 2) continue;
     if (bh > 4 && bh > g->H) continue;
     const uint32_t dy_box = (uint32_t)bd * bh * 1024u;
-    const uint32_t dyb = dy_box * (uint32_t)(g->Cout / 64);
+    const uint32_t dyb = dy_box * (uint32_t)(g->Cout > 64 ? g->Cout / 64 : 1);
     const uint32_t xb = (uint32_t)((p->kd3 ? p->xd_mul * (bd - 1) + 3 : bd) * (bh + 2) * kXW) * 128u;
     const uint32_t stage = (dyb + xb + 1023u) & ~1023u;
     const int stages = (int)(kSmemBudget / stage);
@@ -231,7 +233,7 @@ static bool halo_wgrad_plan(const t2v_conv_geom* g, HaloWgParams* p, int sd2 = 0
   p->xpitch_d = (p->bh + 2) * kXW;
   p->td = (g->D + p->bd - 1) / p->bd; p->th = (g->H + p->bh - 1) / p->bh; p->tw = (g->W + 7) / 8;
   p->tiles_total = g->N * p->td * p->th * p->tw;
-  const int max_pairs = 512 / g->Cout;
+  const int max_pairs = 512 / g->Cout < 8 ? 512 / g->Cout : 8;     // the MMA warp keeps 8 tap-pair descriptors
   const int classes = (p->ntaps + 2 * max_pairs - 1) / (2 * max_pairs);
   int per = (p->ntaps + classes - 1) / classes;
   per = (per + 1) & ~1;

@@ -6,6 +6,7 @@ only talks to the GPU through these functions.  There is no CPU path: every func
 non-CUDA tensors (tests/cpu_kernels.py is a test-only stand-in used to check the autograd formulas).
 """
 import ctypes
+import os
 
 import torch
 
@@ -63,11 +64,25 @@ def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, al
     return dx
 
 
+PAIRED_WGRAD = os.environ.get("T2V_PAIRED_WGRAD", "1") == "1"
+
+
 def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
     """dw (Cout,taps,Cin) fp32 = sum_pos dy[pos,co] x[pos+tap,ci]."""
     require_cuda(dy, x)
     N, D, H, W, Cout = dy.shape
     Cin = x.shape[-1]
+    if (PAIRED_WGRAD and algo == 0 and tuple(k) == (1, 3, 3) and D == 1 and Cin == 32 and Cout in (16, 32)
+            and W % 2 == 0 and W >= 16 and H >= 4 and dy.is_contiguous() and x.is_contiguous()):
+        # 32-channel rows are 64 bytes: TMA and the MMA tiles run half empty.  Pair adjacent w voxels (a free view):
+        # 64-channel rows on the halo-resident kernel, then fold the pair products into the 3 real w taps.
+        dw2 = conv_wgrad(dy.view(N, 1, H, W // 2, 2 * Cout), x.view(N, 1, H, W // 2, 2 * Cin), k)
+        if out is None:
+            out = torch.empty((Cout, 9, Cin), device=x.device, dtype=F32)
+            accumulate = False
+        check(lib().t2v_wgrad_fold_pairs(ptr(dw2), ptr(out), Cout, Cin, 1 if accumulate else 0, stream()),
+              "t2v_wgrad_fold_pairs")
+        return out
     assert x.shape[:4] == dy.shape[:4] and dy.is_contiguous() and x.is_contiguous()
     assert dy.dtype == BF16 and x.dtype == BF16
     taps = k[0] * k[1] * k[2]
