@@ -267,3 +267,33 @@ def test_no_cpu_fallback():
     from txt2vid_b200._lib import T2VError
     with pytest.raises(T2VError):
         K().relu_fwd(torch.zeros(8, dtype=BF))
+
+
+def test_data_prefetcher_ring_delivers_every_batch_intact():
+    """data.data_prefetcher (data/__init__.py:131-156): chunked side-stream copies into a ring of four staging slots,
+    slot reuse guarded by events two hand-outs back.  Each batch must arrive intact and in order even when the
+    consumer's work (a long kernel per batch) lags behind the host."""
+    from txt2vid_b200.data import data_prefetcher
+    old = data_prefetcher.CHUNK_BYTES
+    data_prefetcher.CHUNK_BYTES = 1 << 16                   # force many pieces per copy
+    try:
+        n = 14
+        host = [(torch.full((64, 4, 3, 16, 16), float(i)).pin_memory(), torch.full((64, 7), i, dtype=torch.long), [7] * 64)
+                for i in range(n)]
+        pf = data_prefetcher(iter(host), device="cuda")
+        big = torch.randn(4096, 4096, device="cuda")
+        sums, toks = [], []
+        x, y = pf.next()
+        while x is not None:
+            for _ in range(3):                               # consumer work that keeps the device behind the host
+                big = torch.tanh(big @ big * 1e-4)
+            sums.append(x.sum() / x.numel())                 # consumed on the compute stream, after the lag
+            toks.append(torch.stack((y[0].min(), y[0].max())))
+            assert y[1] == [7] * 64
+            x, y = pf.next()
+        torch.cuda.synchronize()
+        assert len(sums) == n
+        assert [float(s) for s in sums] == [float(i) for i in range(n)]
+        assert [t.tolist() for t in toks] == [[i, i] for i in range(n)]
+    finally:
+        data_prefetcher.CHUNK_BYTES = old
