@@ -77,3 +77,48 @@ def test_tc_wgrad_small_channels(case):
     err = float((dw - ref).abs().max() / ref.abs().max())
     print(case, err)
     assert err < 1e-4
+
+
+def test_public_train_loop_with_graphs(tmp_path, capsys):
+    """trainer.train (gan/trainer.py:111-333) end to end on synthetic batches: pinned host data through data_prefetcher,
+    CUDA-graph iterations, lagged loss logging.  Every iteration's losses must reach the rolling averages (finite,
+    moving) and the log lines must be printed."""
+    from txt2vid_b200 import trainer as T
+    B = 8
+    dev, gan, losses, optD, optG, params, _ = _setup(B)
+    seen = []
+    real_update = T.RollingAvg.update
+
+    class Data(object):
+        def __init__(self, n):
+            from txt2vid_b200.data import SyntheticVideoCaptions
+            self.src = SyntheticVideoCaptions(B, n, vocab_size=1000)
+
+        def __len__(self):
+            return len(self.src)
+
+        def __iter__(self):
+            return iter(self.src)
+
+    for k, v in dict(batch_size=B, sample_batch_size=B, out=str(tmp_path / "out"), out_samples=str(tmp_path / "samples"),
+                     loss_window_size=4, log_period=3, save_initial=False, save_initial_examples=False,
+                     save_example_period=10 ** 9, save_model_period=10 ** 9, cuda_graphs=True, debug=False).items():
+        setattr(params, k, v)
+    orig = T.LaggedLosses._deliver
+
+    def spy(self, k):
+        self.events[k].synchronize()
+        seen.append((float(self.slots[k][0]), float(self.slots[k][1])))
+        return orig(self, k)
+    T.LaggedLosses._deliver = spy
+    try:
+        T.train(gan=gan, num_epoch=1, dataset=Data(7), device=dev, optD=optD, optG=optG, params=params, vocab=None,
+                losses=losses, channel_first=True, end2end=False)
+    finally:
+        T.LaggedLosses._deliver = orig
+    out = capsys.readouterr().out
+    # 2 eager warm-up iterations push through the same path; all 7 iterations are delivered exactly once
+    assert len(seen) == 7, seen
+    assert all(np.isfinite(a) and np.isfinite(b) for a, b in seen)
+    assert len({round(a, 4) for a, _ in seen}) > 3
+    assert "Iter 3" in out and "Iter 6" in out

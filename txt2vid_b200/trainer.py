@@ -343,6 +343,43 @@ class GraphedTrainStep(object):
                 st_["step"] = opt._step_count
 
 
+class LaggedLosses(object):
+    """Loss logging without stalling the launch pipeline (graph mode): every iteration's (lossD, lossG) is written into
+    a pinned host slot by an SM copy kernel over UVA -- a cudaMemcpyAsync D2H would queue behind the prefetcher's H2D
+    pieces, and float(tensor) waits for everything enqueued so far -- and handed to the rolling averages `lag`
+    iterations later, when its event has long fired.  drain() delivers what is pending (before a log line / a
+    checkpoint name / the end of an epoch).  With lag = 0 this is the reference's float(loss) per iteration."""
+
+    def __init__(self, sink, lag=2, device=None):
+        self.sink, self.lag = sink, lag
+        self.cuda = device is not None and torch.device(device).type == 'cuda' and lag > 0
+        self.pending = []
+        if self.cuda:
+            self.slots = [torch.zeros(2).pin_memory() for _ in range(lag + 1)]
+            self.events = [torch.cuda.Event() for _ in range(lag + 1)]
+            self.i = 0
+
+    def push(self, ld, lg):
+        if not self.cuda:
+            self.sink(float(ld), float(lg))
+            return
+        k = self.i % (self.lag + 1)
+        self.i += 1
+        K.multi_copy([torch.stack((ld.detach().float().reshape(()), lg.detach().float().reshape(())))], [self.slots[k]])
+        self.events[k].record()
+        self.pending.append(k)
+        while len(self.pending) > self.lag:
+            self._deliver(self.pending.pop(0))
+
+    def _deliver(self, k):
+        self.events[k].synchronize()
+        self.sink(float(self.slots[k][0]), float(self.slots[k][1]))
+
+    def drain(self):
+        while self.pending:
+            self._deliver(self.pending.pop(0))
+
+
 def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=None, params=None, vocab=None,
           losses=None, channel_first=True, end2end=True, dist=None):
     """gan/trainer.py:111-333."""
@@ -359,11 +396,16 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
     avg_data_load, avg_iter = RollingAvg(params.log_period), RollingAvg(params.log_period)
     data_load_watch, iter_watch = Stopwatch(), Stopwatch()
 
+    def _log_losses(d, g):
+        discrim_loss.update(d)
+        gen_loss.update(g)
+
     graphed = None
     if getattr(params, 'cuda_graphs', False) and torch.device(device).type == 'cuda' and not end2end \
             and params.discrim_steps == 1 and params.gen_steps == 1:
         graphed = GraphedTrainStep(gan, optD, optG, params, losses, torch.device(device), channel_first=channel_first,
                                    end2end=False, dist=dist)
+    lagged = LaggedLosses(_log_losses, lag=2 if graphed is not None else 0, device=device)
 
     for epoch in range(num_epoch):
         if params.log_period > 0:
@@ -385,8 +427,12 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
             else:
                 ld, lg, fake, xs, cond = train_iteration(gan, x, y, device, optD, optG, params, losses,
                                                          channel_first=channel_first, end2end=end2end, dist=dist)
-            discrim_loss.update(float(ld))          # the reference's two host syncs per iteration
-            gen_loss.update(float(lg))
+            # the reference's two host syncs per iteration (trainer.py:243,264); in graph mode the values reach the
+            # rolling averages two iterations late so that the host stays ahead of the device
+            lagged.push(ld, lg)
+            saving = (iteration == 1 and params.save_initial) or iteration % params.save_example_period == 0
+            if saving or (params.log_period > 0 and iteration % params.log_period == 0):
+                lagged.drain()
 
             if (iteration == 1 and params.save_initial) or iteration % params.save_example_period == 0:
                 to_save = {'optG': optG.state_dict(), 'optD': optD.state_dict()}
@@ -422,3 +468,4 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
             iter_watch.start()
             x, y = prefetcher.next()
             i += 1
+        lagged.drain()
