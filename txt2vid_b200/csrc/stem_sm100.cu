@@ -225,11 +225,9 @@ stem_fprop_kernel(const __grid_constant__ CUtensorMap tmW, const StemParams p) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
           }
-          uint4* op = reinterpret_cast<uint4*>(p.y + pos * 64 + c);
-#pragma unroll
-          for (int j = 0; j < 2; ++j)
-            op[j] = make_uint4(pack_bf16x2(f[8 * j], f[8 * j + 1]), pack_bf16x2(f[8 * j + 2], f[8 * j + 3]),
-                               pack_bf16x2(f[8 * j + 4], f[8 * j + 5]), pack_bf16x2(f[8 * j + 6], f[8 * j + 7]));
+          st_global_v8(p.y + pos * 64 + c,
+                       make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])),
+                       make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15])));
         }
       }
       tc_fence_before();

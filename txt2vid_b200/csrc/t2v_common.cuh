@@ -184,6 +184,14 @@ T2V_DEVINL void red_add_v4(float* dst, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(dst), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
 }
 
+// One 32-byte store (SASS STG.E.256): a conv epilogue thread owns 16 bf16 output channels of its row; two 16-byte
+// stores half-fill each 32-byte sector twice (ncu: 2x the store sectors of the output tensor)
+T2V_DEVINL void st_global_v8(void* dst, const uint4& a, const uint4& b) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(dst), "r"(a.x), "r"(a.y), "r"(a.z),
+               "r"(a.w), "r"(b.x), "r"(b.y), "r"(b.z), "r"(b.w)
+               : "memory");
+}
+
 __host__ __device__ inline uint32_t make_idesc_bf16(uint32_t M, uint32_t N, uint32_t a_mn_major,
                                                     uint32_t b_mn_major) {
   uint32_t d = 0;
