@@ -229,7 +229,7 @@ def run_b200(args):
         e2e_state["pf"] = data_prefetcher(((host[i % nb][0], host[i % nb][1], host[i % nb][2]) for i in range(n)),
                                           device=device)
 
-    LAG = 2                                                       # the host logs step i-2 while step i is enqueued
+    LAG = int(os.environ.get("T2V_E2E_LAG", "2"))                  # the host logs step i-LAG while step i is enqueued
     loss_host = [torch.zeros(2).pin_memory() for _ in range(LAG + 1)]
     loss_evt = [torch.cuda.Event() for _ in range(LAG + 1)]
     variant = os.environ.get("T2V_E2E_VARIANT", "")      # diagnosis only: "nopf" = resident inputs, "noloss" = no read-back

@@ -3,6 +3,8 @@ txt2vid/data/__init__.py:260-355 Vocab / collate_fn), a pinned-memory prefetcher
 `data_prefetcher.next()` contract (:131-156), and synthetic batches of the shapes SURVEY.md 8(d) names.
 The reference's file/LMDB datasets, DALI hooks and caches are out of scope.
 """
+import os
+
 import torch
 
 
@@ -89,8 +91,8 @@ class data_prefetcher(object):
     them with the graph replay that follows (100-115 ms); a host-side wait on the PREVIOUS step's event stalls the
     host, which must stay more than one step ahead of the device for back-to-back graph launches (100 ms); with the
     guard two steps back the event has always fired and the copies overlap (91 ms)."""
-    CHUNK_BYTES = 48 << 20
-    SLOTS = 4
+    CHUNK_BYTES = int(os.environ.get("T2V_PF_CHUNK_MB", "48")) << 20
+    SLOTS = int(os.environ.get("T2V_PF_SLOTS", "4"))
     GUARD = "host"
 
     def __init__(self, loader, device=None):
