@@ -73,6 +73,11 @@ int t2v_profile_read6(double* host_out18);
  * x: bf16 CL, w: bf16 [Cout][taps][Cin], bias: fp32[Cout] or NULL, residual: bf16 CL [..,Cout] or NULL */
 int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                    const void* residual, void* y, uint32_t epi_flags, int algo, void* stream);
+/* y = conv(x, w) + conv1x1x1(x2, w2) + bias: a residual block's identity_map convolution fused into the main path's
+ * last convolution as extra K of the same implicit GEMM (DownBlock, models/layers.py:224-243): the skip tensor is never
+ * written or re-read.  x2 bf16 CL (N,D,H,W,Cin2), w2 bf16 [Cout][Cin2]; Cin and Cin2 multiples of 64.          */
+int t2v_conv_fprop_skip(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, const void* x2,
+                        const void* w2, int32_t Cin2, void* y, uint32_t epi_flags, void* stream);
 /* dx = conv_transpose(dy, w): same engine, fed with the weight pack made by t2v_pack_dgrad_weight:
  * wT bf16 [Cin][taps (flipped)][Cout]; g is the FORWARD geometry. */
 int t2v_conv_dgrad(const t2v_conv_geom* g, const void* dy, const void* wT, const void* residual,

@@ -99,6 +99,14 @@ def conv_wgrad_sd2(dy, x, out=None, accumulate=False):
     return conv_wgrad(full, x, (3, 3, 3), out=out, accumulate=accumulate)
 
 
+def conv_fprop_skip(x, w, bias, x2, w2, k=(3, 3, 3), relu=False):
+    y = conv_fprop(x, w, bias, None, k, False, True) + conv_fprop(x2, w2.reshape(w2.shape[0], 1, -1), None, None,
+                                                                  (1, 1, 1), False, True)
+    if relu:
+        y = torch.relu(y)
+    return y.to(STORE)
+
+
 def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0, relu_ref=None):
     # wT (Cin,taps,Cout) with reversed taps == the forward weight of the adjoint convolution
     if relu_ref is None:

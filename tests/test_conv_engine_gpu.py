@@ -261,6 +261,23 @@ def test_stem_direct(shape):
     assert e < 1.5e-2 and e_w < 2e-3 and _rel(dw2, 2 * gref) < 2e-3
 
 
+@pytest.mark.parametrize("case", [(4, 4, 8, 8, 64, 128, 64), (3, 2, 4, 4, 128, 256, 128), (2, 1, 4, 4, 256, 512, 256),
+                                  (5, 1, 2, 2, 512, 1024, 512), (2, 2, 6, 10, 64, 128, 64)])
+def test_fprop_fused_skip(case):
+    """y = conv3^3(h, w) + conv1^3(x, ws) + b in one implicit GEMM (t2v_conv_fprop_skip) vs the two-launch form."""
+    from txt2vid_b200 import kernels as K
+    N, D, H, W, Cin, Cout, Cin2 = case
+    h, w = _mk(N, D, H, W, Cin, Cout, (3, 3, 3), seed=13)
+    x, ws = _mk(N, D, H, W, Cin2, Cout, (1, 1, 1), seed=14)
+    bias = torch.randn(Cout, device="cuda")
+    y = K.conv_fprop_skip(h, w, bias, x, ws, k=(3, 3, 3))
+    ref = _ref_conv(h, w, (3, 3, 3), bias) + _ref_conv(x, ws, (1, 1, 1))
+    e = _rel(y, ref)
+    two = K.conv_fprop(h, w, bias=bias, residual=K.conv_fprop(x, ws, k=(1, 1, 1)), k=(3, 3, 3))
+    _log("fused skip case=%s rel=%.3e (two-launch form %.3e)" % (case, e, _rel(two, ref)))
+    assert e < 1.5e-2
+
+
 def test_sd2_unsupported_shapes():
     from txt2vid_b200 import kernels as K
     assert not K.conv_sd2_supported((4, 16, 8, 8), 64, 64)      # level 0: 8x8 planes stay on the stride-1 kernel

@@ -190,10 +190,14 @@ class DownBlock(nn.Module):
     def forward_cl(self, x):
         m = self.main.inner_module
         c1 = self.main.identity_map[0]
-        skip = ops.conv(x, c1.weight, c1.bias)
         # both ReLU backward masks ride in the data-gradient epilogues of their (single) consumers
         h = ops.conv(ops.relu(x, later=True), m[1].weight, m[1].bias, relu=True, x_relu=True, relu_later=True)
-        h = ops.conv(h, m[3].weight, m[3].bias, residual=skip, x_relu=True)
+        if SKIP_FUSE and x.shape[-1] % 64 == 0 and h.shape[-1] % 64 == 0 and tuple(c1.weight.shape[2:]) == (1, 1, 1):
+            # the 1^3 skip convolution is extra K of the second convolution's implicit GEMM
+            h = ops.conv_skip(h, x, m[3].weight, m[3].bias, c1.weight, c1.bias, h_relu=True)
+        else:
+            skip = ops.conv(x, c1.weight, c1.bias)
+            h = ops.conv(h, m[3].weight, m[3].bias, residual=skip, x_relu=True)
         k, s, p = ops.down_sample_cfg(h.shape)
         return ops.avg_pool(h, k, s, p)
 
@@ -291,6 +295,7 @@ class ConvLSTM(nn.Module):
 
 STEM_SD2 = os.environ.get("T2V_STEM_SD2", "1") == "1"
 STEM_DIRECT = os.environ.get("T2V_STEM_DIRECT", "1") == "1"
+SKIP_FUSE = os.environ.get("T2V_SKIP_FUSE", "1") == "1"
 
 
 class Resnet3D(nn.Module):

@@ -9,6 +9,8 @@ bool igemm_wgrad_supported(const t2v_conv_geom* g);
 int igemm_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                        uint32_t, cudaStream_t);
 int igemm_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+int igemm_fprop_launch_aux(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*, uint32_t,
+                           cudaStream_t, const void*, const void*, int);
 bool halo_wgrad_supported(const t2v_conv_geom* g);
 bool halo_fprop_supported(const t2v_conv_geom* g);
 int halo_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
@@ -139,6 +141,14 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_wgrad_launch(g, dy, x, dw, accumulate, s);
   if (algo != T2V_ALGO_TC_GENERIC && halo_wgrad_supported(g)) return halo_wgrad_launch(g, dy, x, dw, accumulate, s, 0);
   return igemm_wgrad_launch(g, dy, x, dw, accumulate, s);
+}
+
+int t2v_conv_fprop_skip(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, const void* x2,
+                        const void* w2, int32_t Cin2, void* y, uint32_t epi_flags, void* stream) {
+  if (!g || !x || !w || !x2 || !w2 || !y) return T2V_ERR_ARG;
+  if (!igemm_fprop_supported(g) || g->Cin % 64 || Cin2 % 64) return T2V_ERR_ARG;
+  return igemm_fprop_launch_aux(g, x, w, bias, nullptr, y, epi_flags, reinterpret_cast<cudaStream_t>(stream), x2, w2,
+                                Cin2);
 }
 
 int t2v_conv_sd2_supported(const t2v_conv_geom* g) { return (g && halo_sd2_supported(g)) ? 1 : 0; }

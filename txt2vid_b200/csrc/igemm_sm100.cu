@@ -35,6 +35,7 @@ struct IgemmParams {
   int lo_d, hi_d, lo_h, hi_h, lo_w, hi_w;  // live tap ranges (dead taps read only padding)
   int cblocks;                 // Cin / BLOCK_K
   int num_k_blocks;
+  int aux_k_blocks;            // extra k-blocks of a fused 1x1x1 convolution of a second tensor (same positions)
   int stages;
   uint32_t stage_bytes, a_bytes, b_bytes;
   uint32_t idesc, tmem_cols;
@@ -59,6 +60,7 @@ struct SwizzleOf {
 template <int BLOCK_K>
 __global__ void __launch_bounds__(kThreads, 2)
 igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                    const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
@@ -82,6 +84,10 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
     tma_prefetch_desc(&tmB);
+    if (p.aux_k_blocks > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
     for (int s = 0; s < p.stages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -119,6 +125,17 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
         tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + c0, col0);
         if (++stage == p.stages) { stage = 0; phase ^= 1u; }
       }
+      // fused skip connection: y += conv1x1x1(x2, w2), accumulated into the same TMEM tile (layers.py:224-243:
+      // DownBlock's identity_map convolution is added to the main path; here it is extra K of the same GEMM)
+      for (int kb = 0; kb < p.aux_k_blocks; ++kb) {
+        mbar_wait(&empty_bar[stage], phase ^ 1u);
+        uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+        uint8_t* sb = sa + p.a_bytes;
+        mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+        tma_load_5d(sa, &tmA2, &full_bar[stage], kb * BLOCK_K, w0, h0, d0, n0);
+        tma_load_2d(sb, &tmB2, &full_bar[stage], kb * BLOCK_K, col0);
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
     }
   } else if (warp == 1) {
     int stage = 0;
@@ -127,7 +144,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     // (descriptors then stay in uniform registers: no ELECT/R2UR waterfall in front of every UTCHMMA)
     const uint32_t d_hi = desc_hi(SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
     const uint32_t leader = elect_one();
-    for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+    const int nkb = p.num_k_blocks + p.aux_k_blocks;
+    for (int kb = 0; kb < nkb; ++kb) {
       mbar_wait(&full_bar[stage], phase);
       tc_fence_after();
       const uint32_t sa16 = smem_u32(smem + (size_t)stage * p.stage_bytes) >> 4;
@@ -141,7 +159,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       }
       if (leader) {
         umma_commit(&empty_bar[stage]);
-        if (kb == p.num_k_blocks - 1) umma_commit(accum_bar);
+        if (kb == nkb - 1) umma_commit(accum_bar);
       }
       __syncwarp();
       if (++stage == p.stages) { stage = 0; phase ^= 1u; }
@@ -443,8 +461,19 @@ static int fill_common(IgemmParams& p, const t2v_conv_geom* g) {
   return (p.hi_d - p.lo_d) * (p.hi_h - p.lo_h) * (p.hi_w - p.lo_w);
 }
 
+int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
+                           const void* residual, void* y, uint32_t flags, cudaStream_t stream, const void* x2,
+                           const void* w2, int Cin2);
+
 int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, uint32_t flags, cudaStream_t stream) {
+  return igemm_fprop_launch_aux(g, x, w, bias, residual, y, flags, stream, nullptr, nullptr, 0);
+}
+
+// x2 / w2 / Cin2: optional fused 1x1x1 convolution of a second tensor over the same positions (w2 bf16 [Cout][Cin2])
+int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
+                           const void* residual, void* y, uint32_t flags, cudaStream_t stream, const void* x2,
+                           const void* w2, int Cin2) {
   if (!igemm_fprop_supported(g)) return T2V_ERR_ARG;
   IgemmParams p{};
   const int ntaps = fill_common(p, g);
@@ -460,6 +489,10 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
     while (p.BN > 64 && p.BN % 32 == 0 && mtiles_total * ((g->Cout + p.BN - 1) / p.BN) < 120) p.BN /= 2;
   p.cblocks = g->Cin / BLOCK_K;
   p.num_k_blocks = ntaps * p.cblocks;
+  if (x2 != nullptr) {
+    if (!w2 || Cin2 <= 0 || Cin2 % BLOCK_K) return T2V_ERR_ARG;
+    p.aux_k_blocks = Cin2 / BLOCK_K;
+  }
   p.a_bytes = 128u * BLOCK_K * 2u;
   p.b_bytes = (uint32_t)p.BN * BLOCK_K * 2u;
   p.stage_bytes = (p.a_bytes + p.b_bytes + 1023u) & ~1023u;
@@ -474,7 +507,8 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
   int stages = (int)(budget / p.stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
-  if (stages > p.num_k_blocks) stages = p.num_k_blocks < 2 ? 2 : p.num_k_blocks;
+  if (stages > p.num_k_blocks + p.aux_k_blocks)
+    stages = p.num_k_blocks + p.aux_k_blocks < 2 ? 2 : p.num_k_blocks + p.aux_k_blocks;
   p.stages = stages;
   p.idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);
   p.tmem_cols = (uint32_t)(pow2_ceil(p.BN) < 32 ? 32 : pow2_ceil(p.BN));
@@ -490,16 +524,24 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
   if (rc) return rc;
   rc = make_w_map(&tmB, w, g->Cout, p.taps_total * g->Cin, BLOCK_K, p.BN);
   if (rc) return rc;
+  CUtensorMap tmA2 = tmA, tmB2 = tmB;
+  if (p.aux_k_blocks > 0) {
+    rc = make_act_map(&tmA2, x2, g->N, g->D, g->H, g->W, Cin2, BLOCK_K, p.bw, p.bh, p.bd, p.bn);
+    if (rc) return rc;
+    rc = make_w_map(&tmB2, w2, g->Cout, Cin2, BLOCK_K, p.BN);
+    if (rc) return rc;
+  }
 
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
   dim3 grid(p.tn * p.td * p.th * p.tw, (g->Cout + p.BN - 1) / p.BN, 1);
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, p);
+    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, p);
   };
   ProfRec rec;
   if (g_prof_on)
-    prof_begin(stream, &rec, 0, 2.0 * g->N * g->D * g->H * g->W * (double)g->Cin * g->Cout * ntaps, g,
+    prof_begin(stream, &rec, 0,
+               2.0 * g->N * g->D * g->H * g->W * ((double)g->Cin * ntaps + (double)(x2 ? Cin2 : 0)) * g->Cout, g,
                (int)(grid.x * grid.y));
   if (BLOCK_K == 64) launch(igemm_fprop_kernel<64>);
   else if (BLOCK_K == 32) launch(igemm_fprop_kernel<32>);

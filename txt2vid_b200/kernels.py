@@ -44,6 +44,23 @@ def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=
     return y
 
 
+def conv_fprop_skip(x, w, bias, x2, w2, k=(3, 3, 3), relu=False):
+    """y = conv(x, w) + conv1x1x1(x2, w2) + bias in one implicit GEMM (the 1x1x1 convolution is extra K).
+    x (N,D,H,W,Cin), x2 (N,D,H,W,Cin2) bf16; w (Cout,taps,Cin), w2 (Cout,1,Cin2) bf16; Cin, Cin2 multiples of 64."""
+    require_cuda(x, w, bias, x2, w2)
+    N, D, H, W, Cin = x.shape
+    Cout, Cin2 = w.shape[0], x2.shape[-1]
+    assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin and tuple(x2.shape[:4]) == (N, D, H, W)
+    assert w2.shape[0] == Cout and w2.numel() == Cout * Cin2 and Cin % 64 == 0 and Cin2 % 64 == 0
+    assert all(t.is_contiguous() and t.dtype == BF16 for t in (x, w, x2, w2))
+    assert bias is None or (bias.dtype == F32 and bias.numel() == Cout)
+    y = torch.empty((N, D, H, W, Cout), device=x.device, dtype=BF16)
+    g = _geom(N, D, H, W, Cin, Cout, k)
+    check(lib().t2v_conv_fprop_skip(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(x2), ptr(w2), Cin2, ptr(y),
+                                    _lib.EPI_RELU if relu else 0, stream()), "t2v_conv_fprop_skip")
+    return y
+
+
 def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0, relu_ref=None):
     """dy (N,D,H,W,Cout) bf16, wT (Cin,taps,Cout) bf16 (from pack_dgrad_weight) -> dx (N,D,H,W,Cin).
     relu_ref (dx-shaped bf16): dx is zeroed where relu_ref <= 0 (the ReLU in front of the convolution, fused)."""

@@ -239,6 +239,57 @@ class ConvF(Function):
         return dx, dw, db, dres, None, None, None
 
 
+class ConvSkipF(Function):
+    """y = conv(h, w) + b + conv1x1x1(x, ws) + bs: the last convolution of a DownBlock with the block's identity_map
+    convolution (models/layers.py:224-243) fused in as extra K of the same implicit GEMM -- the skip tensor is never
+    written or re-read, and the two bias gradients (the same column sum of dy) are computed once.  h_relu as in ConvF's
+    x_relu.  The backward is composed of the differentiable conv Functions, so second-order graphs work unchanged."""
+
+    @staticmethod
+    def forward(ctx, h, x, weight, bias, wskip, bskip, h_relu):
+        k = kernel_of(weight)
+        Cout = weight.shape[0]
+        wp = PACKS.get(weight, "fprop", Cout, h.shape[-1])
+        ws = PACKS.get(wskip, "fprop", Cout, x.shape[-1])
+        weight._t2v_conv = wskip._t2v_conv = True
+        b = None
+        if bias is not None or bskip is not None:
+            b = (bias.detach() if bias is not None else 0) + (bskip.detach() if bskip is not None else 0)
+        ctx.h_relu = h_relu
+        ctx.has_b = (bias is not None, bskip is not None)
+        ctx.save_for_backward(h, x, weight, wskip)
+        return K.conv_fprop_skip(h, wp, b, x, ws, k)
+
+    @staticmethod
+    def backward(ctx, dy):
+        h, x, weight, wskip = ctx.saved_tensors
+        dy = dy.contiguous()
+        dh = dx = dw = db = dws = dbs = None
+        if ctx.needs_input_grad[0]:
+            if not ctx.h_relu:
+                dh = ConvDgradF.apply(dy, weight, h.shape[-1])
+            elif torch.is_grad_enabled():
+                dh = ReluBwdF.apply(ConvDgradF.apply(dy, weight, h.shape[-1]), h)
+            else:
+                dh = K.conv_dgrad(dy, PACKS.get(weight, "dgrad", dy.shape[-1], h.shape[-1]), kernel_of(weight),
+                                  relu_ref=h)
+        if ctx.needs_input_grad[1]:
+            dx = ConvDgradF.apply(dy, wskip, x.shape[-1])
+        if ctx.needs_input_grad[2]:
+            dw = _wgrad(dy, h, weight)
+        if ctx.needs_input_grad[4]:
+            dws = _wgrad(dy, x, wskip)
+        if (ctx.has_b[0] and ctx.needs_input_grad[3]) or (ctx.has_b[1] and ctx.needs_input_grad[5]):
+            s = SumRowsF.apply(dy)[:weight.shape[0]]
+            db = s if ctx.has_b[0] and ctx.needs_input_grad[3] else None
+            dbs = s if ctx.has_b[1] and ctx.needs_input_grad[5] else None
+        return dh, dx, dw, db, dws, dbs, None
+
+
+def conv_skip(h, x, weight, bias, wskip, bskip, h_relu=False):
+    return ConvSkipF.apply(h, x, weight, bias, wskip, bskip, h_relu and FUSE_RELU_BWD)
+
+
 class ConvDgradF(Function):
     """dx = conv_transpose(dy, w)  (the data gradient of ConvF, itself differentiable)."""
 
