@@ -183,6 +183,8 @@ int t2v_col2im3(const void* dcol, float* dx, int64_t N, int32_t C, int32_t D, in
                 void* stream);
 /* out[c] = sum_rows x[row,c] (bias gradients)                                                    */
 int t2v_sum_rows(const void* x, float* out, int64_t P, int32_t C, void* stream);
+/* same, out += column sums (no memset): bias gradients accumulated straight into the parameter's gradient buffer */
+int t2v_sum_rows_acc(const void* x, float* out, int64_t P, int32_t C, void* stream);
 /* torch.sum(x,[2,3,4]) resnet3d.py:48: out fp32 (N,C) = sum_s x (N,S,C); and its adjoint          */
 int t2v_sum_spatial(const void* x, float* out, int64_t N, int64_t S, int32_t C, void* stream);
 int t2v_broadcast_spatial(const float* g, void* y, int64_t N, int64_t S, int32_t C, void* stream);

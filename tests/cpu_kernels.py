@@ -278,8 +278,12 @@ def col2im3(dcol, C):
     return dxp[:, :, 1:-1, 1:-1, 1:-1].contiguous()
 
 
-def sum_rows(x):
-    return x.float().reshape(-1, x.shape[-1]).sum(0)
+def sum_rows(x, out=None):
+    s = x.float().reshape(-1, x.shape[-1]).sum(0)
+    if out is None:
+        return s
+    out += s
+    return out
 
 
 def sum_spatial(x):

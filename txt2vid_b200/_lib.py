@@ -97,6 +97,7 @@ SIGNATURES = {
     "t2v_im2col3": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_col2im3": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_sum_rows": [_P, _P, c_i64, c_i32, _P],
+    "t2v_sum_rows_acc": [_P, _P, c_i64, c_i32, _P],
     "t2v_sum_spatial": [_P, _P, c_i64, c_i64, c_i32, _P],
     "t2v_broadcast_spatial": [_P, _P, c_i64, c_i64, c_i32, _P],
     "t2v_bn_stats": [_P, _P, c_i64, c_i32, _P],

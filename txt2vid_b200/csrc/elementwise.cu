@@ -944,8 +944,15 @@ static void row_split(long long P, int C, dim3* grid, long long* rows_per_block)
   *rows_per_block = (P + slices - 1) / slices;
   *grid = dim3(cg, (unsigned)slices, 1);
 }
+static int sum_rows_impl(const void* x, float* out, int64_t P, int32_t C, int accumulate, void* stream);
 int t2v_sum_rows(const void* x, float* out, int64_t P, int32_t C, void* stream) {
-  cudaMemsetAsync(out, 0, sizeof(float) * C, STREAM);
+  return sum_rows_impl(x, out, P, C, 0, stream);
+}
+int t2v_sum_rows_acc(const void* x, float* out, int64_t P, int32_t C, void* stream) {
+  return sum_rows_impl(x, out, P, C, 1, stream);
+}
+static int sum_rows_impl(const void* x, float* out, int64_t P, int32_t C, int accumulate, void* stream) {
+  if (!accumulate) cudaMemsetAsync(out, 0, sizeof(float) * C, STREAM);
   if (P == 0) return T2V_OK;
   if (colred_ok(C)) {
     ColRed cr{};

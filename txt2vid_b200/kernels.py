@@ -453,11 +453,15 @@ def col2im3(dcol, C):
     return dx
 
 
-def sum_rows(x):
-    """bf16 (..., C) -> fp32 (C,) sum over all leading dims."""
-    require_cuda(x)
+def sum_rows(x, out=None):
+    """bf16 (..., C) -> fp32 (C,) sum over all leading dims; with `out` (fp32 (C,)): out += the sums."""
+    require_cuda(x, out)
     assert x.dtype == BF16 and x.is_contiguous()
     C = x.shape[-1]
+    if out is not None:
+        assert out.dtype == F32 and out.numel() == C and out.is_contiguous()
+        check(lib().t2v_sum_rows_acc(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows_acc")
+        return out
     out = torch.empty((C,), device=x.device, dtype=F32)
     check(lib().t2v_sum_rows(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows")
     return out

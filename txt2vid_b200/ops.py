@@ -136,6 +136,8 @@ def mark_conv_weights(module):
     for m in module.modules():
         if id(m) not in skip and isinstance(m, (torch.nn.Conv2d, torch.nn.Conv3d, torch.nn.Linear)):
             m.weight._t2v_conv = True
+            if m.bias is not None and isinstance(m, (torch.nn.Conv2d, torch.nn.Conv3d)):
+                m.bias._t2v_bias = True
     module._t2v_marked = True
 
 
@@ -146,6 +148,13 @@ def zero_grads(module):
         mark_conv_weights(module)
     bufs = []
     for p in module.parameters():
+        if GRAD_SINKS and p.requires_grad and getattr(p, "_t2v_bias", False) and p.dim() == 1 and p.numel() % 16 == 0:
+            # conv biases: the column-sum kernel adds into the gradient buffer (t2v_sum_rows_acc)
+            if p.grad is None or not getattr(p, "_t2v_bias_sink", False):
+                p.grad = torch.empty_like(p)
+                p._t2v_bias_sink = True
+            bufs.append(p.grad)
+            continue
         if not (GRAD_SINKS and p.requires_grad and _sinkable(p)):
             p.grad = None
             continue
@@ -173,6 +182,15 @@ def _wgrad(dy, x, weight, sd2=False):
             K.conv_wgrad(dy, x, kernel_of(weight), out=sink, accumulate=True)
         return None
     return (ConvSd2WgradF if sd2 else ConvWgradF).apply(dy, x, weight)
+
+
+def _bias_grad(dy, bias, Cout):
+    """Bias gradient of a convolution (column sums of dy): into the bias' gradient buffer on first-order passes."""
+    if (bias is not None and getattr(bias, "_t2v_bias_sink", False) and bias.grad is not None
+            and not torch.is_grad_enabled() and dy.shape[-1] == Cout == bias.numel()):
+        K.sum_rows(dy, out=bias.grad)
+        return None
+    return SumRowsF.apply(dy)[:Cout]
 
 
 def _pad_bias(bias, CoutP):
@@ -211,6 +229,7 @@ class ConvF(Function):
         ctx.relu = relu and not relu_later
         ctx.x_relu = x_relu
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         ctx.has_res = residual is not None
         ctx.save_for_backward(x, weight, y if ctx.relu else None)
         return y
@@ -233,7 +252,7 @@ class ConvF(Function):
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dy, x, weight)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = SumRowsF.apply(dy)[:weight.shape[0]]
+            db = _bias_grad(dy, ctx.bias_ref, weight.shape[0])
         if ctx.has_res and ctx.needs_input_grad[3]:
             dres = dy
         return dx, dw, db, dres, None, None, None
@@ -257,6 +276,7 @@ class ConvSkipF(Function):
             b = (bias.detach() if bias is not None else 0) + (bskip.detach() if bskip is not None else 0)
         ctx.h_relu = h_relu
         ctx.has_b = (bias is not None, bskip is not None)
+        ctx.bias_refs = (bias, bskip)
         ctx.save_for_backward(h, x, weight, wskip)
         return K.conv_fprop_skip(h, wp, b, x, ws, k)
 
@@ -279,10 +299,18 @@ class ConvSkipF(Function):
             dw = _wgrad(dy, h, weight)
         if ctx.needs_input_grad[4]:
             dws = _wgrad(dy, x, wskip)
-        if (ctx.has_b[0] and ctx.needs_input_grad[3]) or (ctx.has_b[1] and ctx.needs_input_grad[5]):
-            s = SumRowsF.apply(dy)[:weight.shape[0]]
-            db = s if ctx.has_b[0] and ctx.needs_input_grad[3] else None
-            dbs = s if ctx.has_b[1] and ctx.needs_input_grad[5] else None
+        want = (ctx.has_b[0] and ctx.needs_input_grad[3], ctx.has_b[1] and ctx.needs_input_grad[5])
+        if want[0] or want[1]:
+            sinks = [b is not None and getattr(b, "_t2v_bias_sink", False) and b.grad is not None
+                     for b in ctx.bias_refs]
+            if not torch.is_grad_enabled() and all(s_ or not w_ for s_, w_ in zip(sinks, want)):
+                for b, w_ in zip(ctx.bias_refs, want):          # the same column sums, added into both buffers
+                    if w_:
+                        _bias_grad(dy, b, weight.shape[0])
+            else:
+                s = SumRowsF.apply(dy)[:weight.shape[0]]
+                db = s if want[0] else None
+                dbs = s if want[1] else None
         return dh, dx, dw, db, dws, dbs, None
 
 
@@ -350,6 +378,7 @@ class ConvSd2F(Function):
         wp = PACKS.get(weight, "fprop", weight.shape[0], x.shape[-1])
         weight._t2v_conv = True
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         ctx.x_relu = x_relu
         ctx.save_for_backward(x, weight)
         return K.conv_fprop_sd2(x, wp, _pad_bias(bias, weight.shape[0]))
@@ -369,7 +398,7 @@ class ConvSd2F(Function):
         if ctx.needs_input_grad[1]:
             dw = _wgrad(dy, x, weight, sd2=True)
         if ctx.has_bias and ctx.needs_input_grad[2]:
-            db = SumRowsF.apply(dy)[:weight.shape[0]]
+            db = _bias_grad(dy, ctx.bias_ref, weight.shape[0])
         return dx, dw, db, None
 
 
@@ -819,6 +848,7 @@ class StemConvF(Function):
     def forward(ctx, x, xc, weight, bias):
         weight._t2v_conv = True
         ctx.has_bias = bias is not None
+        ctx.bias_ref = bias
         ctx.x_leaf = x.is_leaf
         ctx.save_for_backward(xc, weight)
         return K.stem_fprop(xc, _stem_pack(weight), None if bias is None else bias.detach(), True)
@@ -834,7 +864,7 @@ class StemConvF(Function):
         if ctx.needs_input_grad[2]:
             dw = StemWgradF.apply(dy, xc, weight)
         if ctx.has_bias and ctx.needs_input_grad[3]:
-            db = SumRowsF.apply(dy)[:weight.shape[0]]
+            db = _bias_grad(dy, ctx.bias_ref, weight.shape[0])
         return dx, None, dw, db
 
 
