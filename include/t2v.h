@@ -248,6 +248,9 @@ int t2v_adam_step(int32_t count, float* const* host_params, const float* const* 
 /* gradient bucket pack / unpack for the data-parallel all-reduce (fp32, memory order): dst[i][:] = src[i][:]  */
 int t2v_multi_copy(int32_t count, const float* const* host_src, float* const* host_dst, const int64_t* host_sizes,
                    void* stream);
+/* Bulk copy by `ctas` resident CTAs with streaming loads / stores; src may be PINNED host memory (UVA): the input
+ * batch of data/__init__.py:131-156's prefetcher without the copy engine.  nbytes a multiple of 16.            */
+int t2v_stream_copy(const void* src, void* dst, int64_t nbytes, int32_t ctas, void* stream);
 
 #ifdef __cplusplus
 }

@@ -297,3 +297,28 @@ def test_data_prefetcher_ring_delivers_every_batch_intact():
         assert [t.tolist() for t in toks] == [[i, i] for i in range(n)]
     finally:
         data_prefetcher.CHUNK_BYTES = old
+
+
+def test_data_prefetcher_uint8_frames_normalised_like_the_reference_transforms():
+    """uint8 frames through data_prefetcher == transforms.ToTensor() + Normalize(0.5, 0.5) on the CPU, bit for bit."""
+    from txt2vid_b200.data import data_prefetcher
+    g = torch.Generator().manual_seed(3)
+    frames = torch.randint(0, 256, (6, 4, 3, 16, 16), generator=g, dtype=torch.uint8)
+    ref = frames.float().div(255).sub(0.5).div(0.5)
+    pf = data_prefetcher(iter([(frames.pin_memory(), torch.zeros(6, 5, dtype=torch.long), [5] * 6)]), device="cuda")
+    x, y = pf.next()
+    torch.cuda.synchronize()
+    assert x.dtype == torch.float32 and torch.equal(x.cpu(), ref)
+
+
+def test_stream_copy_from_pinned_host_memory():
+    """t2v_stream_copy: bulk copy by a few resident CTAs, source in pinned host memory (UVA) or on the device."""
+    g = torch.Generator().manual_seed(5)
+    h = torch.rand(3, 1 << 20, generator=g).pin_memory()
+    d = torch.empty_like(h, device="cuda")
+    K().stream_copy(h, d, ctas=8)
+    torch.cuda.synchronize()
+    assert torch.equal(d.cpu(), h)
+    d2 = torch.empty_like(d)
+    K().stream_copy(d, d2, ctas=16)
+    assert torch.equal(d2, d)

@@ -74,6 +74,7 @@ SIGNATURES = {
     "t2v_stem_wgrad": [_P, _P, c_i32, _P, c_i64, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_rgb_to_cl": [_P, _P, _P, c_i64, c_i64, _P],
     "t2v_wgrad_fold_pairs": [_P, _P, c_i32, c_i32, c_i32, _P],
+    "t2v_stream_copy": [_P, _P, c_i64, c_i32, _P],
     "t2v_gconv_fprop": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_dgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_wgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, c_i32, _P],

@@ -94,6 +94,7 @@ class data_prefetcher(object):
     CHUNK_BYTES = int(os.environ.get("T2V_PF_CHUNK_MB", "48")) << 20
     SLOTS = int(os.environ.get("T2V_PF_SLOTS", "4"))
     GUARD = "host"
+    SM_COPY_CTAS = int(os.environ.get("T2V_PF_SM_COPY_CTAS", "0"))   # > 0: bulk copy by an SM kernel over UVA (experimental)
 
     def __init__(self, loader, device=None):
         self.loader = iter(loader)
@@ -103,6 +104,8 @@ class data_prefetcher(object):
         self._slots, self._slot = tuple({} for _ in range(self.SLOTS)), 0
         self._handed = [None] * self.SLOTS      # event recorded when the slot's batch was handed to the consumer
         self._prev_event = None
+        self._norm = [None] * self.SLOTS        # fp32 images of uint8 clips (see _normalize)
+        self._deferred = False
         self._preload()
 
     def _to_dev(self, t, key):
@@ -118,6 +121,10 @@ class data_prefetcher(object):
         # replayed graph for its whole duration (step 100.6 -> 117.5 ms); the same bytes in <= 64 MB pieces overlap
         # (102.4 ms): scripts/h2d_probe.py
         nbytes = t.numel() * t.element_size()
+        if self.SM_COPY_CTAS > 0 and nbytes >= (1 << 20) and nbytes % 16 == 0 and t.is_contiguous():
+            from . import kernels as K
+            K.stream_copy(t, buf, self.SM_COPY_CTAS)
+            return buf
         pieces = min(t.size(0), -(-nbytes // self.CHUNK_BYTES)) if t.dim() > 0 and t.is_contiguous() else 1
         if pieces <= 1:
             buf.copy_(t, non_blocking=True)
@@ -125,6 +132,19 @@ class data_prefetcher(object):
             for d, h in zip(buf.chunk(pieces), t.chunk(pieces)):
                 d.copy_(h, non_blocking=True)
         return buf
+
+    def _normalize(self, frames_u8):
+        """uint8 frames -> the reference's transforms.ToTensor() + Normalize(0.5, 0.5) (data/__init__.py:362-364) in
+        fp32 on the device (side stream): x / 255, then (x - 0.5) / 0.5 -- the same IEEE operations, so the same values.
+        A loader that hands out the frames as stored moves a quarter of the bytes over PCIe."""
+        out = self._norm[self._slot]
+        if out is None or out.shape != frames_u8.shape:
+            out = self._norm[self._slot] = torch.empty(frames_u8.shape, dtype=torch.float32, device=self.device)
+        if getattr(self, "_c255", None) is None:
+            # a TENSOR divisor: ATen's CUDA kernel multiplies by the reciprocal of a scalar divisor (1 ulp off)
+            self._c255 = torch.full((1,), 255.0, device=self.device)
+        torch.div(frames_u8, self._c255, out=out)
+        return out.sub_(0.5).div_(0.5)
 
     def _preload(self):
         try:
@@ -142,14 +162,32 @@ class data_prefetcher(object):
                     self.stream.wait_event(free)
             with torch.cuda.stream(self.stream):
                 self.next_x = self._to_dev(batch[0], 0)
+                if isinstance(self.next_x, torch.Tensor) and self.next_x.dtype == torch.uint8:
+                    self.next_x = self._normalize(self.next_x)
                 self.next_y = [self._to_dev(a, 1 + i) for i, a in enumerate(batch[1:])]
         else:
             self.next_x, self.next_y = batch[0], list(batch[1:])
 
-    def next(self):
+    def preload(self):
+        """Stage the following batch now (after next(preload=False)): callers that launch their step first keep the
+        step's own small transfers ahead of the bulk copy in the copy-engine queue."""
+        if self._deferred:
+            self._deferred = False
+            self._preload()
+
+    def next(self, preload=True):
+        if self._deferred:
+            self.preload()
         if self.stream is not None:
             torch.cuda.current_stream().wait_stream(self.stream)
         x, y = self.next_x, self.next_y
+        if x is not None and not preload:
+            if self.stream is not None:
+                ev = torch.cuda.Event()
+                ev.record()
+                self._handed[(self._slot - 1) % self.SLOTS] = ev
+            self._deferred = True
+            return x, y
         if x is not None:
             if self.stream is not None:
                 # fires when everything enqueued so far (the step of the PREVIOUS batch) has run; it guards the slot
@@ -168,18 +206,22 @@ class SyntheticVideoCaptions(object):
     SURVEY.md 8(d).  Stands in for get_loader(...) in benchmarks and tests."""
 
     def __init__(self, batch_size, num_batches, vocab_size=1000, frames=16, size=64, channels=3, captions=True,
-                 seed=1234):
+                 seed=1234, as_uint8=False):
         self.B, self.n, self.V = batch_size, num_batches, vocab_size
         self.T, self.S, self.C = frames, size, channels
         self.captions = captions
         self.seed = seed
+        self.as_uint8 = as_uint8        # frames as stored (uint8); data_prefetcher applies ToTensor + Normalize on the device
 
     def __len__(self):
         return self.n
 
     def batch(self, i):
         g = torch.Generator().manual_seed(self.seed + i)
-        x = torch.rand(self.B, self.C, self.T, self.S, self.S, generator=g) * 2 - 1
+        if self.as_uint8:
+            x = torch.randint(0, 256, (self.B, self.C, self.T, self.S, self.S), generator=g, dtype=torch.uint8)
+        else:
+            x = torch.rand(self.B, self.C, self.T, self.S, self.S, generator=g) * 2 - 1
         x = x.permute(0, 2, 1, 3, 4)                         # loader order (B,T,C,H,W); train() permutes back
         if not self.captions:
             return (x,)

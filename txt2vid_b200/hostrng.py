@@ -71,14 +71,22 @@ class StaticDraws(EagerDraws):
     def refresh(self, slot=0):
         """Draw the next iteration's values in the recorded (= reference) order and stage them on the device.
         The copies are asynchronous: the caller owns `slot` (a pinned staging set nobody is still reading)."""
-        for (kind, n), h, d in zip(self.calls, self.host[slot % self.RING], self.dev):
+        hs = self.host[slot % self.RING]
+        for (kind, n), h in zip(self.calls, hs):
             if kind == "bt":
                 h[0] = int(torch.randint(n, (1,)))
             elif kind == "perm":
                 h.copy_(torch.from_numpy(np.ascontiguousarray(gen_perm(n))))
             else:
                 h.copy_(torch.rand(n))
-            d.copy_(h, non_blocking=True)
+        if self.device.type == "cuda":
+            # one SM copy kernel reading the pinned slots over UVA (not ~14 cudaMemcpyAsync on the compute stream:
+            # those queue behind the prefetcher's H2D pieces on the copy engine and stall the step)
+            from . import kernels as K
+            K.multi_copy([h.view(torch.float32) for h in hs], [d.view(torch.float32) for d in self.dev])
+        else:
+            for h, d in zip(hs, self.dev):
+                d.copy_(h)
 
     def begin_iteration(self):
         self.i = 0

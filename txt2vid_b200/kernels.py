@@ -675,12 +675,28 @@ def adam_step(params, grads, ms, vs, lr, beta1, beta2, eps, step, grad_scale=1.0
                               beta2, eps, step, grad_scale, ptr(dyn), stream()), "t2v_adam_step")
 
 
+def stream_copy(src, dst, ctas=32):
+    """dst <- src (same byte size, contiguous), by `ctas` resident CTAs; src may be pinned host memory."""
+    if not ((src.is_cuda or src.is_pinned()) and dst.is_cuda):
+        raise _lib.T2VError("stream_copy needs a CUDA or pinned source and a CUDA destination")
+    nbytes = src.numel() * src.element_size()
+    assert nbytes == dst.numel() * dst.element_size() and src.is_contiguous() and dst.is_contiguous()
+    assert nbytes % 16 == 0 and src.data_ptr() % 16 == 0 and dst.data_ptr() % 16 == 0
+    check(lib().t2v_stream_copy(ptr(src), ptr(dst), nbytes, ctas, stream()), "t2v_stream_copy")
+    return dst
+
+
 def multi_copy(srcs, dsts):
-    """dst[i].memory <- src[i].memory for lists of equally laid-out fp32 tensors (gradient buckets)."""
+    """dst[i].memory <- src[i].memory for lists of equally laid-out fp32 tensors (gradient buckets).  Either side may
+    be PINNED host memory (read / written by the SMs over UVA): small per-step host values and the loss read-back
+    travel this way, because a cudaMemcpyAsync on the compute stream queues behind the prefetcher's H2D pieces on
+    the copy engine."""
     n = len(srcs)
     if n == 0:
         return
-    require_cuda(*srcs)
+    for t in list(srcs) + list(dsts):
+        if not (t.is_cuda or t.is_pinned()):
+            raise _lib.T2VError("multi_copy needs CUDA or pinned host tensors (got %s)" % t.device)
     arr = ctypes.c_void_p * n
     sizes = (ctypes.c_int64 * n)(*[s.numel() for s in srcs])
     for s, d in zip(srcs, dsts):

@@ -230,7 +230,7 @@ class GraphedTrainStep(object):
         h = opt._dyn_host[slot]
         h[0] = opt.param_groups[0]["lr"] / (1.0 - b1 ** step)
         h[1] = 1.0 / (1.0 - b2 ** step) ** 0.5
-        opt.dyn.copy_(h, non_blocking=True)
+        K.multi_copy([h], [opt.dyn])            # UVA read of the pinned slot (see hostrng.StaticDraws.refresh)
 
     def _capture(self, x, cond):
         """Capture only: nothing executes here.  The caller replays right afterwards."""
@@ -310,7 +310,10 @@ class GraphedTrainStep(object):
         else:
             self.static_x.copy_(x, non_blocking=True)
         if cond is not None:
-            self.static_cond.copy_(cond)
+            if cond.dtype == torch.float32 and cond.is_contiguous() and self.static_cond.is_contiguous():
+                K.multi_copy([cond], [self.static_cond])
+            else:
+                self.static_cond.copy_(cond)
         slot = self.replays % self.ring
         self.replays += 1
         if self.stage_evt[slot] is not None:
@@ -414,7 +417,7 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
         iter_watch.start()
         i = 0
         prefetcher = data_prefetcher(dataset, device=device)
-        x, y = prefetcher.next()
+        x, y = prefetcher.next(preload=False)
         while x is not None:
             iteration = epoch * len(dataset) + i + 1
             data_load_watch.stop()
@@ -427,6 +430,7 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
             else:
                 ld, lg, fake, xs, cond = train_iteration(gan, x, y, device, optD, optG, params, losses,
                                                          channel_first=channel_first, end2end=end2end, dist=dist)
+            prefetcher.preload()                 # the next batch's bulk copy is enqueued behind this iteration's launch
             # the reference's two host syncs per iteration (trainer.py:243,264); in graph mode the values reach the
             # rolling averages two iterations late so that the host stays ahead of the device
             lagged.push(ld, lg)
@@ -466,6 +470,6 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
             iter_watch.stop()
             avg_iter.update(iter_watch.elapsed_time)
             iter_watch.start()
-            x, y = prefetcher.next()
+            x, y = prefetcher.next(preload=False)
             i += 1
         lagged.drain()
