@@ -1,0 +1,108 @@
+"""CPU: host-side pieces added around the kernels -- checkpoint compatibility with the reference, the
+position-pair identity behind the small-channel weight gradients, lagged loss logging, the prefetcher's CPU path."""
+import os
+import sys
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import build_product_models
+
+REF = "/root/reference"
+
+
+def test_checkpoint_roundtrip_through_cond_gan(tmp_path):
+    """CondGan.save_dict / load_from_dict (gan/cond_gan.py:186-217): keys gen / cond / <discriminator name>, the
+    discriminator's parameters under `single_discrim.module.*`; torch.save -> torch.load -> fresh modules, exact."""
+    from txt2vid_b200.gan import CondGan
+    txt, gen, dis = build_product_models(True, V=50, seed=3)
+    gan = CondGan(gen=gen, discrims=[dis], cond_encoder=txt, discrim_names=["video"])
+    path = str(tmp_path / "iter_1")
+    torch.save(gan.save_dict(), path)
+    loaded = torch.load(path)
+    assert set(loaded) == {"gen", "cond", "video"}
+    assert any(k.startswith("single_discrim.module.") for k in loaded["video"])
+    txt2, gen2, dis2 = build_product_models(True, V=50, seed=4)
+    gan2 = CondGan(gen=gen2, discrims=[dis2], cond_encoder=txt2, discrim_names=["video"])
+    gan2.load_from_dict(loaded)
+    for a, b in ((gen, gen2), (dis, dis2), (txt, txt2)):
+        sa, sb = a.state_dict(), b.state_dict()
+        assert list(sa) == list(sb)
+        assert all(torch.equal(sa[k], sb[k]) for k in sa)
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout is only present in the build container")
+def test_state_dicts_interchange_with_the_reference_modules():
+    """A reference-trained checkpoint loads into the product modules and vice versa (strict): same keys, same shapes
+    (models/tganv2_cond/{gen,discrim}.py, models/txt/basic.py)."""
+    # import the REFERENCE's txt2vid package in isolation from this repo's namespace package of the same name
+    stash = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "txt2vid" or k.startswith("txt2vid.")}
+    sys.path.insert(0, REF)
+    try:
+        from txt2vid.models.tganv2_cond.gen import MultiScaleGen as RefGen
+        from txt2vid.models.tganv2_cond.discrim import MultiScaleDiscrim as RefDis
+        from txt2vid.models.txt.basic import Seq2Seq as RefTxt
+        assert sys.modules["txt2vid.models.tganv2_cond.gen"].__file__.startswith(REF)
+    except ImportError as e:
+        pytest.skip("reference modules not importable here: %r" % (e,))
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "txt2vid" or k.startswith("txt2vid.")]:
+            del sys.modules[k]
+        sys.modules.update(stash)
+    txt, gen, dis = build_product_models(True, V=50, seed=3)
+    rgen, rdis, rtxt = RefGen(width=64, height=64, cond_dim=256), RefDis(cond_dim=256), RefTxt(vocab_size=50)
+    for prod, ref in ((gen, rgen), (dis, rdis), (txt, rtxt)):
+        ref.load_state_dict(prod.state_dict(), strict=True)            # product checkpoint -> reference
+        prod.load_state_dict(ref.state_dict(), strict=True)            # reference checkpoint -> product
+        sp, sr = prod.state_dict(), ref.state_dict()
+        assert list(sp) == list(sr)
+        assert all(sp[k].shape == sr[k].shape and torch.equal(sp[k].float(), sr[k].float()) for k in sp)
+
+
+def test_position_pair_identity_of_small_channel_weight_gradients():
+    """kernels.conv_wgrad runs 32-channel (1,3,3) weight gradients on PAIRS of adjacent w voxels (64-channel views)
+    and folds dw2[(pw,co)][a_h, s][(qw,ci)] into the real taps: shift a_w - 1 = 2 s + qw - pw (t2v_wgrad_fold_pairs).
+    Here the same algebra in plain torch against the direct weight gradient."""
+    g = torch.Generator().manual_seed(0)
+    N, H, W, Ci, Co = 3, 6, 8, 4, 5
+    x = torch.randn(N, H, W, Ci, generator=g, dtype=torch.float64)
+    dy = torch.randn(N, H, W, Co, generator=g, dtype=torch.float64)
+    direct = torch.nn.grad.conv2d_weight(x.permute(0, 3, 1, 2), (Co, Ci, 3, 3), dy.permute(0, 3, 1, 2), padding=1)
+    x2, dy2 = x.reshape(N, H, W // 2, 2 * Ci), dy.reshape(N, H, W // 2, 2 * Co)
+    dw2 = torch.nn.grad.conv2d_weight(x2.permute(0, 3, 1, 2), (2 * Co, 2 * Ci, 3, 3), dy2.permute(0, 3, 1, 2), padding=1)
+    folded = torch.zeros_like(direct)
+    for a_w in range(3):
+        for s in (-1, 0, 1):
+            for pw in (0, 1):
+                for qw in (0, 1):
+                    if 2 * s + qw - pw == a_w - 1:
+                        folded[:, :, :, a_w] += dw2[pw * Co:(pw + 1) * Co, qw * Ci:(qw + 1) * Ci, :, s + 1]
+    assert torch.allclose(folded, direct, rtol=1e-12, atol=1e-12)
+
+
+def test_lagged_losses_cpu_path_is_immediate():
+    from txt2vid_b200.trainer import LaggedLosses
+    seen = []
+    ll = LaggedLosses(lambda d, g: seen.append((d, g)), lag=2, device="cpu")
+    ll.push(torch.tensor(1.5), torch.tensor(2.5))
+    assert seen == [(1.5, 2.5)]
+    ll.drain()
+    assert seen == [(1.5, 2.5)]
+
+
+def test_prefetcher_cpu_path_and_deferred_preload():
+    """data_prefetcher on a CPU device is a plain iterator; next(preload=False) + preload() deliver the same batches."""
+    from txt2vid_b200.data import data_prefetcher
+    batches = [(torch.full((2, 3), float(i)), torch.full((2, 4), i, dtype=torch.long), [4, 4]) for i in range(5)]
+    for deferred in (False, True):
+        pf = data_prefetcher(iter(batches), device="cpu")
+        got = []
+        x, y = pf.next(preload=not deferred)
+        while x is not None:
+            got.append((float(x[0, 0]), int(y[0][0, 0]), y[1]))
+            if deferred:
+                pf.preload()
+            x, y = pf.next(preload=not deferred)
+        assert got == [(float(i), i, [4, 4]) for i in range(5)]
