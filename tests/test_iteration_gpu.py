@@ -42,3 +42,40 @@ def test_config5_128x128x32_iteration_on_b200():
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/iteration_parity_tganv2_cond_128x128x32_B8.json", "w") as f:
         json.dump({"report": rep}, f)
+
+
+def test_eval_mode_generation_matches_oracle():
+    """eval-mode sampling (gan/trainer.py:44-90, models/tganv2_cond/gen.py:101,114-115): no subsampling,
+    ONE full-resolution output, BatchNorm on its running statistics.  Running statistics are first moved off their
+    initial values by one training-mode forward (both sides update them with the same momentum formula)."""
+    import oracle.txt2vid_oracle as O
+    from helpers import build_product_models, state_to_cpu
+    from txt2vid_b200 import ops
+    ops.PACKS.clear()
+    B = 8
+    txt, gen, dis = build_product_models(True, V=100, seed=11)
+    sd = O.as_leaves(state_to_cpu(gen))
+    g = torch.Generator().manual_seed(3)
+    z, cond = torch.randn(B, 256, generator=g), torch.randn(B, 256, generator=g)
+    # training-mode forward on both sides with the same frame offsets -> updated running statistics
+    new_buf = {}
+    O.gen_forward(sd, z, cond, [1, 0, 1], True, 16, new_buf)
+    for k, v in new_buf.items():
+        sd[k] = v
+    gen = gen.cuda()
+    draws = iter([1, 0, 1])
+    gen.subsample.draw = lambda: next(draws)
+    gen.train()
+    with torch.no_grad():
+        gen(z.cuda(), cond=cond.cuda())
+    # eval-mode generation
+    z2, cond2 = torch.randn(B, 256, generator=g), torch.randn(B, 256, generator=g)
+    with torch.no_grad():
+        ref = O.gen_forward(sd, z2, cond2, None, False, 16)
+    gen.eval()
+    with torch.no_grad():
+        got = gen(z2.cuda(), cond=cond2.cuda())
+    assert len(got) == len(ref) == 1 and tuple(got[0].shape) == tuple(ref[0].shape) == (B, 3, 16, 64, 64)
+    err = float((got[0].float().cpu() - ref[0]).norm() / ref[0].norm())
+    print("eval-mode generation, relative L2 vs oracle: %.3e" % err)
+    assert err < 6e-2
