@@ -79,7 +79,9 @@ def grad_like_weight(dw3, weight):
 
 
 class _PackCache(object):
-    """bf16 operand packs per parameter, rebuilt when the parameter changes."""
+    """bf16 operand packs per parameter, rebuilt when the parameter changes.  Entries are keyed by the parameter's
+    MEMORY (data pointer + shape), not by the Python object: differentiable views of a parameter (stem_weight_2d)
+    are new objects on every call and would otherwise leave one dead entry per iteration behind."""
 
     def __init__(self):
         self.store = {}
@@ -87,22 +89,34 @@ class _PackCache(object):
     def _key(self, w):
         return (w._version, w.data_ptr(), _EPOCH[0])
 
+    @staticmethod
+    def _slot_of(w):
+        return (w.data_ptr(), tuple(w.shape))
+
     def get(self, w, kind, CoutP, CinP):
-        ent = self.store.get(id(w))
+        ident = self._slot_of(w)
+        ent = self.store.get(ident)
         key = self._key(w)
         if ent is None or ent[0] != key:
             ent = (key, {})
-            self.store[id(w)] = ent
+            self.store[ident] = ent
         slot = (kind, CoutP, CinP)
         if slot not in ent[1]:
             with torch.no_grad():
                 w3 = w3_view(w).detach()       # may re-home the parameter's memory (channels-last)
             if kind == "fprop":
-                ent[1][slot] = K.pack_weight(w3, CoutP, CinP)
+                pack = K.pack_weight(w3, CoutP, CinP)
             else:
-                ent[1][slot] = K.pack_dgrad_weight(w3, CoutP, CinP)
-            ent = (self._key(w), ent[1])          # w3_view may have re-homed the parameter
-            self.store[id(w)] = ent
+                pack = K.pack_dgrad_weight(w3, CoutP, CinP)
+            if self._slot_of(w) != ident:     # w3_view re-homed the parameter: file the pack under its new memory
+                self.store.pop(ident, None)
+                ident = self._slot_of(w)
+                ent = (self._key(w), {})
+                self.store[ident] = ent
+            else:
+                ent = (self._key(w), ent[1])
+                self.store[ident] = ent
+            ent[1][slot] = pack
         return ent[1][slot]
 
     def clear(self):
@@ -810,13 +824,13 @@ class Col2im3F(Function):
 
 def _stem_pack(weight):
     """(64, 3, 3,3,3) parameter -> bf16 (64, 128) operand of t2v_stem_fprop: k = tap * 4 + c, zero padded."""
-    ent = PACKS.store.get(("stem", id(weight)))
+    ent = PACKS.store.get(("stem", weight.data_ptr()))
     key = PACKS._key(weight)
     if ent is None or ent[0] != key:
         with torch.no_grad():
             wp = K.stem_pack_weight(w3_view(weight).detach())                      # (64, 27, 3) fp32 -> (64, 128)
         ent = (PACKS._key(weight), wp)
-        PACKS.store[("stem", id(weight))] = ent
+        PACKS.store[("stem", weight.data_ptr())] = ent
     return ent[1]
 
 
