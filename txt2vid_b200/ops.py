@@ -11,6 +11,7 @@ channels-last memory ([Cout][taps][Cin]) so that packing is a cast and the weigh
 kernels write is the parameter gradient's memory.
 """
 import os
+import weakref
 
 import torch
 from torch.autograd import Function
@@ -79,9 +80,10 @@ def grad_like_weight(dw3, weight):
 
 
 class _PackCache(object):
-    """bf16 operand packs per parameter, rebuilt when the parameter changes.  Entries are keyed by the parameter's
-    MEMORY (data pointer + shape), not by the Python object: differentiable views of a parameter (stem_weight_2d)
-    are new objects on every call and would otherwise leave one dead entry per iteration behind."""
+    """bf16 operand packs per parameter, rebuilt when the parameter changes.  Entries are keyed by the OWNING tensor
+    (the parameter itself, or the parameter a differentiable view such as stem_weight_2d was taken from) plus the
+    view's geometry, and carry a weak reference to the owner: a view is a new Python object on every call (no dead
+    entry per iteration), and a new model whose parameters land on a freed model's addresses never sees its packs."""
 
     def __init__(self):
         self.store = {}
@@ -90,16 +92,26 @@ class _PackCache(object):
         return (w._version, w.data_ptr(), _EPOCH[0])
 
     @staticmethod
-    def _slot_of(w):
-        return (w.data_ptr(), tuple(w.shape))
+    def _owner(w):
+        base = getattr(w, "_base", None)
+        return base if base is not None else w
+
+    def _slot_of(self, w):
+        return (id(self._owner(w)), tuple(w.shape), tuple(w.stride()))
+
+    def _lookup(self, ident, w):
+        ent = self.store.get(ident)
+        if ent is None or ent[0] != self._key(w) or ent[2]() is not self._owner(w):
+            if len(self.store) > 4096:               # forget the packs of tensors that no longer exist
+                for k in [k for k, e in self.store.items() if e[2]() is None]:
+                    del self.store[k]
+            ent = (self._key(w), {}, weakref.ref(self._owner(w)))
+            self.store[ident] = ent
+        return ent
 
     def get(self, w, kind, CoutP, CinP):
         ident = self._slot_of(w)
-        ent = self.store.get(ident)
-        key = self._key(w)
-        if ent is None or ent[0] != key:
-            ent = (key, {})
-            self.store[ident] = ent
+        ent = self._lookup(ident, w)
         slot = (kind, CoutP, CinP)
         if slot not in ent[1]:
             with torch.no_grad():
@@ -108,13 +120,10 @@ class _PackCache(object):
                 pack = K.pack_weight(w3, CoutP, CinP)
             else:
                 pack = K.pack_dgrad_weight(w3, CoutP, CinP)
-            if self._slot_of(w) != ident:     # w3_view re-homed the parameter: file the pack under its new memory
+            if self._slot_of(w) != ident or ent[0] != self._key(w):     # w3_view re-homed the parameter
                 self.store.pop(ident, None)
                 ident = self._slot_of(w)
-                ent = (self._key(w), {})
-                self.store[ident] = ent
-            else:
-                ent = (self._key(w), ent[1])
+                ent = (self._key(w), {}, weakref.ref(self._owner(w)))
                 self.store[ident] = ent
             ent[1][slot] = pack
         return ent[1][slot]
@@ -824,13 +833,13 @@ class Col2im3F(Function):
 
 def _stem_pack(weight):
     """(64, 3, 3,3,3) parameter -> bf16 (64, 128) operand of t2v_stem_fprop: k = tap * 4 + c, zero padded."""
-    ent = PACKS.store.get(("stem", weight.data_ptr()))
+    ent = PACKS.store.get(("stem", id(weight)))
     key = PACKS._key(weight)
-    if ent is None or ent[0] != key:
+    if ent is None or ent[0] != key or ent[2]() is not weight:
         with torch.no_grad():
             wp = K.stem_pack_weight(w3_view(weight).detach())                      # (64, 27, 3) fp32 -> (64, 128)
-        ent = (PACKS._key(weight), wp)
-        PACKS.store[("stem", weight.data_ptr())] = ent
+        ent = (PACKS._key(weight), wp, weakref.ref(weight))
+        PACKS.store[("stem", id(weight))] = ent
     return ent[1]
 
 
