@@ -106,3 +106,55 @@ def test_prefetcher_cpu_path_and_deferred_preload():
                 pf.preload()
             x, y = pf.next(preload=not deferred)
         assert got == [(float(i), i, [4, 4]) for i in range(5)]
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout is only present in the build container")
+def test_caption_pretraining_step_matches_the_reference():
+    """one optimisation step of train/txt.py:166-181 (encode -> teacher-forced decode -> cross entropy
+    -> Adam) on identical weights and sentences: same loss, same decoded symbols, same updated weights."""
+    stash = {k: sys.modules.pop(k) for k in list(sys.modules) if k == "txt2vid" or k.startswith("txt2vid.")}
+    sys.path.insert(0, REF)
+    try:
+        from txt2vid.models.txt.basic import Seq2Seq as RefTxt
+        assert sys.modules["txt2vid.models.txt.basic"].__file__.startswith(REF)
+    except ImportError as e:
+        pytest.skip("reference modules not importable here: %r" % (e,))
+    finally:
+        sys.path.remove(REF)
+        for k in [k for k in sys.modules if k == "txt2vid" or k.startswith("txt2vid.")]:
+            del sys.modules[k]
+        sys.modules.update(stash)
+    import contextlib, io
+    from torch.nn.utils.rnn import pack_padded_sequence, pad_packed_sequence
+    from txt2vid_b200.text import Seq2Seq
+    from txt2vid_b200.train_txt import collate_fn, pretrain_step
+    V = 40
+    torch.manual_seed(5)
+    with contextlib.redirect_stdout(io.StringIO()):
+        ref = RefTxt(vocab_size=V)
+    prod = Seq2Seq(vocab_size=V)
+    prod.load_state_dict(ref.state_dict(), strict=True)
+    g = torch.Generator().manual_seed(1)
+    sents = []
+    for L in (9, 7, 7, 4):
+        s = torch.randint(4, V, (L,), generator=g).float()
+        s[0], s[-1] = 1, 2
+        sents.append(s)
+    sent, lengths = collate_fn(list(sents))
+    for tf in (True, False):
+        opt_r = torch.optim.Adam(ref.parameters(), lr=1e-3)
+        opt_p = torch.optim.Adam(prod.parameters(), lr=1e-3)
+        # the reference's loop body, verbatim order (train/txt.py:166-181)
+        ref.zero_grad()
+        _, hid, _ = ref.encode(sent, lengths=lengths)
+        targets, _ = pad_packed_sequence(pack_padded_sequence(sent, lengths, batch_first=True), batch_first=True,
+                                         total_length=lengths[0])
+        dec, sym = ref.decode(true_inputs=sent, initial_hidden=hid, max_seq_len=lengths[0], teacher_force=tf)
+        loss_r = torch.nn.CrossEntropyLoss()(dec.permute(0, 2, 1), targets)
+        loss_r.backward()
+        opt_r.step()
+        loss_p, sym_p = pretrain_step(prod, sent, lengths, opt_p, teacher_force=tf)
+        assert abs(float(loss_p) - float(loss_r)) <= 1e-6 * abs(float(loss_r)), (float(loss_p), float(loss_r))
+        assert torch.equal(sym_p, sym)
+        for (n, a), (_, b) in zip(prod.state_dict().items(), ref.state_dict().items()):
+            assert torch.allclose(a, b, rtol=1e-6, atol=1e-7), n
