@@ -44,6 +44,8 @@ extern "C" {
 #define T2V_EPI_RELU_MASK 4u  /* the `residual` pointer is a ReLU reference r (bf16 CL, output-shaped): instead of
                                * adding it, zero the output where r <= 0 -- the backward of the ReLU that produced the
                                * convolution's input, fused into the data-gradient epilogue (layers.py:230-232) */
+#define T2V_EPI_RES_F32 8u    /* the `residual` / ReLU-reference pointer is fp32 CL (fp32 activation storage, generic
+                               * tcgen05 kernel only) */
 
 /* Stride-1, "same"-padded convolution geometry (every conv on the TGANv2 path:
  * models/layers.py:174,177,183,231,233,237,251; models/resnet3d.py:12-17; 1x1(x1) convs of the
@@ -251,6 +253,146 @@ int t2v_multi_copy(int32_t count, const float* const* host_src, float* const* ho
 /* Bulk copy by `ctas` resident CTAs with streaming loads / stores; src may be PINNED host memory (UVA): the input
  * batch of data/__init__.py:131-156's prefetcher without the copy engine.  nbytes a multiple of 16.            */
 int t2v_stream_copy(const void* src, void* dst, int64_t nbytes, int32_t ctas, void* stream);
+
+/* ---------------------------------------------------------------------------------------------------------
+ * fp32 ACTIVATION STORAGE (the "fp32 parity mode": BASELINE north_star, 1e-3 relative on losses and gradients).
+ * Every entry point above whose activations are bf16 CL has a twin with the suffix _f32 and the SAME signature
+ * in which those tensors are fp32 CL (same kernels instantiated for float storage; arithmetic is fp32 in both).
+ * The tcgen05 engine keeps its bf16 tensor pipe: fp32 activations are split into bf16 hi + lo parts
+ * (t2v_split_bf16x3), weights likewise, and hi*hi + lo*hi + hi*lo is accumulated in fp32 by the SAME kernels along a
+ * 3x longer K (fprop / dgrad: channel-concatenated operands, T2V_EPI_OUT_F32 | T2V_EPI_RES_F32) or 3x more
+ * positions (wgrad): ~2^-17 relative error per product.                                                         */
+int t2v_relu_fwd_f32(const void* x, void* y, int64_t n, void* stream);
+int t2v_relu_bwd_f32(const void* dy, const void* ref, void* dx, int64_t n, void* stream);
+int t2v_leaky_relu_fwd_f32(const void* x, void* y, int64_t n, float slope, void* stream);
+int t2v_leaky_relu_bwd_f32(const void* dy, const void* ref, void* dx, int64_t n, float slope, void* stream);
+int t2v_tanh_fwd_f32(const void* x, void* y, int64_t n, void* stream);
+int t2v_tanh_bwd_f32(const void* dy, const void* y, void* dx, int64_t n, void* stream);
+int t2v_avgpool_fwd_f32(const void* x, const void* residual, void* y, const int32_t* in_shape, const int32_t* kernel,
+                        const int32_t* stride, const int32_t* pad, void* stream);
+int t2v_avgpool_bwd_f32(const void* dy, void* dx, const int32_t* in_shape, const int32_t* kernel,
+                        const int32_t* stride, const int32_t* pad, void* stream);
+int t2v_upsample2x_fwd_f32(const void* x, void* y, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int t2v_upsample2x_bwd_f32(const void* dy, void* dx, int32_t N, int32_t H, int32_t W, int32_t C, void* stream);
+int t2v_nchw_to_cl_f32(const float* x, void* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
+int t2v_cl_to_nchw_f32(const void* x, float* y, int64_t N, int32_t C, int64_t S, int32_t Cp, void* stream);
+int t2v_im2col3_f32(const float* x, void* col, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                    void* stream);
+int t2v_col2im3_f32(const void* dcol, float* dx, int64_t N, int32_t C, int32_t D, int32_t H, int32_t W, int32_t Kp,
+                    void* stream);
+int t2v_sum_rows_f32(const void* x, float* out, int64_t P, int32_t C, void* stream);
+int t2v_sum_rows_acc_f32(const void* x, float* out, int64_t P, int32_t C, void* stream);
+int t2v_sum_spatial_f32(const void* x, float* out, int64_t N, int64_t S, int32_t C, void* stream);
+int t2v_broadcast_spatial_f32(const float* g, void* y, int64_t N, int64_t S, int32_t C, void* stream);
+int t2v_bn_stats_f32(const void* x, float* stats, int64_t P, int32_t C, void* stream);
+int t2v_bn_apply_f32(const void* x, const float* scale_shift, void* y, int64_t N, int32_t H, int32_t W, int32_t C,
+                     int32_t relu, int32_t up, void* stream);
+int t2v_bn_bwd_f32(const void* dy, const void* x, const float* scale_shift, const float* mean_invstd, float* red,
+                   void* dx, int64_t N, int32_t H, int32_t W, int32_t C, int32_t relu, int32_t up, void* stream);
+int t2v_render_fwd_f32(const void* pre, float* y, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, int32_t Cp,
+                       void* stream);
+int t2v_render_bwd_f32(const float* dy, const float* y, void* dpre, int32_t B, int32_t T, int32_t H, int32_t W,
+                       int32_t C, int32_t Cp, void* stream);
+int t2v_lstm_cell_fwd_f32(const float* gates, const float* c_prev, float* c, void* h, float* h32, int64_t P,
+                          int32_t Hd, void* stream);
+int t2v_lstm_cell_bwd_f32(const float* gates, const float* c_prev, const float* c, const float* dh,
+                          const float* dc_next, void* dgates, float* dc_prev, int64_t P, int32_t Hd, void* stream);
+/* general convolution with fp32 x / w / dy (CUDA-core FMA: exact fp32) */
+int t2v_gconv_fprop_f32(const t2v_gconv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                        int32_t out_f32, void* stream);
+int t2v_gconv_dgrad_f32(const t2v_gconv_geom* g, const void* dy, const void* w, const float* bias, void* dx,
+                        int32_t out_f32, void* stream);
+int t2v_gconv_wgrad_f32(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
+                        void* stream);
+/* x fp32 [rows][C] -> bf16 hi = bf16(x), lo = bf16(x - hi); layout 0: out [rows][3C] = [hi | lo | hi] (A operand of
+ * fprop / dgrad; the weight pack is [hi | hi | lo] along K), 1: out [3 rows][C] = [hi ; lo ; hi] (dy of wgrad),
+ * 2: out [3 rows][C] = [hi ; hi ; lo] (x of wgrad).  C a multiple of 4.                                        */
+int t2v_split_bf16x3(const float* x, void* out, int64_t rows, int32_t C, int32_t layout, void* stream);
+
+/* scale / add / dot on CL activations (bf16; _f32 twins): the non-local block's gamma * o + x
+ * (models/layers.py:36,68) with its gradients, and the gradient penalty's sum ||g||^2 (gan/losses.py:180-186).
+ * s, out: ONE fp32 on the device.  n elements, multiple of 8.                                                 */
+int t2v_scale(const void* x, const float* s, void* y, int64_t n, void* stream);                  /* y = s * x       */
+int t2v_scale_add(const void* o, const void* x, const float* s, void* y, int64_t n, void* stream); /* y = s*o + x (s NULL: 1) */
+int t2v_dot(const void* a, const void* b, float* out, int64_t n, void* stream);                 /* out = sum a*b   */
+int t2v_scale_f32(const void* x, const float* s, void* y, int64_t n, void* stream);
+int t2v_scale_add_f32(const void* o, const void* x, const float* s, void* y, int64_t n, void* stream);
+int t2v_dot_f32(const void* a, const void* b, float* out, int64_t n, void* stream);
+/* CL [rows][Cp] -> fp32 [rows][c] (first c channels), and its adjoint (zero padding) */
+int t2v_cl_slice_f32(const void* x, float* y, int64_t rows, int32_t Cp, int32_t c, void* stream);
+int t2v_f32_pad_cl(const float* x, void* y, int64_t rows, int32_t Cp, int32_t c, void* stream);
+int t2v_cl_slice_f32_f32(const void* x, float* y, int64_t rows, int32_t Cp, int32_t c, void* stream);
+int t2v_f32_pad_cl_f32(const float* x, void* y, int64_t rows, int32_t Cp, int32_t c, void* stream);
+
+/* Non-local block core as differentiable fp32 primitives (models/layers.py:23-36, 52-68): replaces F.max_pool2d/3d,
+ * torch.bmm and F.softmax on the discriminator's block, which the gradient penalty differentiates twice.
+ * x fp32 [maps][H][W][c] (maps = N*D; pooling window (1,2,2)), idx u8 = arg-max voxel 0..3 of each window.     */
+int t2v_maxpool122_fwd(const float* x, float* y, void* idx, int64_t maps, int32_t H, int32_t W, int32_t c,
+                       void* stream);
+int t2v_pool122_gather(const float* x, const void* idx, float* y, int64_t maps, int32_t H, int32_t W, int32_t c,
+                       void* stream);
+int t2v_pool122_scatter(const float* dy, const void* idx, float* dx, int64_t maps, int32_t H, int32_t W, int32_t c,
+                        void* stream);
+/* C[b] (M x N) = op(A[b]) op(B[b]), row-major fp32; trans_a: A[b] stored K x M; trans_b: B[b] stored N x K       */
+int t2v_bmm_f32(const float* A, const float* B, float* C, int32_t batch, int32_t M, int32_t N, int32_t K,
+                int32_t trans_a, int32_t trans_b, void* stream);
+/* row softmax; dS = beta * (dbeta - <beta, dbeta>); and the derivative of that map against a cotangent u
+ * (g_beta / g_dbeta may be NULL)                                                                               */
+int t2v_softmax_fwd(const float* S, float* out, int64_t rows, int32_t cols, void* stream);
+int t2v_softmax_bwd(const float* beta, const float* dbeta, float* dS, int64_t rows, int32_t cols, void* stream);
+int t2v_softmax_bwd_bwd(const float* beta, const float* dbeta, const float* u, float* g_beta, float* g_dbeta,
+                        int64_t rows, int32_t cols, void* stream);
+
+/* The discriminator's Linear(F [+ E], 1) heads (models/resnet3d.py:50-55) on fp32 features (B,F) [and captions
+ * (B,E), may be NULL]: out[b] = [feat | cond][b] . w + bias;  data gradient (outer product);  weight / bias gradient
+ * (accumulate = 1 adds into dw / db).  Each is the derivative of another, so the penalty's double backward stays on
+ * these kernels.                                                                                               */
+int t2v_head_fwd(const float* feat, const float* cond, const float* w, const float* bias, float* out, int32_t B,
+                 int32_t F, int32_t E, void* stream);
+int t2v_head_bwd_data(const float* dpred, const float* w, float* dfeat, float* dcond, int32_t B, int32_t F, int32_t E,
+                      void* stream);
+int t2v_head_bwd_weight(const float* dpred, const float* feat, const float* cond, float* dw, float* db, int32_t B,
+                        int32_t F, int32_t E, int32_t accumulate, void* stream);
+/* Loss reduction over all (level, prediction pair) entries in one launch (gan/cond_gan.py:51-61,108-112):
+ * out = sum_e weight_e / n_e * sum_j f(b_e[j] - a_e[j]); mode 0: f = softplus (RSGANLoss, gan/losses.py:74-85),
+ * mode 1: f = identity (WassersteinGanLoss, losses.py:55-68).  bwd ADDS into da / db (entries may share tensors;
+ * NULL = not needed); gout = d(out) on the device.  At most 24 entries.                                         */
+int t2v_rel_loss_fwd(int32_t count, const float* const* host_a, const float* const* host_b, const int32_t* host_n,
+                     const float* host_weight, int32_t mode, float* out, void* stream);
+int t2v_rel_loss_bwd(int32_t count, const float* const* host_a, const float* const* host_b, float* const* host_da,
+                     float* const* host_db, const int32_t* host_n, const float* host_weight, int32_t mode,
+                     const float* gout, void* stream);
+/* x_hat[b] = alpha[b] * real[b] + (1 - alpha[b]) * fake[b]  (gan/losses.py:140-145), fp32 (B, S)                 */
+int t2v_lerp_rows(const float* real, const float* fake, const float* alpha, float* out, int64_t B, int64_t S,
+                  void* stream);
+
+/* Caption encoder / decoder recurrence (models/txt/basic.py:18-19,49-101: nn.Embedding + nn.LSTM on a
+ * PackedSequence), replacing cuDNN.  gx fp32 [B][L][ndir][4H] = W_ih x + b_ih + b_hh (one GEMM on the engine);
+ * whhT fp32 [ndir][H][4H] from t2v_lstm_pack_whh(whh [ndir][4H][H]); lengths int32 [B] (descending as
+ * pack_padded_sequence requires); h0 / c0 fp32 [ndir][B][H] or NULL.  out / hprev: CL storage type [B][L][ndir*H]
+ * (zeros at padded steps; hprev = the state entering each step, NULL to skip); gates / cells: fp32 saved for
+ * backward (NULL to skip); hn / cn fp32 [ndir][B][H].  bwd: dgates [B][L][ndir*4H] storage type.                 */
+int t2v_lstm_pack_whh(const float* whh, float* whhT, int32_t ndir, int32_t H, void* stream);
+int t2v_lstm_seq_fwd(const float* gx, const float* whhT, const int32_t* lengths, const float* h0, const float* c0,
+                     void* out, void* hprev, float* gates, float* cells, float* hn, float* cn, int32_t B, int32_t L,
+                     int32_t H, int32_t ndir, void* stream);
+int t2v_lstm_seq_bwd(const float* whh, const int32_t* lengths, const float* c0, const float* gates,
+                     const float* cells, const void* dout, const float* dhn, const float* dcn, void* dgates,
+                     float* dh0, float* dc0, int32_t B, int32_t L, int32_t H, int32_t ndir, void* stream);
+int t2v_lstm_seq_fwd_f32(const float* gx, const float* whhT, const int32_t* lengths, const float* h0, const float* c0,
+                         void* out, void* hprev, float* gates, float* cells, float* hn, float* cn, int32_t B,
+                         int32_t L, int32_t H, int32_t ndir, void* stream);
+int t2v_lstm_seq_bwd_f32(const float* whh, const int32_t* lengths, const float* c0, const float* gates,
+                         const float* cells, const void* dout, const float* dhn, const float* dcn, void* dgates,
+                         float* dh0, float* dc0, int32_t B, int32_t L, int32_t H, int32_t ndir, void* stream);
+/* nn.Embedding: out[row] = weight[tokens[row]] (int64 tokens, bit-exact gather) and its weight gradient       */
+int t2v_embedding_fwd(const int64_t* tokens, const float* weight, void* out, int64_t rows, int32_t E, void* stream);
+int t2v_embedding_bwd(const int64_t* tokens, const void* dout, float* dweight, int64_t rows, int32_t E, int64_t V,
+                      void* stream);
+int t2v_embedding_fwd_f32(const int64_t* tokens, const float* weight, void* out, int64_t rows, int32_t E,
+                          void* stream);
+int t2v_embedding_bwd_f32(const int64_t* tokens, const void* dout, float* dweight, int64_t rows, int32_t E, int64_t V,
+                          void* stream);
 
 #ifdef __cplusplus
 }

@@ -40,9 +40,9 @@ def nearest_resize(x, size):
     """gan/trainer.py:149 -- F.interpolate(x, size=(T, fs, fs)) (mode 'nearest'): src = floor(dst*in/out)."""
     B, C, T, H, W = x.shape
     t, h, w = size
-    it = (torch.arange(t) * T) // t
-    ih = (torch.arange(h) * H) // h
-    iw = (torch.arange(w) * W) // w
+    it = (torch.arange(t, device=x.device) * T) // t
+    ih = (torch.arange(h, device=x.device) * H) // h
+    iw = (torch.arange(w, device=x.device) * W) // w
     return x[:, :, it][:, :, :, ih][:, :, :, :, iw]
 
 
@@ -165,8 +165,8 @@ def conv_lstm(x, sd, p, steps):
     after step 0 (:79) -- so Wx*(0) contributes only its bias."""
     B, _, fh, fw = x.shape
     hid = sd[p + ".Whi.weight"].shape[0]
-    h = torch.zeros(B, hid, fh, fw)
-    c = torch.zeros(B, hid, fh, fw)
+    h = torch.zeros(B, hid, fh, fw, device=x.device)
+    c = torch.zeros(B, hid, fh, fw, device=x.device)
     outs = []
     for step in range(steps):
         xi = x if step == 0 else torch.zeros_like(x)
@@ -285,7 +285,7 @@ def seq2seq_encode(sd, tokens, lengths, num_layers=4, p="encoder."):
     the backward direction starts at each sample's own last token.  Returns (out, hn)."""
     emb = F.embedding(tokens, sd[p + "embed.weight"])         # (B, L, E)
     B, L = tokens.shape
-    lens = torch.as_tensor(lengths)
+    lens = torch.as_tensor(lengths, device=tokens.device)
     H = sd[p + "lstm.weight_hh_l0"].shape[1]
     inp = emb
     h_last = None
@@ -296,8 +296,8 @@ def seq2seq_encode(sd, tokens, lengths, num_layers=4, p="encoder."):
             w_ih = sd[p + "lstm.weight_ih_l%d%s" % (layer, suffix)]
             w_hh = sd[p + "lstm.weight_hh_l%d%s" % (layer, suffix)]
             b = sd[p + "lstm.bias_ih_l%d%s" % (layer, suffix)] + sd[p + "lstm.bias_hh_l%d%s" % (layer, suffix)]
-            h = torch.zeros(B, H)
-            c = torch.zeros(B, H)
+            h = torch.zeros(B, H, device=emb.device)
+            c = torch.zeros(B, H, device=emb.device)
             out = [None] * L
             order = range(L) if direction == 0 else range(L - 1, -1, -1)
             for t in order:
@@ -386,7 +386,7 @@ def gradient_penalty(sd, real_x, fake_x, real_cond, fake_cond, alphas):
     p = discrim_prefix(sd)
     total = 0
     for i in range(len(real_x)):
-        a = alphas[i].clone().requires_grad_(True)
+        a = alphas[i].to(real_x[i].device).clone().requires_grad_(True)
         ax = a.expand_as(real_x[i])
         xh = ax * real_x[i] + (1 - ax) * fake_x[i]
         ch = None
@@ -505,7 +505,7 @@ def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN
     # ---- D step (cond_gan.py:156-164, trainer.py:230-243)
     fake_cond = None
     if conds is not None:
-        fc0 = conds[0][torch.as_tensor(draws["perm"])]
+        fc0 = conds[0][torch.as_tensor(draws["perm"], device=conds[0].device)]
         fake_cond = [fc0[0:c.size(0)] for c in conds]
     ld = discrim_loss(sd_d, xs, [f.detach() for f in fake], conds, fake_cond, draws["alphas"], loss, gp_lambda)
     d_names = param_names(sd_d)
@@ -526,12 +526,6 @@ def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN
     for k, v in new_buf.items():
         sd_g[k] = v
     return out
-
-
-def draw_iteration_randoms(B, n_levels=4, conditional=True, gp=True, subsample_input=True):
-    """Host RNG draws of one iteration in the reference's order, EXCEPT z, which the
-    caller draws between bt_real and bt_fake:  use draw_real() -> z -> draw_rest()."""
-    raise NotImplementedError("use draw_real / draw_rest")
 
 
 def draw_real(n_levels=4, subsample_input=True):

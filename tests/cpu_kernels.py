@@ -439,3 +439,189 @@ def multi_copy(srcs, dsts):
         for s, d in zip(srcs, dsts):
             d.view(-1)[:] = torch.as_strided(s, (s.numel(),), (1,), s.storage_offset()) if not s.is_contiguous() \
                 else s.reshape(-1)
+
+
+# ------------------------------------------------------------------------------------- round-2 kernels
+def gconv_pack(w3):
+    return w3.contiguous().to(STORE)
+
+
+def scale(x, s):
+    return (x.float() * s.float()).to(x.dtype)
+
+
+def scale_add(o, x, s=None):
+    return (o.float() * (1.0 if s is None else s.float()) + x.float()).to(x.dtype)
+
+
+def dot(a, b):
+    return (a.float() * b.float()).sum()
+
+
+def cl_slice_f32(x, c):
+    return x[..., :c].float().contiguous()
+
+
+def f32_pad_cl(x, Cp, dtype=None):
+    y = torch.zeros(tuple(x.shape[:-1]) + (Cp,), dtype=dtype or STORE, device=x.device)
+    y[..., :x.shape[-1]] = x.to(y.dtype)
+    return y
+
+
+def maxpool122_fwd(x):
+    M, H, W, c = x.shape
+    win = x.view(M, H // 2, 2, W // 2, 2, c).permute(0, 1, 3, 5, 2, 4).reshape(M, H // 2, W // 2, c, 4)
+    y, idx = win.max(dim=-1)
+    # first maximum, as the kernel: torch.max returns an arbitrary one on ties; recompute deterministically
+    first = (win == y.unsqueeze(-1)).float().argmax(dim=-1)
+    return y.contiguous(), first.to(torch.uint8).contiguous()
+
+
+def pool122_gather(x, idx):
+    M, H, W, c = x.shape
+    win = x.view(M, H // 2, 2, W // 2, 2, c).permute(0, 1, 3, 5, 2, 4).reshape(M, H // 2, W // 2, c, 4)
+    return win.gather(-1, idx.long().unsqueeze(-1)).squeeze(-1).contiguous()
+
+
+def pool122_scatter(dy, idx):
+    M, Hp, Wp, c = dy.shape
+    win = torch.zeros((M, Hp, Wp, c, 4), dtype=dy.dtype, device=dy.device)
+    win.scatter_(-1, idx.long().unsqueeze(-1), dy.unsqueeze(-1))
+    return win.view(M, Hp, Wp, c, 2, 2).permute(0, 1, 4, 2, 5, 3).reshape(M, 2 * Hp, 2 * Wp, c).contiguous()
+
+
+def bmm(a, b, ta=False, tb=False):
+    return torch.bmm(a.transpose(1, 2) if ta else a, b.transpose(1, 2) if tb else b).contiguous()
+
+
+def softmax_fwd(s):
+    return torch.softmax(s, -1)
+
+
+def softmax_bwd(beta, dbeta):
+    return beta * (dbeta - (beta * dbeta).sum(-1, keepdim=True))
+
+
+def softmax_bwd_bwd(beta, dbeta, u):
+    s = (beta * dbeta).sum(-1, keepdim=True)
+    t = (beta * u).sum(-1, keepdim=True)
+    return u * (dbeta - s) - dbeta * t, beta * (u - t)
+
+
+def head_fwd(feat, cond, w, bias):
+    x = feat if cond is None else torch.cat((feat, cond), dim=1)
+    out = x @ w
+    return out + bias.reshape(()) if bias is not None else out
+
+
+def head_bwd_data(dpred, w, F_, E):
+    g = dpred.reshape(-1, 1) * w.reshape(1, -1)
+    return g[:, :F_].contiguous(), (g[:, F_:F_ + E].contiguous() if E else None)
+
+
+def head_bwd_weight(dpred, feat, cond, want_bias=True):
+    x = feat if cond is None else torch.cat((feat, cond), dim=1)
+    return dpred.reshape(1, -1) @ x, (dpred.sum().reshape(1) if want_bias else None)
+
+
+def rel_loss_fwd(a_list, b_list, weights, mode):
+    tot = 0
+    for a, b, w in zip(a_list, b_list, weights):
+        d = b - a
+        tot = tot + w * (F.softplus(d) if mode == 0 else d).mean()
+    return tot.reshape(())
+
+
+def rel_loss_bwd(a_list, b_list, da_list, db_list, weights, mode, gout):
+    for a, b, da, db, w in zip(a_list, b_list, da_list, db_list, weights):
+        d = b - a
+        fp = (torch.sigmoid(d) if mode == 0 else torch.ones_like(d)) * (gout * w / a.numel())
+        if da is not None:
+            da -= fp
+        if db is not None:
+            db += fp
+
+
+def lerp_rows(real, fake, alpha):
+    a = alpha.view([-1] + [1] * (real.dim() - 1))
+    return a * real + (1 - a) * fake
+
+
+def lstm_pack_whh(whh):
+    return whh.transpose(1, 2).contiguous()
+
+
+def lstm_seq_fwd(gx, whhT, lengths, h0, c0, save=True):
+    B, L = gx.shape[0], gx.shape[1]
+    ndir, H = whhT.shape[0], whhT.shape[1]
+    g4 = gx.view(B, L, ndir, 4 * H)
+    out = torch.zeros((B, L, ndir * H))
+    hprev = torch.zeros((B, L, ndir * H))
+    gates = torch.zeros((B, L, ndir, 4 * H))
+    cells = torch.zeros((B, L, ndir, H))
+    hn, cn = torch.zeros((ndir, B, H)), torch.zeros((ndir, B, H))
+    lens = lengths.long()
+    for d in range(ndir):
+        h = h0[d].clone() if h0 is not None else torch.zeros(B, H)
+        c = c0[d].clone() if c0 is not None else torch.zeros(B, H)
+        for s in range(L):
+            t = s if d == 0 else L - 1 - s
+            live = (lens > t).unsqueeze(1)
+            pre = g4[:, t, d] + h @ whhT[d]
+            gi, gf, gg, go = pre.chunk(4, dim=1)
+            gi, gf, gg, go = torch.sigmoid(gi), torch.sigmoid(gf), torch.tanh(gg), torch.sigmoid(go)
+            c_new = gf * c + gi * gg
+            h_new = go * torch.tanh(c_new)
+            hprev[:, t, d * H:(d + 1) * H] = torch.where(live, h, torch.zeros_like(h))
+            gates[:, t, d] = torch.where(live, torch.cat((gi, gf, gg, go), 1), torch.zeros(B, 4 * H))
+            cells[:, t, d] = torch.where(live, c_new, torch.zeros_like(c))
+            out[:, t, d * H:(d + 1) * H] = torch.where(live, h_new, torch.zeros_like(h))
+            h = torch.where(live, h_new, h)
+            c = torch.where(live, c_new, c)
+        hn[d], cn[d] = h, c
+    if not save:
+        return out.to(STORE), None, None, None, hn, cn
+    return out.to(STORE), hprev.to(STORE), gates.view(B, L, ndir * 4 * H), cells.view(B, L, ndir * H), hn, cn
+
+
+def lstm_seq_bwd(whh, lengths, c0, gates, cells, dout, dhn, dcn):
+    ndir, H = whh.shape[0], whh.shape[2]
+    B, L = gates.shape[0], gates.shape[1]
+    g4, c4 = gates.view(B, L, ndir, 4 * H), cells.view(B, L, ndir, H)
+    dg = torch.zeros((B, L, ndir, 4 * H))
+    dh0, dc0 = torch.zeros((ndir, B, H)), torch.zeros((ndir, B, H))
+    lens = lengths.long()
+    for d in range(ndir):
+        dh = dhn[d].clone() if dhn is not None else torch.zeros(B, H)
+        dc = dcn[d].clone() if dcn is not None else torch.zeros(B, H)
+        for s in range(L - 1, -1, -1):
+            t = s if d == 0 else L - 1 - s
+            live = (lens > t).unsqueeze(1)
+            gi, gf, gg, go = g4[:, t, d].chunk(4, dim=1)
+            tp = t - 1 if d == 0 else t + 1
+            cp0 = c0[d] if c0 is not None else torch.zeros(B, H)
+            if 0 <= tp < L:
+                cp = torch.where((lens > tp).unsqueeze(1), c4[:, tp, d], cp0)
+            else:
+                cp = cp0
+            tc = torch.tanh(c4[:, t, d])
+            dhv = dh + (dout[:, t, d * H:(d + 1) * H].float() if dout is not None else 0)
+            dcv = dc + dhv * go * (1 - tc * tc)
+            step = torch.cat((dcv * gg * gi * (1 - gi), dcv * cp * gf * (1 - gf), dcv * gi * (1 - gg * gg),
+                              dhv * tc * go * (1 - go)), 1)
+            step = torch.where(live, step, torch.zeros_like(step))
+            dg[:, t, d] = step
+            dh = torch.where(live, step @ whh[d], dh)
+            dc = torch.where(live, dcv * gf, dc)
+        dh0[d], dc0[d] = dh, dc
+    return dg.view(B, L, ndir * 4 * H).to(STORE), dh0, dc0
+
+
+def embedding_fwd(tokens, weight):
+    return weight[tokens].to(STORE)
+
+
+def embedding_bwd(tokens, dout, V):
+    dw = torch.zeros((V, dout.shape[-1]))
+    dw.index_add_(0, tokens.reshape(-1), dout.float().reshape(-1, dout.shape[-1]))
+    return dw

@@ -62,9 +62,12 @@ def test_reflection_on_reference_paths():
     assert hasattr(d, "sub_discrims") and len(d.sub_discrims) == 4 and hasattr(loss, "discrim_loss")
 
 
-def test_losses_match_oracle():
+def test_losses_match_oracle(monkeypatch):
+    """RSGAN / Wasserstein run on the fused reduction kernel (ops.rel_loss): here with the kernel's executable spec"""
+    import cpu_kernels
     import oracle.txt2vid_oracle as O
-    from txt2vid_b200 import gan
+    from txt2vid_b200 import gan, ops
+    monkeypatch.setattr(ops, "K", cpu_kernels)
     torch.manual_seed(0)
     f, r = torch.randn(8, 1), torch.randn(8, 1)
     pairs = [(gan.RSGANLoss(), O.RSGAN), (gan.WassersteinGanLoss(), O.Wasserstein), (gan.RaLSGANLoss(), O.RaLSGAN),

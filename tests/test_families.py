@@ -244,3 +244,46 @@ def test_tcwyt_product_gpu():
     worst = _compare(orc, got, 2e-2, 0.25, groups + [("G", orc["gG"], got["gG"])])
     print("tcwyt gpu: lossD %.5f (oracle %.5f) lossG %.5f (oracle %.5f) worst grad L2 %s"
           % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))
+
+
+@pytest.fixture()
+def fp32_mode():
+    from txt2vid_b200 import ops
+    ops.set_precision("fp32")
+    yield
+    ops.set_precision("bf16")
+
+
+@pytest.mark.gpu
+def test_tgan_product_gpu_fp32_mode(fp32_mode):
+    """fp32 storage mode through the real kernels (general convolutions in fp32 FMA, typed BatchNorm / activation
+    kernels, tcgen05 Linear layers on bf16 hi/lo splits): BASELINE's fp32 bar, 1e-3 on both losses THEMSELVES and on
+    the generated clip; gradients against the fp64 oracle at the level the fp32 oracle itself reaches (see the module
+    docstring)."""
+    import oracle.families_oracle as O
+    fx = golden("tgan_B8.json")
+    gen, dis = build_tgan()
+    x, z = _synth(fx["B"], 16, 64, fx["input_seed"]), torch.tensor(fx["z"])
+    f64 = torch.float64
+    orc = O.tgan_iteration(O.leaves(gen.state_dict(), f64), O.leaves(dis.state_dict(), f64), x.double(), z.double())
+    got = product_tgan_iteration(gen.cuda(), dis.cuda(), x.cuda(), z.cuda())
+    for k in ("lossD", "lossG", "d_real", "d_fake"):
+        assert abs(got[k] - orc[k]) <= 1e-3 * abs(orc[k]), (k, got[k], orc[k])
+    worst = _compare(orc, got, 1e-3, 1e-2, [("D", orc["gD"], got["gD"]), ("G", orc["gG"], got["gG"])], wgan_tol=1e-3)
+    print("tgan gpu fp32 mode: lossD %.6f (oracle %.6f) lossG %.6f (oracle %.6f) worst grad L2 %s"
+          % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))
+
+
+@pytest.mark.gpu
+def test_tcwyt_product_gpu_fp32_mode(fp32_mode):
+    import oracle.families_oracle as O
+    fx = golden("tcwyt_B4.json")
+    mods = build_tcwyt()
+    x, z, cond = _synth(fx["B"], 16, 48, fx["input_seed"]), torch.tensor(fx["z"]), torch.tensor(fx["cond"])
+    sds = [O.leaves(m.state_dict(), torch.float64) for m in mods]
+    orc = O.tcwyt_iteration(*sds, x.double(), z.double(), cond.double())
+    got = product_tcwyt_iteration([m.cuda() for m in mods], x.cuda(), z.cuda(), cond.cuda())
+    groups = [(n, orc["gD"][n], got["gD"][n]) for n in ("video", "frame", "motion", "map")]
+    worst = _compare(orc, got, 1e-3, 2e-2, groups + [("G", orc["gG"], got["gG"])])
+    print("tcwyt gpu fp32 mode: lossD %.6f (oracle %.6f) lossG %.6f (oracle %.6f) worst grad L2 %s"
+          % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))

@@ -28,6 +28,47 @@ def test_full_iteration_on_b200(name, conditional):
         json.dump({"launches": int(launches), "report": rep}, f)
 
 
+def _record(tag, payload):
+    import json, os
+    os.makedirs("gpurun_out", exist_ok=True)
+    with open("gpurun_out/iteration_parity_%s.json" % tag, "w") as f:
+        json.dump(payload, f)
+
+
+@pytest.mark.parametrize("name,conditional,perturb", [("tganv2_cond_B8.json", True, False),
+                                                      ("tganv2_cond_B8.json", True, True),
+                                                      ("tganv2_uncond_B8.json", False, False)])
+def test_full_iteration_fp32_mode_on_b200(name, conditional, perturb):
+    """BASELINE north_star, fp32 bar: one full iteration through the REAL kernels in the fp32 storage mode (same
+    typed kernels instantiated for float, tcgen05 engine on bf16 hi/lo operand splits) within 1e-3 relative of the
+    oracle on both losses, the generated clips and the gradients of G and D -- with the non-local blocks switched on
+    (gamma = 0.5) and non-trivial BatchNorm affine parameters in the `perturb` case."""
+    from test_product_vs_oracle_cpu import adam_update_stats
+    from txt2vid_b200 import _lib, ops
+    ops.PACKS.clear()
+    n0 = _lib.lib().t2v_launch_count()
+    orc, got = run_product_iteration(conditional, golden(name), "cuda", perturb=perturb, precision="fp32")
+    launches = _lib.lib().t2v_launch_count() - n0
+    assert launches > 500
+    rep = compare(orc, got, 1e-3, 1e-3, 0.999999, 1e-3)
+    assert rep["gradD"]["worst"][1] < 4e-3 and rep["gradG"]["worst"][1] < 4e-3, rep
+    rep["adamD"], rep["adamG"] = adam_update_stats(orc, got, "D"), adam_update_stats(orc, got, "G")
+    # first Adam step = -lr * g / (|g| + eps): elements whose gradient is at rounding level may flip sign
+    assert rep["adamD"] < 2e-2 and rep["adamG"] < 2e-2, rep
+    _record("%s_fp32%s" % (name.split(".")[0], "_attn_on" if perturb else ""),
+            {"precision": "fp32", "perturb": perturb, "launches": int(launches), "report": rep})
+
+
+def test_full_iteration_bf16_attention_on_b200():
+    """bf16 mode with the non-local blocks ON (gamma = 0.5) and non-trivial BatchNorm affine parameters"""
+    from txt2vid_b200 import ops
+    ops.PACKS.clear()
+    orc, got = run_product_iteration(True, golden("tganv2_cond_B8.json"), "cuda", perturb=True, precision="bf16")
+    rep = compare(orc, got, 2e-2, 0.25, 0.97, 6e-2)
+    assert rep["gradD"]["l2"] < 5e-2 and rep["gradD"]["cos"] > 0.998, rep
+    _record("tganv2_cond_B8_bf16_attn_on", {"precision": "bf16", "perturb": True, "report": rep})
+
+
 def test_config5_128x128x32_iteration_on_b200():
     """BASELINE configs[4]: TGANv2 conditional at 128x128x32 (ConvLSTM plane 2x2, frame sizes 16/32/64/128), one full
     iteration at B = 8 against the oracle on the same weights / inputs / host-RNG stream.  Same bars as the 64x64x16

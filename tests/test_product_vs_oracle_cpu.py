@@ -20,7 +20,38 @@ def emulated(monkeypatch):
     ops.PACKS.clear()
 
 
-def run_product_iteration(conditional, fx, device="cpu", size=64, frames=16, frame_sizes=(8, 16, 32, 64)):
+def perturb_models(*modules, seed=7):
+    """at init the non-local blocks are no-ops (gamma = 0) and BatchNorm is the identity affine map, so an
+    init-weight iteration never checks them.  Move them off their initial values: attention gamma = 0.5, BatchNorm
+    weight ~ 1 + 0.1 N(0,1), bias ~ 0.1 N(0,1)."""
+    g = torch.Generator().manual_seed(seed)
+    with torch.no_grad():
+        for mod in modules:
+            if mod is None:
+                continue
+            for m in mod.modules():
+                if isinstance(getattr(m, "gamma", None), torch.nn.Parameter):
+                    m.gamma.fill_(0.5)
+                if isinstance(m, torch.nn.modules.batchnorm._BatchNorm):
+                    m.weight.add_(0.1 * torch.randn(m.weight.shape, generator=g))
+                    m.bias.add_(0.1 * torch.randn(m.bias.shape, generator=g))
+
+
+def run_product_iteration(conditional, fx, device="cpu", size=64, frames=16, frame_sizes=(8, 16, 32, 64),
+                          perturb=False, precision=None):
+    """precision: None (leave the product's mode alone: CPU emulation tests), "bf16" or "fp32" (GPU: ops.set_precision
+    for the duration of the call)."""
+    if precision is None:
+        return _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb)
+    from txt2vid_b200 import ops
+    ops.set_precision(precision)
+    try:
+        return _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb)
+    finally:
+        ops.set_precision("bf16")
+
+
+def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb):
     import oracle.txt2vid_oracle as O
     from txt2vid_b200.gan import CondGan, MixedGanLoss, RSGANLoss
     from txt2vid_b200.optim import FusedAdam
@@ -28,6 +59,8 @@ def run_product_iteration(conditional, fx, device="cpu", size=64, frames=16, fra
     B, V = fx["config"]["B"], fx["config"]["V"]
     txt, gen, dis = build_product_models(conditional, V=V, seed=fx["config"]["seed"], width=size, height=size,
                                          num_frames=frames)
+    if perturb:
+        perturb_models(gen, dis)
     sds = {"gen": state_to_cpu(gen), "dis": state_to_cpu(dis), "txt": None if txt is None else state_to_cpu(txt)}
     rng_t, rng_n = torch.get_rng_state(), np.random.get_state()
     x, tokens, lengths = synth_batch(B, V, T=frames, S=size, seed=fx["config"]["data_seed"])
@@ -97,8 +130,25 @@ def run_product_iteration(conditional, fx, device="cpu", size=64, frames=16, fra
                                                  channel_first=True, end2end=False, z=z_prod.to(device))
     finally:
         T.multiscale_data = real_ms
+    # weights after the two Adam steps: the oracle's Adam updated sd_g / sd_d in place
+    orc["paramsG"] = {n: sd_g[n].detach().clone() for n in O.param_names(sd_g)}
+    orc["paramsD"] = {n: sd_d[n].detach().clone() for n in O.param_names(sd_d)}
+    orc["params0G"], orc["params0D"] = sds["gen"], sds["dis"]
     return orc, {"lossD": float(ld), "lossG": float(lg), "fake": [f.detach().float().cpu() for f in fake],
-                 "real_levels": [t.detach().float().cpu() for t in xs], **grads}
+                 "real_levels": [t.detach().float().cpu() for t in xs],
+                 "paramsG": {n: p.detach().float().cpu() for n, p in gen.named_parameters()},
+                 "paramsD": {n: p.detach().float().cpu() for n, p in dis.named_parameters()}, **grads}
+
+
+def adam_update_stats(orc, got, part):
+    """relative L2 deviation of the Adam UPDATE (w_after - w_before) summed over all tensors of G or D"""
+    num = den = 0.0
+    for n, w1 in orc["params" + part].items():
+        w0 = orc["params0" + part][n].double()
+        du_o, du_p = w1.double() - w0, got["params" + part][n].double() - w0
+        num += float((du_p - du_o).norm()) ** 2
+        den += float(du_o.norm()) ** 2
+    return (num / max(den, 1e-300)) ** 0.5
 
 
 def grad_stats(got, orc):
@@ -136,6 +186,19 @@ def compare(orc, got, loss_tol, grad_l2_tol, grad_cos_min, fake_tol):
     for part in ("gradD", "gradG"):
         assert report[part]["l2"] < grad_l2_tol and report[part]["cos"] > grad_cos_min, report
     return report
+
+
+def test_full_iteration_fp32_formulas_attention_on(emulated):
+    """Same with the non-local blocks switched ON (gamma = 0.5) and non-trivial BatchNorm affine parameters: checks the
+    attention primitives -- including their double backward under the gradient penalty -- against the oracle's
+    F.max_pool / bmm / softmax composition."""
+    cpu_kernels.set_store_dtype(torch.float32)
+    try:
+        orc, got = run_product_iteration(True, golden("tganv2_cond_B8.json"), "cpu", perturb=True)
+    finally:
+        cpu_kernels.set_store_dtype(torch.bfloat16)
+    rep = compare(orc, got, 1e-3, 1e-3, 0.999999, 1e-3)
+    assert rep["gradD"]["worst"][1] < 3e-3 and rep["gradG"]["worst"][1] < 3e-3, rep
 
 
 @pytest.mark.parametrize("name,conditional", [("tganv2_cond_B8.json", True), ("tganv2_uncond_B8.json", False)])

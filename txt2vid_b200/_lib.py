@@ -14,7 +14,7 @@ LIB_PATH = os.path.join(_HERE, "libt2v_b200.so")
 
 T2V_OK = 0
 ALGO_AUTO, ALGO_TC, ALGO_SIMT, ALGO_TC_GENERIC = 0, 1, 2, 3
-EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK = 1, 2, 4
+EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK, EPI_RES_F32 = 1, 2, 4, 8
 
 
 class ConvGeom(ctypes.Structure):
@@ -117,6 +117,44 @@ SIGNATURES = {
     "t2v_adam_step": [c_i32, _PP, _PP, _PP, _PP, ctypes.POINTER(c_i64), c_float, c_float, c_float, c_float, c_i32,
                       c_float, _P, _P],
 }
+
+# fp32 activation storage: every storage-typed entry point has an _f32 twin with the same signature
+_TYPED = ["t2v_relu_fwd", "t2v_relu_bwd", "t2v_leaky_relu_fwd", "t2v_leaky_relu_bwd", "t2v_tanh_fwd", "t2v_tanh_bwd",
+          "t2v_avgpool_fwd", "t2v_avgpool_bwd", "t2v_upsample2x_fwd", "t2v_upsample2x_bwd", "t2v_nchw_to_cl",
+          "t2v_cl_to_nchw", "t2v_im2col3", "t2v_col2im3", "t2v_sum_rows", "t2v_sum_rows_acc", "t2v_sum_spatial",
+          "t2v_broadcast_spatial", "t2v_bn_stats", "t2v_bn_apply", "t2v_bn_bwd", "t2v_render_fwd", "t2v_render_bwd",
+          "t2v_lstm_cell_fwd", "t2v_lstm_cell_bwd", "t2v_gconv_fprop", "t2v_gconv_dgrad", "t2v_gconv_wgrad",
+          "t2v_scale", "t2v_scale_add", "t2v_dot", "t2v_cl_slice_f32", "t2v_f32_pad_cl", "t2v_lstm_seq_fwd",
+          "t2v_lstm_seq_bwd", "t2v_embedding_fwd", "t2v_embedding_bwd"]
+_F32P = ctypes.POINTER(ctypes.c_float)
+SIGNATURES.update({
+    "t2v_split_bf16x3": [_P, _P, c_i64, c_i32, c_i32, _P],
+    "t2v_scale": [_P, _P, _P, c_i64, _P],
+    "t2v_scale_add": [_P, _P, _P, _P, c_i64, _P],
+    "t2v_dot": [_P, _P, _P, c_i64, _P],
+    "t2v_cl_slice_f32": [_P, _P, c_i64, c_i32, c_i32, _P],
+    "t2v_f32_pad_cl": [_P, _P, c_i64, c_i32, c_i32, _P],
+    "t2v_maxpool122_fwd": [_P, _P, _P, c_i64, c_i32, c_i32, c_i32, _P],
+    "t2v_pool122_gather": [_P, _P, _P, c_i64, c_i32, c_i32, c_i32, _P],
+    "t2v_pool122_scatter": [_P, _P, _P, c_i64, c_i32, c_i32, c_i32, _P],
+    "t2v_bmm_f32": [_P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_softmax_fwd": [_P, _P, c_i64, c_i32, _P],
+    "t2v_softmax_bwd": [_P, _P, _P, c_i64, c_i32, _P],
+    "t2v_softmax_bwd_bwd": [_P, _P, _P, _P, _P, c_i64, c_i32, _P],
+    "t2v_head_fwd": [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, _P],
+    "t2v_head_bwd_data": [_P, _P, _P, _P, c_i32, c_i32, c_i32, _P],
+    "t2v_head_bwd_weight": [_P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_rel_loss_fwd": [c_i32, _PP, _PP, _I32P, _F32P, c_i32, _P, _P],
+    "t2v_rel_loss_bwd": [c_i32, _PP, _PP, _PP, _PP, _I32P, _F32P, c_i32, _P, _P],
+    "t2v_lerp_rows": [_P, _P, _P, _P, c_i64, c_i64, _P],
+    "t2v_lstm_pack_whh": [_P, _P, c_i32, c_i32, _P],
+    "t2v_lstm_seq_fwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_lstm_seq_bwd": [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_embedding_fwd": [_P, _P, _P, c_i64, c_i32, _P],
+    "t2v_embedding_bwd": [_P, _P, _P, c_i64, c_i32, c_i64, _P],
+})
+for _n in _TYPED:
+    SIGNATURES[_n + "_f32"] = SIGNATURES[_n]
 _RESTYPES = {"t2v_launch_count": ctypes.c_ulonglong}
 
 
@@ -125,6 +163,11 @@ def _declare(l):
         fn = getattr(l, name)
         fn.argtypes = argtypes
         fn.restype = _RESTYPES.get(name, c_int)
+
+
+def typed(name, t):
+    """entry point for the storage type of tensor t: `name` (bf16) or its fp32 twin `name_f32`"""
+    return getattr(lib(), name + "_f32" if t.dtype == torch.float32 else name)
 
 
 def ptr(t):

@@ -192,7 +192,8 @@ class DownBlock(nn.Module):
         c1 = self.main.identity_map[0]
         # both ReLU backward masks ride in the data-gradient epilogues of their (single) consumers
         h = ops.conv(ops.relu(x, later=True), m[1].weight, m[1].bias, relu=True, x_relu=True, relu_later=True)
-        if SKIP_FUSE and x.shape[-1] % 64 == 0 and h.shape[-1] % 64 == 0 and tuple(c1.weight.shape[2:]) == (1, 1, 1):
+        if SKIP_FUSE and not ops.fp32_mode() and x.shape[-1] % 64 == 0 and h.shape[-1] % 64 == 0 \
+                and tuple(c1.weight.shape[2:]) == (1, 1, 1):
             # the 1^3 skip convolution is extra K of the second convolution's implicit GEMM
             h = ops.conv_skip(h, x, m[3].weight, m[3].bias, c1.weight, c1.bias, h_relu=True)
         else:
@@ -325,7 +326,7 @@ class Resnet3D(nn.Module):
     def features(self, x):
         """fp32 (B,C,T,H,W) -> fp32 (B, F) sum-pooled trunk features."""
         m = self.res_block.inner_module
-        if STEM_DIRECT and x.shape[1] == 3 and m[0].weight.shape[0] == 64:
+        if STEM_DIRECT and not ops.fp32_mode() and x.shape[1] == 3 and m[0].weight.shape[0] == 64:
             # RGB padded to 16 channels (skip path) and to 4 channels (stem gather) in one pass;
             # first conv (K = 27*3 = 81): im2col tile gathered into shared memory, tensor-core GEMM, bias + ReLU
             xc, xc4 = ops.rgb_to_cl(x)
@@ -337,7 +338,7 @@ class Resnet3D(nn.Module):
         c1 = self.res_block.identity_map[1]
         pk, ps = (1, 2, 2), (2, 2, 2)                                 # AvgPool3d((1,2,2), 2): stride 2 in ALL dims
         skip = ops.conv(ops.avg_pool(xc, pk, ps), c1.weight, c1.bias)
-        if STEM_SD2 and ops.K.conv_sd2_supported(h.shape, h.shape[-1], m[2].weight.shape[0], tuple(m[2].weight.shape[2:])):
+        if STEM_SD2 and not ops.fp32_mode() and ops.K.conv_sd2_supported(h.shape, h.shape[-1], m[2].weight.shape[0], tuple(m[2].weight.shape[2:])):
             # the pool keeps only the even d planes of this convolution (kernel 1, stride 2 along d): compute only those
             h = ops.conv_sd2(h, m[2].weight, m[2].bias, x_relu=True)
             h = ops.avg_pool(h, pk, (1, 2, 2), residual=skip)
@@ -352,7 +353,7 @@ class Resnet3D(nn.Module):
         """(uncond, cond, feat) from trunk features (resnet3d.py:50-57)"""
         uncond = ops.head_linear(feat, self.fc_uncond.weight, self.fc_uncond.bias)
         if cond is not None:
-            c = ops.head_linear(torch.cat((feat, cond), dim=1), self.fc.weight, self.fc.bias)
+            c = ops.head_linear(feat, self.fc.weight, self.fc.bias, cond=cond)     # Linear on cat(feat, cond), no cat
             return uncond, c, feat
         return uncond, None, feat
 
@@ -365,6 +366,6 @@ class Resnet3D(nn.Module):
             computed_features = feat
             uncond = ops.head_linear(feat, self.fc_uncond.weight, self.fc_uncond.bias)
         if cond is not None:
-            c = ops.head_linear(torch.cat((feat, cond), dim=1), self.fc.weight, self.fc.bias)
+            c = ops.head_linear(feat, self.fc.weight, self.fc.bias, cond=cond)
             return uncond, c, computed_features
         return uncond, None, computed_features

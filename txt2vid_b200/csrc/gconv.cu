@@ -16,12 +16,13 @@ namespace t2v {
 
 static constexpr int GT = 64, GK = 16;
 
+template <typename ST>
 struct GconvParams {
   t2v_gconv_geom g;
   long long Pi, Po;            // input / output positions
-  const __nv_bfloat16* x;      // [N][Di][Hi][Wi][Ci]
-  const __nv_bfloat16* w;      // [Co][taps][Ci]
-  const __nv_bfloat16* dy;     // [N][Do][Ho][Wo][Co]
+  const ST* x;      // [N][Di][Hi][Wi][Ci]   (ST = bf16, or fp32 in the fp32 parity mode)
+  const ST* w;      // [Co][taps][Ci]
+  const ST* dy;     // [N][Do][Ho][Wo][Co]
   const float* bias;
   void* out;
   int out_f32;
@@ -37,7 +38,8 @@ __device__ __forceinline__ void decode_pos(long long pos, int D, int H, int W, i
 }
 
 // y[opos, co] = sum_{tap, ci} x[n, od*sd - pd + a_d, oh*sh - ph + a_h, ow*sw - pw + a_w, ci] * w[co, tap, ci]
-__global__ void __launch_bounds__(256) gconv_fprop_kernel(const GconvParams p) {
+template <typename ST>
+__global__ void __launch_bounds__(256) gconv_fprop_kernel(const GconvParams<ST> p) {
   __shared__ float As[GK][GT + 1];
   __shared__ float Bs[GK][GT + 1];
   const t2v_gconv_geom& g = p.g;
@@ -106,7 +108,8 @@ __global__ void __launch_bounds__(256) gconv_fprop_kernel(const GconvParams p) {
 }
 
 // dx[ipos, ci] = sum_{tap, co : (i + p - a) % s == 0} dy[n, (id+pd-a_d)/sd, ..., co] * w[co, tap, ci]   (+ bias[ci])
-__global__ void __launch_bounds__(256) gconv_dgrad_kernel(const GconvParams p) {
+template <typename ST>
+__global__ void __launch_bounds__(256) gconv_dgrad_kernel(const GconvParams<ST> p) {
   __shared__ float As[GK][GT + 1];
   __shared__ float Bs[GK][GT + 1];
   const t2v_gconv_geom& g = p.g;
@@ -177,7 +180,8 @@ __global__ void __launch_bounds__(256) gconv_dgrad_kernel(const GconvParams p) {
 }
 
 // dw[co, tap, ci] += sum_opos dy[opos, co] * x[ipos(opos, tap), ci];  grid = (co tiles, ci tiles, taps * splits)
-__global__ void __launch_bounds__(256) gconv_wgrad_kernel(const GconvParams p) {
+template <typename ST>
+__global__ void __launch_bounds__(256) gconv_wgrad_kernel(const GconvParams<ST> p) {
   __shared__ float As[GK][GT + 1];   // [pos][co]
   __shared__ float Bs[GK][GT + 1];   // [pos][ci]
   const t2v_gconv_geom& g = p.g;
@@ -245,8 +249,9 @@ static bool gconv_ok(const t2v_gconv_geom* g) {
          g->Wo == oe(g->Wi, g->kw, g->sw, g->pw);
 }
 
-static GconvParams gconv_params(const t2v_gconv_geom* g) {
-  GconvParams p{};
+template <typename ST>
+static GconvParams<ST> gconv_params(const t2v_gconv_geom* g) {
+  GconvParams<ST> p{};
   p.g = *g;
   p.Pi = (long long)g->N * g->Di * g->Hi * g->Wi;
   p.Po = (long long)g->N * g->Do * g->Ho * g->Wo;
@@ -257,40 +262,42 @@ static GconvParams gconv_params(const t2v_gconv_geom* g) {
 
 using namespace t2v;
 
-extern "C" {
 
-int t2v_gconv_fprop(const t2v_gconv_geom* g, const void* x, const void* w, const float* bias, void* y,
+template <typename ST>
+static int gconv_fprop_impl(const t2v_gconv_geom* g, const void* x, const void* w, const float* bias, void* y,
                     int32_t out_f32, void* stream) {
   if (!gconv_ok(g) || !x || !w || !y) return T2V_ERR_ARG;
-  GconvParams p = gconv_params(g);
-  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
-  p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+  GconvParams<ST> p = gconv_params<ST>(g);
+  p.x = reinterpret_cast<const ST*>(x);
+  p.w = reinterpret_cast<const ST*>(w);
   p.bias = bias; p.out = y; p.out_f32 = out_f32;
   dim3 grid((unsigned)((p.Po + GT - 1) / GT), (unsigned)((g->Cout + GT - 1) / GT), 1);
-  gconv_fprop_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  gconv_fprop_kernel<ST><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   return check_last("gconv_fprop");
 }
 
-int t2v_gconv_dgrad(const t2v_gconv_geom* g, const void* dy, const void* w, const float* bias, void* dx,
+template <typename ST>
+static int gconv_dgrad_impl(const t2v_gconv_geom* g, const void* dy, const void* w, const float* bias, void* dx,
                     int32_t out_f32, void* stream) {
   if (!gconv_ok(g) || !dy || !w || !dx) return T2V_ERR_ARG;
-  GconvParams p = gconv_params(g);
-  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
-  p.w = reinterpret_cast<const __nv_bfloat16*>(w);
+  GconvParams<ST> p = gconv_params<ST>(g);
+  p.dy = reinterpret_cast<const ST*>(dy);
+  p.w = reinterpret_cast<const ST*>(w);
   p.bias = bias; p.out = dx; p.out_f32 = out_f32;
   dim3 grid((unsigned)((p.Pi + GT - 1) / GT), (unsigned)((g->Cin + GT - 1) / GT), 1);
-  gconv_dgrad_kernel<<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
+  gconv_dgrad_kernel<ST><<<grid, 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   return check_last("gconv_dgrad");
 }
 
-int t2v_gconv_wgrad(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
+template <typename ST>
+static int gconv_wgrad_impl(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
                     void* stream) {
   if (!gconv_ok(g) || !dy || !x || !dw) return T2V_ERR_ARG;
-  GconvParams p = gconv_params(g);
-  p.dy = reinterpret_cast<const __nv_bfloat16*>(dy);
-  p.x = reinterpret_cast<const __nv_bfloat16*>(x);
+  GconvParams<ST> p = gconv_params<ST>(g);
+  p.dy = reinterpret_cast<const ST*>(dy);
+  p.x = reinterpret_cast<const ST*>(x);
   p.dw = dw;
   const int taps = g->kd * g->kh * g->kw;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
@@ -303,9 +310,39 @@ int t2v_gconv_wgrad(const t2v_gconv_geom* g, const void* dy, const void* x, floa
   if ((long long)taps * splits > 65535) splits = 65535 / taps;
   p.splits = (int)splits;
   dim3 grid((unsigned)((g->Cout + GT - 1) / GT), (unsigned)((g->Cin + GT - 1) / GT), (unsigned)(taps * splits));
-  gconv_wgrad_kernel<<<grid, 256, 0, s>>>(p);
+  gconv_wgrad_kernel<ST><<<grid, 256, 0, s>>>(p);
   count_launch();
   return check_last("gconv_wgrad");
 }
 
+
+
+extern "C" {
+int t2v_gconv_fprop(const t2v_gconv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                    int32_t out_f32, void* stream) {
+  return gconv_fprop_impl<__nv_bfloat16>(g, x, w, bias, y, out_f32, stream);
+}
+int t2v_gconv_dgrad(const t2v_gconv_geom* g, const void* dy, const void* w, const float* bias, void* dx,
+                    int32_t out_f32, void* stream) {
+  return gconv_dgrad_impl<__nv_bfloat16>(g, dy, w, bias, dx, out_f32, stream);
+}
+int t2v_gconv_wgrad(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
+                    void* stream) {
+  return gconv_wgrad_impl<__nv_bfloat16>(g, dy, x, dw, accumulate, stream);
+}
+/* fp32 storage (the 1e-3 parity mode): x / w / dy fp32, output always fp32 */
+int t2v_gconv_fprop_f32(const t2v_gconv_geom* g, const void* x, const void* w, const float* bias, void* y,
+                        int32_t out_f32, void* stream) {
+  (void)out_f32;
+  return gconv_fprop_impl<float>(g, x, w, bias, y, 1, stream);
+}
+int t2v_gconv_dgrad_f32(const t2v_gconv_geom* g, const void* dy, const void* w, const float* bias, void* dx,
+                        int32_t out_f32, void* stream) {
+  (void)out_f32;
+  return gconv_dgrad_impl<float>(g, dy, w, bias, dx, 1, stream);
+}
+int t2v_gconv_wgrad_f32(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
+                        void* stream) {
+  return gconv_wgrad_impl<float>(g, dy, x, dw, accumulate, stream);
+}
 }  // extern "C"

@@ -42,7 +42,7 @@ struct IgemmParams {
   const float* bias;
   const __nv_bfloat16* residual;
   void* out;
-  int out_f32, relu, relu_mask;
+  int out_f32, relu, relu_mask, res_f32;
   // wgrad only
   float* dw;
   int taps_total, splits, tiles_total, atomic_out;
@@ -193,7 +193,21 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
             f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
           }
         }
-        if (p.residual != nullptr) {
+        if (p.residual != nullptr && p.res_f32) {
+          // fp32 residual / ReLU reference (fp32 activation storage: the 1e-3 parity mode)
+          const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) +
+                                                             pos * p.Cout + col);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float4 r4 = rp[j];
+            if (p.relu_mask) {
+              f[4 * j + 0] = r4.x > 0.f ? f[4 * j + 0] : 0.f; f[4 * j + 1] = r4.y > 0.f ? f[4 * j + 1] : 0.f;
+              f[4 * j + 2] = r4.z > 0.f ? f[4 * j + 2] : 0.f; f[4 * j + 3] = r4.w > 0.f ? f[4 * j + 3] : 0.f;
+            } else {
+              f[4 * j + 0] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+            }
+          }
+        } else if (p.residual != nullptr) {
           const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pos * p.Cout + col);
 #pragma unroll
           for (int j = 0; j < 2; ++j) {
@@ -518,6 +532,7 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
   p.out_f32 = (flags & T2V_EPI_OUT_F32) ? 1 : 0;
   p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
   p.relu_mask = (flags & T2V_EPI_RELU_MASK) ? 1 : 0;
+  p.res_f32 = (flags & T2V_EPI_RES_F32) ? 1 : 0;
 
   CUtensorMap tmA, tmB;
   int rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, g->Cin, BLOCK_K, p.bw, p.bh, p.bd, p.bn);

@@ -26,6 +26,7 @@ inline int check_last(const char* /*what*/) {
 // ---------------------------------------------------------------- small math
 T2V_DEVINL float bf2f(__nv_bfloat16 v) { return __bfloat162float(v); }
 T2V_DEVINL __nv_bfloat16 f2bf(float v) { return __float2bfloat16_rn(v); }
+T2V_DEVINL float bf2f(float v) { return v; }   // fp32-storage instantiations of the typed kernels
 
 T2V_DEVINL uint32_t pack_bf16x2(float lo, float hi) {
   __nv_bfloat162 v = __floats2bfloat162_rn(lo, hi);

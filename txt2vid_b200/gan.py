@@ -10,7 +10,7 @@ import torch
 import torch.nn as nn
 import torch.nn.functional as F
 
-from . import hostrng
+from . import hostrng, ops
 
 
 def get_labels_for(x, label):
@@ -63,6 +63,8 @@ class HingeGanLoss(LabelledGanLoss):
 
 class WassersteinGanLoss(object):
     def discrim_loss(self, fake=None, real=None):
+        if real.numel() == fake.numel():
+            return ops.rel_loss([(real, fake, 1.0)], 1)          # mean(fake - real), one reduction kernel
         return -(real.mean() - fake.mean())
 
     def gen_loss(self, fake=None, real=None):
@@ -80,7 +82,7 @@ class RSGANLoss(object):
 
     def _rel(self, a, b):
         if self.bce:
-            return F.softplus(b - a).mean()
+            return ops.rel_loss([(a, b, 1.0)], 0)                # mean softplus(b - a), one reduction kernel
         return self.loss(a - b, get_labels_for(a, 1))
 
     def discrim_loss(self, fake=None, real=None):
@@ -120,6 +122,19 @@ class RaLSGANLoss(object):
         return (torch.mean((real - torch.mean(fake) + 1) ** 2) + torch.mean((fake - torch.mean(real) - 1) ** 2)) / 2
 
 
+def fused_loss_mode(loss, which):
+    """0 (RSGAN, BCE form) when `loss` -- the bound discrim_loss / gen_loss of a loss object (train/gan.py:156) --
+    can be evaluated over all pyramid levels and prediction pairs by ONE reduction kernel (ops.rel_loss); None
+    otherwise (the generic per-level composition of gan/cond_gan.py:51-61 is used)."""
+    obj = getattr(loss, "__self__", None)
+    if isinstance(obj, MixedGanLoss):
+        obj = obj.d_loss if which == "d" else obj.g_loss
+    if isinstance(obj, RSGANLoss) and obj.bce and getattr(loss, "__name__", "") == ("discrim_loss" if which == "d"
+                                                                                   else "gen_loss"):
+        return 0
+    return None
+
+
 def _gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xbar=None, real_cond=None,
                       fake_cond=None, zero_center=False, combine=torch.mean):
     """gan/losses.py:135-186.  alpha ~ U(0,1) per sample from the CPU generator (created on CPU, then moved,
@@ -127,21 +142,26 @@ def _gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xb
     B = real_x.size(0)
     assert real_x.dim() in (4, 5)
     alpha = hostrng.CURRENT.alpha(B, real_x.device)            # B draws from the CPU generator, as the reference
-    a = alpha.view([B] + [1] * (real_x.dim() - 1))
-    xh = (a * real_x + (1 - a) * fake_x).requires_grad_(True)
+
+    def lerp(r, f):
+        if not (r.requires_grad or f.requires_grad) and r.dtype == torch.float32:
+            return ops.K.lerp_rows(r.contiguous(), f.contiguous(), alpha.reshape(-1).contiguous()).requires_grad_(True)
+        a = alpha.view([B] + [1] * (r.dim() - 1))
+        return (a * r + (1 - a) * f).requires_grad_(True)
+    xh = lerp(real_x, fake_x)
     xbarh = None
     if real_xbar is not None and fake_xbar is not None:
-        ab = alpha.view([B] + [1] * (real_xbar.dim() - 1))
-        xbarh = (ab * real_xbar + (1 - ab) * fake_xbar).requires_grad_(True)
+        xbarh = lerp(real_xbar, fake_xbar)
     ch = None
     if real_cond is not None and fake_cond is not None:
-        ac = alpha.view(B, 1)
-        ch = (ac * real_cond + (1 - ac) * fake_cond).requires_grad_(True)
+        ch = lerp(real_cond, fake_cond)
     u, c, _ = discrim(x=xh, cond=ch, xbar=xbarh)
     outs = [u] + ([c] if c is not None else [])
     ins = [xh] + ([ch] if ch is not None else []) + ([xbarh] if xbarh is not None else [])
     g = torch.autograd.grad(outputs=outs, inputs=ins, grad_outputs=[torch.ones_like(o) for o in outs],
                             create_graph=True, retain_graph=True, only_inputs=True)[0]
+    if zero_center and combine is torch.sum and g.numel() % 8 == 0:
+        return ops.DotF.apply(g.contiguous(), g.contiguous())        # sum_b ||g_b||^2, one reduction kernel
     n2 = g.reshape(B, -1).pow(2).sum(dim=1)
     return combine(n2) if zero_center else combine((n2.sqrt() - 1) ** 2)
 
@@ -162,7 +182,10 @@ def gradient_penalty(discrim, real_x=None, real_xbar=None, fake_x=None, fake_xba
         total.append(_gradient_penalty(discrim.sub_discrims[i], real_x=real_x[i], real_xbar=rxb, real_cond=rc,
                                        fake_x=fake_x[i], fake_xbar=fxb, fake_cond=fc, zero_center=True,
                                        combine=torch.sum))
-    return torch.stack(total).sum()
+    out = total[0]
+    for t in total[1:]:
+        out = out + t
+    return out
 
 
 import os as _os
@@ -195,6 +218,10 @@ class CondGan(object):
         return self.sample_mapping(x) if self.sample_mapping is not None and x is not None else None
 
     def _discrim_weighted_sum(self, losses):
+        if isinstance(losses, (list, tuple)):
+            if len(losses) == 1 and self.discrim_lambdas is None:
+                return losses[0]                       # mean of one element
+            losses = torch.stack(list(losses))
         if self.discrim_lambdas is None:
             return torch.mean(losses)
         return torch.sum(torch.tensor(self.discrim_lambdas, device=losses.device) * losses)
@@ -220,10 +247,19 @@ class CondGan(object):
                                   computed_features=[t[-1] for t in real_cc])
                 if not pair:
                     fake_cc = discrim(x=fake, cond=real_cond, xbar=fake_mapping)
-                l_u = self._mean_over_levels(loss, fake_cc, real_cc, 0)
-                l_c = (self._mean_over_levels(loss, fake_cc, real_cc, 1) +
-                       self._mean_over_levels(loss, real_ic, real_cc, 1)) / 2
-                l = (l_u + l_c) / 2.0
+                mode = fused_loss_mode(loss, "d")
+                if mode is not None:
+                    # (mean_i L(f_u, r_u) + (mean_i L(f_c, r_c) + mean_i L(ric_c, r_c)) / 2) / 2 in one kernel
+                    n = float(len(real_cc))
+                    pairs = [(r[0], f[0], 0.5 / n) for f, r in zip(fake_cc, real_cc)]
+                    pairs += [(r[1], f[1], 0.25 / n) for f, r in zip(fake_cc, real_cc)]
+                    pairs += [(r[1], f[1], 0.25 / n) for f, r in zip(real_ic, real_cc)]
+                    l = ops.rel_loss(pairs, mode)
+                else:
+                    l_u = self._mean_over_levels(loss, fake_cc, real_cc, 0)
+                    l_c = (self._mean_over_levels(loss, fake_cc, real_cc, 1) +
+                           self._mean_over_levels(loss, real_ic, real_cc, 1)) / 2
+                    l = (l_u + l_c) / 2.0
         else:
             if real is not None and fake is not None and loss is not None and hasattr(discrim, "forward_pair") \
                     and real_mapping is None and fake_mapping is None and PAIR_D_STEP:
@@ -235,7 +271,12 @@ class CondGan(object):
                 if fake is not None:
                     fake_pred = [f[0] for f in discrim(x=fake, cond=None, xbar=fake_mapping)]
             if loss is not None and fake_pred is not None and real_pred is not None:
-                l = torch.stack([loss(fake=f, real=r) for f, r in zip(fake_pred, real_pred)]).mean()
+                mode = fused_loss_mode(loss, "d")
+                if mode is not None:
+                    n = float(len(real_pred))
+                    l = ops.rel_loss([(r, f, 1.0 / n) for f, r in zip(fake_pred, real_pred)], mode)
+                else:
+                    l = torch.stack([loss(fake=f, real=r) for f, r in zip(fake_pred, real_pred)]).mean()
         if l is not None and gp_lambda > 0:
             l = l + gp_lambda * gradient_penalty(discrim, real_x=real, real_xbar=real_mapping, fake_x=fake,
                                                  fake_xbar=fake_mapping, real_cond=real_cond, fake_cond=fake_cond)
@@ -251,14 +292,25 @@ class CondGan(object):
         losses = []
         for r, name, discrim in zip(real_pred, self.discrim_names, self.discrims):
             fake_cc = discrim(x=fake, cond=cond, xbar=fake_mapping)
+            mode = fused_loss_mode(loss, "g")
+            pick = lambda t: t[0] if isinstance(t, (tuple, list)) else t
+            fused = mode is not None
+            n = float(len(fake_cc))
             if cond is None:
-                pick = lambda t: t[0] if isinstance(t, (tuple, list)) else t
-                losses.append(torch.stack([loss(fake=pick(ff), real=pick(rr)) for ff, rr in zip(fake_cc, r)]).mean())
+                if fused:        # RSGAN generator loss: softplus(real - fake): a = fake, b = real
+                    losses.append(ops.rel_loss([(pick(ff), pick(rr), 1.0 / n) for ff, rr in zip(fake_cc, r)], mode))
+                else:
+                    losses.append(torch.stack([loss(fake=pick(ff), real=pick(rr))
+                                               for ff, rr in zip(fake_cc, r)]).mean())
+            elif fused:
+                pairs = [(ff[0], rr[0], 0.5 / n) for ff, rr in zip(fake_cc, r)]
+                pairs += [(ff[1], rr[1], 0.5 / n) for ff, rr in zip(fake_cc, r)]
+                losses.append(ops.rel_loss(pairs, mode))
             else:
                 l_u = self._mean_over_levels(loss, fake_cc, r, 0)
                 l_c = self._mean_over_levels(loss, fake_cc, r, 1)
                 losses.append((l_c + l_u) / 2.0)
-        return self._discrim_weighted_sum(torch.stack(losses))
+        return self._discrim_weighted_sum(losses)
 
     def all_discrim_forward(self, fake=None, real=None, cond=None, loss=None, gp_lambda=-1):
         """cond_gan.py:121-154: mismatched captions = a non-identity permutation of the level-0 captions
@@ -285,7 +337,7 @@ class CondGan(object):
         if self.cond_encoder is not None:
             self.cond_encoder.zero_grad()
         losses, _, _ = self.all_discrim_forward(real=real, fake=fake, cond=cond, loss=loss, gp_lambda=gp_lambda)
-        return self._discrim_weighted_sum(torch.stack(losses))
+        return self._discrim_weighted_sum(losses)
 
     def count_params(self):
         from .util import count_params

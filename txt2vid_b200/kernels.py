@@ -16,6 +16,38 @@ from ._lib import ConvGeom, GconvGeom, check, lib, ptr, require_cuda, stream
 BF16 = torch.bfloat16
 F32 = torch.float32
 
+# Activation storage type of the tensors the wrappers CREATE at fp32 boundaries (layout conversion, operand packs,
+# broadcast / render / LSTM outputs).  bf16 is the product; fp32 is the parity mode of BASELINE's north_star (1e-3 on
+# losses and gradients): same kernels instantiated for float storage, and the tcgen05 engine fed with bf16 hi / lo
+# operand splits (see conv_fprop).  Elementwise wrappers follow the dtype of their input.
+STORE = BF16
+
+
+def set_store_dtype(dt):
+    global STORE
+    assert dt in (BF16, F32)
+    STORE = dt
+
+
+def _act(*ts):
+    for t in ts:
+        assert t is None or (t.dtype in (BF16, F32) and t.is_contiguous()), (None if t is None else (t.dtype, t.shape))
+
+
+def split3(x, layout):
+    """fp32 (..., C) -> bf16 hi/lo split for the tensor pipe: layout 0 (..., 3C) = [hi|lo|hi]; 1 / 2: (3N, ..., C) =
+    [hi;lo;hi] / [hi;hi;lo] concatenated along the leading dim."""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    C = x.shape[-1]
+    rows = x.numel() // C
+    if layout == 0:
+        out = torch.empty(tuple(x.shape[:-1]) + (3 * C,), device=x.device, dtype=BF16)
+    else:
+        out = torch.empty((3 * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=BF16)
+    check(lib().t2v_split_bf16x3(ptr(x), ptr(out), rows, C, layout, stream()), "t2v_split_bf16x3")
+    return out
+
 
 def _geom(N, D, H, W, Cin, Cout, k):
     kd, kh, kw = k
@@ -28,17 +60,25 @@ def _i32(*vals):
 
 # ------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=False, algo=0):
-    """x (N,D,H,W,Cin) bf16, w (Cout,taps,Cin) bf16 -> y (N,D,H,W,Cout) bf16|f32."""
+    """x (N,D,H,W,Cin) bf16, w (Cout,taps,Cin) bf16 -> y (N,D,H,W,Cout) bf16|f32.
+    fp32 storage: x fp32, w the K-concatenated pack (Cout,taps,3*Cin) of pack_weight -> y fp32 (residual fp32)."""
     require_cuda(x, w, bias, residual)
     N, D, H, W, Cin = x.shape
     Cout = w.shape[0]
+    f32 = x.dtype == F32
+    if f32:
+        assert w.shape[2] == 3 * Cin, (w.shape, Cin)
+        x = split3(x, 0)
+        Cin, out_f32 = 3 * Cin, True
+        assert residual is None or residual.dtype == F32
     assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
     assert x.is_contiguous() and w.is_contiguous() and x.dtype == BF16 and w.dtype == BF16
     assert bias is None or (bias.dtype == F32 and bias.numel() == Cout)
-    assert residual is None or (residual.dtype == BF16 and residual.is_contiguous())
+    assert residual is None or (residual.dtype == (F32 if f32 else BF16) and residual.is_contiguous())
     y = torch.empty((N, D, H, W, Cout), device=x.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
-    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0)
+    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0) | \
+        (_lib.EPI_RES_F32 if (f32 and residual is not None) else 0)
     check(lib().t2v_conv_fprop(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), flags, algo,
                                stream()), "t2v_conv_fprop")
     return y
@@ -63,19 +103,25 @@ def conv_fprop_skip(x, w, bias, x2, w2, k=(3, 3, 3), relu=False):
 
 def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0, relu_ref=None):
     """dy (N,D,H,W,Cout) bf16, wT (Cin,taps,Cout) bf16 (from pack_dgrad_weight) -> dx (N,D,H,W,Cin).
-    relu_ref (dx-shaped bf16): dx is zeroed where relu_ref <= 0 (the ReLU in front of the convolution, fused)."""
+    relu_ref (dx-shaped): dx is zeroed where relu_ref <= 0 (the ReLU in front of the convolution, fused).
+    fp32 storage: dy fp32, wT (Cin,taps,3*Cout) -> dx fp32."""
     require_cuda(dy, wT, residual, relu_ref)
+    f32 = dy.dtype == F32
     if relu_ref is not None:
-        assert residual is None and relu_ref.is_contiguous() and relu_ref.dtype == BF16
+        assert residual is None and relu_ref.is_contiguous() and relu_ref.dtype == dy.dtype
         assert tuple(relu_ref.shape) == tuple(dy.shape[:4]) + (wT.shape[0],)
         residual = relu_ref
     N, D, H, W, Cout = dy.shape
     Cin = wT.shape[0]
+    if f32:
+        assert wT.shape[2] == 3 * Cout
+        dy = split3(dy, 0)
+        Cout, out_f32 = 3 * Cout, True
     assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and dy.dtype == BF16
     dx = torch.empty((N, D, H, W, Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
     flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0) | \
-        (_lib.EPI_RELU_MASK if relu_ref is not None else 0)
+        (_lib.EPI_RELU_MASK if relu_ref is not None else 0) | (_lib.EPI_RES_F32 if (f32 and residual is not None) else 0)
     check(lib().t2v_conv_dgrad(ctypes.byref(g), ptr(dy), ptr(wT), ptr(residual), ptr(dx), flags, algo, stream()),
           "t2v_conv_dgrad")
     return dx
@@ -87,6 +133,9 @@ PAIRED_WGRAD = os.environ.get("T2V_PAIRED_WGRAD", "1") == "1"
 def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
     """dw (Cout,taps,Cin) fp32 = sum_pos dy[pos,co] x[pos+tap,ci]."""
     require_cuda(dy, x)
+    if dy.dtype == F32:
+        assert x.dtype == F32
+        dy, x = split3(dy, 1), split3(x, 2)          # sum over 3N "samples" = hi*hi + lo*hi + hi*lo
     N, D, H, W, Cout = dy.shape
     Cin = x.shape[-1]
     if (PAIRED_WGRAD and algo == 0 and tuple(k) == (1, 3, 3) and D == 1 and Cin == 32 and Cout in (16, 32)
@@ -218,12 +267,8 @@ def cast_f32(src):
     return dst
 
 
-def pack_weight(w, CoutP=None, CinP=None):
-    """w (Cout,taps,Cin) fp32 -> bf16 (CoutP,taps,CinP), zero padded (plain cast when unpadded)."""
-    require_cuda(w)
-    assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
+def _pack_weight_bf16(w, CoutP, CinP):
     Cout, taps, Cin = w.shape
-    CoutP, CinP = CoutP or Cout, CinP or Cin
     if CoutP == Cout and CinP == Cin:
         return cast_bf16(w)
     dst = torch.zeros((CoutP, taps, CinP), device=w.device, dtype=BF16)
@@ -231,16 +276,46 @@ def pack_weight(w, CoutP=None, CinP=None):
     return dst
 
 
-def pack_dgrad_weight(w, CoutP=None, CinP=None):
-    """w (Cout,taps,Cin) fp32 -> (CinP,taps,CoutP) bf16 with the tap order reversed."""
-    require_cuda(w)
-    assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
+def _pack_dgrad_bf16(w, CoutP, CinP):
     Cout, taps, Cin = w.shape
-    CoutP, CinP = CoutP or Cout, CinP or Cin
     alloc = torch.empty if (CoutP == Cout and CinP == Cin) else torch.zeros
     wT = alloc((CinP, taps, CoutP), device=w.device, dtype=BF16)
     check(lib().t2v_pack_dgrad_weight(ptr(w), ptr(wT), Cout, taps, Cin, CoutP, stream()), "t2v_pack_dgrad_weight")
     return wT
+
+
+def _hi_lo(w):
+    """fp32 weight -> (hi as fp32, lo = w - hi), hi = the bf16 rounding of w (once per weight version: tiny tensors)"""
+    hi = cast_f32(cast_bf16(w))
+    return hi, (w - hi).contiguous()
+
+
+def pack_weight(w, CoutP=None, CinP=None):
+    """w (Cout,taps,Cin) fp32 -> bf16 (CoutP,taps,CinP), zero padded (plain cast when unpadded).
+    fp32 storage mode: (CoutP,taps,3*CinP) = [hi | hi | lo] along K, matching split3(x, 0) = [hi | lo | hi]."""
+    require_cuda(w)
+    assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
+    Cout, taps, Cin = w.shape
+    CoutP, CinP = CoutP or Cout, CinP or Cin
+    if STORE == F32:
+        hi, lo = _hi_lo(w)
+        ph, pl = _pack_weight_bf16(hi, CoutP, CinP), _pack_weight_bf16(lo, CoutP, CinP)
+        return torch.cat((ph, ph, pl), dim=2).contiguous()
+    return _pack_weight_bf16(w, CoutP, CinP)
+
+
+def pack_dgrad_weight(w, CoutP=None, CinP=None):
+    """w (Cout,taps,Cin) fp32 -> (CinP,taps,CoutP) bf16 with the tap order reversed
+    (fp32 storage mode: (CinP,taps,3*CoutP) = [hi | hi | lo])."""
+    require_cuda(w)
+    assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
+    Cout, taps, Cin = w.shape
+    CoutP, CinP = CoutP or Cout, CinP or Cin
+    if STORE == F32:
+        hi, lo = _hi_lo(w)
+        ph, pl = _pack_dgrad_bf16(hi, CoutP, CinP), _pack_dgrad_bf16(lo, CoutP, CinP)
+        return torch.cat((ph, ph, pl), dim=2).contiguous()
+    return _pack_dgrad_bf16(w, CoutP, CinP)
 
 
 def unpack_wgrad(dwp, Cout, Cin):
@@ -266,32 +341,43 @@ def _ggeom(N, in_sp, Cin, Cout, k, s, p):
                      s[0], s[1], s[2], p[0], p[1], p[2]), out_sp
 
 
+def gconv_pack(w3):
+    """operand of the general convolution kernels: bf16 cast of the fp32 (Cout,taps,Cin) weight, or the fp32 weight
+    itself in the fp32 storage mode (CUDA-core FMA: exact)"""
+    require_cuda(w3)
+    return w3.contiguous() if STORE == F32 else cast_bf16(w3.contiguous())
+
+
 def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
-    """Strided convolution: x (N,Di,Hi,Wi,Cin) bf16, w (Cout,taps,Cin) bf16 -> y (N,Do,Ho,Wo,Cout)."""
+    """Strided convolution: x (N,Di,Hi,Wi,Cin), w (Cout,taps,Cin) (both bf16, or both fp32) -> y (N,Do,Ho,Wo,Cout)."""
     require_cuda(x, w, bias)
     N, Di, Hi, Wi, Cin = x.shape
     Cout = w.shape[0]
-    assert x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    _act(x, w)
+    assert x.dtype == w.dtype
     assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
     g, osp = _ggeom(N, (Di, Hi, Wi), Cin, Cout, k, s, p)
+    out_f32 = out_f32 or x.dtype == F32
     y = torch.empty((N, osp[0], osp[1], osp[2], Cout), device=x.device, dtype=F32 if out_f32 else BF16)
-    check(lib().t2v_gconv_fprop(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), 1 if out_f32 else 0, stream()),
-          "t2v_gconv_fprop")
+    check(_lib.typed("t2v_gconv_fprop", x)(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), 1 if out_f32 else 0,
+                                           stream()), "t2v_gconv_fprop")
     return y
 
 
 def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
-    """Data gradient of gconv_fprop == forward of a transposed convolution: dy (N,Do,Ho,Wo,Cout) bf16,
-    w (Cout,taps,Cin) bf16 -> dx (N,Di,Hi,Wi,Cin); in_sp = (Di,Hi,Wi); bias fp32 (Cin,) or None."""
+    """Data gradient of gconv_fprop == forward of a transposed convolution: dy (N,Do,Ho,Wo,Cout),
+    w (Cout,taps,Cin) -> dx (N,Di,Hi,Wi,Cin); in_sp = (Di,Hi,Wi); bias fp32 (Cin,) or None."""
     require_cuda(dy, w, bias)
     N, Cout = dy.shape[0], dy.shape[-1]
     Cin = w.shape[2]
-    assert dy.dtype == BF16 and w.dtype == BF16 and dy.is_contiguous() and w.is_contiguous() and w.shape[0] == Cout
+    _act(dy, w)
+    assert dy.dtype == w.dtype and w.shape[0] == Cout
     g, osp = _ggeom(N, tuple(in_sp), Cin, Cout, k, s, p)
     assert tuple(osp) == tuple(dy.shape[1:4]), (osp, dy.shape)
+    out_f32 = out_f32 or dy.dtype == F32
     dx = torch.empty((N, in_sp[0], in_sp[1], in_sp[2], Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
-    check(lib().t2v_gconv_dgrad(ctypes.byref(g), ptr(dy), ptr(w), ptr(bias), ptr(dx), 1 if out_f32 else 0, stream()),
-          "t2v_gconv_dgrad")
+    check(_lib.typed("t2v_gconv_dgrad", dy)(ctypes.byref(g), ptr(dy), ptr(w), ptr(bias), ptr(dx), 1 if out_f32 else 0,
+                                            stream()), "t2v_gconv_dgrad")
     return dx
 
 
@@ -300,62 +386,105 @@ def gconv_wgrad(dy, x, k, s, p):
     require_cuda(dy, x)
     N, Di, Hi, Wi, Cin = x.shape
     Cout = dy.shape[-1]
-    assert dy.dtype == BF16 and x.dtype == BF16 and dy.is_contiguous() and x.is_contiguous()
+    _act(dy, x)
+    assert dy.dtype == x.dtype
     g, osp = _ggeom(N, (Di, Hi, Wi), Cin, Cout, k, s, p)
     assert tuple(osp) == tuple(dy.shape[1:4]), (osp, dy.shape)
     dw = torch.empty((Cout, k[0] * k[1] * k[2], Cin), device=x.device, dtype=F32)
-    check(lib().t2v_gconv_wgrad(ctypes.byref(g), ptr(dy), ptr(x), ptr(dw), 0, stream()), "t2v_gconv_wgrad")
+    check(_lib.typed("t2v_gconv_wgrad", dy)(ctypes.byref(g), ptr(dy), ptr(x), ptr(dw), 0, stream()), "t2v_gconv_wgrad")
     return dw
 
 
-def leaky_relu_fwd(x, slope):
+def _unary(name, x, *extra):
     require_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
+    _act(x)
     y = torch.empty_like(x)
-    check(lib().t2v_leaky_relu_fwd(ptr(x), ptr(y), x.numel(), float(slope), stream()), "t2v_leaky_relu_fwd")
+    check(_lib.typed(name, x)(ptr(x), ptr(y), x.numel(), *extra, stream()), name)
     return y
+
+
+def _binary(name, a, b, *extra):
+    require_cuda(a, b)
+    _act(a, b)
+    assert a.dtype == b.dtype and a.numel() == b.numel(), (a.dtype, b.dtype, a.shape, b.shape)
+    y = torch.empty_like(a)
+    check(_lib.typed(name, a)(ptr(a), ptr(b), ptr(y), a.numel(), *extra, stream()), name)
+    return y
+
+
+def leaky_relu_fwd(x, slope):
+    return _unary("t2v_leaky_relu_fwd", x, float(slope))
 
 
 def leaky_relu_bwd(dy, ref, slope):
-    require_cuda(dy, ref)
-    assert dy.dtype == BF16 and ref.dtype == BF16 and dy.is_contiguous() and ref.is_contiguous()
-    dx = torch.empty_like(dy)
-    check(lib().t2v_leaky_relu_bwd(ptr(dy), ptr(ref), ptr(dx), dy.numel(), float(slope), stream()),
-          "t2v_leaky_relu_bwd")
-    return dx
+    return _binary("t2v_leaky_relu_bwd", dy, ref, float(slope))
 
 
 def tanh_fwd(x):
-    require_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
-    y = torch.empty_like(x)
-    check(lib().t2v_tanh_fwd(ptr(x), ptr(y), x.numel(), stream()), "t2v_tanh_fwd")
-    return y
+    return _unary("t2v_tanh_fwd", x)
 
 
 def tanh_bwd(dy, y):
-    require_cuda(dy, y)
-    assert dy.dtype == BF16 and y.dtype == BF16 and dy.is_contiguous() and y.is_contiguous()
-    dx = torch.empty_like(dy)
-    check(lib().t2v_tanh_bwd(ptr(dy), ptr(y), ptr(dx), dy.numel(), stream()), "t2v_tanh_bwd")
-    return dx
+    return _binary("t2v_tanh_bwd", dy, y)
 
 
 # ------------------------------------------------------------------------------------- pointwise / pooling
 def relu_fwd(x):
-    require_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
-    y = torch.empty_like(x)
-    check(lib().t2v_relu_fwd(ptr(x), ptr(y), x.numel(), stream()), "t2v_relu_fwd")
-    return y
+    return _unary("t2v_relu_fwd", x)
 
 
 def relu_bwd(dy, ref):
-    require_cuda(dy, ref)
-    assert dy.dtype == BF16 and ref.dtype == BF16 and dy.is_contiguous() and ref.is_contiguous()
-    dx = torch.empty_like(dy)
-    check(lib().t2v_relu_bwd(ptr(dy), ptr(ref), ptr(dx), dy.numel(), stream()), "t2v_relu_bwd")
-    return dx
+    return _binary("t2v_relu_bwd", dy, ref)
+
+
+def scale(x, s):
+    """y = s * x; s: 0-d / 1-element fp32 CUDA tensor"""
+    require_cuda(x, s)
+    _act(x)
+    assert s.dtype == F32 and s.numel() == 1
+    y = torch.empty_like(x)
+    check(_lib.typed("t2v_scale", x)(ptr(x), ptr(s), ptr(y), x.numel(), stream()), "t2v_scale")
+    return y
+
+
+def scale_add(o, x, s=None):
+    """y = s * o + x (s None: y = o + x)"""
+    require_cuda(o, x, s)
+    _act(o, x)
+    assert o.dtype == x.dtype and o.numel() == x.numel() and (s is None or (s.dtype == F32 and s.numel() == 1))
+    y = torch.empty_like(x)
+    check(_lib.typed("t2v_scale_add", x)(ptr(o), ptr(x), ptr(s), ptr(y), x.numel(), stream()), "t2v_scale_add")
+    return y
+
+
+def dot(a, b):
+    """0-d fp32 = sum a * b"""
+    require_cuda(a, b)
+    _act(a, b)
+    assert a.dtype == b.dtype and a.numel() == b.numel()
+    out = torch.empty((), device=a.device, dtype=F32)
+    check(_lib.typed("t2v_dot", a)(ptr(a), ptr(b), ptr(out), a.numel(), stream()), "t2v_dot")
+    return out
+
+
+def cl_slice_f32(x, c):
+    """CL (..., Cp) -> fp32 (..., c): the first c channels"""
+    require_cuda(x)
+    _act(x)
+    Cp = x.shape[-1]
+    y = torch.empty(tuple(x.shape[:-1]) + (c,), device=x.device, dtype=F32)
+    check(_lib.typed("t2v_cl_slice_f32", x)(ptr(x), ptr(y), x.numel() // Cp, Cp, c, stream()), "t2v_cl_slice_f32")
+    return y
+
+
+def f32_pad_cl(x, Cp, dtype=None):
+    """fp32 (..., c) -> CL storage (..., Cp), zero channel padding"""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous()
+    c = x.shape[-1]
+    y = torch.empty(tuple(x.shape[:-1]) + (Cp,), device=x.device, dtype=dtype or STORE)
+    check(_lib.typed("t2v_f32_pad_cl", y)(ptr(x), ptr(y), x.numel() // c, Cp, c, stream()), "t2v_f32_pad_cl")
+    return y
 
 
 def pool_out_shape(in_shape, kernel, stride, pad):
@@ -366,56 +495,60 @@ def pool_out_shape(in_shape, kernel, stride, pad):
 
 def avgpool_fwd(x, kernel, stride, pad, residual=None):
     require_cuda(x, residual)
-    assert x.dtype == BF16 and x.is_contiguous()
-    y = torch.empty(pool_out_shape(x.shape, kernel, stride, pad), device=x.device, dtype=BF16)
-    assert residual is None or (residual.shape == y.shape and residual.is_contiguous())
-    check(lib().t2v_avgpool_fwd(ptr(x), ptr(residual), ptr(y), _i32(*x.shape), _i32(*kernel), _i32(*stride),
-                                _i32(*pad), stream()), "t2v_avgpool_fwd")
+    _act(x, residual)
+    y = torch.empty(pool_out_shape(x.shape, kernel, stride, pad), device=x.device, dtype=x.dtype)
+    assert residual is None or (residual.shape == y.shape and residual.dtype == x.dtype)
+    check(_lib.typed("t2v_avgpool_fwd", x)(ptr(x), ptr(residual), ptr(y), _i32(*x.shape), _i32(*kernel),
+                                           _i32(*stride), _i32(*pad), stream()), "t2v_avgpool_fwd")
     return y
 
 
 def avgpool_bwd(dy, in_shape, kernel, stride, pad):
     require_cuda(dy)
-    assert dy.dtype == BF16 and dy.is_contiguous()
+    _act(dy)
     assert tuple(dy.shape) == tuple(pool_out_shape(in_shape, kernel, stride, pad))
-    dx = torch.empty(tuple(in_shape), device=dy.device, dtype=BF16)
-    check(lib().t2v_avgpool_bwd(ptr(dy), ptr(dx), _i32(*in_shape), _i32(*kernel), _i32(*stride), _i32(*pad),
-                                stream()), "t2v_avgpool_bwd")
+    dx = torch.empty(tuple(in_shape), device=dy.device, dtype=dy.dtype)
+    check(_lib.typed("t2v_avgpool_bwd", dy)(ptr(dy), ptr(dx), _i32(*in_shape), _i32(*kernel), _i32(*stride),
+                                            _i32(*pad), stream()), "t2v_avgpool_bwd")
     return dx
 
 
 def upsample2x_fwd(x):
     require_cuda(x)
     N, D, H, W, C = x.shape
-    assert D == 1 and x.dtype == BF16 and x.is_contiguous()
-    y = torch.empty((N, 1, 2 * H, 2 * W, C), device=x.device, dtype=BF16)
-    check(lib().t2v_upsample2x_fwd(ptr(x), ptr(y), N, H, W, C, stream()), "t2v_upsample2x_fwd")
+    _act(x)
+    assert D == 1
+    y = torch.empty((N, 1, 2 * H, 2 * W, C), device=x.device, dtype=x.dtype)
+    check(_lib.typed("t2v_upsample2x_fwd", x)(ptr(x), ptr(y), N, H, W, C, stream()), "t2v_upsample2x_fwd")
     return y
 
 
 def upsample2x_bwd(dy):
     require_cuda(dy)
     N, D, H2, W2, C = dy.shape
-    assert D == 1 and dy.dtype == BF16 and dy.is_contiguous()
-    dx = torch.empty((N, 1, H2 // 2, W2 // 2, C), device=dy.device, dtype=BF16)
-    check(lib().t2v_upsample2x_bwd(ptr(dy), ptr(dx), N, H2 // 2, W2 // 2, C, stream()), "t2v_upsample2x_bwd")
+    _act(dy)
+    assert D == 1
+    dx = torch.empty((N, 1, H2 // 2, W2 // 2, C), device=dy.device, dtype=dy.dtype)
+    check(_lib.typed("t2v_upsample2x_bwd", dy)(ptr(dy), ptr(dx), N, H2 // 2, W2 // 2, C, stream()),
+          "t2v_upsample2x_bwd")
     return dx
 
 
 def nchw_to_cl(x, Cp):
-    """fp32 (N,C,D,H,W) -> bf16 (N,D,H,W,Cp), padded channels zero."""
+    """fp32 (N,C,D,H,W) -> CL storage (N,D,H,W,Cp), padded channels zero."""
     require_cuda(x)
     assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
     N, C, D, H, W = x.shape
-    y = torch.empty((N, D, H, W, Cp), device=x.device, dtype=BF16)
-    check(lib().t2v_nchw_to_cl(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_nchw_to_cl")
+    y = torch.empty((N, D, H, W, Cp), device=x.device, dtype=STORE)
+    check(_lib.typed("t2v_nchw_to_cl", y)(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_nchw_to_cl")
     return y
 
 
 def rgb_to_cl(x, want4=True):
-    """fp32 (N,3,D,H,W) -> bf16 (N,D,H,W,16) and (optionally) bf16 (N,D,H,W,4), zero padded, in one pass."""
+    """fp32 (N,3,D,H,W) -> bf16 (N,D,H,W,16) and (optionally) bf16 (N,D,H,W,4), zero padded, in one pass
+    (bf16 storage only: the direct stem kernels read the 4-channel copy)."""
     require_cuda(x)
-    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5 and x.shape[1] == 3
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5 and x.shape[1] == 3 and STORE == BF16
     N, C, D, H, W = x.shape
     y16 = torch.empty((N, D, H, W, 16), device=x.device, dtype=BF16)
     y4 = torch.empty((N, D, H, W, 4), device=x.device, dtype=BF16) if want4 else None
@@ -424,73 +557,75 @@ def rgb_to_cl(x, want4=True):
 
 
 def cl_to_nchw(x, C):
-    """bf16 (N,D,H,W,Cp) -> fp32 (N,C,D,H,W) (first C channels)."""
+    """CL (N,D,H,W,Cp) -> fp32 (N,C,D,H,W) (first C channels)."""
     require_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous() and x.dim() == 5
+    _act(x)
+    assert x.dim() == 5
     N, D, H, W, Cp = x.shape
     y = torch.empty((N, C, D, H, W), device=x.device, dtype=F32)
-    check(lib().t2v_cl_to_nchw(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_cl_to_nchw")
+    check(_lib.typed("t2v_cl_to_nchw", x)(ptr(x), ptr(y), N, C, D * H * W, Cp, stream()), "t2v_cl_to_nchw")
     return y
 
 
 def im2col3(x, Kp):
-    """fp32 (N,C,D,H,W) -> bf16 (N,D,H,W,Kp), col[..., tap*C + c] = x[c] shifted by tap (3^3, zero padded)."""
+    """fp32 (N,C,D,H,W) -> CL storage (N,D,H,W,Kp), col[..., tap*C + c] = x[c] shifted by tap (3^3, zero padded)."""
     require_cuda(x)
     assert x.dtype == F32 and x.is_contiguous() and x.dim() == 5
     N, C, D, H, W = x.shape
-    col = torch.empty((N, D, H, W, Kp), device=x.device, dtype=BF16)
-    check(lib().t2v_im2col3(ptr(x), ptr(col), N, C, D, H, W, Kp, stream()), "t2v_im2col3")
+    col = torch.empty((N, D, H, W, Kp), device=x.device, dtype=STORE)
+    check(_lib.typed("t2v_im2col3", col)(ptr(x), ptr(col), N, C, D, H, W, Kp, stream()), "t2v_im2col3")
     return col
 
 
 def col2im3(dcol, C):
-    """adjoint of im2col3: bf16 (N,D,H,W,Kp) -> fp32 (N,C,D,H,W)."""
+    """adjoint of im2col3: CL (N,D,H,W,Kp) -> fp32 (N,C,D,H,W)."""
     require_cuda(dcol)
-    assert dcol.dtype == BF16 and dcol.is_contiguous() and dcol.dim() == 5
+    _act(dcol)
+    assert dcol.dim() == 5
     N, D, H, W, Kp = dcol.shape
     dx = torch.empty((N, C, D, H, W), device=dcol.device, dtype=F32)
-    check(lib().t2v_col2im3(ptr(dcol), ptr(dx), N, C, D, H, W, Kp, stream()), "t2v_col2im3")
+    check(_lib.typed("t2v_col2im3", dcol)(ptr(dcol), ptr(dx), N, C, D, H, W, Kp, stream()), "t2v_col2im3")
     return dx
 
 
 def sum_rows(x, out=None):
-    """bf16 (..., C) -> fp32 (C,) sum over all leading dims; with `out` (fp32 (C,)): out += the sums."""
+    """CL (..., C) -> fp32 (C,) sum over all leading dims; with `out` (fp32 (C,)): out += the sums."""
     require_cuda(x, out)
-    assert x.dtype == BF16 and x.is_contiguous()
+    _act(x)
     C = x.shape[-1]
     if out is not None:
         assert out.dtype == F32 and out.numel() == C and out.is_contiguous()
-        check(lib().t2v_sum_rows_acc(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows_acc")
+        check(_lib.typed("t2v_sum_rows_acc", x)(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows_acc")
         return out
     out = torch.empty((C,), device=x.device, dtype=F32)
-    check(lib().t2v_sum_rows(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows")
+    check(_lib.typed("t2v_sum_rows", x)(ptr(x), ptr(out), x.numel() // C, C, stream()), "t2v_sum_rows")
     return out
 
 
 def sum_spatial(x):
-    """bf16 (N,D,H,W,C) -> fp32 (N,C)."""
+    """CL (N,D,H,W,C) -> fp32 (N,C)."""
     require_cuda(x)
-    assert x.dtype == BF16 and x.is_contiguous()
+    _act(x)
     N, C = x.shape[0], x.shape[-1]
     out = torch.empty((N, C), device=x.device, dtype=F32)
-    check(lib().t2v_sum_spatial(ptr(x), ptr(out), N, x.numel() // (N * C), C, stream()), "t2v_sum_spatial")
+    check(_lib.typed("t2v_sum_spatial", x)(ptr(x), ptr(out), N, x.numel() // (N * C), C, stream()), "t2v_sum_spatial")
     return out
 
 
 def broadcast_spatial(g, shape):
-    """fp32 (N,C) -> bf16 `shape` = (N,D,H,W,C)."""
+    """fp32 (N,C) -> CL storage `shape` = (N,D,H,W,C)."""
     require_cuda(g)
     assert g.dtype == F32 and g.is_contiguous()
     N, C = g.shape
-    y = torch.empty(tuple(shape), device=g.device, dtype=BF16)
-    check(lib().t2v_broadcast_spatial(ptr(g), ptr(y), N, y.numel() // (N * C), C, stream()),
+    y = torch.empty(tuple(shape), device=g.device, dtype=STORE)
+    check(_lib.typed("t2v_broadcast_spatial", y)(ptr(g), ptr(y), N, y.numel() // (N * C), C, stream()),
           "t2v_broadcast_spatial")
     return y
 
 
 # ------------------------------------------------------------------------------------- BatchNorm (train)
 def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, momentum=0.1, training=True):
-    """x (N,1,H,W,C) bf16 -> y (N,1,up*H,up*W,C), plus (mean_invstd, scale_shift) fp32 [2C] for backward.
+    """x (N,1,H,W,C) CL -> y (N,1,up*H,up*W,C), plus (mean_invstd, scale_shift) fp32 [2C] for backward.
     training=False normalises with the running statistics (no update).  `relu` is the fused activation code:
     0/False none, 1/True ReLU, 2 LeakyReLU(0.2).  With up == 1 any CL shape is accepted (statistics over all
     leading dims: BatchNorm1d/2d/3d)."""
@@ -499,14 +634,15 @@ def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, mo
     if up == 1 and x.shape[1] != 1:
         x = x.reshape(-1, 1, 1, 1, x.shape[-1])
     N, D, H, W, C = x.shape
-    assert D == 1 and x.dtype == BF16 and x.is_contiguous()
+    _act(x)
+    assert D == 1
     dev = x.device
     mean_invstd = torch.empty((2 * C,), device=dev, dtype=F32)
     scale_shift = torch.empty((2 * C,), device=dev, dtype=F32)
     if training:
         stats = torch.empty((2 * C,), device=dev, dtype=F32)
         P = N * H * W
-        check(lib().t2v_bn_stats(ptr(x), ptr(stats), P, C, stream()), "t2v_bn_stats")
+        check(_lib.typed("t2v_bn_stats", x)(ptr(x), ptr(stats), P, C, stream()), "t2v_bn_stats")
         check(lib().t2v_bn_finalize(ptr(stats), ptr(gamma), ptr(beta), ptr(running_mean), ptr(running_var),
                                     ptr(mean_invstd), ptr(scale_shift), C, P, eps, momentum, stream()),
               "t2v_bn_finalize")
@@ -515,8 +651,8 @@ def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, mo
         stats = torch.cat((running_mean, running_var + running_mean * running_mean)).contiguous()
         check(lib().t2v_bn_finalize(ptr(stats), ptr(gamma), ptr(beta), None, None, ptr(mean_invstd),
                                     ptr(scale_shift), C, 1, eps, momentum, stream()), "t2v_bn_finalize")
-    y = torch.empty((N, 1, up * H, up * W, C), device=dev, dtype=BF16)
-    check(lib().t2v_bn_apply(ptr(x), ptr(scale_shift), ptr(y), N, H, W, C, int(relu), up, stream()),
+    y = torch.empty((N, 1, up * H, up * W, C), device=dev, dtype=x.dtype)
+    check(_lib.typed("t2v_bn_apply", x)(ptr(x), ptr(scale_shift), ptr(y), N, H, W, C, int(relu), up, stream()),
           "t2v_bn_apply")
     if up == 1:
         y = y.view(shape0)
@@ -524,18 +660,19 @@ def bn_forward(x, gamma, beta, running_mean, running_var, relu, up, eps=1e-5, mo
 
 
 def bn_backward(dy, x, mean_invstd, scale_shift, relu, up):
-    """-> dx (x-shaped bf16), dgamma fp32 [C], dbeta fp32 [C]."""
+    """-> dx (x-shaped CL), dgamma fp32 [C], dbeta fp32 [C]."""
     require_cuda(dy, x)
     shape0 = tuple(x.shape)
     if up == 1 and x.shape[1] != 1:
         x = x.reshape(-1, 1, 1, 1, x.shape[-1])
         dy = dy.reshape(x.shape)
     N, D, H, W, C = x.shape
-    assert dy.is_contiguous() and dy.dtype == BF16 and tuple(dy.shape) == (N, 1, up * H, up * W, C)
+    _act(dy, x)
+    assert dy.dtype == x.dtype and tuple(dy.shape) == (N, 1, up * H, up * W, C)
     red = torch.empty((2 * C,), device=x.device, dtype=F32)
     dx = torch.empty_like(x)
-    check(lib().t2v_bn_bwd(ptr(dy), ptr(x), ptr(scale_shift), ptr(mean_invstd), ptr(red), ptr(dx), N, H, W, C,
-                           int(relu), up, stream()), "t2v_bn_bwd")
+    check(_lib.typed("t2v_bn_bwd", x)(ptr(dy), ptr(x), ptr(scale_shift), ptr(mean_invstd), ptr(red), ptr(dx), N, H, W,
+                                      C, int(relu), up, stream()), "t2v_bn_bwd")
     return dx.view(shape0), red[C:], red[:C]
 
 
@@ -568,9 +705,10 @@ def render_fwd(pre, B, T, C):
     """pre (B*T,1,H,W,Cp) bf16 -> tanh -> fp32 (B,C,T,H,W)."""
     require_cuda(pre)
     BT, D, H, W, Cp = pre.shape
-    assert BT == B * T and D == 1 and pre.dtype == BF16 and pre.is_contiguous()
+    _act(pre)
+    assert BT == B * T and D == 1
     y = torch.empty((B, C, T, H, W), device=pre.device, dtype=F32)
-    check(lib().t2v_render_fwd(ptr(pre), ptr(y), B, T, H, W, C, Cp, stream()), "t2v_render_fwd")
+    check(_lib.typed("t2v_render_fwd", pre)(ptr(pre), ptr(y), B, T, H, W, C, Cp, stream()), "t2v_render_fwd")
     return y
 
 
@@ -578,8 +716,8 @@ def render_bwd(dy, y, Cp):
     require_cuda(dy, y)
     B, C, T, H, W = y.shape
     assert dy.dtype == F32 and dy.is_contiguous() and y.is_contiguous()
-    dpre = torch.empty((B * T, 1, H, W, Cp), device=y.device, dtype=BF16)
-    check(lib().t2v_render_bwd(ptr(dy), ptr(y), ptr(dpre), B, T, H, W, C, Cp, stream()), "t2v_render_bwd")
+    dpre = torch.empty((B * T, 1, H, W, Cp), device=y.device, dtype=STORE)
+    check(_lib.typed("t2v_render_bwd", dpre)(ptr(dy), ptr(y), ptr(dpre), B, T, H, W, C, Cp, stream()), "t2v_render_bwd")
     return dpre
 
 
@@ -641,9 +779,9 @@ def lstm_cell_fwd(gates, c_prev, want_h32=False):
     Hd = gates.shape[-1] // 4
     shp = tuple(gates.shape[:-1]) + (Hd,)
     c = torch.empty(shp, device=gates.device, dtype=F32)
-    h = torch.empty(shp, device=gates.device, dtype=BF16)
+    h = torch.empty(shp, device=gates.device, dtype=STORE)
     h32 = torch.empty(shp, device=gates.device, dtype=F32) if want_h32 else None
-    check(lib().t2v_lstm_cell_fwd(ptr(gates), ptr(c_prev), ptr(c), ptr(h), ptr(h32), c.numel() // Hd, Hd, stream()),
+    check(_lib.typed("t2v_lstm_cell_fwd", h)(ptr(gates), ptr(c_prev), ptr(c), ptr(h), ptr(h32), c.numel() // Hd, Hd, stream()),
           "t2v_lstm_cell_fwd")
     return c, h, h32
 
@@ -652,9 +790,9 @@ def lstm_cell_bwd(gates, c_prev, c, dh, dc_next):
     """-> (dgates bf16 (...,4H), dc_prev fp32 (...,H)); dh / dc_next fp32 or None."""
     require_cuda(gates, c)
     Hd = c.shape[-1]
-    dgates = torch.empty(gates.shape, device=gates.device, dtype=BF16)
+    dgates = torch.empty(gates.shape, device=gates.device, dtype=STORE)
     dc_prev = torch.empty_like(c)
-    check(lib().t2v_lstm_cell_bwd(ptr(gates), ptr(c_prev), ptr(c), ptr(dh), ptr(dc_next), ptr(dgates), ptr(dc_prev),
+    check(_lib.typed("t2v_lstm_cell_bwd", dgates)(ptr(gates), ptr(c_prev), ptr(c), ptr(dh), ptr(dc_next), ptr(dgates), ptr(dc_prev),
                                   c.numel() // Hd, Hd, stream()), "t2v_lstm_cell_bwd")
     return dgates, dc_prev
 
@@ -703,3 +841,225 @@ def multi_copy(srcs, dsts):
         assert s.dtype == F32 and d.dtype == F32 and s.numel() == d.numel()
     check(lib().t2v_multi_copy(n, arr(*[s.data_ptr() for s in srcs]), arr(*[d.data_ptr() for d in dsts]), sizes,
                                stream()), "t2v_multi_copy")
+
+
+# ------------------------------------------------------------------------------------- non-local block primitives
+def maxpool122_fwd(x):
+    """fp32 (M, H, W, c) -> (pooled fp32 (M, H/2, W/2, c), idx uint8): max-pool (1,2,2) with recorded arg-max"""
+    require_cuda(x)
+    assert x.dtype == F32 and x.is_contiguous() and x.dim() == 4
+    M, H, W, c = x.shape
+    y = torch.empty((M, H // 2, W // 2, c), device=x.device, dtype=F32)
+    idx = torch.empty((M, H // 2, W // 2, c), device=x.device, dtype=torch.uint8)
+    check(lib().t2v_maxpool122_fwd(ptr(x), ptr(y), ptr(idx), M, H, W, c, stream()), "t2v_maxpool122_fwd")
+    return y, idx
+
+
+def pool122_gather(x, idx):
+    require_cuda(x, idx)
+    assert x.dtype == F32 and x.is_contiguous() and idx.dtype == torch.uint8 and idx.is_contiguous()
+    M, H, W, c = x.shape
+    y = torch.empty(tuple(idx.shape), device=x.device, dtype=F32)
+    check(lib().t2v_pool122_gather(ptr(x), ptr(idx), ptr(y), M, H, W, c, stream()), "t2v_pool122_gather")
+    return y
+
+
+def pool122_scatter(dy, idx):
+    require_cuda(dy, idx)
+    assert dy.dtype == F32 and dy.is_contiguous() and idx.dtype == torch.uint8 and tuple(idx.shape) == tuple(dy.shape)
+    M, Hp, Wp, c = dy.shape
+    dx = torch.empty((M, 2 * Hp, 2 * Wp, c), device=dy.device, dtype=F32)
+    check(lib().t2v_pool122_scatter(ptr(dy), ptr(idx), ptr(dx), M, 2 * Hp, 2 * Wp, c, stream()), "t2v_pool122_scatter")
+    return dx
+
+
+def bmm(a, b, ta=False, tb=False):
+    """fp32 batched C = op(A) op(B): a (n, M, K) [ta: (n, K, M)], b (n, K, N) [tb: (n, N, K)] -> (n, M, N)"""
+    require_cuda(a, b)
+    assert a.dtype == F32 and b.dtype == F32 and a.is_contiguous() and b.is_contiguous() and a.dim() == 3
+    n = a.shape[0]
+    M, K = (a.shape[2], a.shape[1]) if ta else (a.shape[1], a.shape[2])
+    N = b.shape[1] if tb else b.shape[2]
+    assert b.shape[0] == n and (b.shape[2] if tb else b.shape[1]) == K, (a.shape, b.shape, ta, tb)
+    c = torch.empty((n, M, N), device=a.device, dtype=F32)
+    for i0 in range(0, n, 65535):
+        i1 = min(n, i0 + 65535)
+        check(lib().t2v_bmm_f32(ptr(a[i0:i1]), ptr(b[i0:i1]), ptr(c[i0:i1]), i1 - i0, M, N, K, int(ta), int(tb),
+                                stream()), "t2v_bmm_f32")
+    return c
+
+
+def softmax_fwd(s):
+    require_cuda(s)
+    assert s.dtype == F32 and s.is_contiguous()
+    out = torch.empty_like(s)
+    check(lib().t2v_softmax_fwd(ptr(s), ptr(out), s.numel() // s.shape[-1], s.shape[-1], stream()), "t2v_softmax_fwd")
+    return out
+
+
+def softmax_bwd(beta, dbeta):
+    require_cuda(beta, dbeta)
+    assert beta.dtype == F32 and dbeta.dtype == F32 and beta.is_contiguous() and dbeta.is_contiguous()
+    out = torch.empty_like(beta)
+    check(lib().t2v_softmax_bwd(ptr(beta), ptr(dbeta), ptr(out), beta.numel() // beta.shape[-1], beta.shape[-1],
+                                stream()), "t2v_softmax_bwd")
+    return out
+
+
+def softmax_bwd_bwd(beta, dbeta, u):
+    """derivative of softmax_bwd(beta, dbeta) against the cotangent u -> (g_beta, g_dbeta)"""
+    require_cuda(beta, dbeta, u)
+    assert all(t.dtype == F32 and t.is_contiguous() for t in (beta, dbeta, u))
+    gb, gd = torch.empty_like(beta), torch.empty_like(beta)
+    check(lib().t2v_softmax_bwd_bwd(ptr(beta), ptr(dbeta), ptr(u), ptr(gb), ptr(gd), beta.numel() // beta.shape[-1],
+                                    beta.shape[-1], stream()), "t2v_softmax_bwd_bwd")
+    return gb, gd
+
+
+# ------------------------------------------------------------------------------------- heads / losses / penalty
+def head_fwd(feat, cond, w, bias):
+    """[feat | cond] (B, F [+E]) fp32 . w (F [+E],) + bias -> (B,)"""
+    require_cuda(feat, cond, w, bias)
+    B, F_ = feat.shape
+    E = 0 if cond is None else cond.shape[1]
+    assert feat.dtype == F32 and feat.is_contiguous() and w.dtype == F32 and w.is_contiguous() and w.numel() == F_ + E
+    assert cond is None or (cond.dtype == F32 and cond.is_contiguous() and cond.shape[0] == B)
+    out = torch.empty((B,), device=feat.device, dtype=F32)
+    check(lib().t2v_head_fwd(ptr(feat), ptr(cond), ptr(w), ptr(bias), ptr(out), B, F_, E, stream()), "t2v_head_fwd")
+    return out
+
+
+def head_bwd_data(dpred, w, F_, E):
+    """-> (dfeat (B,F), dcond (B,E) or None) = dpred (x) w"""
+    require_cuda(dpred, w)
+    assert dpred.dtype == F32 and dpred.is_contiguous() and w.dtype == F32 and w.is_contiguous()
+    B = dpred.numel()
+    dfeat = torch.empty((B, F_), device=dpred.device, dtype=F32)
+    dcond = torch.empty((B, E), device=dpred.device, dtype=F32) if E else None
+    check(lib().t2v_head_bwd_data(ptr(dpred), ptr(w), ptr(dfeat), ptr(dcond), B, F_, E, stream()), "t2v_head_bwd_data")
+    return dfeat, dcond
+
+
+def head_bwd_weight(dpred, feat, cond, want_bias=True):
+    """-> (dw (F [+E],), db (1,) or None) = sum_b dpred[b] [feat | cond][b]"""
+    require_cuda(dpred, feat, cond)
+    B, F_ = feat.shape
+    E = 0 if cond is None else cond.shape[1]
+    assert dpred.dtype == F32 and dpred.is_contiguous() and dpred.numel() == B and feat.dtype == F32
+    assert feat.is_contiguous() and (cond is None or (cond.dtype == F32 and cond.is_contiguous()))
+    dw = torch.empty((F_ + E,), device=feat.device, dtype=F32)
+    db = torch.empty((1,), device=feat.device, dtype=F32) if want_bias else None
+    check(lib().t2v_head_bwd_weight(ptr(dpred), ptr(feat), ptr(cond), ptr(dw), ptr(db), B, F_, E, 0, stream()),
+          "t2v_head_bwd_weight")
+    return dw, db
+
+
+def _loss_arrays(a_list, b_list, weights):
+    n = len(a_list)
+    arr = ctypes.c_void_p * n
+    for a, b in zip(a_list, b_list):
+        assert a.dtype == F32 and b.dtype == F32 and a.is_contiguous() and b.is_contiguous() and a.numel() == b.numel()
+    ns = (ctypes.c_int32 * n)(*[a.numel() for a in a_list])
+    ws = (ctypes.c_float * n)(*[float(w) for w in weights])
+    return n, arr, ns, ws
+
+
+def rel_loss_fwd(a_list, b_list, weights, mode):
+    """0-d fp32 = sum_e weights[e] * mean_j f(b_e[j] - a_e[j]); mode 0 softplus (RSGAN), 1 identity (WGAN)"""
+    require_cuda(*a_list, *b_list)
+    n, arr, ns, ws = _loss_arrays(a_list, b_list, weights)
+    out = torch.empty((), device=a_list[0].device, dtype=F32)
+    check(lib().t2v_rel_loss_fwd(n, arr(*[t.data_ptr() for t in a_list]), arr(*[t.data_ptr() for t in b_list]), ns, ws,
+                                 int(mode), ptr(out), stream()), "t2v_rel_loss_fwd")
+    return out
+
+
+def rel_loss_bwd(a_list, b_list, da_list, db_list, weights, mode, gout):
+    """da_e / db_e (None to skip; pre-zeroed; entries may share buffers) += d(loss)/d(a_e), d(b_e) * gout"""
+    require_cuda(*a_list, *b_list, gout)
+    n, arr, ns, ws = _loss_arrays(a_list, b_list, weights)
+    assert gout.dtype == F32 and gout.numel() == 1
+    pa = arr(*[None if t is None else t.data_ptr() for t in da_list])
+    pb = arr(*[None if t is None else t.data_ptr() for t in db_list])
+    check(lib().t2v_rel_loss_bwd(n, arr(*[t.data_ptr() for t in a_list]), arr(*[t.data_ptr() for t in b_list]), pa, pb,
+                                 ns, ws, int(mode), ptr(gout), stream()), "t2v_rel_loss_bwd")
+
+
+def lerp_rows(real, fake, alpha):
+    """x_hat[b] = alpha[b] * real[b] + (1 - alpha[b]) * fake[b]; real / fake fp32 (B, ...), alpha fp32 (B,)"""
+    require_cuda(real, fake, alpha)
+    assert real.dtype == F32 and fake.dtype == F32 and alpha.dtype == F32 and real.shape == fake.shape
+    assert real.is_contiguous() and fake.is_contiguous() and alpha.is_contiguous() and alpha.numel() == real.shape[0]
+    out = torch.empty_like(real)
+    B = real.shape[0]
+    check(lib().t2v_lerp_rows(ptr(real), ptr(fake), ptr(alpha), ptr(out), B, real.numel() // max(B, 1), stream()),
+          "t2v_lerp_rows")
+    return out
+
+
+# ------------------------------------------------------------------------------------- caption LSTM
+def lstm_pack_whh(whh):
+    """fp32 (ndir, 4H, H) -> (ndir, H, 4H)"""
+    require_cuda(whh)
+    assert whh.dtype == F32 and whh.is_contiguous() and whh.dim() == 3
+    ndir, H4, H = whh.shape
+    out = torch.empty((ndir, H, H4), device=whh.device, dtype=F32)
+    check(lib().t2v_lstm_pack_whh(ptr(whh), ptr(out), ndir, H, stream()), "t2v_lstm_pack_whh")
+    return out
+
+
+def lstm_seq_fwd(gx, whhT, lengths, h0, c0, save=True):
+    """gx fp32 (B, L, ndir*4H); whhT (ndir, H, 4H); lengths int32 (B,) on the device; h0 / c0 fp32 (ndir, B, H) or None
+    -> out (B, L, ndir*H) storage, hprev (same) | None, gates fp32 | None, cells fp32 | None, hn, cn (ndir, B, H)"""
+    require_cuda(gx, whhT, lengths, h0, c0)
+    B, L = gx.shape[0], gx.shape[1]
+    ndir, H = whhT.shape[0], whhT.shape[1]
+    assert gx.dtype == F32 and gx.is_contiguous() and gx.shape[2] == ndir * 4 * H and lengths.dtype == torch.int32
+    dev = gx.device
+    out = torch.empty((B, L, ndir * H), device=dev, dtype=STORE)
+    hprev = torch.empty_like(out) if save else None
+    gates = torch.empty((B, L, ndir * 4 * H), device=dev, dtype=F32) if save else None
+    cells = torch.empty((B, L, ndir * H), device=dev, dtype=F32) if save else None
+    hn = torch.empty((ndir, B, H), device=dev, dtype=F32)
+    cn = torch.empty((ndir, B, H), device=dev, dtype=F32)
+    check(_lib.typed("t2v_lstm_seq_fwd", out)(ptr(gx), ptr(whhT), ptr(lengths), ptr(h0), ptr(c0), ptr(out), ptr(hprev),
+                                              ptr(gates), ptr(cells), ptr(hn), ptr(cn), B, L, H, ndir, stream()),
+          "t2v_lstm_seq_fwd")
+    return out, hprev, gates, cells, hn, cn
+
+
+def lstm_seq_bwd(whh, lengths, c0, gates, cells, dout, dhn, dcn):
+    """-> dgates (B, L, ndir*4H) storage, dh0, dc0 fp32 (ndir, B, H)"""
+    require_cuda(whh, lengths, gates, cells, dout, dhn, dcn)
+    ndir, H = whh.shape[0], whh.shape[2]
+    B, L = gates.shape[0], gates.shape[1]
+    dev = gates.device
+    assert dout is None or (dout.is_contiguous() and dout.dtype == STORE)
+    dgates = torch.empty((B, L, ndir * 4 * H), device=dev, dtype=STORE)
+    dh0 = torch.empty((ndir, B, H), device=dev, dtype=F32)
+    dc0 = torch.empty((ndir, B, H), device=dev, dtype=F32)
+    check(_lib.typed("t2v_lstm_seq_bwd", dgates)(ptr(whh), ptr(lengths), ptr(c0), ptr(gates), ptr(cells), ptr(dout),
+                                                 ptr(dhn), ptr(dcn), ptr(dgates), ptr(dh0), ptr(dc0), B, L, H, ndir,
+                                                 stream()), "t2v_lstm_seq_bwd")
+    return dgates, dh0, dc0
+
+
+def embedding_fwd(tokens, weight):
+    """int64 (B, L), fp32 (V, E) -> storage (B, L, E)"""
+    require_cuda(tokens, weight)
+    assert tokens.dtype == torch.int64 and tokens.is_contiguous() and weight.dtype == F32 and weight.is_contiguous()
+    E = weight.shape[1]
+    out = torch.empty(tuple(tokens.shape) + (E,), device=weight.device, dtype=STORE)
+    check(_lib.typed("t2v_embedding_fwd", out)(ptr(tokens), ptr(weight), ptr(out), tokens.numel(), E, stream()),
+          "t2v_embedding_fwd")
+    return out
+
+
+def embedding_bwd(tokens, dout, V):
+    require_cuda(tokens, dout)
+    _act(dout)
+    E = dout.shape[-1]
+    dw = torch.empty((V, E), device=dout.device, dtype=F32)
+    check(_lib.typed("t2v_embedding_bwd", dout)(ptr(tokens), ptr(dout), ptr(dw), tokens.numel(), E, V, stream()),
+          "t2v_embedding_bwd")
+    return dw

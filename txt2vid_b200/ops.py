@@ -34,6 +34,27 @@ def round16(c):
     return (c + 15) // 16 * 16
 
 
+# ------------------------------------------------------------------------------------- precision mode
+# "bf16": the product (bf16 activation storage, bf16 tensor-core operands, fp32 accumulation / statistics / master
+#         weights) -- BASELINE north_star's 2e-2 bar;
+# "fp32": fp32 activation storage on the same kernels instantiated for float, the tcgen05 engine fed with bf16 hi / lo
+#         operand splits (16 mantissa bits per operand, fp32 accumulation) -- the 1e-3 bar.  The bf16-only fusions
+#         (direct RGB stem, stride-(2,1,1) stem conv, fused skip conv, fused generator attention) fall back to their
+#         unfused formulations on the generic kernels.
+PRECISION = ["bf16"]
+
+
+def set_precision(mode):
+    assert mode in ("bf16", "fp32"), mode
+    K.set_store_dtype(F32 if mode == "fp32" else BF16)
+    PRECISION[0] = mode
+    PACKS.clear()
+
+
+def fp32_mode():
+    return PRECISION[0] == "fp32"
+
+
 # ------------------------------------------------------------------------------------- weight handling
 def kernel_of(weight):
     """(kd,kh,kw) of a Linear / Conv2d / Conv3d weight."""
@@ -118,6 +139,12 @@ class _PackCache(object):
                 w3 = w3_view(w).detach()       # may re-home the parameter's memory (channels-last)
             if kind == "fprop":
                 pack = K.pack_weight(w3, CoutP, CinP)
+            elif kind == "gconv":                    # general (strided / transposed) convolution kernels
+                if (CoutP, CinP) != (w3.shape[0], w3.shape[2]):
+                    wpad = w3.new_zeros((CoutP, w3.shape[1], CinP))
+                    wpad[:w3.shape[0], :, :w3.shape[2]] = w3
+                    w3 = wpad
+                pack = K.gconv_pack(w3)
             else:
                 pack = K.pack_dgrad_weight(w3, CoutP, CinP)
             if self._slot_of(w) != ident or ent[0] != self._key(w):     # w3_view re-homed the parameter
@@ -499,11 +526,11 @@ class GConvF(Function):
     models/tcwyt/video_discrim.py:12-46, frame_discrim.py:8-49, motion_discrim.py:8-19."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, s, p):
+    def forward(ctx, x, weight, bias, k, s, p, out_f32=False):
         Cout, Cin = weight.shape[0], weight.shape[1]
         CinP, CoutP = x.shape[-1], round16(Cout)
-        wp = PACKS.get(weight, "fprop", CoutP, CinP)
-        y = K.gconv_fprop(x, wp, _pad_bias(bias, CoutP), k, s, p)
+        wp = PACKS.get(weight, "gconv", CoutP, CinP)
+        y = K.gconv_fprop(x, wp, _pad_bias(bias, CoutP), k, s, p, out_f32)
         ctx.cfg = (k, s, p, bias is not None)
         ctx.save_for_backward(x, weight)
         return y
@@ -514,17 +541,19 @@ class GConvF(Function):
         k, s, p, has_bias = ctx.cfg
         x, weight = ctx.saved_tensors
         dy = dy.contiguous()
+        if dy.dtype != x.dtype:                      # fp32 output of a critic's last layer in bf16 storage mode
+            dy = K.cast_bf16(dy)
         Cout, Cin = weight.shape[0], weight.shape[1]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wp = PACKS.get(weight, "fprop", dy.shape[-1], x.shape[-1])
+            wp = PACKS.get(weight, "gconv", dy.shape[-1], x.shape[-1])
             dx = K.gconv_dgrad(dy, wp, None, tuple(x.shape[1:4]), k, s, p)
         if ctx.needs_input_grad[1]:
             dw3 = K.unpack_wgrad(K.gconv_wgrad(dy, x, k, s, p), Cout, Cin)
             dw = grad_like_weight(dw3, weight)
         if has_bias and ctx.needs_input_grad[2]:
             db = K.sum_rows(dy)[:Cout]
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 class GConvTF(Function):
@@ -536,7 +565,7 @@ class GConvTF(Function):
     def forward(ctx, x, weight, bias, k, s, p):
         Cin_t, Cout_t = weight.shape[0], weight.shape[1]
         CinP, CoutP = x.shape[-1], round16(Cout_t)
-        wp = PACKS.get(weight, "fprop", CinP, CoutP)                       # [Cin_t p][taps][Cout_t p]
+        wp = PACKS.get(weight, "gconv", CinP, CoutP)                       # [Cin_t p][taps][Cout_t p]
         out_sp = tuple((i - 1) * ss - 2 * pp + kk for i, ss, pp, kk in zip(x.shape[1:4], s, p, k))
         y = K.gconv_dgrad(x, wp, _pad_bias(bias, CoutP), out_sp, k, s, p)
         ctx.cfg = (k, s, p, bias is not None)
@@ -552,7 +581,7 @@ class GConvTF(Function):
         Cin_t, Cout_t = weight.shape[0], weight.shape[1]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
-            wp = PACKS.get(weight, "fprop", x.shape[-1], dy.shape[-1])
+            wp = PACKS.get(weight, "gconv", x.shape[-1], dy.shape[-1])
             dx = K.gconv_fprop(dy, wp, None, k, s, p)
         if ctx.needs_input_grad[1]:
             dw3 = K.unpack_wgrad(K.gconv_wgrad(x, dy, k, s, p), Cin_t, Cout_t)
@@ -562,10 +591,11 @@ class GConvTF(Function):
         return dx, dw, db, None, None, None
 
 
-def gconv(x, module):
-    """nn.Conv{1,2,3}d container applied to a CL tensor (any stride / padding)."""
+def gconv(x, module, out_f32=False):
+    """nn.Conv{1,2,3}d container applied to a CL tensor (any stride / padding); out_f32: fp32 output (the last layer
+    of a critic: its scalar predictions are not rounded to bf16)."""
     k, s, p = conv_args(module)
-    return GConvF.apply(x, module.weight, module.bias, k, s, p)
+    return GConvF.apply(x, module.weight, module.bias, k, s, p, out_f32)
 
 
 def gconv_transpose(x, module):
@@ -1109,41 +1139,398 @@ class AttentionCoreF(Function):
         return dtheta, dphi, dg, None, None
 
 
+# ---- differentiable primitives (every backward is again one of them: the discriminator's block is differentiated
+# ---- twice by the gradient penalty, gan/losses.py:169-178)
+class ScaleF(Function):
+    """y = s * x  (s: 0-d fp32 tensor on the device)"""
+
+    @staticmethod
+    def forward(ctx, x, s):
+        ctx.save_for_backward(x, s)
+        return K.scale(x, s.detach().reshape(1).float())
+
+    @staticmethod
+    def backward(ctx, dy):
+        x, s = ctx.saved_tensors
+        dy = dy.contiguous()
+        dx = ScaleF.apply(dy, s) if ctx.needs_input_grad[0] else None
+        ds = DotF.apply(dy, x).reshape(s.shape).to(s.dtype) if ctx.needs_input_grad[1] else None
+        return dx, ds
+
+
+class DotF(Function):
+    """0-d fp32 = sum a * b"""
+
+    @staticmethod
+    def forward(ctx, a, b):
+        ctx.save_for_backward(a, b)
+        return K.dot(a, b)
+
+    @staticmethod
+    def backward(ctx, g):
+        a, b = ctx.saved_tensors
+        g = g.contiguous()
+        da = ScaleF.apply(b, g) if ctx.needs_input_grad[0] else None
+        db = ScaleF.apply(a, g) if ctx.needs_input_grad[1] else None
+        return da, db
+
+
+class ScaleAddF(Function):
+    """y = s * o + x: the non-local block's output gamma * o + x (models/layers.py:36,68); s None: y = o + x"""
+
+    @staticmethod
+    def forward(ctx, o, x, s):
+        ctx.save_for_backward(o, s)
+        return K.scale_add(o, x, None if s is None else s.detach().reshape(1).float())
+
+    @staticmethod
+    def backward(ctx, dy):
+        o, s = ctx.saved_tensors
+        dy = dy.contiguous()
+        do = None
+        if ctx.needs_input_grad[0]:
+            do = dy if s is None else ScaleF.apply(dy, s)
+        dx = dy if ctx.needs_input_grad[1] else None
+        ds = None
+        if s is not None and ctx.needs_input_grad[2]:
+            ds = DotF.apply(dy, o).reshape(s.shape).to(s.dtype)
+        return do, dx, ds
+
+
+def scale_add(o, x, s=None):
+    return ScaleAddF.apply(o, x, s)
+
+
+class SliceF32F(Function):
+    """CL (..., Cp) -> fp32 (..., c)"""
+
+    @staticmethod
+    def forward(ctx, x, c):
+        ctx.cfg = (x.shape[-1], x.dtype)
+        return K.cl_slice_f32(x, c)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return PadCLF.apply(dy.contiguous(), ctx.cfg[0], ctx.cfg[1]), None
+
+
+class PadCLF(Function):
+    """fp32 (..., c) -> CL storage (..., Cp), zero padded"""
+
+    @staticmethod
+    def forward(ctx, x, Cp, dtype):
+        ctx.c = x.shape[-1]
+        return K.f32_pad_cl(x, Cp, dtype)
+
+    @staticmethod
+    def backward(ctx, dy):
+        return SliceF32F.apply(dy.contiguous(), ctx.c), None, None
+
+
+class MaxPool122F(Function):
+    """max-pool (1,2,2) on fp32 (M, H, W, c) (F.max_pool2d / max_pool3d of layers.py:26-27,56-57)"""
+
+    @staticmethod
+    def forward(ctx, x):
+        y, idx = K.maxpool122_fwd(x)
+        ctx.save_for_backward(idx)
+        return y
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return PoolScatterF.apply(dy.contiguous(), idx)
+
+
+class PoolScatterF(Function):
+    @staticmethod
+    def forward(ctx, dy, idx):
+        ctx.save_for_backward(idx)
+        return K.pool122_scatter(dy, idx)
+
+    @staticmethod
+    def backward(ctx, ddx):
+        (idx,) = ctx.saved_tensors
+        return PoolGatherF.apply(ddx.contiguous(), idx), None
+
+
+class PoolGatherF(Function):
+    @staticmethod
+    def forward(ctx, x, idx):
+        ctx.save_for_backward(idx)
+        return K.pool122_gather(x, idx)
+
+    @staticmethod
+    def backward(ctx, dy):
+        (idx,) = ctx.saved_tensors
+        return PoolScatterF.apply(dy.contiguous(), idx), None
+
+
+class BmmF(Function):
+    """fp32 batched C = op(A) op(B) (torch.bmm of layers.py:32-33,64-65)"""
+
+    @staticmethod
+    def forward(ctx, a, b, ta, tb):
+        ctx.save_for_backward(a, b)
+        ctx.cfg = (ta, tb)
+        return K.bmm(a, b, ta, tb)
+
+    @staticmethod
+    def backward(ctx, dc):
+        a, b = ctx.saved_tensors
+        ta, tb = ctx.cfg
+        dc = dc.contiguous()
+        da = db = None
+        if ctx.needs_input_grad[0]:
+            da = BmmF.apply(b, dc, tb, True) if ta else BmmF.apply(dc, b, False, not tb)
+        if ctx.needs_input_grad[1]:
+            db = BmmF.apply(dc, a, True, ta) if tb else BmmF.apply(a, dc, not ta, False)
+        return da, db, None, None
+
+
+class SoftmaxF(Function):
+    @staticmethod
+    def forward(ctx, s):
+        beta = K.softmax_fwd(s)
+        ctx.save_for_backward(beta)
+        return beta
+
+    @staticmethod
+    def backward(ctx, dbeta):
+        (beta,) = ctx.saved_tensors
+        return SoftmaxBwdF.apply(beta, dbeta.contiguous())
+
+
+class SoftmaxBwdF(Function):
+    """dS = beta * (dbeta - <beta, dbeta>)"""
+
+    @staticmethod
+    def forward(ctx, beta, dbeta):
+        ctx.save_for_backward(beta, dbeta)
+        return K.softmax_bwd(beta, dbeta)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, u):
+        beta, dbeta = ctx.saved_tensors
+        g_beta, g_dbeta = K.softmax_bwd_bwd(beta, dbeta, u.contiguous())
+        return g_beta, g_dbeta
+
+
+def attention_core(theta, phi, g, c8, c2):
+    """o = softmax(theta . maxpool(phi)^T) . maxpool(g) per sample over all D*H*W positions, pooling (1,2,2)
+    (models/layers.py:25-34, 55-66), from differentiable fp32 primitives.  theta / phi (N,D,H,W,C8p), g (N,D,H,W,C2p)
+    CL -> o (N,D,H,W,round16(c2)) CL."""
+    N, D, H, W, _ = theta.shape
+    th = SliceF32F.apply(theta, c8).reshape(N, D * H * W, c8)
+    ph = MaxPool122F.apply(SliceF32F.apply(phi, c8).reshape(N * D, H, W, c8)).reshape(N, -1, c8)
+    gp = MaxPool122F.apply(SliceF32F.apply(g, c2).reshape(N * D, H, W, c2)).reshape(N, -1, c2)
+    beta = SoftmaxF.apply(BmmF.apply(th, ph, False, True))                  # (N, P, P/4)
+    o = BmmF.apply(beta, gp, False, False)                                  # (N, P, c2)
+    return PadCLF.apply(o.reshape(N, D, H, W, c2), round16(c2), theta.dtype)
+
+
 def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2), fused=False):
     """SA-GAN / non-local block (models/layers.py:23-36 2-D, :52-68 3-D) on a CL tensor.
 
-    The four 1x1(x1) convs run on the tcgen05 engine (channel counts < 16 are zero-padded).  ROUND-1
-    INTERIM: the attention core (max-pool, theta^T phi, softmax, beta g) is plain torch (cuBLAS bmm +
-    ATen softmax) in fp32 -- < 0.1 % of the step's FLOPs -- and is double-differentiable as the
-    gradient penalty requires.  DESIGN.md lists the fused kernel that replaces it."""
-    import torch.nn.functional as Fnn
+    The four 1x1(x1) convs run on the tcgen05 engine (channel counts < 16 are zero-padded).  The attention core is the
+    fused kernel pair t2v_attention_fwd / _bwd where it applies (the generator's block: first-order autograd, bf16
+    storage, c8 <= 8, <= 1024 positions) and the differentiable primitive composition of attention_core otherwise (the
+    discriminator's block, which the gradient penalty differentiates twice; large maps; fp32 storage)."""
     N, D, H, W, C = x.shape
     c8, c2 = w_theta.shape[0], w_g.shape[0]
-    if fused and c8 <= 8 and c2 <= 16 and H % 2 == 0 and W % 2 == 0 and D * H * W <= 1024:   # kernels' smem bound
-        # generator block (first-order autograd is enough): max-pool + QK^T + softmax + beta.g in one kernel
-        o = AttentionCoreF.apply(conv(x, w_theta), conv(x, w_phi), conv(x, w_g), c8, c2)
-        return gamma.to(x.dtype) * conv(o, w_o) + x
-    theta = conv(x, w_theta)[..., :c8].float()
-    phi = conv(x, w_phi)[..., :c8].float()
-    g = conv(x, w_g)[..., :c2].float()
-
-    def mp(t):
-        t = Fnn.max_pool3d(t.permute(0, 4, 1, 2, 3), list(pool))
-        return t.permute(0, 2, 3, 4, 1)
-    theta = theta.reshape(N, D * H * W, c8)
-    phi = mp(phi).reshape(N, -1, c8)
-    g = mp(g).reshape(N, -1, c2)
-    beta = torch.softmax(torch.bmm(theta, phi.transpose(1, 2)), -1)
-    o = torch.bmm(beta, g).reshape(N, D, H, W, c2)
-    c2p = round16(c2)
-    if c2p != c2:
-        o = Fnn.pad(o, (0, c2p - c2))
-    o = conv(o.to(x.dtype).contiguous(), w_o)
-    return gamma.to(x.dtype) * o + x
+    assert tuple(pool) == (1, 2, 2) and H % 2 == 0 and W % 2 == 0
+    theta, phi, g = conv(x, w_theta), conv(x, w_phi), conv(x, w_g)
+    if fused and x.dtype == BF16 and c8 <= 8 and c2 <= 16 and D * H * W <= 1024:   # kernels' shared-memory bound
+        o = AttentionCoreF.apply(theta, phi, g, c8, c2)
+    else:
+        o = attention_core(theta, phi, g, c8, c2)
+    return ScaleAddF.apply(conv(o, w_o), x, gamma)
 
 
-def head_linear(feat, weight, bias):
-    """fc_uncond / fc heads (models/resnet3d.py:50-55) on fp32 (B, F) features.  ROUND-1 INTERIM: ATen
-    (a (B,F)x(F,1) product); the fused sum-pool + two-dot-product kernel is listed in DESIGN.md."""
-    import torch.nn.functional as Fnn
-    return Fnn.linear(feat, weight, bias)
+# ------------------------------------------------------------------------------------- discriminator heads
+class HeadF(Function):
+    """pred (B,) = [feat | cond] . w + b: fc_uncond / fc of models/resnet3d.py:50-55 on fp32 (B, F) features."""
+
+    @staticmethod
+    def forward(ctx, feat, cond, w, b):
+        ctx.save_for_backward(feat, cond, w)
+        ctx.has_b = b is not None
+        return K.head_fwd(feat.contiguous(), None if cond is None else cond.contiguous(), w.detach().reshape(-1),
+                          None if b is None else b.detach())
+
+    @staticmethod
+    def backward(ctx, dpred):
+        feat, cond, w = ctx.saved_tensors
+        dpred = dpred.contiguous()
+        dfeat = dcond = dw = db = None
+        if ctx.needs_input_grad[0] or (cond is not None and ctx.needs_input_grad[1]):
+            dfeat, dcond = HeadBwdDataF.apply(dpred, w, feat.shape[1], 0 if cond is None else cond.shape[1])
+        if ctx.needs_input_grad[2] or (ctx.has_b and ctx.needs_input_grad[3]):
+            dw, db = HeadBwdWeightF.apply(dpred, feat, cond)
+            dw = dw.reshape(w.shape)
+        return (dfeat if ctx.needs_input_grad[0] else None, dcond if (cond is not None and ctx.needs_input_grad[1])
+                else None, dw if ctx.needs_input_grad[2] else None, db if (ctx.has_b and ctx.needs_input_grad[3])
+                else None)
+
+
+class HeadBwdDataF(Function):
+    """(dfeat, dcond | None) = dpred (x) w"""
+
+    @staticmethod
+    def forward(ctx, dpred, w, F_, E):
+        ctx.save_for_backward(dpred, w)
+        return K.head_bwd_data(dpred, w.detach().reshape(-1), F_, E)
+
+    @staticmethod
+    def backward(ctx, ddfeat, ddcond):
+        dpred, w = ctx.saved_tensors
+        ddfeat = ddfeat.contiguous()
+        ddc = None if ddcond is None else ddcond.contiguous()
+        if ddc is None and w.numel() != ddfeat.shape[1]:        # caption slot present but its gradient unused
+            ddc = ddfeat.new_zeros((ddfeat.shape[0], w.numel() - ddfeat.shape[1]))
+        g_dpred = g_w = None
+        if ctx.needs_input_grad[0]:
+            g_dpred = HeadF.apply(ddfeat, ddc, w, None)
+        if ctx.needs_input_grad[1]:
+            g_w = HeadBwdWeightF.apply(dpred, ddfeat, ddc)[0].reshape(w.shape)
+        return g_dpred, g_w, None, None
+
+
+class HeadBwdWeightF(Function):
+    """(dw, db) = (sum_b dpred[b] [feat | cond][b], sum_b dpred[b])"""
+
+    @staticmethod
+    def forward(ctx, dpred, feat, cond):
+        ctx.save_for_backward(dpred, feat, cond)
+        return K.head_bwd_weight(dpred, feat.contiguous(), None if cond is None else cond.contiguous(), True)
+
+    @staticmethod
+    def backward(ctx, ddw, ddb):
+        dpred, feat, cond = ctx.saved_tensors
+        ddw = ddw.contiguous()
+        g_dpred = g_feat = g_cond = None
+        if ctx.needs_input_grad[0]:
+            g_dpred = HeadF.apply(feat, cond, ddw, None if ddb is None else ddb.contiguous())
+        if ctx.needs_input_grad[1] or (cond is not None and ctx.needs_input_grad[2]):
+            g_feat, g_cond = HeadBwdDataF.apply(dpred, ddw, feat.shape[1], 0 if cond is None else cond.shape[1])
+            if cond is None:
+                g_cond = None
+        return g_dpred, g_feat, g_cond
+
+
+def head_linear(feat, weight, bias, cond=None):
+    """fc_uncond / fc heads (models/resnet3d.py:50-55): Linear(F [+ E], 1) on fp32 (B, F) features [and (B, E)
+    captions] -> (B, 1), as one row-dot kernel (no concatenation, no cuBLAS gemv)."""
+    return HeadF.apply(feat, cond, weight, bias).reshape(-1, 1)
+
+
+# ------------------------------------------------------------------------------------- fused loss reduction
+class RelLossF(Function):
+    """sum_e weight_e * mean_j f(b_e[j] - a_e[j]) over ALL (level, prediction-pair) entries in one kernel
+    (gan/cond_gan.py:51-61,108-112 with RSGANLoss / WassersteinGanLoss, gan/losses.py:55-85); mode 0 softplus, 1 id."""
+
+    @staticmethod
+    def forward(ctx, mode, weights, *tensors):
+        n = len(tensors) // 2
+        a_list = [t.detach().reshape(-1).contiguous() for t in tensors[:n]]
+        b_list = [t.detach().reshape(-1).contiguous() for t in tensors[n:]]
+        ctx.cfg = (mode, tuple(weights), n, [tuple(t.shape) for t in tensors])
+        ctx.save_for_backward(*a_list, *b_list)
+        ctx.ids = [id(t) for t in tensors]
+        return K.rel_loss_fwd(a_list, b_list, weights, mode)
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, gout):
+        mode, weights, n, shapes = ctx.cfg
+        saved = ctx.saved_tensors
+        a_list, b_list = list(saved[:n]), list(saved[n:])
+        # one zeroed buffer for every requested gradient; the kernel accumulates (an input may appear in several entries,
+        # but autograd sums the per-argument gradients itself, so every argument gets its own slice)
+        need = [ctx.needs_input_grad[2 + i] for i in range(2 * n)]
+        sizes = [t.numel() for t in saved]
+        buf = torch.zeros(sum(sz for sz, nd in zip(sizes, need) if nd), device=gout.device, dtype=F32)
+        grads, off = [], 0
+        for sz, nd in zip(sizes, need):
+            if nd:
+                grads.append(buf[off:off + sz])
+                off += sz
+            else:
+                grads.append(None)
+        K.rel_loss_bwd(a_list, b_list, grads[:n], grads[n:], weights, mode, gout.contiguous().float().reshape(1))
+        return (None, None) + tuple(None if g is None else g.reshape(shp) for g, shp in zip(grads, shapes))
+
+
+def rel_loss(pairs, mode):
+    """pairs: list of (a, b, weight) -> scalar sum_e weight * mean f(b - a)"""
+    a = [p[0] for p in pairs]
+    b = [p[1] for p in pairs]
+    return RelLossF.apply(mode, [float(p[2]) for p in pairs], *a, *b)
+
+
+# ------------------------------------------------------------------------------------- caption LSTM
+class EmbeddingF(Function):
+    """nn.Embedding (models/txt/basic.py:16,51): bit-exact row gather, gradient by atomic row adds"""
+
+    @staticmethod
+    def forward(ctx, tokens, weight):
+        ctx.save_for_backward(tokens)
+        ctx.V = weight.shape[0]
+        return K.embedding_fwd(tokens.contiguous(), weight.detach())
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout):
+        (tokens,) = ctx.saved_tensors
+        return None, K.embedding_bwd(tokens.contiguous(), dout.contiguous(), ctx.V)
+
+
+class LstmLayerF(Function):
+    """One (bi)directional LSTM layer over a length-masked batch (nn.LSTM on a PackedSequence,
+    models/txt/basic.py:52-56): input projection of all steps and both directions as ONE GEMM on the tcgen05 engine,
+    then the persistent recurrence kernel (t2v_lstm_seq_fwd).  x (B, L, In) storage dtype; lengths int32 (B,) device;
+    h0 / c0 (ndir, B, H) fp32 or None; params = (w_ih, w_hh, b_ih, b_hh) per direction.
+    -> out (B, L, ndir*H) storage, hn, cn (ndir, B, H) fp32."""
+
+    @staticmethod
+    def forward(ctx, x, lengths, h0, c0, *params):
+        ndir = len(params) // 4
+        B, L, In = x.shape
+        w_ih = torch.cat([params[4 * d].detach() for d in range(ndir)], dim=0)            # (ndir*4H, In)
+        w_hh = torch.stack([params[4 * d + 1].detach() for d in range(ndir)], dim=0).contiguous()   # (ndir, 4H, H)
+        bias = torch.cat([(params[4 * d + 2] + params[4 * d + 3]).detach() for d in range(ndir)], dim=0)
+        H = w_hh.shape[2]
+        x5 = x.reshape(B * L, 1, 1, 1, In)
+        gx = K.conv_fprop(x5, K.pack_weight(w_ih.reshape(ndir * 4 * H, 1, In).contiguous()), bias.contiguous(), None,
+                          (1, 1, 1), False, True)
+        h0c = None if h0 is None else h0.detach().float().contiguous()
+        c0c = None if c0 is None else c0.detach().float().contiguous()
+        out, hprev, gates, cells, hn, cn = K.lstm_seq_fwd(gx.reshape(B, L, ndir * 4 * H), K.lstm_pack_whh(w_hh), lengths,
+                                                          h0c, c0c, True)
+        ctx.save_for_backward(x, lengths, c0c, w_ih, w_hh, hprev, gates, cells)
+        ctx.cfg = (ndir, H, In, h0 is not None, c0 is not None)
+        return out, hn, cn
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, dout, dhn, dcn):
+        x, lengths, c0, w_ih, w_hh, hprev, gates, cells = ctx.saved_tensors
+        ndir, H, In, has_h0, has_c0 = ctx.cfg
+        B, L, _ = x.shape
+        dgates, dh0, dc0 = K.lstm_seq_bwd(w_hh, lengths, c0, gates, cells, None if dout is None else dout.contiguous(),
+                                          None if dhn is None else dhn.contiguous().float(),
+                                          None if dcn is None else dcn.contiguous().float())
+        dg5 = dgates.reshape(B * L, 1, 1, 1, ndir * 4 * H)
+        dx = None
+        if ctx.needs_input_grad[0]:
+            dx = K.conv_dgrad(dg5, K.pack_dgrad_weight(w_ih.reshape(ndir * 4 * H, 1, In).contiguous()),
+                              (1, 1, 1)).reshape(B, L, In)
+        dwih = K.conv_wgrad(dg5, x.reshape(B * L, 1, 1, 1, In), (1, 1, 1)).reshape(ndir * 4 * H, In)
+        dwhh = K.conv_wgrad(dg5, hprev.reshape(B * L, 1, 1, 1, ndir * H), (1, 1, 1)).reshape(ndir * 4 * H, ndir * H)
+        db = K.sum_rows(dg5)
+        grads = []
+        for d in range(ndir):
+            r = slice(d * 4 * H, (d + 1) * 4 * H)
+            grads += [dwih[r], dwhh[r, d * H:(d + 1) * H], db[r], db[r]]
+        return (dx, None, dh0 if has_h0 else None, dc0 if has_c0 else None) + tuple(grads)

@@ -88,9 +88,9 @@ class VideoDiscrim(nn.Module):
             c = _bn_lrelu(ops.linear_cl(ops.vec_to_cl(cond), self.cond_map[0]), self.cond_map[1], self.slope)
             h = torch.cat((h, _tile_cond(c, h)), dim=-1)
             h = _bn_lrelu(ops.gconv(h, self.pred[0]), self.pred[1], self.slope)
-            out = ops.gconv(h, self.pred[3])
+            out = ops.gconv(h, self.pred[3], out_f32=True)
         else:
-            out = ops.gconv(h, self.pred)
+            out = ops.gconv(h, self.pred, out_f32=True)
         return out[..., 0].float().reshape(out.shape[0], -1).mean()
 
 
@@ -148,7 +148,7 @@ class _PerFrameDiscrim(nn.Module):
             h = ops.bn_act(ops.conv(f, trunk[0].weight), trunk[1], 2)
             h = torch.cat((h, _tile_cond(sent, h)), dim=-1)
             h = ops.bn_act(ops.conv(h, self.predictor[0].weight), self.predictor[1], 2)
-            o = ops.gconv(h, self.predictor[3])
+            o = ops.gconv(h, self.predictor[3], out_f32=True)
             outs.append(o[..., 0].float().reshape(o.shape[0], -1).squeeze(1))
         return torch.stack(outs, 0)
 
