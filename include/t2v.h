@@ -69,6 +69,9 @@ int t2v_profile_read(double* host_out6);
 int t2v_profile_read4(double* host_out12);
 /* same with the direct RGB-stem kernels as kinds 4 (fprop) and 5 (wgrad) */
 int t2v_profile_read6(double* host_out18);
+/* fraction of the NEXT profiled launch's channel products that are real (zero channel padding excluded from the
+ * roofline's FLOP count); resets to 1 after that launch */
+int t2v_profile_next_scale(double real_fraction);
 
 /* convolution engine (tcgen05 implicit GEMM; replaces F.conv2d/conv3d/linear = cuDNN/cuBLAS)  */
 /* y[n,d,h,w,co] = sum_{taps,ci} x[n,d+a-pd,h+b-ph,w+c-pw,ci] * w[co,a,b,c,ci] + bias[co] (+ residual)

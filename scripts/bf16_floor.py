@@ -44,7 +44,7 @@ def one(conditional, autocast, fx, attn_gamma=0.0, device="cpu"):
     sd_t = None if sds["txt"] is None else O.as_leaves(sds["txt"])
     opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
     opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
-    with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast):
+    with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast, cache_enabled=False):
         out = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
     cpu = lambda d: {k: v.detach().float().cpu() for k, v in d.items()}
     out["gradD"], out["gradG"] = cpu(out["gradD"]), cpu(out["gradG"])

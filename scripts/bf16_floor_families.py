@@ -32,7 +32,7 @@ def main():
         torch.backends.cuda.matmul.allow_tf32 = False
         torch.backends.cudnn.allow_tf32 = False
     dev_sd = lambda m: {k: v.to(device) for k, v in m.state_dict().items()}
-    ac = lambda on: torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=on)
+    ac = lambda on: torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=on, cache_enabled=False)
     # ---- TGAN
     fx = golden("tgan_B8.json")
     gen, dis = T.build_tgan()

@@ -23,7 +23,7 @@ for r in csv.reader(open(out)):
 tot = sum(a[1] for a in agg.values())
 print("total conv-engine time %.2f ms" % tot)
 with open("gpurun_out/conv_shapes_b%s.txt" % batch, "w") as f:
-    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:45]:
+    for key, a in sorted(agg.items(), key=lambda kv: -kv[1][1])[:int(os.environ.get('TOPN', '45'))]:
         line = "%s N=%s D=%s H=%s W=%s Cin=%s Cout=%s k=%s%s%s  n=%d ctas=%d  %.3f ms (%.1f%%)  %.1f TF/s" % (
             ("fprop", "wgrad")[int(key[0])], key[1], key[2], key[3], key[4], key[5], key[6], key[7], key[8], key[9],
             a[0], a[3], a[1], 100 * a[1] / tot, a[2] / a[1] / 1e9)

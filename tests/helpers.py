@@ -71,3 +71,19 @@ def l2rel(a, b, zero_tol=1e-5):
 def state_to_cpu(module):
     return {k: v.detach().float().cpu().clone() if v.dtype.is_floating_point else v.detach().cpu().clone()
             for k, v in module.state_dict().items()}
+
+
+def bf16_bars(tag, factor=1.5):
+    """Bars of the bf16-mode full-iteration parity tests: `factor` x the measured bf16 floor of this network --
+    the ORACLE itself under torch.autocast(bfloat16) (cuDNN / cuBLAS bf16 kernels, fp32 accumulation) against the same
+    oracle in fp32 (TF32 off) on the same weights, inputs and host-RNG stream, measured on a B200 by
+    scripts/bf16_floor.py and committed as profiles/r02_bf16_floor_<tag>.json.  Losses keep BASELINE north_star's own
+    2e-2 bar (they sit far inside it); gradients and generated clips of this un-normalised random-init network are
+    bf16-noise amplified (the floor shows by how much), so their bar is the floor, not a free parameter.
+    -> (loss_tol, gradG_l2_tol, gradG_cos_min, fake_tol, gradD_l2_tol, gradD_cos_min)"""
+    import json
+    with open(os.path.join(ROOT, "profiles", "r02_bf16_floor_%s.json" % tag)) as f:
+        fl = json.load(f)
+    cos_bar = lambda c: 1.0 - factor * factor * (1.0 - c)          # 1 - cos ~ err^2 / 2
+    return (2e-2, factor * fl["gradG"]["l2"], cos_bar(fl["gradG"]["cos"]), factor * fl["fake"],
+            factor * fl["gradD"]["l2"], cos_bar(fl["gradD"]["cos"]))

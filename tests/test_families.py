@@ -145,7 +145,7 @@ def product_tcwyt_iteration(mods, x, z, cond):
     return {"lossD": float(lossD), "lossG": float(lossG), "fake": fake.detach().float().cpu(), "gD": gD, "gG": _grads(gen)}
 
 
-def _compare(orc, got, loss_tol, grad_tol, groups, wgan_tol=None):
+def _compare(orc, got, loss_tol, grad_tol, groups, wgan_tol=None, fake_tol=None):
     if "d_real" in orc:
         # WGAN: lossD = mean D(fake) - mean D(real).  Both critic means are batch averages of mixed-sign per-sample
         # outputs and D(fake) sits on top of a generated clip that already carries the storage rounding, so the
@@ -160,7 +160,8 @@ def _compare(orc, got, loss_tol, grad_tol, groups, wgan_tol=None):
     else:
         assert abs(got["lossD"] - orc["lossD"]) <= loss_tol * max(abs(orc["lossD"]), 1e-3), (got["lossD"], orc["lossD"])
         assert abs(got["lossG"] - orc["lossG"]) <= loss_tol * max(abs(orc["lossG"]), 1e-3), (got["lossG"], orc["lossG"])
-    assert l2rel(got["fake"], orc["fake"]) <= max(loss_tol, 1e-3)      # the generated clip itself
+    fake_err = l2rel(got["fake"], orc["fake"])                           # the generated clip itself
+    assert fake_err <= (fake_tol if fake_tol is not None else max(loss_tol, 1e-3)), fake_err
     worst = {}
     for tag, ref, mine in groups:
         scale = max(float(v.norm()) for v in ref.values())
@@ -172,8 +173,21 @@ def _compare(orc, got, loss_tol, grad_tol, groups, wgan_tol=None):
                 continue
             w = max(w, l2rel(mine[k], g))
         worst[tag] = w
-        assert w <= grad_tol, (tag, w)
+        assert w <= (grad_tol[tag] if isinstance(grad_tol, dict) else grad_tol), (tag, w)
     return worst
+
+
+def _family_floor(family):
+    """measured bf16 floor of the family (the oracle under torch.autocast(bfloat16) vs fp32 on a B200:
+    scripts/bf16_floor_families.py -> profiles/r02_bf16_floor_families.json, one JSON line per family)"""
+    import json
+    import os
+    from helpers import ROOT
+    with open(os.path.join(ROOT, "profiles", "r02_bf16_floor_families.json")) as f:
+        for line in f:
+            if line.strip() and json.loads(line)["family"] == family:
+                return json.loads(line)
+    raise KeyError(family)
 
 
 @pytest.fixture()
@@ -225,7 +239,14 @@ def test_tgan_product_gpu():
     n0 = _lib.lib().t2v_launch_count()
     got = product_tgan_iteration(gen.cuda(), dis.cuda(), x.cuda(), z.cuda())
     assert _lib.lib().t2v_launch_count() - n0 > 100
-    worst = _compare(orc, got, 2e-2, 0.35, [("D", orc["gD"], got["gD"]), ("G", orc["gG"], got["gG"])], wgan_tol=5e-2)
+    # bars = 1.5x the measured bf16 floor: the critic means on the scale |D(real)| + |D(fake)| (the WGAN losses are
+    # near-cancelling differences of those means), the worst per-tensor gradient deviation per network
+    fl = _family_floor("tgan_B8")
+    wgan_tol = 1.5 * max(fl["lossD_over_critic_scale"], fl["lossG_over_critic_scale"])
+    worst = _compare(orc, got, 2e-2, {"D": 1.5 * fl["gradD_worst"], "G": 1.5 * fl["gradG_worst"]},
+                     [("D", orc["gD"], got["gD"]), ("G", orc["gG"], got["gG"])], wgan_tol=wgan_tol,
+                     fake_tol=max(2e-2, 1.5 * fl["fake"]))
+    print("tgan gpu: bars wgan %.3f D %.3f G %.3f;" % (wgan_tol, 1.5 * fl["gradD_worst"], 1.5 * fl["gradG_worst"]), end=" ")
     print("tgan gpu: lossD %.5f (oracle %.5f) lossG %.5f (oracle %.5f) worst grad L2 %s"
           % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))
 
@@ -241,7 +262,11 @@ def test_tcwyt_product_gpu():
     got = product_tcwyt_iteration([m.cuda() for m in mods], x.cuda(), z.cuda(), cond.cuda())
     assert abs(got["lossD"] - fx["lossD"]) <= 2e-2 * abs(fx["lossD"])
     groups = [(n, orc["gD"][n], got["gD"][n]) for n in ("video", "frame", "motion", "map")]
-    worst = _compare(orc, got, 2e-2, 0.25, groups + [("G", orc["gG"], got["gG"])])
+    fl = _family_floor("tcwyt_B4")
+    bars = {n: 1.5 * fl["gradD_%s_worst" % n] for n in ("video", "frame", "motion", "map")}
+    bars["G"] = 1.5 * fl["gradG_worst"]
+    worst = _compare(orc, got, 2e-2, bars, groups + [("G", orc["gG"], got["gG"])], fake_tol=max(2e-2, 1.5 * fl["fake"]))
+    print("tcwyt gpu: bars %s;" % {k: round(v, 3) for k, v in bars.items()}, end=" ")
     print("tcwyt gpu: lossD %.5f (oracle %.5f) lossG %.5f (oracle %.5f) worst grad L2 %s"
           % (got["lossD"], orc["lossD"], got["lossG"], orc["lossG"], worst))
 

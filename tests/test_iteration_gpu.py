@@ -1,11 +1,12 @@
 """GPU: one full TGANv2 training iteration (B=8, 64x64x16) on the sm_100a kernels against the CPU oracle
-on the same weights, inputs and host-RNG stream.  Same thresholds as the CPU emulation test
-(tests/test_product_vs_oracle_cpu.py): losses inside the bf16 bar (2e-2); bit-exact real pyramid; gradient
-agreement pinned at the level bf16 ReLU-mask noise allows."""
+on the same weights, inputs and host-RNG stream.  bf16 mode: losses inside BASELINE north_star's 2e-2 bar, bit-exact
+real pyramid, generated clips and gradients within 1.5x the MEASURED bf16 floor of this network (the oracle itself
+under torch.autocast(bfloat16) vs fp32 on a B200: profiles/r02_bf16_floor_*.json, helpers.bf16_bars).  fp32 mode:
+everything within 1e-3."""
 import pytest
 import torch
 
-from helpers import golden
+from helpers import bf16_bars, golden
 from test_product_vs_oracle_cpu import compare, run_product_iteration
 
 pytestmark = pytest.mark.gpu
@@ -20,8 +21,9 @@ def test_full_iteration_on_b200(name, conditional):
     launches = _lib.lib().t2v_launch_count() - n0
     print("kernel launches in one iteration:", launches)
     assert launches > 500
-    rep = compare(orc, got, 2e-2, 0.25, 0.97, 6e-2)
-    assert rep["gradD"]["l2"] < 5e-2 and rep["gradD"]["cos"] > 0.998, rep
+    loss_tol, g_l2, g_cos, fake_tol, d_l2, d_cos = bf16_bars("cond_g0" if conditional else "uncond_g0")
+    rep = compare(orc, got, loss_tol, g_l2, g_cos, fake_tol)
+    assert rep["gradD"]["l2"] < d_l2 and rep["gradD"]["cos"] > d_cos, rep
     import json, os
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/iteration_parity_%s.json" % name.split(".")[0], "w") as f:
@@ -64,8 +66,9 @@ def test_full_iteration_bf16_attention_on_b200():
     from txt2vid_b200 import ops
     ops.PACKS.clear()
     orc, got = run_product_iteration(True, golden("tganv2_cond_B8.json"), "cuda", perturb=True, precision="bf16")
-    rep = compare(orc, got, 2e-2, 0.25, 0.97, 6e-2)
-    assert rep["gradD"]["l2"] < 5e-2 and rep["gradD"]["cos"] > 0.998, rep
+    loss_tol, g_l2, g_cos, fake_tol, d_l2, d_cos = bf16_bars("cond_g0.5")
+    rep = compare(orc, got, loss_tol, g_l2, g_cos, fake_tol)
+    assert rep["gradD"]["l2"] < d_l2 and rep["gradD"]["cos"] > d_cos, rep
     _record("tganv2_cond_B8_bf16_attn_on", {"precision": "bf16", "perturb": True, "report": rep})
 
 
@@ -77,8 +80,9 @@ def test_config5_128x128x32_iteration_on_b200():
     ops.PACKS.clear()
     fx = {"config": dict(golden("tganv2_cond_B8.json")["config"])}
     orc, got = run_product_iteration(True, fx, "cuda", size=128, frames=32, frame_sizes=(16, 32, 64, 128))
-    rep = compare(orc, got, 2e-2, 0.25, 0.97, 6e-2)
-    assert rep["gradD"]["l2"] < 5e-2 and rep["gradD"]["cos"] > 0.998, rep
+    loss_tol, g_l2, g_cos, fake_tol, d_l2, d_cos = bf16_bars("cond_g0")      # same network, larger planes
+    rep = compare(orc, got, loss_tol, g_l2, g_cos, fake_tol)
+    assert rep["gradD"]["l2"] < d_l2 and rep["gradD"]["cos"] > d_cos, rep
     import json, os
     os.makedirs("gpurun_out", exist_ok=True)
     with open("gpurun_out/iteration_parity_tganv2_cond_128x128x32_B8.json", "w") as f:

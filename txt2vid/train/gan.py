@@ -20,6 +20,14 @@ from txt2vid_b200.util import create_object, init, load, status
 
 def main(args):
     dist = DistContext()
+    if dist.enabled and args.seed is None:
+        # every rank must build the same initial weights: agree on rank 0's random seed
+        import random
+        pick = torch.tensor([random.randint(1, 100000)], dtype=torch.int64)
+        if torch.distributed.get_backend() == "nccl":
+            pick = pick.cuda()
+        torch.distributed.broadcast(pick, src=0)
+        args.seed = int(pick[0])
     seed, device = setup(args)
     status("%d cuda devices available" % torch.cuda.device_count())
     vocab = load(args.vocab) if args.vocab else None
@@ -76,8 +84,16 @@ def main(args):
     if args.G_loss is None:
         args.G_loss = args.D_loss
     losses = MixedGanLoss(g_loss=create_object(args.G_loss), d_loss=create_object(args.D_loss))
-    if dist.enabled and args.gp_lambda > 0:
-        args.gp_lambda *= dist.gp_scale
+    if dist.enabled:
+        # one process per GPU: identical replicas (same seed, then rank 0's weights broadcast to be safe), per-rank
+        # z / caption-permutation streams with SHARED frame offsets, a rank-strided view of the batches, and the
+        # summed gradient penalty rescaled for gradient averaging
+        for m in [gen, txt_encoder, sample_mapping] + list(discrims):
+            dist.broadcast_module(m)
+        dist.seed_ranks(seed)
+        if dataset is not None:
+            dataset = dist.shard(dataset)
+        args.gp_lambda = dist.gp_lambda_for(args.gp_lambda, discrims)
     print("GAN has %d parameters" % gan.count_params())
     if args.test:
         test(gan=gan, num_samples=args.num_samples, dataset=dataset, device=device, params=args,

@@ -24,6 +24,7 @@ int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const floa
 int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
 void prof_enable(int on);
 void prof_read(double* out, int nkinds);
+void prof_next_scale(double s);
 
 __global__ void cast_f32_bf16_kernel(const float* __restrict__ s, __nv_bfloat16* __restrict__ d, long long n) {
   const long long i = ((long long)blockIdx.x * blockDim.x + threadIdx.x) * 4;
@@ -110,6 +111,7 @@ int t2v_profile_enable(int on) { prof_enable(on); return T2V_OK; }
 int t2v_profile_read(double* host_out6) { prof_read(host_out6, 2); return T2V_OK; }
 int t2v_profile_read4(double* host_out12) { prof_read(host_out12, 4); return T2V_OK; }
 int t2v_profile_read6(double* host_out18) { prof_read(host_out18, 6); return T2V_OK; }
+int t2v_profile_next_scale(double real_fraction) { prof_next_scale(real_fraction); return T2V_OK; }
 
 int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                    const void* residual, void* y, uint32_t epi_flags, int algo, void* stream) {

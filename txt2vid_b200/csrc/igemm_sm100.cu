@@ -393,9 +393,14 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
 // engine launch; t2v_profile_read() sums elapsed time and useful (live-tap) FLOPs per kernel kind.
 bool g_prof_on = false;
 static std::vector<ProfRec> g_prof;
+static double g_prof_next_scale = 1.0;
 void prof_enable(int on) { g_prof_on = on != 0; }
+// fraction of the NEXT profiled launch's channels that are real (not zero padding): RGB 3 -> 16, attention
+// theta / phi 4 -> 16, render 3 -> 16; the roofline numerator counts real channels only
+void prof_next_scale(double s) { g_prof_next_scale = s; }
 void prof_begin(cudaStream_t s, ProfRec* r, int kind, double flops, const t2v_conv_geom* g, int ctas) {
-  r->kind = kind; r->flops = flops; r->g = *g; r->ctas = ctas;
+  r->kind = kind; r->flops = flops * g_prof_next_scale; r->g = *g; r->ctas = ctas;
+  g_prof_next_scale = 1.0;
   cudaEventCreate(&r->a); cudaEventCreate(&r->b);
   cudaEventRecord(r->a, s);
 }

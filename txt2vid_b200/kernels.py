@@ -29,6 +29,21 @@ def set_store_dtype(dt):
     STORE = dt
 
 
+PROFILING = [False]
+
+
+def profile_enable(on):
+    """per-launch CUDA-event timing of the conv engine (bench.py roofline pass)"""
+    PROFILING[0] = bool(on)
+    lib().t2v_profile_enable(1 if on else 0)
+
+
+def prof_real_fraction(real, padded):
+    """tell the profiler which fraction of the next conv launch's channel products is real (not zero padding)"""
+    if PROFILING[0] and padded > 0 and real != padded:
+        lib().t2v_profile_next_scale(float(real) / float(padded))
+
+
 def _act(*ts):
     for t in ts:
         assert t is None or (t.dtype in (BF16, F32) and t.is_contiguous()), (None if t is None else (t.dtype, t.shape))

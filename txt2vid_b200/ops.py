@@ -243,6 +243,13 @@ def _bias_grad(dy, bias, Cout):
     return SumRowsF.apply(dy)[:Cout]
 
 
+def _prof_real(weight, CinP, CoutP):
+    """roofline bookkeeping: the next conv launch multiplies CinP x CoutP channel pairs of which weight.shape[:2] are
+    real (zero padding of RGB / attention / render channels is not counted as useful work)"""
+    if K is not None and getattr(K, "PROFILING", [False])[0]:
+        K.prof_real_fraction(weight.shape[0] * weight.shape[1], CinP * CoutP)
+
+
 def _pad_bias(bias, CoutP):
     if bias is None:
         return None
@@ -275,6 +282,7 @@ class ConvF(Function):
         assert CinP >= Cin and CinP % 16 == 0, (CinP, Cin)
         wp = PACKS.get(weight, "fprop", CoutP, CinP)
         weight._t2v_conv = True
+        _prof_real(weight, CinP, CoutP)
         y = K.conv_fprop(x, wp, _pad_bias(bias, CoutP), residual, k, relu)
         ctx.relu = relu and not relu_later
         ctx.x_relu = x_relu
@@ -297,6 +305,7 @@ class ConvF(Function):
             elif torch.is_grad_enabled() or x.shape[-1] % 16 or dy.shape[-1] % 16:
                 dx = ReluBwdF.apply(ConvDgradF.apply(dy, weight, x.shape[-1]), x)
             else:
+                _prof_real(weight, x.shape[-1], dy.shape[-1])
                 dx = K.conv_dgrad(dy, PACKS.get(weight, "dgrad", dy.shape[-1], x.shape[-1]), kernel_of(weight),
                                   relu_ref=x)
         if ctx.needs_input_grad[1]:
@@ -376,6 +385,7 @@ class ConvDgradF(Function):
         k = kernel_of(weight)
         wT = PACKS.get(weight, "dgrad", dy.shape[-1], CinP)
         ctx.save_for_backward(dy, weight)
+        _prof_real(weight, CinP, dy.shape[-1])
         return K.conv_dgrad(dy, wT, k)
 
     @staticmethod
@@ -396,6 +406,7 @@ class ConvWgradF(Function):
     @staticmethod
     def forward(ctx, dy, x, weight):
         k = kernel_of(weight)
+        _prof_real(weight, x.shape[-1], dy.shape[-1])
         dwp = K.conv_wgrad(dy, x, k)
         dw3 = K.unpack_wgrad(dwp, weight.shape[0], weight.shape[1])
         ctx.save_for_backward(dy, x)
@@ -903,13 +914,16 @@ class StemConvF(Function):
         ctx.has_bias = bias is not None
         ctx.bias_ref = bias
         ctx.x_leaf = x.is_leaf
-        ctx.save_for_backward(xc, weight)
-        return K.stem_fprop(xc, _stem_pack(weight), None if bias is None else bias.detach(), True)
+        y = K.stem_fprop(xc, _stem_pack(weight), None if bias is None else bias.detach(), True)
+        ctx.save_for_backward(xc, weight, None if FUSE_RELU_BWD else y)
+        return y
 
     @staticmethod
     def backward(ctx, dy):
-        xc, weight = ctx.saved_tensors
+        xc, weight, y = ctx.saved_tensors
         dy = dy.contiguous()
+        if y is not None:                    # T2V_FUSE_RELU_BWD=0: no consumer applies this op's ReLU mask
+            dy = ReluBwdF.apply(dy, y)
         dx = dw = db = None
         if ctx.needs_input_grad[0] and not (ctx.x_leaf and _SKIP_LEAF_INPUT_GRADS[0] and not torch.is_grad_enabled()):
             w2d = stem_weight_2d(weight)

@@ -36,6 +36,45 @@ class DistContext(object):
         """factor for gp_lambda under gradient averaging (see module docstring)"""
         return float(self.world)
 
+    def gp_lambda_for(self, gp_lambda, discrims):
+        """gp_lambda under gradient AVERAGING across ranks: the multi-scale penalty is a SUM over samples
+        (gan/losses.py:203, combine=torch.sum), so it is scaled by the world size; discriminators without
+        `sub_discrims` use the batch MEAN (losses.py:135, combine=torch.mean), which averaging reproduces as is."""
+        if not self.enabled or gp_lambda <= 0:
+            return gp_lambda
+        if all(hasattr(d, "sub_discrims") for d in discrims):
+            return gp_lambda * self.gp_scale
+        return gp_lambda
+
+    def seed_ranks(self, seed):
+        """Per-rank random streams for everything that must differ between shards (z on the CUDA generator, the
+        caption permutation on numpy), while the torch CPU generator stays SHARED: the frame offsets `bt` of
+        models/layers.py:107-108 are one draw per level per iteration in the reference."""
+        import random
+        import numpy as np
+        torch.manual_seed(seed)                       # CPU generator: identical on every rank
+        if torch.cuda.is_available():
+            torch.cuda.manual_seed(seed + self.rank)
+        np.random.seed(seed + self.rank)
+        random.seed(seed + self.rank)
+
+    def broadcast_module(self, module):
+        """parameters and buffers of rank 0 to every rank (replicas must start identical)"""
+        if not self.enabled or module is None:
+            return
+        for t in list(module.parameters()) + list(module.buffers()):
+            dist.broadcast(t.data, src=0)
+
+    def shard(self, dataset):
+        """every rank iterates its own stride of the batches (rank, rank + world, ...), equal counts on all ranks"""
+        if not self.enabled:
+            return dataset
+        return _RankStride(dataset, self.rank, self.world)
+
+    @property
+    def is_main(self):
+        return self.rank == 0
+
     def barrier(self):
         if self.enabled:
             dist.barrier()
@@ -86,3 +125,22 @@ class DistContext(object):
 def _memory_order(t):
     """1-D view of a dense tensor in memory order (works for channels-last parameter gradients)."""
     return torch.as_strided(t, (t.numel(),), (1,), t.storage_offset())
+
+
+class _RankStride(object):
+    """Iterable view of a batch iterable: batches rank, rank + world, ... ; truncated so that all ranks see the same
+    number of batches (a collective per step must be entered by everyone)."""
+
+    def __init__(self, dataset, rank, world):
+        self.dataset, self.rank, self.world = dataset, rank, world
+
+    def __len__(self):
+        return len(self.dataset) // self.world
+
+    def __iter__(self):
+        n = len(self)
+        for i, batch in enumerate(self.dataset):
+            if i // self.world >= n:
+                return
+            if i % self.world == self.rank:
+                yield batch

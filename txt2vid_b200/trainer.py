@@ -4,7 +4,8 @@ modules.  Differences that do not change results:
   * the real-video pyramid (trainer.py:131-165) runs as bit-exact index kernels on the GPU;
   * `real_pred` for the G step is computed without recording a D-parameter graph: the reference
     back-propagates the G loss into D's (already stepped, about to be zeroed) gradients
-    (trainer.py:247,262) -- wasted work with no observable effect on lossG, G's gradients or D;
+    (trainer.py:247,262) -- wasted work with no observable effect on lossG, G's gradients or D.  With
+    --end2end and a conditional discriminator the graph through the caption embedding IS kept (see _g_phase);
   * an optional `dist` argument (txt2vid_b200.parallel) all-reduces gradients before each optimiser step.
 """
 import sys
@@ -147,19 +148,24 @@ def _d_phase(gan, x, cond, device, params, losses, z, channel_first, end2end, j=
     return st
 
 
-def _g_phase(gan, st, params, losses, j=0):
-    """real_pred + G loss backward (trainer.py:247-262)."""
+def _g_phase(gan, st, params, losses, j=0, end2end=False):
+    """real_pred + G loss backward (trainer.py:247-262).  D's parameter gradients are never needed here (the reference
+    computes and discards them), so D is frozen for the whole phase.  real_pred itself is computed without a graph --
+    EXCEPT with end2end and a conditional discriminator: there the conditional real prediction depends on the
+    (undetached) caption embedding (cond_gan.py:108-112), and relativistic losses send a generator-step gradient
+    through it into the caption encoder, whose parameters are in optG (train/gan.py:84-85)."""
     xs, conds = st["xs"], st["conds"]
-    if j == 0:
-        # trainer.py:247 -- draws the caption permutation again (numpy RNG) although only real_pred is used
-        with torch.no_grad():
-            _, _, st["real_pred"] = gan.all_discrim_forward(real=xs, cond=conds, fake=None, loss=None)
-    else:
-        st["fake"] = gan(st["z"], cond=conds[0] if conds is not None else None)
     dparams = [p_ for d in gan.discrims for p_ in d.parameters()]
-    for p_ in dparams:                                  # D's parameter gradients are not needed here
+    for p_ in dparams:
         p_.requires_grad_(False)
     try:
+        if j == 0:
+            # trainer.py:247 -- draws the caption permutation again (numpy RNG) although only real_pred is used
+            need_graph = end2end and conds is not None and any(c.requires_grad for c in conds)
+            with torch.enable_grad() if need_graph else torch.no_grad():
+                _, _, st["real_pred"] = gan.all_discrim_forward(real=xs, cond=conds, fake=None, loss=None)
+        else:
+            st["fake"] = gan(st["z"], cond=conds[0] if conds is not None else None)
         loss = gan.gen_step(fake=st["fake"], real_pred=st["real_pred"], cond=conds, loss=losses.gen_loss)
         if not params.no_mean_gen_loss:
             loss = loss / params.gen_steps
@@ -186,7 +192,7 @@ def train_iteration(gan, x, y, device, optD, optG, params, losses, channel_first
         optD.step()
         total_d = total_d + st["lossD"]
     for j in range(params.gen_steps):
-        st = _g_phase(gan, st, params, losses, j)
+        st = _g_phase(gan, st, params, losses, j, end2end)
         if dist is not None:
             dist.reduce_grads(optG)
         optG.step()
@@ -342,8 +348,25 @@ class GraphedTrainStep(object):
     def sync_optimizer_state(self):
         """write the replayed step counts back into the optimisers' state (for checkpoints)"""
         for opt in (self.optD, self.optG):
+            if not hasattr(opt, "_step_count"):
+                continue
             for st_ in opt.state.values():
                 st_["step"] = opt._step_count
+
+    def begin_eager_step(self):
+        """An eager iteration between replays (a ragged last batch): the fused Adam must take its bias corrections
+        from the step count, not from the device slot the replays stage, and the count must advance."""
+        self.sync_optimizer_state()
+        self._saved_dyn = []
+        for opt in (self.optD, self.optG):
+            self._saved_dyn.append(getattr(opt, "dyn", None))
+            opt.dyn = None
+
+    def end_eager_step(self):
+        for opt, dyn in zip((self.optD, self.optG), self._saved_dyn):
+            opt.dyn = dyn
+            if hasattr(opt, "_step_count"):
+                opt._step_count = max([st_["step"] for st_ in opt.state.values()] or [opt._step_count])
 
 
 class LaggedLosses(object):
@@ -403,6 +426,7 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
         discrim_loss.update(d)
         gen_loss.update(g)
 
+    main_rank = dist is None or getattr(dist, "is_main", True)     # checkpoints / samples / logs: rank 0 only
     graphed = None
     if getattr(params, 'cuda_graphs', False) and torch.device(device).type == 'cuda' and not end2end \
             and params.discrim_steps == 1 and params.gen_steps == 1:
@@ -428,8 +452,12 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
                 st = getattr(graphed, "state", None) or {}
                 fake, xs, cond = st.get("fake", []), st.get("xs", [x]), st.get("conds")
             else:
+                if graphed is not None:
+                    graphed.begin_eager_step()               # ragged last batch: plain Adam steps, counted
                 ld, lg, fake, xs, cond = train_iteration(gan, x, y, device, optD, optG, params, losses,
                                                          channel_first=channel_first, end2end=end2end, dist=dist)
+                if graphed is not None:
+                    graphed.end_eager_step()
             prefetcher.preload()                 # the next batch's bulk copy is enqueued behind this iteration's launch
             # the reference's two host syncs per iteration (trainer.py:243,264); in graph mode the values reach the
             # rolling averages two iterations late so that the host stays ahead of the device
@@ -438,13 +466,15 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
             if saving or (params.log_period > 0 and iteration % params.log_period == 0):
                 lagged.drain()
 
-            if (iteration == 1 and params.save_initial) or iteration % params.save_example_period == 0:
+            if main_rank and ((iteration == 1 and params.save_initial) or iteration % params.save_example_period == 0):
+                if graphed is not None:
+                    graphed.sync_optimizer_state()           # replays advance the step count outside optimizer.state
                 to_save = {'optG': optG.state_dict(), 'optD': optD.state_dict()}
                 to_save.update(gan.save_dict())
                 torch.save(to_save, '%s/iter_%d_lossG_%.4f_lossD_%.4f' % (params.out, iteration, gen_loss.get(),
                                                                           discrim_loss.get()))
                 del to_save
-            if params.log_period > 0 and iteration % params.log_period == 0:
+            if main_rank and params.log_period > 0 and iteration % params.log_period == 0:
                 sys.stdout.flush()
                 mem = (torch.cuda.max_memory_allocated() / 1e9, torch.cuda.max_memory_reserved() / 1e9) \
                     if torch.cuda.is_available() else (0.0, 0.0)
@@ -454,8 +484,8 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
                                                                 avg_iter.get(), avg_data_load.get()))
                 if torch.cuda.is_available():
                     torch.cuda.reset_peak_memory_stats()
-            if params.save_example_period > 0 and ((iteration == 1 and params.save_initial_examples) or
-                                                   iteration % params.save_example_period == 0):
+            if main_rank and params.save_example_period > 0 and ((iteration == 1 and params.save_initial_examples) or
+                                                                 iteration % params.save_example_period == 0):
                 status('saving to %s (iteration %d)' % (params.out_samples, iteration))
                 save_frames(xs[0], '%s/real_samples.png' % params.out_samples, is_images=params.img_model)
                 for f in fake:
