@@ -3,6 +3,7 @@
 
     python bench.py --gpus N --steps K --warmup W            # this repo's sm_100a path
     python bench.py --impl reference --gpus N --steps K ...  # the reference algorithm on the host CPU cores
+    python bench.py --impl torch_cuda                         # the same iteration on torch eager cuDNN/cuBLAS (B200)
 
 Workload (BASELINE.json configs[3], the configuration the metric is quoted on): TGANv2 conditional,
 64x64x16 clips, Bi-LSTM caption encoder, non-local blocks, RSGAN loss + zero-centred gradient penalty
@@ -116,38 +117,93 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
-def cpu_baseline(steps=2, warmup=1, batch=8):
-    import numpy as np
+def _oracle_arm(device, steps, warmup, batch, autocast=False):
+    """the oracle's train_iteration (reference modules restated on torch ops) on `device`: seconds per iteration"""
     import torch
     import oracle.txt2vid_oracle as O
     from txt2vid_b200.factory import build_models as build_product_models
     from txt2vid_b200.data import SyntheticVideoCaptions
-    cores = os.cpu_count() or 1
-    torch.set_num_threads(cores)
     V = 1000
+    cuda = torch.device(device).type == "cuda"
     with contextlib.redirect_stdout(io.StringIO()):
         txt, gen, dis = build_product_models(True, vocab_size=V, seed=100)     # same constructors/init as the reference
-    sd_g, sd_d, sd_t = (O.as_leaves({k: v.detach().clone() for k, v in m.state_dict().items()}) for m in (gen, dis, txt))
+    sd_g, sd_d, sd_t = (O.as_leaves({k: v.detach().clone().to(device) for k, v in m.state_dict().items()})
+                        for m in (gen, dis, txt))
     del txt, gen, dis
     opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
     opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
     times = []
     for it in range(warmup + steps):
         x, tokens, lengths = SyntheticVideoCaptions(batch, 1, vocab_size=V, seed=1234 + it).batch(0)
-        x = x.permute(0, 2, 1, 3, 4).contiguous()
+        x = x.permute(0, 2, 1, 3, 4).contiguous().to(device)
+        tokens = tokens.to(device)
+        if cuda:
+            torch.cuda.synchronize()
         t0 = time.perf_counter()
         bt_real = O.draw_real(4, True)
-        z = torch.randn(batch, 256)
+        z = torch.randn(batch, 256).to(device)
         draws = O.draw_rest([batch, batch // 2, batch // 4, batch // 8], conditional=True, gp=True)
         draws["bt_real"] = bt_real
-        O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
+        with torch.autocast(torch.device(device).type, dtype=torch.bfloat16, enabled=autocast, cache_enabled=False):
+            out = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
+        if cuda:
+            float(out["lossD"]), float(out["lossG"])
+            torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if it >= warmup:
             times.append(dt)
-    per = sum(times) / len(times)
+    return sum(times) / len(times), len(times)
+
+
+def cpu_baseline(steps=2, warmup=1, batch=8):
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    per, n = _oracle_arm("cpu", steps, warmup, batch)
     return {"value": batch / per, "unit": "videos/s", "cores": cores, "kind": "port", "ms_per_step": per * 1e3,
             "sample": "%d timed iterations of batch %d (same model/loss/optimiser, fp32, torch CPU threads=%d)"
-                      % (len(times), batch, cores)}
+                      % (n, batch, cores)}
+
+
+def library_baseline(batches=(64, 256), steps=3, warmup=2, device="cuda:0"):
+    """The B200 LIBRARY comparator (SURVEY 2.4 "the kernel to beat on the same box"):
+    the same iteration -- the oracle's restatement of the reference modules, i.e. what the reference computes when run
+    on this GPU through PyTorch eager -- on cuDNN / cuBLAS / ATen kernels: fp32 with TF32 off (the reference's
+    numerics) and under torch.autocast(bfloat16) (the library's mixed-precision recipe).  None of this repo's kernels
+    run here.  Largest batch first fails soft (out of memory -> recorded as null)."""
+    import torch
+    torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cudnn.benchmark = True            # the reference sets it (train/setup.py:17)
+    out = {"what": "reference modules (oracle restatement) on torch eager cuDNN/cuBLAS, same iteration, same GPU",
+           "unit": "videos/s", "runs": []}
+    for autocast in (False, True):
+        for bsz in batches:
+            rec = {"precision": "bf16 autocast" if autocast else "fp32 (TF32 off)", "batch": bsz}
+            try:
+                per, n = _oracle_arm(device, steps, warmup, bsz, autocast=autocast)
+                rec.update({"value": bsz / per, "ms_per_step": per * 1e3, "timed_steps": n})
+            except torch.cuda.OutOfMemoryError:
+                rec.update({"value": None, "note": "out of memory"})
+            torch.cuda.empty_cache()
+            out["runs"].append(rec)
+    best = [r for r in out["runs"] if r.get("value")]
+    out["best"] = max(best, key=lambda r: r["value"]) if best else None
+    return out
+
+
+def run_library(args):
+    """--impl torch_cuda: the library comparator alone, one JSON line in the bench format (rank 0)."""
+    if int(os.environ.get("RANK", "0")) != 0:
+        return
+    lb = library_baseline(batches=tuple(args.lib_batches), steps=max(1, args.steps), warmup=max(1, args.warmup))
+    best = lb["best"] or {"value": None, "ms_per_step": None, "batch": None, "precision": None}
+    print(json.dumps({"metric": "TGANv2-cond G+D train videos/sec", "value": best["value"], "unit": "videos/s",
+                      "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "ms_per_step": best["ms_per_step"],
+                      "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+                      "dtype": best["precision"], "data": "synthetic", "impl": "torch_cuda",
+                      "config": {"workload": WORKLOAD, "batch_per_gpu": best["batch"], "device": "cuda:0"},
+                      "library_baseline": lb, "gpu_launches": 0}), flush=True)
 
 
 # =========================================================================================== B200 arm
@@ -383,7 +439,18 @@ def run_b200(args):
             "step_nominal_tflops_per_gpu": value / world * gflop_nominal / 1e3,
             "step_nominal_frac_of_sustained_peak": value / world * gflop_nominal / 1e3 / pk["bf16_tflops_sustained"]}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
-    cpu = None
+    cpu = libb = None
+    launch_mode = "eager" if args.eager else "%d CUDA graph(s) per step" % len(graphed.graphs or ())
+    if not args.no_library_baseline:
+        # free the product's graphs / pools first: the library arm needs its own activations
+        if not args.eager:
+            del graphed
+        del dev
+        torch.cuda.empty_cache()
+        try:
+            libb = library_baseline(batches=tuple(args.lib_batches))
+        except Exception as e:                                    # noqa: BLE001 -- the product's line must still print
+            libb = {"error": repr(e)[:200]}
     if not args.no_cpu_baseline:
         c = cpu_baseline(steps=2, warmup=1, batch=args.cpu_batch)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
@@ -391,7 +458,7 @@ def run_b200(args):
             "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "batch_per_gpu": b, "global_batch": world * b,
-                       "parallelism": "dp%d" % world, "launch": "eager" if args.eager else "%d CUDA graph(s) per step" % len(graphed.graphs or ()),
+                       "parallelism": "dp%d" % world, "launch": launch_mode,
                        "l2": "per-step working set (%.1f GB peak allocated) >> 126 MB L2; "
                        "%d distinct resident batches cycled" % (mem_gb, nb)},
             "e2e": {"value": e2e, "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
@@ -402,7 +469,7 @@ def run_b200(args):
                           "note": "host batches hold the frames as stored (uint8); ToTensor + Normalize on the device"},
             "resident_again_ms_per_step": t_res2 / args.steps * 1e3,
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
-            "peak_mem_gb": mem_gb}
+            "library_baseline": libb, "peak_mem_gb": mem_gb}
     print(json.dumps(line), flush=True)
 
 
@@ -411,16 +478,21 @@ def main():
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
-    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"])
     ap.add_argument("--batch", type=int, default=2048, help="videos per GPU per step (multiple of 8)")
     ap.add_argument("--res", type=int, default=64, choices=[64, 128],
                     help="64: 64x64x16 clips (the metric's configuration); 128: 128x128x32 (BASELINE configs[4])")
     ap.add_argument("--cpu_batch", type=int, default=8)
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_library_baseline", action="store_true")
+    ap.add_argument("--lib_batches", type=int, nargs="+", default=[64, 256],
+                    help="batches of the torch-eager cuDNN comparator (library_baseline / --impl torch_cuda)")
     ap.add_argument("--eager", action="store_true", help="no CUDA graphs: launch every kernel from Python")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.impl == "torch_cuda":
+        run_library(args)
     else:
         run_b200(args)
 

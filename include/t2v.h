@@ -37,6 +37,7 @@ extern "C" {
 #define T2V_ALGO_TC 1     /* force the tcgen05/TMEM/TMA kernel (error if shape unsupported) */
 #define T2V_ALGO_SIMT 2   /* force the CUDA-core kernel (cross-check + odd shapes) */
 #define T2V_ALGO_TC_GENERIC 3 /* force the generic tcgen05 implicit GEMM (skip the halo-resident 64-channel kernels) */
+#define T2V_ALGO_SIMT_F32 4   /* t2v_conv_wgrad only: dy and x are fp32 CL, CUDA-core fp32 FMA (fp32 parity mode) */
 
 /* epilogue flags of t2v_conv_fprop */
 #define T2V_EPI_RELU 1u       /* y = max(y, 0) after bias/residual */
@@ -46,6 +47,9 @@ extern "C" {
                                * convolution's input, fused into the data-gradient epilogue (layers.py:230-232) */
 #define T2V_EPI_RES_F32 8u    /* the `residual` / ReLU-reference pointer is fp32 CL (fp32 activation storage, generic
                                * tcgen05 kernel only) */
+#define T2V_EPI_IN_F32 16u    /* fp32 PARITY mode: x / residual are fp32 CL and w is fp32 [Cout][taps][Cin]; the
+                               * convolution runs as exact fp32 FMAs on the CUDA cores (the reference's numerics; the
+                               * tensor pipe's truncating fp32 accumulator cannot reach 1e-6 on K ~ 1e4), y fp32 */
 
 /* Stride-1, "same"-padded convolution geometry (every conv on the TGANv2 path:
  * models/layers.py:174,177,183,231,233,237,251; models/resnet3d.py:12-17; 1x1(x1) convs of the
@@ -311,6 +315,11 @@ int t2v_gconv_wgrad_f32(const t2v_gconv_geom* g, const void* dy, const void* x, 
  * fprop / dgrad; the weight pack is [hi | hi | lo] along K), 1: out [3 rows][C] = [hi ; lo ; hi] (dy of wgrad),
  * 2: out [3 rows][C] = [hi ; hi ; lo] (x of wgrad).  C a multiple of 4.                                        */
 int t2v_split_bf16x3(const float* x, void* out, int64_t rows, int32_t C, int32_t layout, void* stream);
+/* general form: terms = 3 as above; terms = 6 splits x = a + b + c (24 bits = fp32 operands) and lays out the six
+ * products a a' + b a' + a b' + c a' + a c' + b b': layouts 0 / 1 = [a | b | a | c | a | b] (activations), layout 2
+ * and the weight packs = [a | a | b | a | c | b].  This is the fp32 parity mode's default (error <= 2^-23 per
+ * product: ReLU masks of the fp32 oracle are reproduced, which a 2^-17 split does not guarantee).               */
+int t2v_split_bf16(const float* x, void* out, int64_t rows, int32_t C, int32_t layout, int32_t terms, void* stream);
 
 /* scale / add / dot on CL activations (bf16; _f32 twins): the non-local block's gamma * o + x
  * (models/layers.py:36,68) with its gradients, and the gradient penalty's sum ||g||^2 (gan/losses.py:180-186).

@@ -179,7 +179,7 @@ def conv_lstm(x, sd, p, steps):
     return outs
 
 
-def gen_forward(sd, z, cond, bts, training=True, num_frames=16, new_buffers=None):
+def gen_forward(sd, z, cond, bts, training=True, num_frames=16, new_buffers=None, abstract=None):
     """models/tganv2_cond/gen.py:64-124 (cond) and models/tganv2/gen.py:62-119 (uncond, cond=None).
 
     bts: the 3 frame offsets drawn before levels 1..3 (training only).  Returns the list of rendered
@@ -208,6 +208,8 @@ def gen_forward(sd, z, cond, bts, training=True, num_frames=16, new_buffers=None
                 x = up_block(x, sd, ab + "." + u, training, new_buffers)
         else:
             x = up_block(x, sd, ab, training, new_buffers)
+        if abstract is not None:                        # debugging aid: the abstract map of every level (B_i*T_i,C,H,W)
+            abstract.append(x)
         if i == n_levels - 1 or training:
             r = render_block(x, sd, "render_blocks.%d" % i, training, new_buffers)
             r = r.contiguous().view(-1, T, r.size(1), r.size(2), r.size(3)).permute(0, 2, 1, 3, 4)
@@ -484,8 +486,10 @@ def as_leaves(sd):
 
 def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN, gp_lambda=0.5,
                     frame_sizes=(8, 16, 32, 64), subsample_input=True, opt_g=None, opt_d=None,
-                    num_frames=16):
+                    num_frames=16, reduce=None):
     """One iteration of gan/trainer.py:199-265 (discrim_steps = gen_steps = 1, end2end = False).
+    reduce: optional callable {name: grad} -> {name: grad} applied to the D and to the G gradients right before their
+    optimiser step (data-parallel oracle, SURVEY 8e: the fp32 average over ranks).
 
     x: (B,3,T,H,W) fp32 ("channel_first", trainer.py:203-204).  draws: dict with
       'bt_real' (len(frame_sizes) offsets, trainer.py:145-160), 'bt_fake' (3 offsets, gen.py:101-105),
@@ -512,6 +516,8 @@ def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN
     d_grads = torch.autograd.grad(ld, [sd_d[n] for n in d_names], allow_unused=True)
     out["lossD"] = float(ld.detach())
     out["gradD"] = {n: g for n, g in zip(d_names, d_grads) if g is not None}
+    if reduce is not None:
+        out["gradD"] = reduce(out["gradD"])
     if opt_d is not None:
         opt_d.step(sd_d, out["gradD"])
     # ---- real_pred with the UPDATED D (trainer.py:247), then G step (cond_gan.py:90-118)
@@ -521,6 +527,8 @@ def train_iteration(sd_g, sd_d, sd_txt, x, tokens, lengths, z, draws, loss=RSGAN
     g_grads = torch.autograd.grad(lg, [sd_g[n] for n in g_names], allow_unused=True)
     out["lossG"] = float(lg.detach())
     out["gradG"] = {n: g for n, g in zip(g_names, g_grads) if g is not None}
+    if reduce is not None:
+        out["gradG"] = reduce(out["gradG"])
     if opt_g is not None:
         opt_g.step(sd_g, out["gradG"])
     for k, v in new_buf.items():

@@ -132,7 +132,8 @@ def main():
     B = 8
     z, cond = torch.randn(B, 256, generator=g), torch.randn(B, 256, generator=g)
     zo, co = z.clone().requires_grad_(True), cond.clone().requires_grad_(True)
-    fo = O.gen_forward(sdg, zo, co, [1, 0, 1], True, 16, {})
+    abs_o = []
+    fo = O.gen_forward(sdg, zo, co, [1, 0, 1], True, 16, {}, abstract=abs_o)
     rs = [torch.randn(f.shape, generator=g) for f in fo]
     gnames = [n for n, _ in gen.named_parameters()]
     go = torch.autograd.grad(sum((f * r).sum() for f, r in zip(fo, rs)), [zo, co] + [sdg[n] for n in gnames],
@@ -141,9 +142,19 @@ def main():
     gen.subsample.draw = lambda: next(draws)
     gen.train()
     zp, cp = z.to(DEV).requires_grad_(True), cond.to(DEV).requires_grad_(True)
-    fp = gen(zp, cond=cp)
+    fp, abs_p = gen(zp, cond=cp, return_abstract_maps=True)
+    for i, (a, b) in enumerate(zip(abs_p, abs_o)):
+        print("  level %d abstract map rel %.3e" % (i, l2rel(a.float().cpu(), b)))
     for i, (a, b) in enumerate(zip(fp, fo)):
         print("  level %d fake rel %.3e" % (i, l2rel(a.float().cpu(), b)))
+    # the temporal generator alone
+    with torch.no_grad():
+        x0 = torch.randn(8, 1024, 1, 1, generator=g)
+        ho = torch.stack(O.conv_lstm(x0, sdg, "clstm.cell0", 16), 1)              # (B,T,C,1,1)
+        hp, _ = gen.clstm(x0.to(DEV))
+        hp = torch.stack(hp, 1)
+        for t in (0, 1, 7, 15):
+            print("  conv_lstm step %d rel %.3e" % (t, l2rel(hp[:, t].float().cpu(), ho[:, t])))
     gp = torch.autograd.grad(sum((f * r.to(DEV)).sum() for f, r in zip(fp, rs)), [zp, cp] + list(gen.parameters()),
                              allow_unused=True)
     for n, a, b in zip(["z", "cond"] + gnames, gp, go):

@@ -87,3 +87,9 @@ def bf16_bars(tag, factor=1.5):
     cos_bar = lambda c: 1.0 - factor * factor * (1.0 - c)          # 1 - cos ~ err^2 / 2
     return (2e-2, factor * fl["gradG"]["l2"], cos_bar(fl["gradG"]["cos"]), factor * fl["fake"],
             factor * fl["gradD"]["l2"], cos_bar(fl["gradD"]["cos"]))
+
+
+def fp32_bars():
+    """Bars of the fp32-mode parity tests: BASELINE north_star's 1e-3 on losses, generated clips and gradients.
+    -> (loss_tol, gradG_l2_tol, gradG_cos_min, fake_tol, gradD_l2_tol, gradD_cos_min)"""
+    return (1e-3, 1e-3, 0.999999, 1e-3, 1e-3, 0.999999)

@@ -50,6 +50,29 @@ def test_vocab_and_collate_bit_exact():
         assert (tok[i, L:] == 0).all() and tok[i, L - 1] == 2
 
 
+def test_vocab_and_collate_match_the_reference_fixtures():
+    """SURVEY 8(a) row T against the reference's OWN Vocab / build_vocab / collate_fn and the caption part of
+    Dataset.__getitem__ (data/__init__.py:250-254,260-355): tests/golden/token_fixtures.json was recorded from the live
+    reference by oracle/make_golden_tokens.py (nvidia.dali stubbed).  Bit-exact: vocabulary, token ids, padded int64
+    batches, sort order (stable, longest first), lengths, to_words round trip."""
+    from helpers import golden
+    from txt2vid_b200.data import build_vocab, collate_fn
+    fx = golden("token_fixtures.json")
+    v = build_vocab(fx["vocab_sentences"])
+    assert v.word2idx == fx["word2idx"] and len(v) == fx["len"]
+    enc = []
+    for rec in fx["encoded"]:
+        t = v.encode(rec["sentence"])
+        assert t.dtype == torch.int64 and t.tolist() == rec["tokens"], rec["sentence"]
+        assert v.to_words(t) == rec["words"]
+        enc.append(t)
+    for b in fx["batches"]:
+        data = [(torch.full((2,), float(i)), enc[i]) for i in b["picks"]]
+        vids, tok, lens = collate_fn(data)
+        assert [int(x[0]) for x in vids] == b["order"]
+        assert tok.dtype == torch.int64 and tok.tolist() == b["targets"] and [int(l) for l in lens] == b["lengths"]
+
+
 def test_reflection_on_reference_paths():
     import contextlib
     import io

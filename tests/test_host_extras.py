@@ -181,3 +181,70 @@ def _caption_pretraining_body():
         for (n, a), (_, b) in zip(prod.state_dict().items(), ref.state_dict().items()):
             assert float((a - b).abs().max()) <= 2.1e-3, n          # at most one sign flip of a 1e-3 Adam step
         prod.load_state_dict(ref.state_dict(), strict=True)
+
+
+@pytest.fixture()
+def emulated_fp32(monkeypatch):
+    import cpu_kernels
+    from txt2vid_b200 import ops, optim, trainer
+    for mod in (ops, optim, trainer):
+        monkeypatch.setattr(mod, "K", cpu_kernels)
+    monkeypatch.setattr(ops, "BF16", torch.float32)
+    cpu_kernels.set_store_dtype(torch.float32)
+    ops.PACKS.clear()
+    yield
+    cpu_kernels.set_store_dtype(torch.bfloat16)
+    ops.PACKS.clear()
+
+
+def test_trainer_test_writes_the_reference_sample_files(tmp_path, emulated_fp32):
+    """trainer.test() (gan/trainer.py:44-90) -- eval-mode generator, ONE full-resolution clip per
+    sample, the reference's file names: real_<i>.png, sentences_<i>_<j>.txt (vocab.to_words of the token rows),
+    <h>x<w>_<i>_<j>.jpg.  Host logic on the kernels' executable spec."""
+    from types import SimpleNamespace
+    from txt2vid_b200.data import build_vocab, collate_fn
+    from txt2vid_b200.gan import CondGan
+    from txt2vid_b200.trainer import test as run_test
+    sents = ["digit 3 is left and right.", "digit 7 is top and bottom."]
+    vocab = build_vocab(sents)
+    txt, gen, dis = build_product_models(True, V=len(vocab), seed=5)
+    gan = CondGan(gen=gen, discrims=[dis], cond_encoder=txt, discrim_names=["video"])
+    g = torch.Generator().manual_seed(0)
+    vids = [torch.rand(16, 3, 64, 64, generator=g) * 2 - 1 for _ in sents]          # loader order (T, C, H, W)
+    batch = collate_fn([(v, vocab.encode(s)) for v, s in zip(vids, sents)])
+    params = SimpleNamespace(out_samples=str(tmp_path / "samples"), img_model=False)
+    run_test(gan=gan, num_samples=2, dataset=[batch], device=torch.device("cpu"), params=params, vocab=vocab)
+    assert not gan.gen.training
+    names = sorted(os.listdir(params.out_samples))
+    assert names == ["64x64_0_0.jpg", "64x64_1_0.jpg", "real_0.png", "real_1.png", "sentences_0_0.txt",
+                     "sentences_1_0.txt"], names
+    with open(os.path.join(params.out_samples, "sentences_0_0.txt")) as f:
+        lines = f.read().splitlines()
+    assert lines == ["<start> digit 3 is left and right<end>", "<start> digit 7 is top and bottom<end>"]
+    from PIL import Image
+    im = Image.open(os.path.join(params.out_samples, "64x64_0_0.jpg"))
+    assert im.size == (16 * 64 + 17 * 2, 2 * 64 + 3 * 2)                             # nrow = 16 frames, 2 clips, padding 2
+
+
+@pytest.mark.skipif(not os.path.isdir(REF), reason="the reference checkout is only present in the build container")
+def test_pickled_reference_sentence_model_loads_into_the_product(tmp_path, emulated_fp32):
+    """train/txt.py:190-191 saves the WHOLE caption model with torch.save(model) and train/gan.py:38-42
+    loads that pickle (`--sent_weights`).  A pickle written by the live reference (subprocess with /root/reference on
+    the path) must unpickle under this repo's `txt2vid` namespace into the product's Seq2Seq and encode identically."""
+    import subprocess
+    path, out = str(tmp_path / "sent.pth"), str(tmp_path / "ref_out.pt")
+    code = ("import sys, torch; sys.path.insert(0, %r); torch.manual_seed(7)\n"
+            "from txt2vid.models.txt.basic import Seq2Seq\n"
+            "m = Seq2Seq(vocab_size=40)\n"
+            "tok = torch.tensor([[1, 5, 6, 7, 2], [1, 9, 2, 0, 0]]); lens = [5, 3]\n"
+            "o, (h, c), hn = m.encode(tok, lens)\n"
+            "torch.save(m, %r); torch.save({'tok': tok, 'lens': lens, 'out': o, 'h': h, 'c': c, 'hn': hn}, %r)\n"
+            % (REF, path, out))
+    subprocess.check_call([sys.executable, "-c", code], cwd=str(tmp_path))
+    import txt2vid_b200.text as T
+    m = torch.load(path, weights_only=False)
+    assert type(m) is T.Seq2Seq and type(m.encoder) is T.RecurrentModel
+    ref = torch.load(out)
+    o, (h, c), hn = m.encode(ref["tok"], ref["lens"])
+    for a, b in ((o, ref["out"]), (h, ref["h"]), (c, ref["c"]), (hn, ref["hn"])):
+        assert a.shape == b.shape and float((a.float() - b).abs().max()) < 1e-5

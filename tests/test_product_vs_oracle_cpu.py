@@ -38,20 +38,39 @@ def perturb_models(*modules, seed=7):
 
 
 def run_product_iteration(conditional, fx, device="cpu", size=64, frames=16, frame_sizes=(8, 16, 32, 64),
-                          perturb=False, precision=None):
+                          perturb=False, precision=None, **shard):
     """precision: None (leave the product's mode alone: CPU emulation tests), "bf16" or "fp32" (GPU: ops.set_precision
-    for the duration of the call)."""
+    for the duration of the call).  shard: dist= / gp_lambda= / data_seed= / np_seed= for the N-rank parity tests."""
     if precision is None:
-        return _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb)
+        return _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb, **shard)
     from txt2vid_b200 import ops
     ops.set_precision(precision)
     try:
-        return _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb)
+        return _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb, **shard)
     finally:
         ops.set_precision("bf16")
 
 
-def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb):
+def _mean_over_ranks(grads):
+    """fp32 average of a gradient dict over the ranks of the default process group (the data-parallel oracle)"""
+    import torch.distributed as td
+    world = td.get_world_size()
+    dev = "cuda" if td.get_backend() == "nccl" else "cpu"
+    out = {}
+    for n in sorted(grads):
+        t = grads[n].detach().float().to(dev).contiguous().clone()
+        td.all_reduce(t, op=td.ReduceOp.SUM)
+        out[n] = (t / world).to(grads[n].device)
+    return {n: out[n] for n in grads}
+
+
+def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, perturb, dist=None, gp_lambda=0.5,
+                           data_seed=None, np_seed=None):
+    """dist / gp_lambda / data_seed / np_seed: one rank of a data-parallel run: this rank's own clips,
+    captions and caption permutation stream, the gradient exchange of txt2vid_b200.parallel inside train_iteration,
+    and gp_lambda already multiplied by the world size on BOTH sides -- the oracle runs on this rank's shard alone and
+    its D and G gradients are averaged over the ranks in fp32 before each of its Adam steps (the G step sees the
+    discriminator every rank agreed on)."""
     import oracle.txt2vid_oracle as O
     from txt2vid_b200.gan import CondGan, MixedGanLoss, RSGANLoss
     from txt2vid_b200.optim import FusedAdam
@@ -62,8 +81,11 @@ def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, p
     if perturb:
         perturb_models(gen, dis)
     sds = {"gen": state_to_cpu(gen), "dis": state_to_cpu(dis), "txt": None if txt is None else state_to_cpu(txt)}
+    if np_seed is not None:
+        np.random.seed(np_seed)                   # per-rank caption-permutation stream; torch CPU generator stays shared
     rng_t, rng_n = torch.get_rng_state(), np.random.get_state()
-    x, tokens, lengths = synth_batch(B, V, T=frames, S=size, seed=fx["config"]["data_seed"])
+    x, tokens, lengths = synth_batch(B, V, T=frames, S=size,
+                                     seed=fx["config"]["data_seed"] if data_seed is None else data_seed)
 
     # ---- oracle with the reference's draw order
     bt_real = O.draw_real(4, True)
@@ -75,7 +97,8 @@ def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, p
     opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
     opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
     orc = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d,
-                            frame_sizes=tuple(frame_sizes), num_frames=frames)
+                            frame_sizes=tuple(frame_sizes), num_frames=frames, gp_lambda=gp_lambda,
+                            reduce=_mean_over_ranks if dist is not None else None)
 
     # ---- product on the same RNG stream
     torch.set_rng_state(rng_t)
@@ -93,7 +116,9 @@ def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, p
         orig = opt.step
 
         def step():
-            grads[tag] = {n: p.grad.detach().float().cpu().clone() for n, p in module.named_parameters()
+            # after a data-parallel exchange p.grad holds the SUM over ranks; the 1/N lives in the fused Adam
+            sc = float(getattr(opt, "grad_scale", 1.0) or 1.0)
+            grads[tag] = {n: p.grad.detach().float().cpu().clone() * sc for n, p in module.named_parameters()
                           if p.grad is not None}
             return orig()
         opt.step = step
@@ -126,8 +151,8 @@ def _run_product_iteration(conditional, fx, device, size, frames, frame_sizes, p
     T.multiscale_data = ms
     try:
         ld, lg, fake, xs, cond = train_iteration(gan, xb, y, torch.device(device), optD, optG,
-                                                 train_params(frame_sizes=frame_sizes), losses,
-                                                 channel_first=True, end2end=False, z=z_prod.to(device))
+                                                 train_params(gp_lambda=gp_lambda, frame_sizes=frame_sizes), losses,
+                                                 channel_first=True, end2end=False, z=z_prod.to(device), dist=dist)
     finally:
         T.multiscale_data = real_ms
     # weights after the two Adam steps: the oracle's Adam updated sd_g / sd_d in place

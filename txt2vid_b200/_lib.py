@@ -13,8 +13,8 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libt2v_b200.so")
 
 T2V_OK = 0
-ALGO_AUTO, ALGO_TC, ALGO_SIMT, ALGO_TC_GENERIC = 0, 1, 2, 3
-EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK, EPI_RES_F32 = 1, 2, 4, 8
+ALGO_AUTO, ALGO_TC, ALGO_SIMT, ALGO_TC_GENERIC, ALGO_SIMT_F32 = 0, 1, 2, 3, 4
+EPI_RELU, EPI_OUT_F32, EPI_RELU_MASK, EPI_RES_F32, EPI_IN_F32 = 1, 2, 4, 8, 16
 
 
 class ConvGeom(ctypes.Structure):
@@ -130,6 +130,7 @@ _TYPED = ["t2v_relu_fwd", "t2v_relu_bwd", "t2v_leaky_relu_fwd", "t2v_leaky_relu_
 _F32P = ctypes.POINTER(ctypes.c_float)
 SIGNATURES.update({
     "t2v_split_bf16x3": [_P, _P, c_i64, c_i32, c_i32, _P],
+    "t2v_split_bf16": [_P, _P, c_i64, c_i32, c_i32, c_i32, _P],
     "t2v_scale": [_P, _P, _P, c_i64, _P],
     "t2v_scale_add": [_P, _P, _P, _P, c_i64, _P],
     "t2v_dot": [_P, _P, _P, c_i64, _P],

@@ -21,7 +21,7 @@ int halo_fprop_sd2_launch(const t2v_conv_geom*, const void*, const void*, const 
 int halo_dgrad_sd2_launch(const t2v_conv_geom*, const void*, const void*, const void*, void*, uint32_t, cudaStream_t);
 int simt_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                       uint32_t, cudaStream_t);
-int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+int simt_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t, int in_f32 = 0);
 void prof_enable(int on);
 void prof_read(double* out, int nkinds);
 void prof_next_scale(double s);
@@ -117,6 +117,11 @@ int t2v_conv_fprop(const t2v_conv_geom* g, const void* x, const void* w, const f
                    const void* residual, void* y, uint32_t epi_flags, int algo, void* stream) {
   if (!g || !x || !w || !y) return T2V_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (epi_flags & T2V_EPI_IN_F32) {             // fp32 parity mode: fp32 operands on the CUDA-core FFMA kernel
+    if (algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) return T2V_ERR_ARG;
+    if ((epi_flags & T2V_EPI_RELU_MASK) && !residual) return T2V_ERR_ARG;
+    return simt_fprop_launch(g, x, w, bias, residual, y, epi_flags, s);
+  }
   const bool tc_ok = igemm_fprop_supported(g);
   if ((algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) && !tc_ok) return T2V_ERR_ARG;
   if ((epi_flags & T2V_EPI_RELU_MASK) && (algo == T2V_ALGO_SIMT || !tc_ok || !residual)) return T2V_ERR_ARG;
@@ -139,6 +144,7 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
                    int algo, void* stream) {
   if (!g || !dy || !x || !dw) return T2V_ERR_ARG;
   cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  if (algo == T2V_ALGO_SIMT_F32) return simt_wgrad_launch(g, dy, x, dw, accumulate, s, 1);   // fp32 dy / x
   const bool tc_ok = igemm_wgrad_supported(g);
   if ((algo == T2V_ALGO_TC || algo == T2V_ALGO_TC_GENERIC) && !tc_ok) return T2V_ERR_ARG;
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_wgrad_launch(g, dy, x, dw, accumulate, s);

@@ -19,15 +19,18 @@ static inline unsigned nblocks(long long n, int per) {
   return (unsigned)(b < 1 ? 1 : b);
 }
 
-// ------------------------------------------------------------------------------------ bf16x3 split
-// x fp32 [rows][C] -> hi = bf16(x), lo = bf16(x - hi); layouts:
-//   0: out [rows][3C]  = [hi | lo | hi]     (K-concatenated A operand of fprop / dgrad; weights are [hi | hi | lo])
-//   1: out [3*rows][C] = [hi ; lo ; hi]     (position-concatenated dy operand of wgrad)
-//   2: out [3*rows][C] = [hi ; hi ; lo]     (position-concatenated x operand of wgrad)
-// so that sum_k a_k b_k over the concatenated axis = a_hi b_hi + a_lo b_hi + a_hi b_lo: 16 mantissa bits per operand
-// on the bf16 tensor pipe with fp32 accumulation (relative error ~2^-17 per product).
-__global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int C,
-                              int layout, long long total4) {
+// ------------------------------------------------------------------------------------ bf16 operand split
+// x fp32 [rows][C] -> bf16 parts a = bf16(x), b = bf16(x - a), c = bf16(x - a - b) (x = a + b + c to 24 bits).
+// terms = 3 (16 bits per operand): products a a' + b a' + a b'
+//   layout 0: out [rows][3C]  = [a | b | a]         (K-concatenated A operand of fprop / dgrad; weights [a | a | b])
+//   layout 1: out [3*rows][C] = [a ; b ; a]         (position-concatenated dy operand of wgrad)
+//   layout 2: out [3*rows][C] = [a ; a ; b]         (position-concatenated x operand of wgrad)
+// terms = 6 (24 bits per operand = fp32 operands): a a' + b a' + a b' + c a' + a c' + b b'
+//   layout 0 / 1: [a | b | a | c | a | b],  layout 2 (and the weight packs): [a | a | b | a | c | b]
+// so that sum_k a_k b_k over the concatenated axis is the fp32 product on the bf16 tensor pipe with fp32
+// accumulation (dropped terms b c', c b', c c' <= 2^-24 relative).
+__global__ void split_kernel(const float* __restrict__ x, __nv_bfloat16* __restrict__ out, long long rows, int C,
+                             int layout, int terms, long long total4) {
   const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= total4) return;
   const int c4 = C / 4;
@@ -35,26 +38,25 @@ __global__ void split3_kernel(const float* __restrict__ x, __nv_bfloat16* __rest
   const int c = (int)(i % c4) * 4;
   const float4 v = *reinterpret_cast<const float4*>(x + r * C + c);
   const float f[4] = {v.x, v.y, v.z, v.w};
-  float hi[4], lo[4];
+  float pa[4], pb[4], pc[4];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    hi[j] = bf2f(f2bf(f[j]));
-    lo[j] = f[j] - hi[j];
+    pa[j] = bf2f(f2bf(f[j]));
+    const float r1 = f[j] - pa[j];                 // exact
+    pb[j] = bf2f(f2bf(r1));
+    pc[j] = r1 - pb[j];                            // exact; fits bf16 up to the last fp32 bits
   }
-  const uint2 H = make_uint2(pack_bf16x2(hi[0], hi[1]), pack_bf16x2(hi[2], hi[3]));
-  const uint2 L = make_uint2(pack_bf16x2(lo[0], lo[1]), pack_bf16x2(lo[2], lo[3]));
-  if (layout == 0) {
-    __nv_bfloat16* o = out + r * 3 * C + c;
-    *reinterpret_cast<uint2*>(o) = H;
-    *reinterpret_cast<uint2*>(o + C) = L;
-    *reinterpret_cast<uint2*>(o + 2 * C) = H;
-  } else {
-    __nv_bfloat16* o = out + r * C + c;
-    const long long blk = rows * C;
-    *reinterpret_cast<uint2*>(o) = H;
-    *reinterpret_cast<uint2*>(o + blk) = layout == 1 ? L : H;
-    *reinterpret_cast<uint2*>(o + 2 * blk) = layout == 1 ? H : L;
-  }
+  uint2 P[3];
+  P[0] = make_uint2(pack_bf16x2(pa[0], pa[1]), pack_bf16x2(pa[2], pa[3]));
+  P[1] = make_uint2(pack_bf16x2(pb[0], pb[1]), pack_bf16x2(pb[2], pb[3]));
+  P[2] = make_uint2(pack_bf16x2(pc[0], pc[1]), pack_bf16x2(pc[2], pc[3]));
+  // part index per segment: x-side order (layouts 0, 1) and w-side order (layout 2)
+  const int xs[6] = {0, 1, 0, 2, 0, 1}, ws[6] = {0, 0, 1, 0, 2, 1};
+  const long long seg = layout == 0 ? (long long)C : rows * C;
+  __nv_bfloat16* o = layout == 0 ? out + r * terms * C + c : out + r * C + c;
+#pragma unroll
+  for (int t = 0; t < 6; ++t)
+    if (t < terms) *reinterpret_cast<uint2*>(o + t * seg) = P[layout == 2 ? ws[t] : xs[t]];
 }
 
 // ------------------------------------------------------------------------------------ 1x2x2 max-pool with arg-max
@@ -344,14 +346,17 @@ using namespace t2v;
 
 extern "C" {
 
-int t2v_split_bf16x3(const float* x, void* out, int64_t rows, int32_t C, int32_t layout, void* stream) {
-  if (!x || !out || C % 4 || layout < 0 || layout > 2) return T2V_ERR_ARG;
+int t2v_split_bf16(const float* x, void* out, int64_t rows, int32_t C, int32_t layout, int32_t terms, void* stream) {
+  if (!x || !out || C % 4 || layout < 0 || layout > 2 || (terms != 3 && terms != 6)) return T2V_ERR_ARG;
   const long long total4 = rows * C / 4;
   if (total4 == 0) return T2V_OK;
-  split3_kernel<<<nblocks(total4, 256), 256, 0, STREAM>>>(x, reinterpret_cast<__nv_bfloat16*>(out), rows, C, layout,
-                                                          total4);
+  split_kernel<<<nblocks(total4, 256), 256, 0, STREAM>>>(x, reinterpret_cast<__nv_bfloat16*>(out), rows, C, layout,
+                                                         terms, total4);
   count_launch();
-  return check_last("split_bf16x3");
+  return check_last("split_bf16");
+}
+int t2v_split_bf16x3(const float* x, void* out, int64_t rows, int32_t C, int32_t layout, void* stream) {
+  return t2v_split_bf16(x, out, rows, C, layout, 3, stream);
 }
 
 int t2v_maxpool122_fwd(const float* x, float* y, void* idx, int64_t maps, int32_t H, int32_t W, int32_t c,

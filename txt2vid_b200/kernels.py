@@ -49,18 +49,32 @@ def _act(*ts):
         assert t is None or (t.dtype in (BF16, F32) and t.is_contiguous()), (None if t is None else (t.dtype, t.shape))
 
 
+# fp32 storage mode, convolution engine:
+#   "ffma" (default): fp32 operands, exact fp32 FMAs on the CUDA cores (simt_conv.cu, T2V_EPI_IN_F32): the reference's
+#           own numerics, ~1e-6 per layer -- what the 1e-3 bar on GRADIENTS needs on this network (a forward
+#           deviation of 5e-5 already moves the generator's gradients by 5e-3 through ReLU / BatchNorm, measured);
+#   "tc":   the tcgen05 engine on bf16 part splits of the fp32 operands (SPLIT_TERMS products per fp32 product;
+#           3: 16 bits per operand, 6: 24 bits).  Operands are then exact, but the tensor pipe's fp32 accumulator
+#           truncates on every MMA: 7e-6 relative at K = 1024, 3e-5 at K = 9216, WORSE with more terms (longer
+#           chains) -- scripts/debug_fp32_conv.py, profiles/r02_fp32_engine_accuracy.txt.
+FP32_ENGINE = os.environ.get("T2V_FP32_ENGINE", "ffma")
+SPLIT_TERMS = int(os.environ.get("T2V_FP32_SPLIT", "3"))
+assert SPLIT_TERMS in (3, 6) and FP32_ENGINE in ("ffma", "tc")
+
+
 def split3(x, layout):
-    """fp32 (..., C) -> bf16 hi/lo split for the tensor pipe: layout 0 (..., 3C) = [hi|lo|hi]; 1 / 2: (3N, ..., C) =
-    [hi;lo;hi] / [hi;hi;lo] concatenated along the leading dim."""
+    """fp32 (..., C) -> bf16 part split for the tensor pipe (SPLIT_TERMS = T segments): layout 0 (..., T*C) along the
+    channels; 1 / 2: (T*N, ..., C) along the leading dim, activation-side / weight-side part order."""
     require_cuda(x)
     assert x.dtype == F32 and x.is_contiguous()
     C = x.shape[-1]
     rows = x.numel() // C
+    T = SPLIT_TERMS
     if layout == 0:
-        out = torch.empty(tuple(x.shape[:-1]) + (3 * C,), device=x.device, dtype=BF16)
+        out = torch.empty(tuple(x.shape[:-1]) + (T * C,), device=x.device, dtype=BF16)
     else:
-        out = torch.empty((3 * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=BF16)
-    check(lib().t2v_split_bf16x3(ptr(x), ptr(out), rows, C, layout, stream()), "t2v_split_bf16x3")
+        out = torch.empty((T * x.shape[0],) + tuple(x.shape[1:]), device=x.device, dtype=BF16)
+    check(lib().t2v_split_bf16(ptr(x), ptr(out), rows, C, layout, T, stream()), "t2v_split_bf16")
     return out
 
 
@@ -76,24 +90,30 @@ def _i32(*vals):
 # ------------------------------------------------------------------------------------- conv engine
 def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=False, algo=0):
     """x (N,D,H,W,Cin) bf16, w (Cout,taps,Cin) bf16 -> y (N,D,H,W,Cout) bf16|f32.
-    fp32 storage: x fp32, w the K-concatenated pack (Cout,taps,3*Cin) of pack_weight -> y fp32 (residual fp32)."""
+    fp32 storage: x fp32, w the K-concatenated pack (Cout,taps,T*Cin) of pack_weight, T = SPLIT_TERMS -> y fp32 (residual fp32)."""
     require_cuda(x, w, bias, residual)
     N, D, H, W, Cin = x.shape
     Cout = w.shape[0]
     f32 = x.dtype == F32
-    if f32:
-        assert w.shape[2] == 3 * Cin, (w.shape, Cin)
+    ffma = f32 and w.dtype == F32                 # fp32 parity mode on exact fp32 FMAs
+    if ffma:
+        out_f32 = True
+        assert residual is None or residual.dtype == F32
+    elif f32:
+        assert w.shape[2] == SPLIT_TERMS * Cin, (w.shape, Cin)
         x = split3(x, 0)
-        Cin, out_f32 = 3 * Cin, True
+        Cin, out_f32 = SPLIT_TERMS * Cin, True
         assert residual is None or residual.dtype == F32
     assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
-    assert x.is_contiguous() and w.is_contiguous() and x.dtype == BF16 and w.dtype == BF16
+    assert x.is_contiguous() and w.is_contiguous() and (ffma or (x.dtype == BF16 and w.dtype == BF16))
     assert bias is None or (bias.dtype == F32 and bias.numel() == Cout)
     assert residual is None or (residual.dtype == (F32 if f32 else BF16) and residual.is_contiguous())
     y = torch.empty((N, D, H, W, Cout), device=x.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
     flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0) | \
-        (_lib.EPI_RES_F32 if (f32 and residual is not None) else 0)
+        (_lib.EPI_RES_F32 if (f32 and residual is not None) else 0) | (_lib.EPI_IN_F32 if ffma else 0)
+    if ffma:
+        algo = _lib.ALGO_SIMT
     check(lib().t2v_conv_fprop(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(residual), ptr(y), flags, algo,
                                stream()), "t2v_conv_fprop")
     return y
@@ -119,7 +139,7 @@ def conv_fprop_skip(x, w, bias, x2, w2, k=(3, 3, 3), relu=False):
 def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, algo=0, relu_ref=None):
     """dy (N,D,H,W,Cout) bf16, wT (Cin,taps,Cout) bf16 (from pack_dgrad_weight) -> dx (N,D,H,W,Cin).
     relu_ref (dx-shaped): dx is zeroed where relu_ref <= 0 (the ReLU in front of the convolution, fused).
-    fp32 storage: dy fp32, wT (Cin,taps,3*Cout) -> dx fp32."""
+    fp32 storage: dy fp32, wT (Cin,taps,T*Cout) -> dx fp32."""
     require_cuda(dy, wT, residual, relu_ref)
     f32 = dy.dtype == F32
     if relu_ref is not None:
@@ -128,15 +148,21 @@ def conv_dgrad(dy, wT, k=(3, 3, 3), residual=None, relu=False, out_f32=False, al
         residual = relu_ref
     N, D, H, W, Cout = dy.shape
     Cin = wT.shape[0]
-    if f32:
-        assert wT.shape[2] == 3 * Cout
+    ffma = f32 and wT.dtype == F32
+    if ffma:
+        out_f32 = True
+    elif f32:
+        assert wT.shape[2] == SPLIT_TERMS * Cout
         dy = split3(dy, 0)
-        Cout, out_f32 = 3 * Cout, True
-    assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and dy.dtype == BF16
+        Cout, out_f32 = SPLIT_TERMS * Cout, True
+    assert wT.shape[2] == Cout and dy.is_contiguous() and wT.is_contiguous() and (ffma or dy.dtype == BF16)
     dx = torch.empty((N, D, H, W, Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
     g = _geom(N, D, H, W, Cin, Cout, k)
     flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0) | \
-        (_lib.EPI_RELU_MASK if relu_ref is not None else 0) | (_lib.EPI_RES_F32 if (f32 and residual is not None) else 0)
+        (_lib.EPI_RELU_MASK if relu_ref is not None else 0) | (_lib.EPI_RES_F32 if (f32 and residual is not None) else 0) | \
+        (_lib.EPI_IN_F32 if ffma else 0)
+    if ffma:
+        algo = _lib.ALGO_SIMT
     check(lib().t2v_conv_dgrad(ctypes.byref(g), ptr(dy), ptr(wT), ptr(residual), ptr(dx), flags, algo, stream()),
           "t2v_conv_dgrad")
     return dx
@@ -148,9 +174,21 @@ PAIRED_WGRAD = os.environ.get("T2V_PAIRED_WGRAD", "1") == "1"
 def conv_wgrad(dy, x, k=(3, 3, 3), out=None, accumulate=False, algo=0):
     """dw (Cout,taps,Cin) fp32 = sum_pos dy[pos,co] x[pos+tap,ci]."""
     require_cuda(dy, x)
+    if dy.dtype == F32 and FP32_ENGINE == "ffma":
+        assert x.dtype == F32 and dy.is_contiguous() and x.is_contiguous() and x.shape[:4] == dy.shape[:4]
+        N, D, H, W, Cout = dy.shape
+        Cin = x.shape[-1]
+        taps = k[0] * k[1] * k[2]
+        if out is None:
+            assert not accumulate
+            out = torch.empty((Cout, taps, Cin), device=x.device, dtype=F32)
+        g = _geom(N, D, H, W, Cin, Cout, k)
+        check(lib().t2v_conv_wgrad(ctypes.byref(g), ptr(dy), ptr(x), ptr(out), 1 if accumulate else 0,
+                                   _lib.ALGO_SIMT_F32, stream()), "t2v_conv_wgrad")
+        return out
     if dy.dtype == F32:
         assert x.dtype == F32
-        dy, x = split3(dy, 1), split3(x, 2)          # sum over 3N "samples" = hi*hi + lo*hi + hi*lo
+        dy, x = split3(dy, 1), split3(x, 2)          # sum over T*N "samples" = the part products
     N, D, H, W, Cout = dy.shape
     Cin = x.shape[-1]
     if (PAIRED_WGRAD and algo == 0 and tuple(k) == (1, 3, 3) and D == 1 and Cin == 32 and Cout in (16, 32)
@@ -299,37 +337,54 @@ def _pack_dgrad_bf16(w, CoutP, CinP):
     return wT
 
 
-def _hi_lo(w):
-    """fp32 weight -> (hi as fp32, lo = w - hi), hi = the bf16 rounding of w (once per weight version: tiny tensors)"""
-    hi = cast_f32(cast_bf16(w))
-    return hi, (w - hi).contiguous()
+def _parts(w):
+    """fp32 weight -> its bf16 parts a, b, c as fp32 tensors (w = a + b + c; once per weight version: tiny tensors)"""
+    a = cast_f32(cast_bf16(w))
+    r1 = (w - a).contiguous()
+    b = cast_f32(cast_bf16(r1))
+    return a, b, (r1 - b).contiguous()
+
+
+def _weight_segments(w, pack):
+    a, b, c = _parts(w)
+    pa, pb = pack(a), pack(b)
+    if SPLIT_TERMS == 3:
+        return torch.cat((pa, pa, pb), dim=2).contiguous()
+    pc = pack(c)
+    return torch.cat((pa, pa, pb, pa, pc, pb), dim=2).contiguous()
 
 
 def pack_weight(w, CoutP=None, CinP=None):
     """w (Cout,taps,Cin) fp32 -> bf16 (CoutP,taps,CinP), zero padded (plain cast when unpadded).
-    fp32 storage mode: (CoutP,taps,3*CinP) = [hi | hi | lo] along K, matching split3(x, 0) = [hi | lo | hi]."""
+    fp32 storage mode: (CoutP,taps,T*CinP), the weight-side part order of t2v_split_bf16 along K."""
     require_cuda(w)
     assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
     Cout, taps, Cin = w.shape
     CoutP, CinP = CoutP or Cout, CinP or Cin
+    if STORE == F32 and FP32_ENGINE == "ffma":
+        if (CoutP, CinP) == (Cout, Cin):
+            return w.clone()
+        wp = torch.zeros((CoutP, taps, CinP), device=w.device, dtype=F32)
+        wp[:Cout, :, :Cin] = w
+        return wp
     if STORE == F32:
-        hi, lo = _hi_lo(w)
-        ph, pl = _pack_weight_bf16(hi, CoutP, CinP), _pack_weight_bf16(lo, CoutP, CinP)
-        return torch.cat((ph, ph, pl), dim=2).contiguous()
+        return _weight_segments(w, lambda t: _pack_weight_bf16(t, CoutP, CinP))
     return _pack_weight_bf16(w, CoutP, CinP)
 
 
 def pack_dgrad_weight(w, CoutP=None, CinP=None):
     """w (Cout,taps,Cin) fp32 -> (CinP,taps,CoutP) bf16 with the tap order reversed
-    (fp32 storage mode: (CinP,taps,3*CoutP) = [hi | hi | lo])."""
+    (fp32 storage mode: (CinP,taps,T*CoutP), weight-side part order)."""
     require_cuda(w)
     assert w.dtype == F32 and w.is_contiguous() and w.dim() == 3
     Cout, taps, Cin = w.shape
     CoutP, CinP = CoutP or Cout, CinP or Cin
+    if STORE == F32 and FP32_ENGINE == "ffma":
+        wp = torch.zeros((CinP, taps, CoutP), device=w.device, dtype=F32)
+        wp[:Cin, :, :Cout] = w.flip(1).permute(2, 1, 0)           # tap order reversed, channels transposed
+        return wp
     if STORE == F32:
-        hi, lo = _hi_lo(w)
-        ph, pl = _pack_dgrad_bf16(hi, CoutP, CinP), _pack_dgrad_bf16(lo, CoutP, CinP)
-        return torch.cat((ph, ph, pl), dim=2).contiguous()
+        return _weight_segments(w, lambda t: _pack_dgrad_bf16(t, CoutP, CinP))
     return _pack_dgrad_bf16(w, CoutP, CinP)
 
 

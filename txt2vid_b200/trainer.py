@@ -54,10 +54,7 @@ def multiscale_data(x, cond, frame_sizes, subsample_input, subsampler=None):
     for i in range(n):
         if i != n - 1:
             fs = frame_sizes[i]
-            if x.is_cuda:
-                xs.append(K.pyramid_level(x.contiguous(), fs, fs))
-            else:
-                xs.append(torch.nn.functional.interpolate(x, size=(x.size(2), fs, fs)))
+            xs.append(K.pyramid_level(x.contiguous(), fs, fs))      # index kernel; no CPU path (T2VError off-GPU)
         else:
             xs.append(x)
         if cond is not None:
