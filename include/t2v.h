@@ -95,6 +95,17 @@ int t2v_conv_dgrad(const t2v_conv_geom* g, const void* dy, const void* wT, const
  * accumulate = 0 overwrites dw, 1 adds into it.                                              */
 int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float* dw,
                    int accumulate, int algo, void* stream);
+/* ONE ConvLSTM step (models/conv_lstm.py:32-38, zero peepholes :46-49) as one tcgen05 implicit GEMM whose EPILOGUE is
+ * the cell update: gates = conv(x, w) + b on the tensor pipe (x = the input at step 0, h_{t-1} afterwards; g->Cout =
+ * 4 * hidden), then per output row sigmoid / tanh, c_t = f c_{t-1} + i g, h_t = o tanh(c_t) straight from TMEM.
+ * w_il / bias_il are GATE-INTERLEAVED along Cout: row blk * 128 + gate * 32 + j holds gate `gate` (i, f, g, o) of hidden
+ * unit blk * 32 + j, so one 128-column accumulator tile carries all four gates of 32 units.  Writes gates (fp32
+ * [P][4 hidden], standard [i|f|g|o] order, pre-activation: the backward pass's input), c_out (fp32 [P][hidden]), h_out
+ * (bf16 [P][hidden], the next step's operand) and h_t into its slot of the merged (b, t) frame map h_merged
+ * (bf16 [(n * steps + t) * D*H*W + pos][hidden], tganv2_cond/gen.py:75-76).  c_prev may be NULL (zeros).            */
+int t2v_conv_lstm_step(const t2v_conv_geom* g, const void* x, const void* w_il, const float* bias_il,
+                       const float* c_prev, float* gates, float* c_out, void* h_out, void* h_merged, int32_t t,
+                       int32_t steps, void* stream);
 /* Convolution with stride (2,1,1), kernel 3x3x3, padding 1, 64 -> 64 channels: the second convolution of the
  * discriminator stem (models/resnet3d.py:15) is followed by AvgPool3d((1,2,2), 2) (resnet3d.py:16: kernel 1,
  * stride 2 along d), which never reads its odd output planes; computing only the even planes is the same

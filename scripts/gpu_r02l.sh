@@ -1,0 +1,10 @@
+#!/bin/bash
+mkdir -p gpurun_out
+F='Warn\|Consider\|run_backward'
+timeout 900 python -m pytest tests/test_round2_gpu.py tests/test_conv_engine_gpu.py -m gpu -q --tb=short -p no:cacheprovider -k "lstm or conv_engine" 2>&1 | grep -v "$F" | tail -30 > gpurun_out/pytest_l.log; tail -12 gpurun_out/pytest_l.log
+timeout 1500 python -m pytest tests -m gpu -q --tb=short -p no:cacheprovider 2>&1 | grep -v "$F" | tail -30 > gpurun_out/pytest_l_all.log; tail -8 gpurun_out/pytest_l_all.log
+timeout 600 python bench.py --no_cpu_baseline --no_library_baseline --steps 10 > gpurun_out/bench_l.json 2> gpurun_out/bench_l.err; python - <<PY
+import json
+d=json.loads(open('gpurun_out/bench_l.json').read().strip().splitlines()[-1])
+print(round(d['value']), round(d['ms_per_step'],2), round(d['resident_again_ms_per_step'],2), round(d['e2e']['value']), d['roofline']['conv_engine_all'], d['gpu_launches'])
+PY

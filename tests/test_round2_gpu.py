@@ -393,3 +393,34 @@ def test_adam_kernel_vs_oracle_adam():
         opt.step()
     for i, p_ in enumerate(params):
         assert torch.allclose(p_.detach().cpu(), sd[str(i)], rtol=1e-6, atol=1e-7), i
+
+
+@pytest.mark.parametrize("B,plane,Cin,Hd", [(8, 1, 1024, 1024), (5, 2, 64, 128), (300, 1, 256, 64)])
+def test_fused_lstm_step_equals_gemm_plus_cell_kernel(B, plane, Cin, Hd):
+    """t2v_conv_lstm_step (cell update in the gate GEMM's epilogue, gate-interleaved columns) against the unfused
+    pair t2v_conv_fprop (fp32 gates) + t2v_lstm_cell_fwd on the same operands: gates bit for bit (same MMA order), c and
+    h to fp32 / bf16 rounding, and h written into its (b, t) slot of the merged map."""
+    g = torch.Generator(device="cuda").manual_seed(2)
+    k = (1, 3, 3) if plane > 1 else (1, 1, 1)
+    taps = k[1] * k[2]
+    x = torch.randn(B, 1, plane, plane, Cin, device="cuda", generator=g).to(BF)
+    w = (torch.randn(4 * Hd, taps, Cin, device="cuda", generator=g) / (taps * Cin) ** 0.5)
+    bias = torch.randn(4 * Hd, device="cuda", generator=g)
+    c_prev = torch.randn(B, 1, plane, plane, Hd, device="cuda", generator=g)
+    steps, t = 3, 1
+    gates_ref = K().conv_fprop(x, K().pack_weight(w), bias, None, k, False, True)
+    c_ref, h_ref, _ = K().lstm_cell_fwd(gates_ref, c_prev)
+    il = K().lstm_gate_interleave(Hd, "cuda")
+    merged = torch.zeros(B * steps, 1, plane, plane, Hd, device="cuda", dtype=BF)
+    gates, c, h = K().conv_lstm_step(x, K().pack_weight(w[il].contiguous()), bias[il].contiguous(), c_prev, k, merged, t, steps)
+    # same MMA order -> identical gates; the cell formulas may contract their FMAs differently in the two kernels
+    assert torch.equal(gates, gates_ref)
+    assert float((c - c_ref).abs().max()) <= 1e-6 * float(c_ref.abs().max())
+    assert float((h.float() - h_ref.float()).abs().max()) <= 2.0 ** -8 * float(h_ref.float().abs().max())
+    m = merged.view(B, steps, 1, plane, plane, Hd)
+    assert torch.equal(m[:, t], h) and float(m[:, 0].abs().max()) == 0 and float(m[:, 2].abs().max()) == 0
+    # first step: no previous cell state
+    gates0, c0, h0 = K().conv_lstm_step(x, K().pack_weight(w[il].contiguous()), bias[il].contiguous(), None, k, merged, 0, steps)
+    c_ref0, h_ref0, _ = K().lstm_cell_fwd(gates_ref, None)
+    assert float((c0 - c_ref0).abs().max()) <= 1e-6 * float(c_ref0.abs().max())
+    assert float((h0.float() - h_ref0.float()).abs().max()) <= 2.0 ** -8 * float(h_ref0.float().abs().max())

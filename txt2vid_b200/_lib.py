@@ -64,6 +64,7 @@ SIGNATURES = {
     "t2v_profile_read6": [ctypes.POINTER(ctypes.c_double)],
     "t2v_profile_next_scale": [ctypes.c_double],
     "t2v_conv_fprop": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, c_u32, c_int, _P],
+    "t2v_conv_lstm_step": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, _P, _P, _P, c_i32, c_i32, _P],
     "t2v_conv_fprop_skip": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, _P, c_i32, _P, c_u32, _P],
     "t2v_conv_dgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, _P, c_u32, c_int, _P],
     "t2v_conv_wgrad": [ctypes.POINTER(ConvGeom), _P, _P, _P, c_int, c_int, _P],

@@ -10,7 +10,7 @@ int igemm_fprop_launch(const t2v_conv_geom*, const void*, const void*, const flo
                        uint32_t, cudaStream_t);
 int igemm_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
 int igemm_fprop_launch_aux(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*, uint32_t,
-                           cudaStream_t, const void*, const void*, int);
+                           cudaStream_t, const void*, const void*, int, const LstmEpi* lstm = nullptr);
 bool halo_wgrad_supported(const t2v_conv_geom* g);
 bool halo_fprop_supported(const t2v_conv_geom* g);
 int halo_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
@@ -158,6 +158,15 @@ int t2v_conv_fprop_skip(const t2v_conv_geom* g, const void* x, const void* w, co
   if (!igemm_fprop_supported(g) || g->Cin % 64 || Cin2 % 64) return T2V_ERR_ARG;
   return igemm_fprop_launch_aux(g, x, w, bias, nullptr, y, epi_flags, reinterpret_cast<cudaStream_t>(stream), x2, w2,
                                 Cin2);
+}
+
+int t2v_conv_lstm_step(const t2v_conv_geom* g, const void* x, const void* w_il, const float* bias_il,
+                       const float* c_prev, float* gates, float* c_out, void* h_out, void* h_merged, int32_t t,
+                       int32_t steps, void* stream) {
+  if (!g || !x || !w_il || !bias_il || !gates || !c_out || !h_out || !h_merged) return T2V_ERR_ARG;
+  LstmEpi e{c_prev, c_out, gates, h_out, h_merged, t, steps};
+  return igemm_fprop_launch_aux(g, x, w_il, bias_il, nullptr, h_out, 0u, reinterpret_cast<cudaStream_t>(stream),
+                                nullptr, nullptr, 0, &e);
 }
 
 int t2v_conv_sd2_supported(const t2v_conv_geom* g) { return (g && halo_sd2_supported(g)) ? 1 : 0; }

@@ -43,6 +43,13 @@ struct IgemmParams {
   const __nv_bfloat16* residual;
   void* out;
   int out_f32, relu, relu_mask, res_f32;
+  // fused ConvLSTM cell epilogue (columns gate-interleaved per 32 hidden units: tile = [i | f | g | o] x 32)
+  int lstm, lstm_t, lstm_steps, lstm_plane;
+  const float* c_prev;
+  float* c_out;
+  float* gates_out;
+  __nv_bfloat16* h_out;
+  __nv_bfloat16* h_merged;
   // wgrad only
   float* dw;
   int taps_total, splits, tiles_total, atomic_out;
@@ -57,9 +64,315 @@ struct SwizzleOf {
 };
 
 // ------------------------------------------------------------------------------------ fprop
+// Epilogue of 16 accumulator columns of one output row: bias, residual / ReLU mask, ReLU, store.
+T2V_DEVINL void fprop_epilogue16(const IgemmParams& p, const uint32_t (&v)[16], size_t pos, int col) {
+  float f[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) f[j] = __uint_as_float(v[j]);
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 16; j += 4) {
+      const float4 b = *reinterpret_cast<const float4*>(p.bias + col + j);
+      f[j] += b.x; f[j + 1] += b.y; f[j + 2] += b.z; f[j + 3] += b.w;
+    }
+  }
+  if (p.residual != nullptr && p.res_f32) {
+    // fp32 residual / ReLU reference (fp32 activation storage on the tensor-pipe engine)
+    const float4* rp = reinterpret_cast<const float4*>(reinterpret_cast<const float*>(p.residual) +
+                                                       pos * p.Cout + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const float4 r4 = rp[j];
+      if (p.relu_mask) {
+        f[4 * j + 0] = r4.x > 0.f ? f[4 * j + 0] : 0.f; f[4 * j + 1] = r4.y > 0.f ? f[4 * j + 1] : 0.f;
+        f[4 * j + 2] = r4.z > 0.f ? f[4 * j + 2] : 0.f; f[4 * j + 3] = r4.w > 0.f ? f[4 * j + 3] : 0.f;
+      } else {
+        f[4 * j + 0] += r4.x; f[4 * j + 1] += r4.y; f[4 * j + 2] += r4.z; f[4 * j + 3] += r4.w;
+      }
+    }
+  } else if (p.residual != nullptr) {
+    const uint4* rp = reinterpret_cast<const uint4*>(p.residual + pos * p.Cout + col);
+#pragma unroll
+    for (int j = 0; j < 2; ++j) {
+      const uint4 u = rp[j];
+      const float2 a = unpack_bf16x2(u.x), b = unpack_bf16x2(u.y), cc = unpack_bf16x2(u.z),
+                   dd = unpack_bf16x2(u.w);
+      if (p.relu_mask) {      // the pointer is a ReLU reference: dx = dgrad(dy) * (ref > 0)
+        f[8 * j + 0] = a.x > 0.f ? f[8 * j + 0] : 0.f; f[8 * j + 1] = a.y > 0.f ? f[8 * j + 1] : 0.f;
+        f[8 * j + 2] = b.x > 0.f ? f[8 * j + 2] : 0.f; f[8 * j + 3] = b.y > 0.f ? f[8 * j + 3] : 0.f;
+        f[8 * j + 4] = cc.x > 0.f ? f[8 * j + 4] : 0.f; f[8 * j + 5] = cc.y > 0.f ? f[8 * j + 5] : 0.f;
+        f[8 * j + 6] = dd.x > 0.f ? f[8 * j + 6] : 0.f; f[8 * j + 7] = dd.y > 0.f ? f[8 * j + 7] : 0.f;
+      } else {
+        f[8 * j + 0] += a.x; f[8 * j + 1] += a.y; f[8 * j + 2] += b.x; f[8 * j + 3] += b.y;
+        f[8 * j + 4] += cc.x; f[8 * j + 5] += cc.y; f[8 * j + 6] += dd.x; f[8 * j + 7] += dd.y;
+      }
+    }
+  }
+  if (p.relu) {
+#pragma unroll
+    for (int j = 0; j < 16; ++j) f[j] = fmaxf(f[j], 0.f);
+  }
+  if (p.out_f32) {
+    float4* op = reinterpret_cast<float4*>(reinterpret_cast<float*>(p.out) + pos * p.Cout + col);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) op[j] = make_float4(f[4 * j], f[4 * j + 1], f[4 * j + 2], f[4 * j + 3]);
+  } else {
+    st_global_v8(reinterpret_cast<__nv_bfloat16*>(p.out) + pos * p.Cout + col,
+                 make_uint4(pack_bf16x2(f[0], f[1]), pack_bf16x2(f[2], f[3]), pack_bf16x2(f[4], f[5]), pack_bf16x2(f[6], f[7])),
+                 make_uint4(pack_bf16x2(f[8], f[9]), pack_bf16x2(f[10], f[11]), pack_bf16x2(f[12], f[13]), pack_bf16x2(f[14], f[15])));
+  }
+}
+
+// ConvLSTM cell update on one accumulator row of a gate-interleaved 128-column tile (models/conv_lstm.py:32-38:
+// ci = sigmoid(Wxi x + Whi h + b), cf, cc = cf c + ci tanh(.), co, ch = co tanh(cc); zero peepholes): the four gates
+// of 32 hidden units sit in columns [0,32) [32,64) [64,96) [96,128) of the tile.  Writes the pre-activation gates
+// (fp32, standard [i|f|g|o] layout, for the backward pass), the new cell state (fp32) and the new hidden state
+// (bf16) twice: as the next step's GEMM operand and into its slot of the merged (b, t) frame map.
+T2V_DEVINL void lstm_epilogue_row(const IgemmParams& p, uint32_t taddr, size_t pos, int col0, bool row_ok) {
+  const int Hd = p.Cout >> 2;
+  const int unit0 = (col0 >> 7) << 5;
+  const size_t n = pos / (size_t)p.lstm_plane;
+  const size_t pos2 = (n * p.lstm_steps + p.lstm_t) * p.lstm_plane + (pos - n * p.lstm_plane);
+#pragma unroll 1
+  for (int u = 0; u < 32; u += 8) {
+    uint32_t vi[8], vf[8], vg[8], vo[8];
+    tmem_ld8(taddr + (uint32_t)u, vi);
+    tmem_ld8(taddr + (uint32_t)(32 + u), vf);
+    tmem_ld8(taddr + (uint32_t)(64 + u), vg);
+    tmem_ld8(taddr + (uint32_t)(96 + u), vo);
+    tmem_ld_wait();                      // (the TMEM loads are warp-collective: rows outside the tensor only skip memory)
+    if (!row_ok) continue;
+    float gi[8], gf[8], gg[8], go[8], cn[8], hv[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      gi[j] = __uint_as_float(vi[j]) + p.bias[col0 + u + j];
+      gf[j] = __uint_as_float(vf[j]) + p.bias[col0 + 32 + u + j];
+      gg[j] = __uint_as_float(vg[j]) + p.bias[col0 + 64 + u + j];
+      go[j] = __uint_as_float(vo[j]) + p.bias[col0 + 96 + u + j];
+    }
+    const size_t hidx = pos * Hd + unit0 + u;
+    float cp[8];
+    if (p.c_prev != nullptr) {
+      const float4 a = *reinterpret_cast<const float4*>(p.c_prev + hidx), b = *reinterpret_cast<const float4*>(p.c_prev + hidx + 4);
+      cp[0] = a.x; cp[1] = a.y; cp[2] = a.z; cp[3] = a.w; cp[4] = b.x; cp[5] = b.y; cp[6] = b.z; cp[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) cp[j] = 0.f;
+    }
+    float* gp = p.gates_out + pos * (size_t)p.Cout + unit0 + u;
+    *reinterpret_cast<float4*>(gp) = make_float4(gi[0], gi[1], gi[2], gi[3]);
+    *reinterpret_cast<float4*>(gp + 4) = make_float4(gi[4], gi[5], gi[6], gi[7]);
+    *reinterpret_cast<float4*>(gp + Hd) = make_float4(gf[0], gf[1], gf[2], gf[3]);
+    *reinterpret_cast<float4*>(gp + Hd + 4) = make_float4(gf[4], gf[5], gf[6], gf[7]);
+    *reinterpret_cast<float4*>(gp + 2 * Hd) = make_float4(gg[0], gg[1], gg[2], gg[3]);
+    *reinterpret_cast<float4*>(gp + 2 * Hd + 4) = make_float4(gg[4], gg[5], gg[6], gg[7]);
+    *reinterpret_cast<float4*>(gp + 3 * Hd) = make_float4(go[0], go[1], go[2], go[3]);
+    *reinterpret_cast<float4*>(gp + 3 * Hd + 4) = make_float4(go[4], go[5], go[6], go[7]);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float si = 1.f / (1.f + __expf(-gi[j]));
+      const float sf = 1.f / (1.f + __expf(-gf[j]));
+      const float so = 1.f / (1.f + __expf(-go[j]));
+      cn[j] = sf * cp[j] + si * tanhf(gg[j]);
+      hv[j] = so * tanhf(cn[j]);
+    }
+    *reinterpret_cast<float4*>(p.c_out + hidx) = make_float4(cn[0], cn[1], cn[2], cn[3]);
+    *reinterpret_cast<float4*>(p.c_out + hidx + 4) = make_float4(cn[4], cn[5], cn[6], cn[7]);
+    const uint4 hb = make_uint4(pack_bf16x2(hv[0], hv[1]), pack_bf16x2(hv[2], hv[3]), pack_bf16x2(hv[4], hv[5]),
+                                pack_bf16x2(hv[6], hv[7]));
+    *reinterpret_cast<uint4*>(p.h_out + hidx) = hb;
+    *reinterpret_cast<uint4*>(p.h_merged + pos2 * Hd + unit0 + u) = hb;
+  }
+}
+
+// PERSISTENT: gridDim.x CTAs (a multiple of the SM count, or every tile when there are few) walk the output tiles
+// tile = blockIdx.x, + gridDim.x, ... (m fastest: CTAs running at the same time share the weight tile in L2).
+// The TMA ring runs ahead ACROSS tiles (no pipeline fill / drain per tile), the accumulator is double buffered in
+// TMEM (2 x BN columns): the MMA warp starts tile i+1 while the epilogue warps drain tile i, and barrier init /
+// TMEM allocation / descriptor prefetch are paid once per CTA instead of once per 128-row tile.
+template <int BLOCK_K>
+__global__ void __launch_bounds__(kThreads, 3)
+igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+                   const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
+                   const IgemmParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) &
+                                             ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + (size_t)p.stages * p.stage_bytes);
+  uint64_t* empty_bar = full_bar + p.stages;
+  uint64_t* tfull_bar = empty_bar + p.stages;       // [2] accumulator buffer b holds a finished tile
+  uint64_t* tempty_bar = tfull_bar + 2;             // [2] accumulator buffer b has been drained
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int mtiles = p.tn * p.td * p.th * p.tw;
+  const int total = p.tiles_total;                  // mtiles * column tiles
+
+  if (warp == 0 && lane == 0) {
+    tma_prefetch_desc(&tmA);
+    tma_prefetch_desc(&tmB);
+    if (p.aux_k_blocks > 0) {
+      tma_prefetch_desc(&tmA2);
+      tma_prefetch_desc(&tmB2);
+    }
+    for (int s = 0; s < p.stages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int b = 0; b < 2; ++b) {
+      mbar_init(&tfull_bar[b], 1);
+      mbar_init(&tempty_bar[b], 4);                 // one arrive per epilogue warp
+    }
+    fence_barrier_init();
+  }
+  if (warp == 1) {
+    tmem_alloc(tmem_slot, p.tmem_cols);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+  const uint32_t buf_cols = p.tmem_cols >> 1;       // column stride between the two accumulator buffers
+
+  if (warp == 0) {
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int nkw = p.hi_w - p.lo_w, nkh = p.hi_h - p.lo_h;
+      for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
+        int mt = tile % mtiles;
+        const int col0 = (tile / mtiles) * p.BN;
+        const int tw_i = mt % p.tw; mt /= p.tw;
+        const int th_i = mt % p.th; mt /= p.th;
+        const int td_i = mt % p.td; mt /= p.td;
+        const int n0 = mt * p.bn, d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
+        for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          int t = kb / p.cblocks;
+          const int c0 = (kb - t * p.cblocks) * BLOCK_K;
+          const int a_w = t % nkw + p.lo_w; t /= nkw;
+          const int a_h = t % nkh + p.lo_h; t /= nkh;
+          const int a_d = t + p.lo_d;
+          const int tap = (a_d * p.kh + a_h) * p.kw + a_w;
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_bytes;
+          mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+          tma_load_5d(sa, &tmA, &full_bar[stage], c0, w0 + a_w - p.pw, h0 + a_h - p.ph,
+                      d0 + a_d - p.pd, n0);
+          tma_load_2d(sb, &tmB, &full_bar[stage], tap * p.Cin + c0, col0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+        // fused skip connection: y += conv1x1x1(x2, w2), accumulated into the same TMEM tile (layers.py:224-243:
+        // DownBlock's identity_map convolution is added to the main path; here it is extra K of the same GEMM)
+        for (int kb = 0; kb < p.aux_k_blocks; ++kb) {
+          mbar_wait(&empty_bar[stage], phase ^ 1u);
+          uint8_t* sa = smem + (size_t)stage * p.stage_bytes;
+          uint8_t* sb = sa + p.a_bytes;
+          mbar_expect_tx(&full_bar[stage], p.a_bytes + p.b_bytes);
+          tma_load_5d(sa, &tmA2, &full_bar[stage], kb * BLOCK_K, w0, h0, d0, n0);
+          tma_load_2d(sb, &tmB2, &full_bar[stage], kb * BLOCK_K, col0);
+          if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    int stage = 0;
+    uint32_t phase = 0;
+    // operands are computed warp-uniformly, only the tcgen05 instructions are predicated on the elected lane
+    // (descriptors then stay in uniform registers: no ELECT/R2UR waterfall in front of every UTCHMMA)
+    const uint32_t d_hi = desc_hi(SwizzleOf<BLOCK_K>::sbo, SwizzleOf<BLOCK_K>::layout);
+    const uint32_t leader = elect_one();
+    const int nkb = p.num_k_blocks + p.aux_k_blocks;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      const int buf = it & 1;
+      mbar_wait(&tempty_bar[buf], ((uint32_t)(it >> 1) & 1u) ^ 1u);      // the epilogue drained this buffer
+      tc_fence_after();
+      const uint32_t tmem_d = tmem_base + (uint32_t)buf * buf_cols;
+      for (int kb = 0; kb < nkb; ++kb) {
+        mbar_wait(&full_bar[stage], phase);
+        tc_fence_after();
+        const uint32_t sa16 = smem_u32(smem + (size_t)stage * p.stage_bytes) >> 4;
+        const uint32_t sb16 = sa16 + (p.a_bytes >> 4);
+#pragma unroll
+        for (int k = 0; k < BLOCK_K / 16; ++k) {
+          // advance 16 bf16 = 32 bytes along K inside the swizzle atom: +2 in the (addr>>4) field
+          if (leader)
+            umma_bf16_ss2(tmem_d, desc_lo(sa16 + 2u * k, 0), d_hi, desc_lo(sb16 + 2u * k, 0), d_hi, p.idesc,
+                          (kb | k) != 0 ? 1u : 0u);
+        }
+        if (leader) {
+          umma_commit(&empty_bar[stage]);
+          if (kb == nkb - 1) umma_commit(&tfull_bar[buf]);
+        }
+        __syncwarp();
+        if (++stage == p.stages) { stage = 0; phase ^= 1u; }
+      }
+    }
+  } else {
+    // epilogue: warp w owns TMEM lanes [32*(w%4), +32) = accumulator rows
+    const int q = warp & 3;
+    const int row = q * 32 + lane;
+    int r = row;
+    const int iw = r % p.bw; r /= p.bw;
+    const int ih = r % p.bh; r /= p.bh;
+    const int id = r % p.bd; r /= p.bd;
+    int it = 0;
+    for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
+      int mt = tile % mtiles;
+      const int col0 = (tile / mtiles) * p.BN;
+      const int tw_i = mt % p.tw; mt /= p.tw;
+      const int th_i = mt % p.th; mt /= p.th;
+      const int td_i = mt % p.td; mt /= p.td;
+      const int n = mt * p.bn + r, d = td_i * p.bd + id, h = th_i * p.bh + ih, w = tw_i * p.bw + iw;
+      const bool row_ok = (n < p.N) && (d < p.D) && (h < p.H) && (w < p.W);
+      const size_t pos = (((size_t)n * p.D + d) * p.H + h) * p.W + w;
+      const int buf = it & 1;
+      mbar_wait(&tfull_bar[buf], (uint32_t)(it >> 1) & 1u);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)buf * buf_cols;
+      if (p.lstm) {                                   // warp-uniform: the TMEM loads inside are .sync.aligned
+        lstm_epilogue_row(p, taddr, pos, col0, row_ok);
+        __syncwarp();
+      } else {
+      // software pipeline over 16-column chunks: the TMEM load of chunk c+1 is in flight while chunk c is
+      // converted and stored
+      uint32_t va[16], vb[16];
+      tmem_ld16(taddr, va);
+      for (int c = 0; c < p.BN; c += 32) {
+        tmem_ld_wait();
+        const bool more1 = c + 16 < p.BN;
+        if (more1) tmem_ld16(taddr + (uint32_t)(c + 16), vb);
+        if (row_ok && col0 + c < p.Cout) fprop_epilogue16(p, va, pos, col0 + c);
+        if (more1) {
+          tmem_ld_wait();
+          if (c + 32 < p.BN) tmem_ld16(taddr + (uint32_t)(c + 32), va);
+          if (row_ok && col0 + c + 16 < p.Cout) fprop_epilogue16(p, vb, pos, col0 + c + 16);
+        }
+      }
+      }
+      // all TMEM reads of this buffer have completed (tcgen05.wait::ld): hand it back to the MMA warp
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[buf]);
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, p.tmem_cols);
+  }
+}
+
+// ------------------------------------------------------------------------------------ fprop, one tile per CTA
+// (short K loops / small problems: 56 registers and one accumulator buffer keep up to 6 CTAs resident per SM, which
+// is what hides the load latency there; the persistent kernel below wins once a tile carries >= 8 k-blocks)
 template <int BLOCK_K>
 __global__ void __launch_bounds__(kThreads, 2)
-igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+igemm_fprop_simple_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                    const __grid_constant__ CUtensorMap tmA2, const __grid_constant__ CUtensorMap tmB2,
                    const IgemmParams p) {
   extern __shared__ uint8_t smem_raw[];
@@ -482,7 +795,7 @@ static int fill_common(IgemmParams& p, const t2v_conv_geom* g) {
 
 int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                            const void* residual, void* y, uint32_t flags, cudaStream_t stream, const void* x2,
-                           const void* w2, int Cin2);
+                           const void* w2, int Cin2, const LstmEpi* lstm = nullptr);
 
 int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, uint32_t flags, cudaStream_t stream) {
@@ -492,8 +805,11 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
 // x2 / w2 / Cin2: optional fused 1x1x1 convolution of a second tensor over the same positions (w2 bf16 [Cout][Cin2])
 int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                            const void* residual, void* y, uint32_t flags, cudaStream_t stream, const void* x2,
-                           const void* w2, int Cin2) {
+                           const void* w2, int Cin2, const LstmEpi* lstm) {
   if (!igemm_fprop_supported(g)) return T2V_ERR_ARG;
+  if (lstm && (g->Cout % 128 || !bias || !lstm->c_out || !lstm->gates || !lstm->h_out || !lstm->h_merged ||
+               lstm->steps <= 0 || lstm->t < 0 || lstm->t >= lstm->steps))
+    return T2V_ERR_ARG;
   IgemmParams p{};
   const int ntaps = fill_common(p, g);
   const int BLOCK_K = (g->Cin % 64 == 0) ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
@@ -504,7 +820,7 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
   const int mtiles_total = p.tn * p.td * p.th * p.tw;
   static const int adapt_bn = env_int("T2V_FPROP_ADAPT_BN", 1), two_cta = env_int("T2V_FPROP_2CTA", 1);
   // small problems: narrower N tiles -> more CTAs (the kernel is load-latency bound there, not tensor bound)
-  if (adapt_bn)
+  if (adapt_bn && !lstm)
     while (p.BN > 64 && p.BN % 32 == 0 && mtiles_total * ((g->Cout + p.BN - 1) / p.BN) < 120) p.BN /= 2;
   p.cblocks = g->Cin / BLOCK_K;
   p.num_k_blocks = ntaps * p.cblocks;
@@ -522,15 +838,25 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
   // short K loops over small tiles are latency bound per CTA: trade pipeline depth for residency (measured:
   // 32->32 channels at 64x64, 9 k-blocks of 10 KB: 0.166 -> 0.082 ms with 3 stages and 6 CTAs per SM)
   static const int small_kb = env_int("T2V_FPROP_SMALL_SMEM_KB", 32);
-  if (small_kb > 0 && p.stage_bytes <= 12288u && total_ctas > 4 * 148) budget = (uint32_t)small_kb * 1024u;
+  // persistent + double-buffered accumulator: more than one wave of tiles and K >= T2V_FPROP_PERSIST_MIN_K per tile
+  // (measured in situ at b = 2048: 64..1024-channel 3x3(x3) layers +15..30 %, 1x1 / 16-32-channel layers -10 %)
+  static const int persist_env = env_int("T2V_FPROP_PERSIST", 1), persist_min_k = env_int("T2V_FPROP_PERSIST_MIN_K", 512);
+  const int persist = lstm != nullptr ||        // (the fused LSTM epilogue lives in the persistent kernel)
+      (persist_env && total_ctas > 296 && (p.num_k_blocks + p.aux_k_blocks) * BLOCK_K >= persist_min_k);
+  static const int small_kb_p = env_int("T2V_FPROP_SMALL_SMEM_KB_PERSIST", 48);
+  if (small_kb > 0 && p.stage_bytes <= 12288u && total_ctas > 4 * 148)
+    budget = (uint32_t)(persist ? small_kb_p : small_kb) * 1024u;
   int stages = (int)(budget / p.stage_bytes);
   if (stages < 2) stages = 2;
   if (stages > 8) stages = 8;
-  if (stages > p.num_k_blocks + p.aux_k_blocks)
+  // one tile per CTA: no point in more stages than k-blocks; persistent: the ring runs ahead into the next tiles
+  if (!persist && stages > p.num_k_blocks + p.aux_k_blocks)
     stages = p.num_k_blocks + p.aux_k_blocks < 2 ? 2 : p.num_k_blocks + p.aux_k_blocks;
   p.stages = stages;
   p.idesc = make_idesc_bf16(128, (uint32_t)p.BN, 0, 0);
-  p.tmem_cols = (uint32_t)(pow2_ceil(p.BN) < 32 ? 32 : pow2_ceil(p.BN));
+  // persistent: two accumulator buffers (double-buffered epilogue), each a power-of-two column count >= BN
+  p.tmem_cols = persist ? 2u * (uint32_t)(pow2_ceil(p.BN) < 16 ? 16 : pow2_ceil(p.BN))
+                        : (uint32_t)(pow2_ceil(p.BN) < 32 ? 32 : pow2_ceil(p.BN));
   p.bias = bias;
   p.residual = reinterpret_cast<const __nv_bfloat16*>(residual);
   p.out = y;
@@ -538,6 +864,13 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
   p.relu = (flags & T2V_EPI_RELU) ? 1 : 0;
   p.relu_mask = (flags & T2V_EPI_RELU_MASK) ? 1 : 0;
   p.res_f32 = (flags & T2V_EPI_RES_F32) ? 1 : 0;
+  p.tiles_total = total_ctas;
+  if (lstm) {
+    p.lstm = 1; p.lstm_t = lstm->t; p.lstm_steps = lstm->steps; p.lstm_plane = g->D * g->H * g->W;
+    p.c_prev = lstm->c_prev; p.c_out = lstm->c_out; p.gates_out = lstm->gates;
+    p.h_out = reinterpret_cast<__nv_bfloat16*>(lstm->h_out);
+    p.h_merged = reinterpret_cast<__nv_bfloat16*>(lstm->h_merged);
+  }
 
   CUtensorMap tmA, tmB;
   int rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, g->Cin, BLOCK_K, p.bw, p.bh, p.bd, p.bn);
@@ -552,17 +885,58 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
     if (rc) return rc;
   }
 
-  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
-  dim3 grid(p.tn * p.td * p.th * p.tw, (g->Cout + p.BN - 1) / p.BN, 1);
+  const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 4) * 8 + 16;
+  if (!persist) {                               // one tile per CTA (grid = m tiles x column tiles)
+    dim3 grid2((unsigned)mtiles_total, (unsigned)((g->Cout + p.BN - 1) / p.BN), 1);
+    auto launch2 = [&](auto kern) {
+      cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+      kern<<<grid2, kThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    };
+    ProfRec rec2;
+    if (g_prof_on)
+      prof_begin(stream, &rec2, 0,
+                 2.0 * g->N * g->D * g->H * g->W * ((double)g->Cin * ntaps + (double)(x2 ? Cin2 : 0)) * g->Cout, g,
+                 total_ctas);
+    if (BLOCK_K == 64) launch2(igemm_fprop_simple_kernel<64>);
+    else if (BLOCK_K == 32) launch2(igemm_fprop_simple_kernel<32>);
+    else launch2(igemm_fprop_simple_kernel<16>);
+    if (g_prof_on) prof_end(stream, &rec2);
+    count_launch();
+    return check_last("igemm_fprop");
+  }
+  // persistent grid: as many CTAs as stay resident (shared memory, TMEM columns, threads), each walking
+  // tiles blockIdx.x, + gridDim.x, ...; T2V_FPROP_PERSIST=0 launches one CTA per tile (the round-1 schedule)
+  int grid_x = total_ctas;
   auto launch = [&](auto kern) {
     cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    kern<<<grid, kThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, p);
+    if (persist) {
+      static int regs_cached[3] = {0, 0, 0};
+      int& rc_ = regs_cached[BLOCK_K == 64 ? 0 : (BLOCK_K == 32 ? 1 : 2)];
+      if (rc_ == 0) {
+        cudaFuncAttributes fa{};
+        cudaFuncGetAttributes(&fa, kern);
+        rc_ = fa.numRegs > 0 ? fa.numRegs : 96;
+      }
+      const int regs = (rc_ + 7) & ~7;                                                  // allocation granularity
+      int per_sm = 65536 / (regs * kThreads);                                           // registers ...
+      if (per_sm > (int)((228u * 1024u) / (smem + 1024u))) per_sm = (int)((228u * 1024u) / (smem + 1024u));
+      if (per_sm > 2048 / kThreads) per_sm = 2048 / kThreads;                           // ... shared memory, threads
+      if (per_sm > (int)(512u / p.tmem_cols)) per_sm = (int)(512u / p.tmem_cols);      // ... and TMEM columns
+      if (per_sm < 1) per_sm = 1;
+      if (grid_x > 148 * per_sm) grid_x = 148 * per_sm;
+    }
+    static const int dbg = env_int("T2V_DEBUG_LAUNCH", 0);
+    if (dbg)
+      fprintf(stderr, "igemm_fprop N%d D%d H%d W%d Cin%d Cout%d k%d%d%d: tiles %d grid %d stages %d stage_bytes %u smem %zu "
+              "tmem_cols %u BN %d BLOCK_K %d\n", g->N, g->D, g->H, g->W, g->Cin, g->Cout, g->kd, g->kh, g->kw, total_ctas,
+              grid_x, p.stages, p.stage_bytes, smem, p.tmem_cols, p.BN, BLOCK_K);
+    kern<<<dim3((unsigned)grid_x, 1, 1), kThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, p);
   };
   ProfRec rec;
   if (g_prof_on)
     prof_begin(stream, &rec, 0,
                2.0 * g->N * g->D * g->H * g->W * ((double)g->Cin * ntaps + (double)(x2 ? Cin2 : 0)) * g->Cout, g,
-               (int)(grid.x * grid.y));
+               total_ctas);
   if (BLOCK_K == 64) launch(igemm_fprop_kernel<64>);
   else if (BLOCK_K == 32) launch(igemm_fprop_kernel<32>);
   else launch(igemm_fprop_kernel<16>);

@@ -161,7 +161,24 @@ T2V_DEVINL void tmem_ld16(uint32_t taddr, uint32_t (&r)[16]) {
       : "r"(taddr)
       : "memory");
 }
+T2V_DEVINL void tmem_ld8(uint32_t taddr, uint32_t (&r)[8]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7])
+      : "r"(taddr)
+      : "memory");
+}
 T2V_DEVINL void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// ConvLSTM step fused into the gate GEMM's epilogue (igemm_sm100.cu): the extra operands of t2v_conv_lstm_step
+struct LstmEpi {
+  const float* c_prev;   // fp32 [P][Hd] or null (first step)
+  float* c_out;          // fp32 [P][Hd]
+  float* gates;          // fp32 [P][4 Hd], [i | f | g | o], pre-activation incl. bias (saved for the backward pass)
+  void* h_out;           // bf16 [P][Hd]: the next step's GEMM operand
+  void* h_merged;        // bf16 [(n * steps + t) * plane + pos_in_plane][Hd]: the merged (b, t) frame map
+  int t, steps;
+};
 
 // UMMA shared-memory matrix descriptor (sm_100 format, version 1).
 //   start address >>4 in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 in [46,48),

@@ -119,6 +119,35 @@ def conv_fprop(x, w, bias=None, residual=None, k=(3, 3, 3), relu=False, out_f32=
     return y
 
 
+def lstm_gate_interleave(hidden, device):
+    """row permutation of a [i|f|g|o]-stacked (4*hidden, ...) operand for t2v_conv_lstm_step: new row
+    blk * 128 + gate * 32 + j  <-  old row gate * hidden + blk * 32 + j"""
+    assert hidden % 32 == 0
+    return torch.arange(4 * hidden, device=device).view(4, hidden // 32, 32).permute(1, 0, 2).reshape(-1)
+
+
+def conv_lstm_step(x, w_il, bias_il, c_prev, k, merged, t, steps):
+    """One ConvLSTM step with the cell update in the gate GEMM's epilogue (bf16 storage only).
+    x (B,1,fh,fw,Cin) bf16; w_il (4H,taps,Cin) bf16 / bias_il (4H,) fp32 gate-interleaved (lstm_gate_interleave);
+    c_prev fp32 (B,1,fh,fw,H) or None; merged (B*steps,1,fh,fw,H) bf16: h_t is also written into its (b, t) slot.
+    -> (gates fp32 (B,1,fh,fw,4H) in [i|f|g|o] order, c fp32, h bf16)"""
+    require_cuda(x, w_il, bias_il, c_prev, merged)
+    N, D, H, W, Cin = x.shape
+    C4 = w_il.shape[0]
+    Hd = C4 // 4
+    assert x.dtype == BF16 and w_il.dtype == BF16 and x.is_contiguous() and w_il.is_contiguous() and C4 % 128 == 0
+    assert w_il.shape[1] == k[0] * k[1] * k[2] and w_il.shape[2] == Cin and bias_il.dtype == F32 and bias_il.numel() == C4
+    assert merged.dtype == BF16 and merged.is_contiguous() and merged.numel() == N * steps * D * H * W * Hd
+    assert c_prev is None or (c_prev.dtype == F32 and c_prev.is_contiguous() and c_prev.numel() == N * D * H * W * Hd)
+    gates = torch.empty((N, D, H, W, C4), device=x.device, dtype=F32)
+    c = torch.empty((N, D, H, W, Hd), device=x.device, dtype=F32)
+    h = torch.empty((N, D, H, W, Hd), device=x.device, dtype=BF16)
+    g = _geom(N, D, H, W, Cin, C4, k)
+    check(lib().t2v_conv_lstm_step(ctypes.byref(g), ptr(x), ptr(w_il), ptr(bias_il), ptr(c_prev), ptr(gates), ptr(c),
+                                   ptr(h), ptr(merged), t, steps, stream()), "t2v_conv_lstm_step")
+    return gates, c, h
+
+
 def conv_fprop_skip(x, w, bias, x2, w2, k=(3, 3, 3), relu=False):
     """y = conv(x, w) + conv1x1x1(x2, w2) + bias in one implicit GEMM (the 1x1x1 convolution is extra K).
     x (N,D,H,W,Cin), x2 (N,D,H,W,Cin2) bf16; w (Cout,taps,Cin), w2 (Cout,1,Cin2) bf16; Cin, Cin2 multiples of 64."""

@@ -573,12 +573,12 @@ class GConvTF(Function):
     tgan/temporal_gen.py:16-20, tcwyt/gen.py:14-30."""
 
     @staticmethod
-    def forward(ctx, x, weight, bias, k, s, p):
+    def forward(ctx, x, weight, bias, k, s, p, out_f32=False):
         Cin_t, Cout_t = weight.shape[0], weight.shape[1]
         CinP, CoutP = x.shape[-1], round16(Cout_t)
         wp = PACKS.get(weight, "gconv", CinP, CoutP)                       # [Cin_t p][taps][Cout_t p]
         out_sp = tuple((i - 1) * ss - 2 * pp + kk for i, ss, pp, kk in zip(x.shape[1:4], s, p, k))
-        y = K.gconv_dgrad(x, wp, _pad_bias(bias, CoutP), out_sp, k, s, p)
+        y = K.gconv_dgrad(x, wp, _pad_bias(bias, CoutP), out_sp, k, s, p, out_f32)
         ctx.cfg = (k, s, p, bias is not None)
         ctx.save_for_backward(x, weight)
         return y
@@ -589,6 +589,8 @@ class GConvTF(Function):
         k, s, p, has_bias = ctx.cfg
         x, weight = ctx.saved_tensors
         dy = dy.contiguous()
+        if dy.dtype != x.dtype:                      # fp32 output handed to a BatchNorm (conv_bn_act) in bf16 mode
+            dy = K.cast_bf16(dy)
         Cin_t, Cout_t = weight.shape[0], weight.shape[1]
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
@@ -599,7 +601,7 @@ class GConvTF(Function):
             dw = grad_like_weight(dw3, weight)
         if has_bias and ctx.needs_input_grad[2]:
             db = K.sum_rows(dy)[:Cout_t]
-        return dx, dw, db, None, None, None
+        return dx, dw, db, None, None, None, None
 
 
 def gconv(x, module, out_f32=False):
@@ -609,10 +611,35 @@ def gconv(x, module, out_f32=False):
     return GConvF.apply(x, module.weight, module.bias, k, s, p, out_f32)
 
 
-def gconv_transpose(x, module):
+def gconv_transpose(x, module, out_f32=False):
     """nn.ConvTranspose{1,2,3}d container applied to a CL tensor (output_padding 0)."""
     k, s, p = conv_args(module)
-    return GConvTF.apply(x, module.weight, module.bias, k, s, p)
+    return GConvTF.apply(x, module.weight, module.bias, k, s, p, out_f32)
+
+
+class CastStoreF(Function):
+    """fp32 CL -> the storage dtype (bf16 mode: one rounding); backward: the gradient back in fp32"""
+
+    @staticmethod
+    def forward(ctx, x):
+        return K.cast_bf16(x.contiguous()) if K.STORE == BF16 and x.dtype == F32 else x
+
+    @staticmethod
+    def backward(ctx, dy):
+        return K.cast_f32(dy.contiguous()) if dy.dtype == BF16 else dy
+
+
+def conv_bn_act(x, conv_module, bn, act, transpose=False):
+    """(transposed) convolution -> BatchNorm (batch statistics) -> activation of the TGAN / TCWYT stacks
+    (models/tgan/gen.py:33-43, tgan/temporal_gen.py:26-33, tcwyt/gen.py:13-33, tcwyt/video_discrim.py:11-26,
+    tcwyt/frame_discrim.py:8-18).  The convolution's fp32 accumulator goes to the BatchNorm UNROUNDED (statistics,
+    normalisation and activation in fp32, typed kernels) and only the activation's output is rounded to bf16 for
+    the next convolution: one rounding per layer instead of two, and batch statistics of B = 8 samples that are not
+    computed from bf16-rounded values (the critics' means of these families are near-cancelling sums)."""
+    f = gconv_transpose if transpose else gconv
+    if fp32_mode():
+        return bn_act(f(x, conv_module), bn, act)
+    return CastStoreF.apply(bn_act(f(x, conv_module, out_f32=True), bn, act))
 
 
 class LeakyF(Function):
@@ -1066,11 +1093,15 @@ def gather_frames(x, B, T, bt):
 
 
 # ------------------------------------------------------------------------------------- ConvLSTM
+LSTM_FUSED = os.environ.get("T2V_LSTM_FUSED", "1") == "1"
+
+
 class ConvLstmF(Function):
     """The whole TGANv2 temporal generator (models/conv_lstm.py:32-38,75-97): `steps` LSTM steps on a
     (B, 1, fh, fw, C) CL plane.  Step 0 sees the input, later steps see zeros (so Wx*(0) = bias);
-    peepholes are identically zero in the reference.  Per step: ONE gate GEMM on the tensor cores
-    ([i|f|g|o] packed along Cout) + one fused cell-update kernel.  Output: (B*steps, 1, fh, fw, C)
+    peepholes are identically zero in the reference.  Per step: ONE kernel -- the gate GEMM on the tensor cores
+    ([i|f|g|o] interleaved along Cout) with the sigmoid / tanh cell update as its epilogue (t2v_conv_lstm_step; the
+    fp32 parity mode keeps the unfused GEMM + cell kernel).  Output: (B*steps, 1, fh, fw, C)
     merged-frame map in (b, t) order (tganv2_cond/gen.py:75-76,91-96)."""
 
     @staticmethod
@@ -1080,19 +1111,34 @@ class ConvLstmF(Function):
         Hd = wh.shape[0] // 4
         taps = wx.shape[1]
         k = (1, 3, 3) if taps == 9 else (1, 1, 1)
-        wx_p = K.pack_weight(wx.detach().contiguous())
-        wh_p = K.pack_weight(wh.detach().contiguous())
         gates, cs, hs = [], [], []
         h = c = None
-        for t in range(steps):
-            src = x if t == 0 else h
-            wp = wx_p if t == 0 else wh_p
-            g = K.conv_fprop(src, wp, bx.detach(), None, k, False, True)           # fp32 (B,1,fh,fw,4Hd)
-            c, h, _ = K.lstm_cell_fwd(g, c)
-            gates.append(g)
-            cs.append(c)
-            hs.append(h)
-        out = torch.stack(hs, dim=1).reshape(B * steps, 1, fh, fw, Hd)              # (b, t) frame order
+        if LSTM_FUSED and not fp32_mode() and hasattr(K, "conv_lstm_step") and Hd % 32 == 0 and x.shape[-1] % 16 == 0:
+            # gate GEMM + sigmoid / tanh cell update in ONE kernel per step (t2v_conv_lstm_step): the gates are
+            # interleaved per 32 hidden units along Cout so that an accumulator tile carries [i|f|g|o] of its units;
+            # h_t goes to the next step's operand AND to its (b, t) slot of the merged frame map from the epilogue
+            il = K.lstm_gate_interleave(Hd, x.device)
+            wx_p = K.pack_weight(wx.detach()[il].contiguous())
+            wh_p = K.pack_weight(wh.detach()[il].contiguous())
+            b_il = bx.detach()[il].contiguous()
+            out = torch.empty((B * steps, 1, fh, fw, Hd), device=x.device, dtype=x.dtype)
+            for t in range(steps):
+                g, c, h = K.conv_lstm_step(x if t == 0 else h, wx_p if t == 0 else wh_p, b_il, c, k, out, t, steps)
+                gates.append(g)
+                cs.append(c)
+                hs.append(h)
+        else:
+            wx_p = K.pack_weight(wx.detach().contiguous())
+            wh_p = K.pack_weight(wh.detach().contiguous())
+            for t in range(steps):
+                src = x if t == 0 else h
+                wp = wx_p if t == 0 else wh_p
+                g = K.conv_fprop(src, wp, bx.detach(), None, k, False, True)           # fp32 (B,1,fh,fw,4Hd)
+                c, h, _ = K.lstm_cell_fwd(g, c)
+                gates.append(g)
+                cs.append(c)
+                hs.append(h)
+            out = torch.stack(hs, dim=1).reshape(B * steps, 1, fh, fw, Hd)              # (b, t) frame order
         ctx.save_for_backward(x, wx, wh, *gates, *cs, *hs)
         ctx.cfg = (steps, k, Hd)
         return out

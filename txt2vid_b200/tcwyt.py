@@ -17,6 +17,13 @@ def _bn_lrelu(x, bn, slope):
     return ops.leaky_relu(ops.bn_act(x, bn, 0), slope)
 
 
+def _conv_bn_lrelu(x, conv, bn, slope):
+    """Conv3d -> BatchNorm3d -> LeakyReLU with the BatchNorm fed from the convolution's fp32 accumulator"""
+    if abs(slope - 0.2) < 1e-12:
+        return ops.conv_bn_act(x, conv, bn, 2)
+    return ops.leaky_relu(ops.conv_bn_act(x, conv, bn, 0), slope)
+
+
 def _tile_cond(c_cl, like):
     """(B,1,1,1,C) -> broadcast over the spatial extent of `like` (the reference's expand / sent_dupe loops)."""
     B, D, H, W, _ = like.shape
@@ -54,7 +61,7 @@ class Gen(nn.Module):
         h = ops.vec_to_cl(x.reshape(B, x.size(1)))
         h = ops.bn_act(ops.linear_cl(h, self.input_map[0]), self.input_map[1], 2)
         for i in (0, 3, 6, 9):
-            h = ops.bn_act(ops.gconv_transpose(h, self.seq[i]), self.seq[i + 1], 2)
+            h = ops.conv_bn_act(h, self.seq[i], self.seq[i + 1], 2, transpose=True)
         pre = ops.gconv_transpose(h, self.seq[12])                    # (B, T, H, W, Cp)
         _, T, H, W, Cp = pre.shape
         return ops.render_tail(pre.reshape(B * T, 1, H, W, Cp), B, T, self.num_channels)
@@ -83,11 +90,11 @@ class VideoDiscrim(nn.Module):
     def forward(self, x=None, cond=None, xbar=None):
         h = ops.leaky_relu(ops.gconv(ops.to_cl(x), self.x_map[0]), self.slope)
         for i in (2, 5, 8):
-            h = _bn_lrelu(ops.gconv(h, self.x_map[i]), self.x_map[i + 1], self.slope)
+            h = _conv_bn_lrelu(h, self.x_map[i], self.x_map[i + 1], self.slope)
         if cond is not None:
             c = _bn_lrelu(ops.linear_cl(ops.vec_to_cl(cond), self.cond_map[0]), self.cond_map[1], self.slope)
             h = torch.cat((h, _tile_cond(c, h)), dim=-1)
-            h = _bn_lrelu(ops.gconv(h, self.pred[0]), self.pred[1], self.slope)
+            h = _conv_bn_lrelu(h, self.pred[0], self.pred[1], self.slope)
             out = ops.gconv(h, self.pred[3], out_f32=True)
         else:
             out = ops.gconv(h, self.pred, out_f32=True)
@@ -113,9 +120,9 @@ class FrameMap(nn.Module):
         out = []
         for t in range(xc.shape[1]):
             h = xc[:, t:t + 1].contiguous()
-            h = ops.bn_act(ops.gconv(h, m[0]), m[1], 2)
-            h = ops.bn_act(ops.gconv(h, m[3]), m[4], 2)
-            h = ops.bn_act(ops.gconv(h, m[6]), m[7], 2)
+            h = ops.conv_bn_act(h, m[0], m[1], 2)
+            h = ops.conv_bn_act(h, m[3], m[4], 2)
+            h = ops.conv_bn_act(h, m[6], m[7], 2)
             out.append(ops.gconv(h, m[9]))
         return out
 

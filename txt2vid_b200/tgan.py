@@ -31,10 +31,10 @@ class FrameSeedGenerator(nn.Module):
 
     def forward_cl(self, z_cl):
         """CL (B,1,1,1,zsP) -> CL (B,1,1,16,zfP), tanh applied."""
-        h = ops.bn_act(ops.gconv_transpose(z_cl, self.dc0), self.bn0, 1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc1), self.bn1, 1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc2), self.bn2, 1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc3), self.bn3, 1)
+        h = ops.conv_bn_act(z_cl, self.dc0, self.bn0, 1, transpose=True)
+        h = ops.conv_bn_act(h, self.dc1, self.bn1, 1, transpose=True)
+        h = ops.conv_bn_act(h, self.dc2, self.bn2, 1, transpose=True)
+        h = ops.conv_bn_act(h, self.dc3, self.bn3, 1, transpose=True)
         return ops.tanh(ops.gconv_transpose(h, self.dc4))
 
     def forward(self, z_slow):
@@ -77,10 +77,10 @@ class VideoFrameGenerator(nn.Module):
     def forward_cl(self, zs_cl, zf_cl):
         """-> pre-tanh CL (n, 1, 64, 64, round16(out_channels))"""
         h = torch.cat((self._bottom(zs_cl, self.l0s, self.bn0s), self._bottom(zf_cl, self.l0f, self.bn0f)), dim=-1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc1), self.bn1, 1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc2), self.bn2, 1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc3), self.bn3, 1)
-        h = ops.bn_act(ops.gconv_transpose(h, self.dc4), self.bn4, 1)
+        h = ops.conv_bn_act(h, self.dc1, self.bn1, 1, transpose=True)
+        h = ops.conv_bn_act(h, self.dc2, self.bn2, 1, transpose=True)
+        h = ops.conv_bn_act(h, self.dc3, self.bn3, 1, transpose=True)
+        h = ops.conv_bn_act(h, self.dc4, self.bn4, 1, transpose=True)
         return ops.gconv_transpose(h, self.dc5)
 
     def forward(self, z_slow, z_fast):
