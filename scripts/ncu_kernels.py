@@ -15,6 +15,7 @@ def mk(N, D, H, W, Cin, Cout, k, seed=0):
     return x, w, dy
 
 REPS = 2      # first rep = warm-up (outside the profiler range), second rep is captured
+SCALE = int(os.environ.get("BATCH_SCALE", "1"))     # 2: the shapes of the default bench batch (2048 / GPU)
 shapes = [
     ("stem conv2 64->64 3^3 level 0 (stride 1)", (1024, 16, 8, 8, 64, 64, (3, 3, 3))),
     ("G up2 conv1 256->128 @8x8", (16384, 1, 8, 8, 256, 128, (1, 3, 3))),
@@ -24,6 +25,7 @@ shapes = [
     ("G level3 32->32 @64x64", (256, 1, 64, 64, 32, 32, (1, 3, 3))),
     ("stem conv1 as 1x1 GEMM 96->64 level 1", (512, 8, 16, 16, 96, 64, (1, 1, 1))),
 ]
+shapes = [(n, (c[0] * SCALE,) + tuple(c[1:])) for n, c in shapes]
 for name, case in shapes:
     x, w, dy = mk(*case)
     k = case[6]

@@ -31,7 +31,10 @@ def _worker(rank, world, port, out):
     lin = torch.nn.Linear(5, 3)
     # one weight in channels-last memory, like the product's re-homed conv weights
     conv.weight.data = conv.weight.data.contiguous(memory_format=torch.channels_last_3d)
-    params = list(conv.parameters()) + list(lin.parameters())
+    # a ConvLSTM-style 3x3 kernel on a 1x1 plane: only its centre tap is exchanged
+    clstm = torch.nn.Conv2d(4, 6, 3, 1, 1, bias=False)
+    clstm.weight._t2v_live_tap = (1, 1)
+    params = list(conv.parameters()) + list(lin.parameters()) + list(clstm.parameters())
     g = torch.Generator().manual_seed(100 + rank)
     for p in params:
         p.grad = torch.empty_like(p, memory_format=torch.preserve_format)
@@ -44,6 +47,7 @@ def _worker(rank, world, port, out):
     np.random.seed(100 + rank)
     bts = [hostrng.EagerDraws().bt(2) for _ in range(7)]
     perm = hostrng.EagerDraws().perm(8, "cpu").tolist()
+    assert ctx.last_bucket_bytes == 4 * (sum(p.numel() for p in params[:-1]) + 6 * 4)
     out[rank] = {"local": local, "reduced": [p.grad.clone() for p in params], "bts": bts, "perm": perm,
                  "strides": [p.grad.stride() for p in params]}
     torch.distributed.barrier()
@@ -56,9 +60,17 @@ def test_reduce_grads_world2():
     out = mgr.dict()
     mp.spawn(_worker, args=(world, port, out), nprocs=world, join=True)
     r0, r1 = out[0], out[1]
-    for a, b, m0, m1 in zip(r0["local"], r1["local"], r0["reduced"], r1["reduced"]):
+    n = len(r0["local"])
+    for i, (a, b, m0, m1) in enumerate(zip(r0["local"], r1["local"], r0["reduced"], r1["reduced"])):
         mean = (a + b) / 2
-        assert torch.allclose(m0, mean, atol=1e-6) and torch.allclose(m1, mean, atol=1e-6)
+        if i < n - 1:
+            assert torch.allclose(m0, mean, atol=1e-6) and torch.allclose(m1, mean, atol=1e-6)
+        else:                                    # tagged kernel: centre tap averaged, the other taps left as they were
+            assert torch.allclose(m0[:, :, 1, 1], mean[:, :, 1, 1], atol=1e-6)
+            assert torch.allclose(m1[:, :, 1, 1], mean[:, :, 1, 1], atol=1e-6)
+            keep = torch.ones(3, 3, dtype=torch.bool)
+            keep[1, 1] = False
+            assert torch.equal(m0[:, :, keep], a[:, :, keep]) and torch.equal(m1[:, :, keep], b[:, :, keep])
     assert r0["bts"] == r1["bts"]
     assert r0["perm"] != r1["perm"]
     assert r0["strides"][0] == r1["strides"][0] and r0["strides"][0][1] == 1      # layout preserved (channels-last)

@@ -282,7 +282,13 @@ class ConvLSTM(nn.Module):
 
     def forward_cl(self, x):
         """x (B,1,fh,fw,C) -> merged-frame map (B*step, 1, fh, fw, H) in (b, t) order."""
-        wx, wh, bx = self.cell0.stacked(x.shape[2] == 1 and x.shape[3] == 1)
+        one = x.shape[2] == 1 and x.shape[3] == 1
+        wx, wh, bx = self.cell0.stacked(one)
+        # on a 1x1 plane only the centre tap of the eight 3x3 kernels ever receives a gradient (8/9 of the 75.5 M
+        # entries stay exactly zero): the data-parallel exchange reduces that tap alone (parallel.reduce_grads)
+        for m in (self.cell0.Wxi, self.cell0.Whi, self.cell0.Wxf, self.cell0.Whf, self.cell0.Wxc, self.cell0.Whc,
+                  self.cell0.Wxo, self.cell0.Who):
+            m.weight._t2v_live_tap = (1, 1) if one else None
         return ops.ConvLstmF.apply(x, wx, wh, bx, self.step)
 
     def forward(self, input):

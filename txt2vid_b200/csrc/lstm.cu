@@ -13,6 +13,8 @@
 //     then three GEMMs on the engine (dX = dG W_ih, dW_ih = dG^T X, dW_hh = dG^T h_prev) and one column sum.
 // Gate order i, f, g, o (PyTorch).  All state math is fp32; `ST` is the activation storage type of the sequence
 // tensors that feed GEMMs (bf16, or fp32 in the fp32 parity mode).
+#include <cstdlib>
+
 #include "t2v_common.cuh"
 
 namespace t2v {
@@ -122,6 +124,103 @@ __global__ void lstm_seq_fwd_kernel(const LstmSeq p) {
     if (b >= nb) continue;
     p.hn[((size_t)dir * p.B + b0 + b) * H + j] = h[b];
     p.cn[((size_t)dir * p.B + b0 + b) * H + j] = c[b];
+  }
+}
+
+// Shared-memory-resident variant for the bf16 storage mode (H <= 128): W_hh^T lives in shared memory as bf16,
+// gate-interleaved [k][j][i|f|g|o] (one 8-byte load per k and thread; H * 4H * 2 B = 128 KB at H = 128), instead of
+// being streamed from L2 on every time step (the walk above is bound by the latency of those loads: 37 us per step at
+// B = 1024).  256 threads: thread (j, half) owns hidden unit j of 8 of the CTA's 16 samples; h_{t-1} is kept
+// k-major in shared memory so that the 8 samples of a thread are two broadcast 16-byte loads per k.  Same fp32 state
+// math and masking as above; the recurrent weights carry the bf16 rounding every GEMM operand of this mode has.
+static constexpr int kLstmSmemThreads = 256;
+__global__ void __launch_bounds__(kLstmSmemThreads, 1) lstm_seq_fwd_smem_kernel(const LstmSeq p) {
+  extern __shared__ __align__(16) uint8_t lsm[];
+  const int H = p.H, tid = threadIdx.x, j = tid % H, half = tid / H, dir = blockIdx.y;
+  const int per = kLstmBT / (kLstmSmemThreads / H);            // samples per thread (8 at H = 128)
+  uint2* wsm = reinterpret_cast<uint2*>(lsm);                   // [H k][H j] x 4 bf16
+  float* hsm = reinterpret_cast<float*>(lsm + (size_t)H * H * 8);   // [H k][kLstmBT]
+  const int b0 = blockIdx.x * kLstmBT;
+  const int nb = min(kLstmBT, p.B - b0);
+  const float* wT = p.whhT + (size_t)dir * H * 4 * H;
+  for (int i = tid; i < H * H; i += blockDim.x) {
+    const int k = i / H, jj = i % H;
+    const float* w = wT + (size_t)k * 4 * H + jj;
+    wsm[i] = make_uint2(pack_bf16x2(w[0], w[H]), pack_bf16x2(w[2 * H], w[3 * H]));
+  }
+  float c[8], h[8];
+  int len[8];
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int bb = half * per + b;
+    const bool ok = b < per && bb < nb;
+    len[b] = ok ? p.lengths[b0 + bb] : 0;
+    h[b] = (ok && p.h0) ? p.h0[((size_t)dir * p.B + b0 + bb) * H + j] : 0.f;
+    c[b] = (ok && p.c0) ? p.c0[((size_t)dir * p.B + b0 + bb) * H + j] : 0.f;
+    if (b < per) hsm[j * kLstmBT + bb] = h[b];
+  }
+  __syncthreads();
+  __nv_bfloat16* out = reinterpret_cast<__nv_bfloat16*>(p.out);
+  __nv_bfloat16* hprev = reinterpret_cast<__nv_bfloat16*>(p.hprev);
+  for (int s = 0; s < p.L; ++s) {
+    const int t = dir == 0 ? s : p.L - 1 - s;
+    float acc[8][4];
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int bb = half * per + b;
+      if (b < per && bb < nb && t < len[b]) {
+        const float* g = p.gx + (((size_t)(b0 + bb) * p.L + t) * p.ndir + dir) * 4 * H;
+        acc[b][0] = g[j]; acc[b][1] = g[H + j]; acc[b][2] = g[2 * H + j]; acc[b][3] = g[3 * H + j];
+      } else {
+        acc[b][0] = acc[b][1] = acc[b][2] = acc[b][3] = 0.f;
+      }
+    }
+#pragma unroll 4
+    for (int k = 0; k < H; ++k) {
+      const uint2 wq = wsm[k * H + j];
+      const float2 w01 = unpack_bf16x2(wq.x), w23 = unpack_bf16x2(wq.y);
+      const float4 ha = *reinterpret_cast<const float4*>(hsm + k * kLstmBT + half * per);
+      const float4 hb = *reinterpret_cast<const float4*>(hsm + k * kLstmBT + half * per + 4);
+      const float hv[8] = {ha.x, ha.y, ha.z, ha.w, hb.x, hb.y, hb.z, hb.w};
+#pragma unroll
+      for (int b = 0; b < 8; ++b) {
+        acc[b][0] = fmaf(hv[b], w01.x, acc[b][0]); acc[b][1] = fmaf(hv[b], w01.y, acc[b][1]);
+        acc[b][2] = fmaf(hv[b], w23.x, acc[b][2]); acc[b][3] = fmaf(hv[b], w23.y, acc[b][3]);
+      }
+    }
+    __syncthreads();                            // every thread has finished reading h_{t-1}
+#pragma unroll
+    for (int b = 0; b < 8; ++b) {
+      const int bb = half * per + b;
+      if (b >= per || bb >= nb) continue;
+      const size_t row = (size_t)(b0 + bb) * p.L + t;
+      const bool live = t < len[b];
+      float hv = 0.f, hp = 0.f;
+      if (live) {
+        const float gi = sigmoidf_(acc[b][0]), gf = sigmoidf_(acc[b][1]), gg = tanhf(acc[b][2]),
+                    go = sigmoidf_(acc[b][3]);
+        hp = h[b];
+        c[b] = gf * c[b] + gi * gg;
+        h[b] = go * tanhf(c[b]);
+        hv = h[b];
+        hsm[j * kLstmBT + bb] = hv;
+        if (p.gates) {
+          float* gs = p.gates + (row * p.ndir + dir) * 4 * H;
+          gs[j] = gi; gs[H + j] = gf; gs[2 * H + j] = gg; gs[3 * H + j] = go;
+        }
+        if (p.cells) p.cells[(row * p.ndir + dir) * H + j] = c[b];
+      }
+      out[row * p.ndir * H + dir * H + j] = f2bf(hv);
+      if (hprev) hprev[row * p.ndir * H + dir * H + j] = f2bf(hp);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int b = 0; b < 8; ++b) {
+    const int bb = half * per + b;
+    if (b >= per || bb >= nb) continue;
+    p.hn[((size_t)dir * p.B + b0 + bb) * H + j] = h[b];
+    p.cn[((size_t)dir * p.B + b0 + bb) * H + j] = c[b];
   }
 }
 
@@ -238,6 +337,14 @@ template <typename ST>
 static int lstm_fwd_impl(LstmSeq p, cudaStream_t s) {
   if (p.H % 32 || p.H > 1024 || p.B <= 0 || p.L <= 0 || p.ndir < 1 || p.ndir > 2) return T2V_ERR_ARG;
   dim3 grid((p.B + kLstmBT - 1) / kLstmBT, p.ndir, 1);
+  static const int use_smem = [] { const char* e = getenv("T2V_LSTM_SMEM"); return e ? atoi(e) : 1; }();
+  if (use_smem && sizeof(ST) == 2 && p.H == 128) {            // bf16 storage mode: recurrent weights resident in smem
+    const size_t smem = (size_t)p.H * p.H * 8 + sizeof(float) * kLstmBT * p.H;
+    cudaFuncSetAttribute(lstm_seq_fwd_smem_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    lstm_seq_fwd_smem_kernel<<<grid, kLstmSmemThreads, smem, s>>>(p);
+    count_launch();
+    return check_last("lstm_seq_fwd");
+  }
   lstm_seq_fwd_kernel<ST><<<grid, p.H, sizeof(float) * kLstmBT * p.H, s>>>(p);
   count_launch();
   return check_last("lstm_seq_fwd");

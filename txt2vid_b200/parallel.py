@@ -86,22 +86,37 @@ class DistContext(object):
         params = [p for g in optimizer.param_groups for p in g["params"] if p.grad is not None]
         if not params:
             return
+        # a 4-D weight tagged with `_t2v_live_tap` (ConvLSTM kernels on a 1x1 plane) only has gradient in that one
+        # 3x3 tap: exchange the (Cout, Cin) slice, leave the structurally-zero taps alone
+        def live(p):
+            tap = getattr(p, "_t2v_live_tap", None)
+            return tap if (tap is not None and p.dim() == 4) else None
+        dense = [p for p in params if live(p) is None]
+        sliced = [p for p in params if live(p) is not None]
         key = id(optimizer)
-        total = sum(p.numel() for p in params)
+        total = sum(p.numel() for p in dense) + sum(p.shape[0] * p.shape[1] for p in sliced)
         flat = self._flat.get(key)
         if flat is None or flat.numel() != total or flat.device != params[0].device:
             flat = torch.empty(total, device=params[0].device, dtype=torch.float32)
             self._flat[key] = flat
         views, off = [], 0
-        for p in params:
+        for p in dense:
             views.append(flat[off:off + p.numel()])
             off += p.numel()
-        grads = [p.grad for p in params]
+        grads = [p.grad for p in dense]
+        slices = []
+        for p in sliced:
+            n = p.shape[0] * p.shape[1]
+            a, b = live(p)
+            slices.append((p.grad[:, :, a, b], flat[off:off + n].view(p.shape[0], p.shape[1])))
+            off += n
         if flat.is_cuda:
             K.multi_copy(grads, views)
         else:                                   # gloo / CPU tests of the host logic
             for g, v in zip(grads, views):
                 v.copy_(_memory_order(g))
+        for g, v in slices:
+            v.copy_(g)
         dist.all_reduce(flat, op=dist.ReduceOp.SUM)
         if hasattr(optimizer, "grad_scale"):
             optimizer.grad_scale = 1.0 / self.world           # the 1/N is folded into the fused Adam kernel
@@ -112,6 +127,9 @@ class DistContext(object):
         else:
             for g, v in zip(grads, views):
                 _memory_order(g).copy_(v)
+        for g, v in slices:
+            g.copy_(v)
+        self.last_bucket_bytes = 4 * total
 
     def all_reduce_max(self, value):
         if not self.enabled:
