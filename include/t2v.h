@@ -153,6 +153,39 @@ int t2v_gconv_dgrad(const t2v_gconv_geom* g, const void* dy, const void* w, cons
 /* dw[Cout][taps][Cin] (+)= sum_pos dy[pos,co] * x[in(pos,tap),ci]  (fp32)                              */
 int t2v_gconv_wgrad(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
                     void* stream);
+/* Stride-2 convolutions / transposed convolutions of the TGAN and TCWYT families on the tcgen05 engine
+ * (models/tcwyt/video_discrim.py:12-25, tcwyt/frame_discrim.py:9-21, tcwyt/gen.py:18-26, tgan/gen.py:20-23,
+ * tgan/temporal_gen.py:112-115).  A kernel-4 / stride-2 / padding-1 axis reads inputs 2o-1 .. 2o+2 for output o: with
+ * the input grouped in blocks of two samples aligned at odd positions (block b = samples 2b-1, 2b; b = 0..O) output
+ * o reads exactly blocks o and o+1 -- a DENSE kernel-2 stride-1 convolution over a block tensor with 2^s * C channels.
+ * Per axis `m`: 2 = kernel 4 / stride 2 / padding 1 (even extent), 1 = kernel 1 / stride 1 / padding 0.
+ *   t2v_s2d_shift: x (N,D,H,W,C) -> xs (N,D',H',W',Cp), D' = D/2+1 on a strided axis, channel = phase * creal + c for
+ *     the creal <= C real channels, phase = ((pd * 2) + ph) * 2 + pw over the strided axes; channels >= 2^s * creal and
+ *     samples outside x are zero.  elem_bytes = 2 (bf16) or 4 (fp32).  t2v_d2s_shift is the inverse (channels
+ *     >= creal of x are zeroed): a bit-exact index kernel pair.                                                    */
+int t2v_s2d_shift(const void* x, void* xs, int64_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t creal,
+                  int32_t md, int32_t mh, int32_t mw, int32_t Cp, int32_t elem_bytes, void* stream);
+int t2v_d2s_shift(const void* xs, void* x, int64_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t creal,
+                  int32_t md, int32_t mh, int32_t mw, int32_t Cp, int32_t elem_bytes, void* stream);
+/* w bf16 [Co][k taps][Ci] (k = 4 per strided axis) -> the block convolution's operand: bf16 [Co][3^s taps][Cp]
+ * (engine tap t = block offset + 1; tap 0 of a strided axis stays zero and is never read), or with transposed = 1 the
+ * data-gradient / transposed-convolution operand bf16 [Cp][3^s taps reversed][Co]                                 */
+int t2v_s2d_embed_weight(const void* w, void* we, int32_t Co, int32_t Ci, int32_t creal, int32_t Cp, int32_t md,
+                         int32_t mh, int32_t mw, int32_t transposed, void* stream);
+/* dwe fp32 [Co][3^s][Cp] (t2v_conv_wgrad_win on the block tensor) -> dw fp32 [Co][k taps][Ci]                     */
+int t2v_s2d_extract_wgrad(const float* dwe, float* dw, int32_t Co, int32_t Ci, int32_t creal, int32_t Cp, int32_t md,
+                          int32_t mh, int32_t mw, void* stream);
+/* out fp32 [Cp]: out[ph * creal + c] = bias[c] for ph < phases, zero beyond (bias of a transposed convolution in block form) */
+int t2v_s2d_tile_bias(const float* bias, float* out, int32_t creal, int32_t phases, int32_t Cp, void* stream);
+/* Windowed implicit GEMM on the generic tcgen05 kernels: g = geometry of the OUTPUT positions (fprop) / of dy
+ * (wgrad); win9 = {iD, iH, iW, lo_d, hi_d, lo_h, hi_h, lo_w, hi_w}: extents of the tensor the taps read (x) and the live
+ * tap range per axis (tap t reads coordinate o + t - k/2, out-of-range coordinates read zero).  Weight layouts as in
+ * t2v_conv_fprop / t2v_conv_wgrad (all k taps present in memory, only the live ones touched).  epi_flags: T2V_EPI_RELU,
+ * T2V_EPI_OUT_F32.                                                                                                 */
+int t2v_conv_fprop_win(const t2v_conv_geom* g, const int32_t* win9, const void* x, const void* w, const float* bias,
+                       void* y, uint32_t epi_flags, void* stream);
+int t2v_conv_wgrad_win(const t2v_conv_geom* g, const int32_t* win9, const void* dy, const void* x, float* dw,
+                       int accumulate, void* stream);
 /* fp32 master weight [Cout][taps][Cin] -> bf16 same layout (fprop operand)                    */
 int t2v_cast_f32_to_bf16(const float* src, void* dst, int64_t n, void* stream);
 int t2v_cast_bf16_to_f32(const void* src, float* dst, int64_t n, void* stream);

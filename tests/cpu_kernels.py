@@ -193,13 +193,13 @@ def _w5g(w, k):
     return w.float().view(Cout, k[0], k[1], k[2], Cin).permute(0, 4, 1, 2, 3)
 
 
-def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
+def gconv_fprop(x, w, bias, k, s, p, out_f32=False, cin_real=None):
     y = F.conv3d(x.float().permute(0, 4, 1, 2, 3), _w5g(w, k), bias, stride=tuple(s), padding=tuple(p))
     y = y.permute(0, 2, 3, 4, 1).contiguous()
     return y if out_f32 else y.to(STORE)
 
 
-def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
+def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False, cin_real=None):
     osp = [(o - 1) * ss - 2 * pp + kk for o, ss, pp, kk in zip(dy.shape[1:4], s, p, k)]
     opad = [i - o for i, o in zip(in_sp, osp)]
     dx = F.conv_transpose3d(dy.float().permute(0, 4, 1, 2, 3), _w5g(w, k), bias, stride=tuple(s), padding=tuple(p),
@@ -208,7 +208,7 @@ def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
     return dx if out_f32 else dx.to(STORE)
 
 
-def gconv_wgrad(dy, x, k, s, p):
+def gconv_wgrad(dy, x, k, s, p, cin_real=None):
     Cout, Cin = dy.shape[-1], x.shape[-1]
     g = torch.nn.grad.conv3d_weight(x.float().permute(0, 4, 1, 2, 3), (Cout, Cin) + tuple(k),
                                     dy.float().permute(0, 4, 1, 2, 3), stride=tuple(s), padding=tuple(p))

@@ -8,9 +8,11 @@ bool igemm_fprop_supported(const t2v_conv_geom* g);
 bool igemm_wgrad_supported(const t2v_conv_geom* g);
 int igemm_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
                        uint32_t, cudaStream_t);
-int igemm_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t);
+int igemm_wgrad_launch(const t2v_conv_geom*, const void*, const void*, float*, int, cudaStream_t,
+                       const ConvWindow* win = nullptr);
 int igemm_fprop_launch_aux(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*, uint32_t,
-                           cudaStream_t, const void*, const void*, int, const LstmEpi* lstm = nullptr);
+                           cudaStream_t, const void*, const void*, int, const LstmEpi* lstm = nullptr,
+                           const ConvWindow* win = nullptr);
 bool halo_wgrad_supported(const t2v_conv_geom* g);
 bool halo_fprop_supported(const t2v_conv_geom* g);
 int halo_fprop_launch(const t2v_conv_geom*, const void*, const void*, const float*, const void*, void*,
@@ -150,6 +152,29 @@ int t2v_conv_wgrad(const t2v_conv_geom* g, const void* dy, const void* x, float*
   if (algo == T2V_ALGO_SIMT || !tc_ok) return simt_wgrad_launch(g, dy, x, dw, accumulate, s);
   if (algo != T2V_ALGO_TC_GENERIC && halo_wgrad_supported(g)) return halo_wgrad_launch(g, dy, x, dw, accumulate, s, 0);
   return igemm_wgrad_launch(g, dy, x, dw, accumulate, s);
+}
+
+static bool fill_window(ConvWindow* cw, const int32_t* w9) {
+  if (!w9) return false;
+  cw->iD = w9[0]; cw->iH = w9[1]; cw->iW = w9[2];
+  cw->lo_d = w9[3]; cw->hi_d = w9[4]; cw->lo_h = w9[5]; cw->hi_h = w9[6]; cw->lo_w = w9[7]; cw->hi_w = w9[8];
+  return cw->iD > 0 && cw->iH > 0 && cw->iW > 0;
+}
+
+int t2v_conv_fprop_win(const t2v_conv_geom* g, const int32_t* win9, const void* x, const void* w, const float* bias,
+                       void* y, uint32_t epi_flags, void* stream) {
+  ConvWindow cw;
+  if (!g || !x || !w || !y || !fill_window(&cw, win9)) return T2V_ERR_ARG;
+  if (epi_flags & ~(T2V_EPI_RELU | T2V_EPI_OUT_F32)) return T2V_ERR_ARG;
+  return igemm_fprop_launch_aux(g, x, w, bias, nullptr, y, epi_flags, reinterpret_cast<cudaStream_t>(stream), nullptr,
+                                nullptr, 0, nullptr, &cw);
+}
+
+int t2v_conv_wgrad_win(const t2v_conv_geom* g, const int32_t* win9, const void* dy, const void* x, float* dw,
+                       int accumulate, void* stream) {
+  ConvWindow cw;
+  if (!g || !dy || !x || !dw || !fill_window(&cw, win9)) return T2V_ERR_ARG;
+  return igemm_wgrad_launch(g, dy, x, dw, accumulate, reinterpret_cast<cudaStream_t>(stream), &cw);
 }
 
 int t2v_conv_fprop_skip(const t2v_conv_geom* g, const void* x, const void* w, const float* bias, const void* x2,

@@ -782,20 +782,23 @@ bool igemm_wgrad_supported(const t2v_conv_geom* g) {
   return igemm_fprop_supported(g);
 }
 
-static int fill_common(IgemmParams& p, const t2v_conv_geom* g) {
+static int fill_common(IgemmParams& p, const t2v_conv_geom* g, const ConvWindow* win = nullptr) {
   p.N = g->N; p.D = g->D; p.H = g->H; p.W = g->W; p.Cin = g->Cin; p.Cout = g->Cout;
   p.kd = g->kd; p.kh = g->kh; p.kw = g->kw;
   p.pd = g->kd / 2; p.ph = g->kh / 2; p.pw = g->kw / 2;
   live_taps(g->kd, g->D, &p.lo_d, &p.hi_d);
   live_taps(g->kh, g->H, &p.lo_h, &p.hi_h);
   live_taps(g->kw, g->W, &p.lo_w, &p.hi_w);
+  if (win) {
+    p.lo_d = win->lo_d; p.hi_d = win->hi_d; p.lo_h = win->lo_h; p.hi_h = win->hi_h; p.lo_w = win->lo_w; p.hi_w = win->hi_w;
+  }
   p.taps_total = g->kd * g->kh * g->kw;
   return (p.hi_d - p.lo_d) * (p.hi_h - p.lo_h) * (p.hi_w - p.lo_w);
 }
 
 int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                            const void* residual, void* y, uint32_t flags, cudaStream_t stream, const void* x2,
-                           const void* w2, int Cin2, const LstmEpi* lstm = nullptr);
+                           const void* w2, int Cin2, const LstmEpi* lstm = nullptr, const ConvWindow* win = nullptr);
 
 int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                        const void* residual, void* y, uint32_t flags, cudaStream_t stream) {
@@ -805,13 +808,16 @@ int igemm_fprop_launch(const t2v_conv_geom* g, const void* x, const void* w, con
 // x2 / w2 / Cin2: optional fused 1x1x1 convolution of a second tensor over the same positions (w2 bf16 [Cout][Cin2])
 int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w, const float* bias,
                            const void* residual, void* y, uint32_t flags, cudaStream_t stream, const void* x2,
-                           const void* w2, int Cin2, const LstmEpi* lstm) {
+                           const void* w2, int Cin2, const LstmEpi* lstm, const ConvWindow* win) {
   if (!igemm_fprop_supported(g)) return T2V_ERR_ARG;
+  if (win && (x2 || lstm || win->lo_d < 0 || win->hi_d > g->kd || win->lo_h < 0 || win->hi_h > g->kh || win->lo_w < 0 ||
+              win->hi_w > g->kw || win->lo_d >= win->hi_d || win->lo_h >= win->hi_h || win->lo_w >= win->hi_w))
+    return T2V_ERR_ARG;
   if (lstm && (g->Cout % 128 || !bias || !lstm->c_out || !lstm->gates || !lstm->h_out || !lstm->h_merged ||
                lstm->steps <= 0 || lstm->t < 0 || lstm->t >= lstm->steps))
     return T2V_ERR_ARG;
   IgemmParams p{};
-  const int ntaps = fill_common(p, g);
+  const int ntaps = fill_common(p, g, win);
   const int BLOCK_K = (g->Cin % 64 == 0) ? 64 : (g->Cin % 32 == 0 ? 32 : 16);
   choose_box(128, g->N, g->D, g->H, g->W, &p.bn, &p.bd, &p.bh, &p.bw);
   p.tn = (g->N + p.bn - 1) / p.bn; p.td = (g->D + p.bd - 1) / p.bd;
@@ -873,7 +879,8 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
   }
 
   CUtensorMap tmA, tmB;
-  int rc = make_act_map(&tmA, x, g->N, g->D, g->H, g->W, g->Cin, BLOCK_K, p.bw, p.bh, p.bd, p.bn);
+  int rc = make_act_map(&tmA, x, g->N, win ? win->iD : g->D, win ? win->iH : g->H, win ? win->iW : g->W, g->Cin, BLOCK_K,
+                        p.bw, p.bh, p.bd, p.bn);
   if (rc) return rc;
   rc = make_w_map(&tmB, w, g->Cout, p.taps_total * g->Cin, BLOCK_K, p.BN);
   if (rc) return rc;
@@ -946,10 +953,13 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
 }
 
 int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, float* dw, int accumulate,
-                       cudaStream_t stream) {
+                       cudaStream_t stream, const ConvWindow* win) {
   if (!igemm_wgrad_supported(g)) return T2V_ERR_ARG;
+  if (win && (win->lo_d < 0 || win->hi_d > g->kd || win->lo_h < 0 || win->hi_h > g->kh || win->lo_w < 0 ||
+              win->hi_w > g->kw || win->lo_d >= win->hi_d || win->lo_h >= win->hi_h || win->lo_w >= win->hi_w))
+    return T2V_ERR_ARG;
   IgemmParams p{};
-  const int ntaps = fill_common(p, g);
+  const int ntaps = fill_common(p, g, win);
   choose_box(kWgradPos, g->N, g->D, g->H, g->W, &p.bn, &p.bd, &p.bh, &p.bw);
   p.tn = (g->N + p.bn - 1) / p.bn; p.td = (g->D + p.bd - 1) / p.bd;
   p.th = (g->H + p.bh - 1) / p.bh; p.tw = (g->W + p.bw - 1) / p.bw;
@@ -988,7 +998,8 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   CUtensorMap tmDy, tmX;
   int rc = make_act_map(&tmDy, dy, g->N, g->D, g->H, g->W, g->Cout, 64, p.bw, p.bh, p.bd, p.bn);
   if (rc) return rc;
-  rc = make_act_map(&tmX, x, g->N, g->D, g->H, g->W, g->Cin, 64, p.bw, p.bh, p.bd, p.bn);
+  rc = make_act_map(&tmX, x, g->N, win ? win->iD : g->D, win ? win->iH : g->H, win ? win->iW : g->W, g->Cin, 64, p.bw,
+                    p.bh, p.bd, p.bn);
   if (rc) return rc;
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 1) * 8 + 16;
   dim3 grid(mtiles, ntiles, ntaps * splits);

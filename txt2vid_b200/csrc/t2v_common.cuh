@@ -180,6 +180,15 @@ struct LstmEpi {
   int t, steps;
 };
 
+// Window of a convolution whose input extents differ from its output extents (t2v_conv_fprop_win / _wgrad_win): the
+// kernels only see the input through its tensor map (coordinates + out-of-bounds zero fill), so the tile grid walks
+// the OUTPUT positions of the geometry while the input map takes these extents, and the live tap range per axis is
+// given explicitly (tap t reads input coordinate o + t - k/2).
+struct ConvWindow {
+  int iD, iH, iW;
+  int lo_d, hi_d, lo_h, hi_h, lo_w, hi_w;
+};
+
 // UMMA shared-memory matrix descriptor (sm_100 format, version 1).
 //   start address >>4 in [0,14), LBO>>4 in [16,30), SBO>>4 in [32,46), version=1 in [46,48),
 //   layout type in [61,64): 0 none, 2 = 128B swizzle, 4 = 64B, 6 = 32B.

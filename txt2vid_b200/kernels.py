@@ -447,7 +447,150 @@ def gconv_pack(w3):
     return w3.contiguous() if STORE == F32 else cast_bf16(w3.contiguous())
 
 
-def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
+# --- kernel-4 / stride-2 / padding-1 layers on the tcgen05 engine (csrc/s2d.cu: shifted space-to-depth blocks) --------
+GCONV_TC = os.environ.get("T2V_GCONV_TC", "1") == "1"
+
+
+def round16(c):
+    return (c + 15) // 16 * 16
+
+
+def s2d_modes(k, s, p, in_sp):
+    """per-axis mode of the block formulation: 2 = kernel 4 / stride 2 / padding 1 on an even extent, 1 = kernel 1 /
+    stride 1 / padding 0; None when the layer is of another kind (it stays on the CUDA-core general convolution)"""
+    modes = []
+    for kk, ss, pp, e in zip(k, s, p, in_sp):
+        if (kk, ss, pp) == (4, 2, 1) and e % 2 == 0:
+            modes.append(2)
+        elif (kk, ss, pp) == (1, 1, 0):
+            modes.append(1)
+        else:
+            return None
+    return tuple(modes) if 2 in modes else None
+
+
+def _s2d_phases(modes):
+    return 2 ** sum(1 for m in modes if m == 2)
+
+
+def s2d_block_extents(sp, modes):
+    return tuple(e // 2 + 1 if m == 2 else e for e, m in zip(sp, modes))
+
+
+def s2d_shift(x, modes, creal=None):
+    """x (N,D,H,W,C) -> block tensor (N,D',H',W',round16(P*creal)): block b of a strided axis = samples (2b-1, 2b)"""
+    require_cuda(x)
+    N, D, H, W, C = x.shape
+    creal = C if creal is None else creal
+    Cp = round16(_s2d_phases(modes) * creal)
+    Db, Hb, Wb = s2d_block_extents((D, H, W), modes)
+    assert x.is_contiguous()
+    xs = torch.empty((N, Db, Hb, Wb, Cp), device=x.device, dtype=x.dtype)
+    check(lib().t2v_s2d_shift(ptr(x), ptr(xs), N, D, H, W, C, creal, modes[0], modes[1], modes[2], Cp,
+                              x.element_size(), stream()), "t2v_s2d_shift")
+    return xs
+
+
+def d2s_shift(xs, modes, sp, C, creal=None):
+    """inverse of s2d_shift: block tensor -> (N,D,H,W,C) (channels >= creal zero)"""
+    require_cuda(xs)
+    N, Cp = xs.shape[0], xs.shape[-1]
+    creal = C if creal is None else creal
+    assert xs.is_contiguous() and tuple(xs.shape[1:4]) == s2d_block_extents(sp, modes), (xs.shape, sp, modes)
+    x = torch.empty((N, sp[0], sp[1], sp[2], C), device=xs.device, dtype=xs.dtype)
+    check(lib().t2v_d2s_shift(ptr(xs), ptr(x), N, sp[0], sp[1], sp[2], C, creal, modes[0], modes[1], modes[2], Cp,
+                              xs.element_size(), stream()), "t2v_d2s_shift")
+    return x
+
+
+def s2d_embed_weight(w, modes, creal=None, transposed=False):
+    """w bf16 (Co, k taps, Ci) -> bf16 (Co, 3^s, Cp) | transposed (Cp, 3^s reversed, Co); cached on the pack tensor"""
+    require_cuda(w)
+    Co, taps, Ci = w.shape
+    creal = Ci if creal is None else creal
+    key = (modes, creal, transposed)
+    cache = getattr(w, "_t2v_s2d", None)
+    if cache is None:
+        cache = {}
+        w._t2v_s2d = cache
+    if key in cache:
+        return cache[key]
+    assert w.dtype == BF16 and w.is_contiguous() and taps == 4 ** sum(1 for m in modes if m == 2)
+    Cp = round16(_s2d_phases(modes) * creal)
+    ntap = 3 ** sum(1 for m in modes if m == 2)
+    we = torch.empty((Cp, ntap, Co) if transposed else (Co, ntap, Cp), device=w.device, dtype=BF16)
+    check(lib().t2v_s2d_embed_weight(ptr(w), ptr(we), Co, Ci, creal, Cp, modes[0], modes[1], modes[2],
+                                     1 if transposed else 0, stream()), "t2v_s2d_embed_weight")
+    cache[key] = we
+    return we
+
+
+def s2d_extract_wgrad(dwe, modes, Ci, creal=None):
+    """dwe fp32 (Co, 3^s, Cp) -> dw fp32 (Co, k taps, Ci)"""
+    require_cuda(dwe)
+    Co, ntap, Cp = dwe.shape
+    creal = Ci if creal is None else creal
+    taps = 4 ** sum(1 for m in modes if m == 2)
+    assert dwe.dtype == F32 and dwe.is_contiguous()
+    dw = torch.empty((Co, taps, Ci), device=dwe.device, dtype=F32)
+    check(lib().t2v_s2d_extract_wgrad(ptr(dwe), ptr(dw), Co, Ci, creal, Cp, modes[0], modes[1], modes[2], stream()),
+          "t2v_s2d_extract_wgrad")
+    return dw
+
+
+def s2d_tile_bias(bias, creal, phases, Cp):
+    """fp32 (>= creal,) -> fp32 (Cp,): out[ph * creal + c] = bias[c] (the bias of a transposed convolution in block form)"""
+    require_cuda(bias)
+    out = torch.empty((Cp,), device=bias.device, dtype=F32)
+    check(lib().t2v_s2d_tile_bias(ptr(bias), ptr(out), creal, phases, Cp, stream()), "t2v_s2d_tile_bias")
+    return out
+
+
+def _win9(in_sp, lo_hi):
+    return _i32(in_sp[0], in_sp[1], in_sp[2], lo_hi[0][0], lo_hi[0][1], lo_hi[1][0], lo_hi[1][1], lo_hi[2][0],
+                lo_hi[2][1])
+
+
+def conv_fprop_win(x, w, bias, out_sp, k, lo_hi, relu=False, out_f32=False):
+    """windowed implicit GEMM: x (N,iD,iH,iW,Cin) bf16, w (Cout, kd*kh*kw, Cin) bf16 -> y (N,*out_sp,Cout); tap t of an
+    axis reads x at o + t - k/2 (zero outside x), only taps lo <= t < hi are live"""
+    require_cuda(x, w, bias)
+    N, Cin = x.shape[0], x.shape[-1]
+    Cout = w.shape[0]
+    assert x.dtype == BF16 and w.dtype == BF16 and x.is_contiguous() and w.is_contiguous()
+    assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
+    assert bias is None or (bias.dtype == F32 and bias.numel() == Cout)
+    y = torch.empty((N, out_sp[0], out_sp[1], out_sp[2], Cout), device=x.device, dtype=F32 if out_f32 else BF16)
+    g = _geom(N, out_sp[0], out_sp[1], out_sp[2], Cin, Cout, k)
+    flags = (_lib.EPI_RELU if relu else 0) | (_lib.EPI_OUT_F32 if out_f32 else 0)
+    check(lib().t2v_conv_fprop_win(ctypes.byref(g), _win9(x.shape[1:4], lo_hi), ptr(x), ptr(w), ptr(bias), ptr(y), flags,
+                                   stream()), "t2v_conv_fprop_win")
+    return y
+
+
+def conv_wgrad_win(dy, x, k, lo_hi):
+    """dw (Cout, kd*kh*kw, Cin) fp32 = sum_pos dy[pos, co] x[pos + t - k/2, ci] over the live taps (others zero)"""
+    require_cuda(dy, x)
+    N, Cout, Cin = dy.shape[0], dy.shape[-1], x.shape[-1]
+    assert dy.dtype == BF16 and x.dtype == BF16 and dy.is_contiguous() and x.is_contiguous() and x.shape[0] == N
+    dw = torch.empty((Cout, k[0] * k[1] * k[2], Cin), device=x.device, dtype=F32)
+    g = _geom(N, dy.shape[1], dy.shape[2], dy.shape[3], Cin, Cout, k)
+    check(lib().t2v_conv_wgrad_win(ctypes.byref(g), _win9(x.shape[1:4], lo_hi), ptr(dy), ptr(x), ptr(dw), 0, stream()),
+          "t2v_conv_wgrad_win")
+    return dw
+
+
+def _s2d_engine_args(modes, dgrad=False):
+    ke = tuple(3 if m == 2 else 1 for m in modes)
+    live = (0, 2) if dgrad else (1, 3)
+    return ke, tuple(live if m == 2 else (0, 1) for m in modes)
+
+
+def _s2d_route(t, k, s, p, in_sp):
+    return s2d_modes(k, s, p, in_sp) if (GCONV_TC and t.dtype == BF16) else None
+
+
+def gconv_fprop(x, w, bias, k, s, p, out_f32=False, cin_real=None):
     """Strided convolution: x (N,Di,Hi,Wi,Cin), w (Cout,taps,Cin) (both bf16, or both fp32) -> y (N,Do,Ho,Wo,Cout)."""
     require_cuda(x, w, bias)
     N, Di, Hi, Wi, Cin = x.shape
@@ -456,6 +599,11 @@ def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
     assert x.dtype == w.dtype
     assert w.shape[1] == k[0] * k[1] * k[2] and w.shape[2] == Cin, (w.shape, k, Cin)
     g, osp = _ggeom(N, (Di, Hi, Wi), Cin, Cout, k, s, p)
+    modes = _s2d_route(x, k, s, p, (Di, Hi, Wi))
+    if modes is not None:                       # k4 s2 p1: dense kernel-2 implicit GEMM over the shifted block tensor
+        ke, live = _s2d_engine_args(modes)
+        return conv_fprop_win(s2d_shift(x, modes, cin_real), s2d_embed_weight(w, modes, cin_real), bias, osp, ke, live,
+                              out_f32=out_f32)
     out_f32 = out_f32 or x.dtype == F32
     y = torch.empty((N, osp[0], osp[1], osp[2], Cout), device=x.device, dtype=F32 if out_f32 else BF16)
     check(_lib.typed("t2v_gconv_fprop", x)(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), 1 if out_f32 else 0,
@@ -463,7 +611,7 @@ def gconv_fprop(x, w, bias, k, s, p, out_f32=False):
     return y
 
 
-def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
+def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False, cin_real=None):
     """Data gradient of gconv_fprop == forward of a transposed convolution: dy (N,Do,Ho,Wo,Cout),
     w (Cout,taps,Cin) -> dx (N,Di,Hi,Wi,Cin); in_sp = (Di,Hi,Wi); bias fp32 (Cin,) or None."""
     require_cuda(dy, w, bias)
@@ -473,6 +621,14 @@ def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
     assert dy.dtype == w.dtype and w.shape[0] == Cout
     g, osp = _ggeom(N, tuple(in_sp), Cin, Cout, k, s, p)
     assert tuple(osp) == tuple(dy.shape[1:4]), (osp, dy.shape)
+    modes = _s2d_route(dy, k, s, p, tuple(in_sp))
+    if modes is not None:                       # the same GEMM with the transposed pack, then the inverse block permute
+        ke, live = _s2d_engine_args(modes, dgrad=True)
+        creal = Cin if cin_real is None else cin_real
+        weT = s2d_embed_weight(w, modes, creal, transposed=True)
+        be = None if bias is None else s2d_tile_bias(bias, creal, _s2d_phases(modes), weT.shape[0])
+        dxs = conv_fprop_win(dy, weT, be, s2d_block_extents(tuple(in_sp), modes), ke, live, out_f32=out_f32)
+        return d2s_shift(dxs, modes, tuple(in_sp), Cin, creal)
     out_f32 = out_f32 or dy.dtype == F32
     dx = torch.empty((N, in_sp[0], in_sp[1], in_sp[2], Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
     check(_lib.typed("t2v_gconv_dgrad", dy)(ctypes.byref(g), ptr(dy), ptr(w), ptr(bias), ptr(dx), 1 if out_f32 else 0,
@@ -480,7 +636,7 @@ def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False):
     return dx
 
 
-def gconv_wgrad(dy, x, k, s, p):
+def gconv_wgrad(dy, x, k, s, p, cin_real=None):
     """dw (Cout,taps,Cin) fp32 = sum_pos dy[pos,co] * x[in(pos,tap),ci]."""
     require_cuda(dy, x)
     N, Di, Hi, Wi, Cin = x.shape
@@ -489,6 +645,11 @@ def gconv_wgrad(dy, x, k, s, p):
     assert dy.dtype == x.dtype
     g, osp = _ggeom(N, (Di, Hi, Wi), Cin, Cout, k, s, p)
     assert tuple(osp) == tuple(dy.shape[1:4]), (osp, dy.shape)
+    modes = _s2d_route(x, k, s, p, (Di, Hi, Wi))
+    if modes is not None:
+        ke, live = _s2d_engine_args(modes)
+        dwe = conv_wgrad_win(dy, s2d_shift(x, modes, cin_real), ke, live)
+        return s2d_extract_wgrad(dwe, modes, Cin, cin_real)
     dw = torch.empty((Cout, k[0] * k[1] * k[2], Cin), device=x.device, dtype=F32)
     check(_lib.typed("t2v_gconv_wgrad", dy)(ctypes.byref(g), ptr(dy), ptr(x), ptr(dw), 0, stream()), "t2v_gconv_wgrad")
     return dw

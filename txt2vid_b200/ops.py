@@ -541,7 +541,7 @@ class GConvF(Function):
         Cout, Cin = weight.shape[0], weight.shape[1]
         CinP, CoutP = x.shape[-1], round16(Cout)
         wp = PACKS.get(weight, "gconv", CoutP, CinP)
-        y = K.gconv_fprop(x, wp, _pad_bias(bias, CoutP), k, s, p, out_f32)
+        y = K.gconv_fprop(x, wp, _pad_bias(bias, CoutP), k, s, p, out_f32, cin_real=Cin)
         ctx.cfg = (k, s, p, bias is not None)
         ctx.save_for_backward(x, weight)
         return y
@@ -558,9 +558,9 @@ class GConvF(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wp = PACKS.get(weight, "gconv", dy.shape[-1], x.shape[-1])
-            dx = K.gconv_dgrad(dy, wp, None, tuple(x.shape[1:4]), k, s, p)
+            dx = K.gconv_dgrad(dy, wp, None, tuple(x.shape[1:4]), k, s, p, cin_real=Cin)
         if ctx.needs_input_grad[1]:
-            dw3 = K.unpack_wgrad(K.gconv_wgrad(dy, x, k, s, p), Cout, Cin)
+            dw3 = K.unpack_wgrad(K.gconv_wgrad(dy, x, k, s, p, cin_real=Cin), Cout, Cin)
             dw = grad_like_weight(dw3, weight)
         if has_bias and ctx.needs_input_grad[2]:
             db = K.sum_rows(dy)[:Cout]
@@ -578,7 +578,7 @@ class GConvTF(Function):
         CinP, CoutP = x.shape[-1], round16(Cout_t)
         wp = PACKS.get(weight, "gconv", CinP, CoutP)                       # [Cin_t p][taps][Cout_t p]
         out_sp = tuple((i - 1) * ss - 2 * pp + kk for i, ss, pp, kk in zip(x.shape[1:4], s, p, k))
-        y = K.gconv_dgrad(x, wp, _pad_bias(bias, CoutP), out_sp, k, s, p, out_f32)
+        y = K.gconv_dgrad(x, wp, _pad_bias(bias, CoutP), out_sp, k, s, p, out_f32, cin_real=Cout_t)
         ctx.cfg = (k, s, p, bias is not None)
         ctx.save_for_backward(x, weight)
         return y
@@ -595,9 +595,9 @@ class GConvTF(Function):
         dx = dw = db = None
         if ctx.needs_input_grad[0]:
             wp = PACKS.get(weight, "gconv", x.shape[-1], dy.shape[-1])
-            dx = K.gconv_fprop(dy, wp, None, k, s, p)
+            dx = K.gconv_fprop(dy, wp, None, k, s, p, cin_real=Cout_t)
         if ctx.needs_input_grad[1]:
-            dw3 = K.unpack_wgrad(K.gconv_wgrad(x, dy, k, s, p), Cin_t, Cout_t)
+            dw3 = K.unpack_wgrad(K.gconv_wgrad(x, dy, k, s, p, cin_real=Cout_t), Cin_t, Cout_t)
             dw = grad_like_weight(dw3, weight)
         if has_bias and ctx.needs_input_grad[2]:
             db = K.sum_rows(dy)[:Cout_t]
