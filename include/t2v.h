@@ -175,6 +175,9 @@ int t2v_s2d_embed_weight(const void* w, void* we, int32_t Co, int32_t Ci, int32_
 /* dwe fp32 [Co][3^s][Cp] (t2v_conv_wgrad_win on the block tensor) -> dw fp32 [Co][k taps][Ci]                     */
 int t2v_s2d_extract_wgrad(const float* dwe, float* dw, int32_t Co, int32_t Ci, int32_t creal, int32_t Cp, int32_t md,
                           int32_t mh, int32_t mw, void* stream);
+/* bf16 [Co][taps][Ci] -> bf16 [Ci][taps reversed][Co]: operand of the data gradient / transposed convolution of a
+ * stride-1 layer made from the bf16 forward pack (tgan/gen.py:24 ConvTranspose2d k3 s1 p1, tcwyt/gen.py:14,30)   */
+int t2v_transpose_flip_bf16(const void* w, void* wT, int32_t Co, int32_t taps, int32_t Ci, void* stream);
 /* out fp32 [Cp]: out[ph * creal + c] = bias[c] for ph < phases, zero beyond (bias of a transposed convolution in block form) */
 int t2v_s2d_tile_bias(const float* bias, float* out, int32_t creal, int32_t phases, int32_t Cp, void* stream);
 /* Windowed implicit GEMM on the generic tcgen05 kernels: g = geometry of the OUTPUT positions (fprop) / of dy

@@ -143,6 +143,17 @@ __global__ void s2d_extract_wgrad_kernel(const float* __restrict__ dwe, float* _
   dw[i] = v;
 }
 
+// wT[ci][taps - 1 - t][co] = w[co][t][ci]: the data-gradient / transposed-convolution operand of a stride-1 layer
+__global__ void transpose_flip_kernel(const __nv_bfloat16* __restrict__ w, __nv_bfloat16* __restrict__ wT, int Co,
+                                      int taps, int Ci, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int co = (int)(i % Co);
+  const int t = taps - 1 - (int)((i / Co) % taps);
+  const int ci = (int)(i / ((long long)Co * taps));
+  wT[i] = w[((long long)co * taps + t) * Ci + ci];
+}
+
 __global__ void s2d_tile_bias_kernel(const float* __restrict__ bias, float* __restrict__ out, int creal, int phases,
                                      int Cp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -230,6 +241,15 @@ int t2v_s2d_embed_weight(const void* w, void* we, int32_t Co, int32_t Ci, int32_
       reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(we), p);
   count_launch();
   return check_last("s2d_embed_weight");
+}
+
+int t2v_transpose_flip_bf16(const void* w, void* wT, int32_t Co, int32_t taps, int32_t Ci, void* stream) {
+  if (!w || !wT || Co <= 0 || taps <= 0 || Ci <= 0) return T2V_ERR_ARG;
+  const long long total = (long long)Co * taps * Ci;
+  transpose_flip_kernel<<<blocks_for(total, 256), 256, 0, reinterpret_cast<cudaStream_t>(stream)>>>(
+      reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(wT), Co, taps, Ci, total);
+  count_launch();
+  return check_last("transpose_flip_bf16");
 }
 
 int t2v_s2d_tile_bias(const float* bias, float* out, int32_t creal, int32_t phases, int32_t Cp, void* stream) {

@@ -590,6 +590,38 @@ def _s2d_route(t, k, s, p, in_sp):
     return s2d_modes(k, s, p, in_sp) if (GCONV_TC and t.dtype == BF16) else None
 
 
+def transpose_flip(w, flat=False):
+    """bf16 (Co, taps, Ci) -> bf16 (Ci, taps reversed, Co), or with flat=True the plain matrix transpose
+    (taps * Ci, 1, Co) of the pack read as (Co, taps * Ci); cached on the pack tensor"""
+    require_cuda(w)
+    cache = getattr(w, "_t2v_wT", None)
+    if cache is None:
+        cache = {}
+        w._t2v_wT = cache
+    if flat in cache:
+        return cache[flat]
+    Co, taps, Ci = w.shape
+    if flat:
+        taps, Ci = 1, taps * Ci
+    assert w.dtype == BF16 and w.is_contiguous()
+    wT = torch.empty((Ci, taps, Co), device=w.device, dtype=BF16)
+    check(lib().t2v_transpose_flip_bf16(ptr(w), ptr(wT), Co, taps, Ci, stream()), "t2v_transpose_flip_bf16")
+    cache[flat] = wT
+    return wT
+
+
+def _engine_route(t, k, s, p, in_sp):
+    """'same': every axis kernel 1 / padding 0 or kernel 3 / padding 1 at stride 1 (the engine's own domain);
+    'full': the kernel covers the whole input (padding 0, one output position): a Linear layer over taps * Cin"""
+    if not (GCONV_TC and t.dtype == BF16):
+        return None
+    if all(ss == 1 and (kk, pp) in ((1, 0), (3, 1)) for kk, ss, pp in zip(k, s, p)):
+        return "same"
+    if tuple(k) == tuple(in_sp) and all(pp == 0 for pp in p):
+        return "full"
+    return None
+
+
 def gconv_fprop(x, w, bias, k, s, p, out_f32=False, cin_real=None):
     """Strided convolution: x (N,Di,Hi,Wi,Cin), w (Cout,taps,Cin) (both bf16, or both fp32) -> y (N,Do,Ho,Wo,Cout)."""
     require_cuda(x, w, bias)
@@ -604,6 +636,11 @@ def gconv_fprop(x, w, bias, k, s, p, out_f32=False, cin_real=None):
         ke, live = _s2d_engine_args(modes)
         return conv_fprop_win(s2d_shift(x, modes, cin_real), s2d_embed_weight(w, modes, cin_real), bias, osp, ke, live,
                               out_f32=out_f32)
+    route = _engine_route(x, k, s, p, (Di, Hi, Wi))
+    if route == "same":
+        return conv_fprop(x, w, bias, k=tuple(k), out_f32=out_f32)
+    if route == "full":
+        return conv_fprop(x.view(N, 1, 1, 1, -1), w.view(Cout, 1, -1), bias, k=(1, 1, 1), out_f32=out_f32)
     out_f32 = out_f32 or x.dtype == F32
     y = torch.empty((N, osp[0], osp[1], osp[2], Cout), device=x.device, dtype=F32 if out_f32 else BF16)
     check(_lib.typed("t2v_gconv_fprop", x)(ctypes.byref(g), ptr(x), ptr(w), ptr(bias), ptr(y), 1 if out_f32 else 0,
@@ -629,6 +666,15 @@ def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False, cin_real=None):
         be = None if bias is None else s2d_tile_bias(bias, creal, _s2d_phases(modes), weT.shape[0])
         dxs = conv_fprop_win(dy, weT, be, s2d_block_extents(tuple(in_sp), modes), ke, live, out_f32=out_f32)
         return d2s_shift(dxs, modes, tuple(in_sp), Cin, creal)
+    route = _engine_route(dy, k, s, p, tuple(in_sp))
+    if route == "same":
+        return conv_fprop(dy, transpose_flip(w), bias, k=tuple(k), out_f32=out_f32)
+    if route == "full":
+        taps = w.shape[1]
+        be = None if bias is None else s2d_tile_bias(bias, Cin, taps, taps * Cin)
+        dx = conv_fprop(dy.view(N, 1, 1, 1, Cout), transpose_flip(w, flat=True), be, k=(1, 1, 1),
+                        out_f32=out_f32)
+        return dx.view(N, in_sp[0], in_sp[1], in_sp[2], Cin)
     out_f32 = out_f32 or dy.dtype == F32
     dx = torch.empty((N, in_sp[0], in_sp[1], in_sp[2], Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
     check(_lib.typed("t2v_gconv_dgrad", dy)(ctypes.byref(g), ptr(dy), ptr(w), ptr(bias), ptr(dx), 1 if out_f32 else 0,
@@ -650,6 +696,12 @@ def gconv_wgrad(dy, x, k, s, p, cin_real=None):
         ke, live = _s2d_engine_args(modes)
         dwe = conv_wgrad_win(dy, s2d_shift(x, modes, cin_real), ke, live)
         return s2d_extract_wgrad(dwe, modes, Cin, cin_real)
+    route = _engine_route(x, k, s, p, (Di, Hi, Wi))
+    if route == "same":
+        return conv_wgrad(dy, x, k=tuple(k))
+    if route == "full":
+        taps = k[0] * k[1] * k[2]
+        return conv_wgrad(dy.view(N, 1, 1, 1, Cout), x.view(N, 1, 1, 1, taps * Cin), k=(1, 1, 1)).view(Cout, taps, Cin)
     dw = torch.empty((Cout, k[0] * k[1] * k[2], Cin), device=x.device, dtype=F32)
     check(_lib.typed("t2v_gconv_wgrad", dy)(ctypes.byref(g), ptr(dy), ptr(x), ptr(dw), 0, stream()), "t2v_gconv_wgrad")
     return dw
