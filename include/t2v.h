@@ -153,6 +153,19 @@ int t2v_gconv_dgrad(const t2v_gconv_geom* g, const void* dy, const void* w, cons
 /* dw[Cout][taps][Cin] (+)= sum_pos dy[pos,co] * x[in(pos,tap),ci]  (fp32)                              */
 int t2v_gconv_wgrad(const t2v_gconv_geom* g, const void* dy, const void* x, float* dw, int32_t accumulate,
                     void* stream);
+/* On-device input pipeline.
+ * t2v_moving_digits: frames of data/synthetic/generate.py:18-47: black RGB frames with the oh x ow grey patch
+ *   bank[digit[b]] pasted at pos[b][t] = (x, y) (host-computed, int32 [B][T][2]); out uint8 as stored or (out_f32) fp32
+ *   through ToTensor + Normalize(0.5, 0.5) (data/__init__.py:362-364); layout 0 = (B,T,3,H,W), 1 = (B,3,T,H,W).
+ * t2v_grammar_tokens: int64 tokens [B][8] of "digit {cls} is {a} and {b}." as Vocab.tokenize + collate_fn produce them
+ *   (data/__init__.py:260-355); table int64[23] = {START, "digit", "0".."9", "is", "and", END, 4 x (a, b)}, move =
+ *   horizontal * 2 + forward (generate.py:144-166).
+ * t2v_u8_normalize: dst = (src / 255 - 0.5) / 0.5 with IEEE division (the values of the reference's CPU transform). */
+int t2v_moving_digits(const void* bank, const int32_t* digit, const int32_t* pos, void* out, int32_t B, int32_t T,
+                      int32_t H, int32_t W, int32_t oh, int32_t ow, int32_t out_f32, int32_t layout, void* stream);
+int t2v_grammar_tokens(const int32_t* cls, const int32_t* move, const int64_t* table, int64_t* tokens, int32_t B,
+                       void* stream);
+int t2v_u8_normalize(const void* src, float* dst, int64_t n, void* stream);
 /* Stride-2 convolutions / transposed convolutions of the TGAN and TCWYT families on the tcgen05 engine
  * (models/tcwyt/video_discrim.py:12-25, tcwyt/frame_discrim.py:9-21, tcwyt/gen.py:18-26, tgan/gen.py:20-23,
  * tgan/temporal_gen.py:112-115).  A kernel-4 / stride-2 / padding-1 axis reads inputs 2o-1 .. 2o+2 for output o: with

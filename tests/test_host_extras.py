@@ -183,6 +183,24 @@ def _caption_pretraining_body():
         prod.load_state_dict(ref.state_dict(), strict=True)
 
 
+def test_caption_pretraining_golden_fixture_through_the_executable_spec(monkeypatch):
+    """The committed fixture of oracle/make_golden_caption_pretrain.py (recorded from the live reference) against the
+    product's host logic + autograd formulas on the CPU spec kernels (fp32): the same check the GPU test
+    test_round2_gpu.py::test_caption_pretraining_step_vs_reference_golden runs through the real kernels."""
+    import cpu_kernels
+    from txt2vid_b200 import ops
+    monkeypatch.setattr(ops, "K", cpu_kernels)
+    cpu_kernels.set_store_dtype(torch.float32)
+    ops.PACKS.clear()
+    try:
+        from test_round2_gpu import run_caption_pretrain_against_golden
+        rep = run_caption_pretrain_against_golden("cpu", 1e-5, 1e-4, 1e-3)
+        assert rep["teacher_force"]["loss"] < 1e-5
+    finally:
+        cpu_kernels.set_store_dtype(torch.bfloat16)
+        ops.PACKS.clear()
+
+
 @pytest.fixture()
 def emulated_fp32(monkeypatch):
     import cpu_kernels

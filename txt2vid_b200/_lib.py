@@ -80,6 +80,9 @@ SIGNATURES = {
     "t2v_gconv_fprop": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_dgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, _P, c_i32, _P],
     "t2v_gconv_wgrad": [ctypes.POINTER(GconvGeom), _P, _P, _P, c_i32, _P],
+    "t2v_moving_digits": [_P, _P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_grammar_tokens": [_P, _P, _P, _P, c_i32, _P],
+    "t2v_u8_normalize": [_P, _P, c_i64, _P],
     "t2v_s2d_shift": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_d2s_shift": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_s2d_embed_weight": [_P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],

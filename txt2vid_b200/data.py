@@ -111,6 +111,8 @@ class data_prefetcher(object):
     def _to_dev(self, t, key):
         if not isinstance(t, torch.Tensor) or self.device.type != 'cuda':
             return t
+        if t.is_cuda:                            # an on-device generator (MovingDigits) hands out resident batches
+            return t
         if not t.is_pinned():
             t = t.pin_memory()
         bufs = self._slots[self._slot]
@@ -140,11 +142,8 @@ class data_prefetcher(object):
         out = self._norm[self._slot]
         if out is None or out.shape != frames_u8.shape:
             out = self._norm[self._slot] = torch.empty(frames_u8.shape, dtype=torch.float32, device=self.device)
-        if getattr(self, "_c255", None) is None:
-            # a TENSOR divisor: ATen's CUDA kernel multiplies by the reciprocal of a scalar divisor (1 ulp off)
-            self._c255 = torch.full((1,), 255.0, device=self.device)
-        torch.div(frames_u8, self._c255, out=out)
-        return out.sub_(0.5).div_(0.5)
+        from . import kernels as K
+        return K.u8_normalize(frames_u8, out)             # t2v_u8_normalize: IEEE division, bit-exact (tested)
 
     def _preload(self):
         try:
@@ -236,3 +235,120 @@ class SyntheticVideoCaptions(object):
     def __iter__(self):
         for i in range(self.n):
             yield self.batch(i)
+
+
+class MovingDigits(object):
+    """On-device synthetic moving-MNIST batches with their captions: the generator of
+    txt2vid/data/synthetic/generate.py:59-182 re-designed so that only a few integers per clip cross PCIe.
+
+    Host: the per-clip random decisions in the REFERENCE'S RNG ORDER (numpy for class / digit / coordinates, `random`
+    for animation length / axis / direction, generate.py:82-166) and the per-frame patch positions of generate_frames
+    (:18-47, float64 arithmetic truncated to int32).  Device: t2v_moving_digits pastes the patches from a resident digit
+    bank into the clips (bit-exact frames, stored uint8 or already ToTensor + Normalize'd fp32) and t2v_grammar_tokens
+    writes the token rows Vocab.tokenize + collate_fn would produce for the sentences.  A batch is B * (T + 1) * 2 + 2 B
+    int32 over PCIe instead of B * T * 3 * H * W floats.  Iterating yields (clips (B,T,3,H,W), tokens (B,8), lengths):
+    the loader contract of data/__init__.py:326-355, usable as `dataset` of trainer.train() (data_prefetcher passes
+    resident tensors through).
+
+    bank: {class: uint8 array (n_c, oh, ow)} (MNIST resized to 28 x 28 in the reference, generate.py:184-207)."""
+
+    MOVES = (("bottom", "top"), ("top", "bottom"), ("right", "left"), ("left", "right"))   # horizontal * 2 + forward
+
+    def __init__(self, batch_size, num_batches, bank, vocab=None, frames=16, size=64, device="cuda", as_uint8=False,
+                 seed=None):
+        import numpy as np
+        self.B, self.n, self.T, self.W, self.H = batch_size, num_batches, frames, size, size
+        self.device, self.as_uint8 = torch.device(device), as_uint8
+        self.classes = sorted(bank.keys())
+        self.counts = [len(bank[c]) for c in self.classes]
+        self.offsets = [0]
+        for n in self.counts:
+            self.offsets.append(self.offsets[-1] + n)
+        flat = np.concatenate([np.asarray(bank[c], dtype=np.uint8) for c in self.classes], axis=0)
+        self.oh, self.ow = int(flat.shape[1]), int(flat.shape[2])
+        self.bank = torch.from_numpy(flat).contiguous().to(self.device)
+        self.vocab = vocab if vocab is not None else build_vocab(self.all_sentences())
+        v = self.vocab
+        table = [v(v.START), v("digit")] + [v(str(c)) for c in range(10)] + [v("is"), v("and"), v(v.END)]
+        for a, b in self.MOVES:
+            table += [v(a), v(b)]
+        self.table = torch.tensor(table, dtype=torch.int64, device=self.device)
+        if seed is not None:
+            import random
+            random.seed(seed)
+            np.random.seed(seed)
+
+    @classmethod
+    def all_sentences(cls):
+        return ["digit %d is %s and %s." % (c, a, b) for c in range(10) for a, b in cls.MOVES]
+
+    def __len__(self):
+        return self.n
+
+    def draw(self):
+        """One clip's decisions, consuming numpy / random exactly as generate_examples does per example."""
+        import random
+        import numpy as np
+        W, H, T = self.W, self.H, self.T
+        ci = int(np.random.randint(0, len(self.classes)))
+        di = int(np.random.randint(0, self.counts[ci]))
+        anim = random.randint(int(0.1 * T), T)
+        horizontal = random.randint(0, 1)
+        forward = random.randint(0, 1)
+        if horizontal:
+            y = int(np.random.randint(0, H))
+            x1 = int(np.random.randint(0, int(0.1 * W)))
+            x2 = int(np.random.randint(int(0.9 * W), W))
+            a, b = [x1, y], [x2, y]
+        else:
+            x = int(np.random.randint(0, W))
+            y1 = int(np.random.randint(0, int(0.1 * H)))
+            y2 = int(np.random.randint(int(0.9 * H), H))
+            a, b = [x, y1], [x, y2]
+        if not forward:
+            a, b = b, a
+        lim = (W - self.ow, H - self.oh)
+        a = [min(max(a[k], 0), lim[k]) for k in (0, 1)]
+        b = [min(max(b[k], 0), lim[k]) for k in (0, 1)]
+        return {"cls": self.classes[ci], "digit": self.offsets[ci] + di, "anim": anim, "move": horizontal * 2 + forward,
+                "a": a, "b": b}
+
+    @staticmethod
+    def frame_positions(a, b, frames, anim, bounce=True):
+        """Top-left corner of the patch in every frame: the walk of generate_frames (generate.py:24-43): the fraction
+        (i - start + 1) / (anim + 1) clipped to [0, 1] moves the patch from `a` to `b`; on frame i == end the window
+        advances by `anim` and the end points swap (the bounce); coordinates truncate toward zero like
+        np.array(..., dtype=np.int32)."""
+        import numpy as np
+        src, dst = np.array(a), np.array(b)
+        start, end = 0, anim
+        out = []
+        for i in range(frames):
+            frac = float(np.clip((i - start + 1) / (end - start + 1), 0, 1))
+            p = np.array(src + (dst - src) * frac, dtype=np.int32)
+            if bounce and i == end:
+                start, end = start + anim, end + anim
+                src, dst = dst, src
+            out.append([int(p[0]), int(p[1])])
+        return out
+
+    def sentence(self, d):
+        a, b = self.MOVES[d["move"]]
+        return "digit %d is %s and %s." % (d["cls"], a, b)
+
+    def batch(self, draws=None):
+        draws = draws if draws is not None else [self.draw() for _ in range(self.B)]
+        B = len(draws)
+        pos = torch.tensor([self.frame_positions(d["a"], d["b"], self.T, d["anim"]) for d in draws], dtype=torch.int32)
+        small = torch.tensor([[d["digit"], d["cls"], d["move"]] for d in draws], dtype=torch.int32)
+        if self.device.type == "cuda":
+            pos, small = pos.pin_memory().to(self.device, non_blocking=True), small.pin_memory().to(self.device, non_blocking=True)
+        from . import kernels as K
+        small = small.t().contiguous()
+        clips = K.moving_digits(self.bank, small[0], pos, self.T, self.H, self.W, out_f32=not self.as_uint8, layout=0)
+        tokens = K.grammar_tokens(small[1], small[2], self.table)
+        return clips, tokens, [8] * B
+
+    def __iter__(self):
+        for _ in range(self.n):
+            yield self.batch()

@@ -1375,3 +1375,39 @@ def embedding_bwd(tokens, dout, V):
     check(_lib.typed("t2v_embedding_bwd", dout)(ptr(tokens), ptr(dout), ptr(dw), tokens.numel(), E, V, stream()),
           "t2v_embedding_bwd")
     return dw
+
+
+# ------------------------------------------------------------------------------------- on-device input pipeline (8 f1)
+def u8_normalize(src, out=None):
+    """uint8 frames -> fp32 (x / 255 - 0.5) / 0.5: transforms.ToTensor() + Normalize(0.5, 0.5), data/__init__.py:362-364"""
+    require_cuda(src)
+    assert src.dtype == torch.uint8 and src.is_contiguous()
+    if out is None:
+        out = torch.empty(src.shape, device=src.device, dtype=F32)
+    assert out.dtype == F32 and out.is_contiguous() and out.numel() == src.numel()
+    check(lib().t2v_u8_normalize(ptr(src), ptr(out), src.numel(), stream()), "t2v_u8_normalize")
+    return out
+
+
+def moving_digits(bank, digit, pos, T, H, W, out_f32=False, layout=0):
+    """bank uint8 (n, oh, ow), digit int32 (B,), pos int32 (B, T, 2) = (x, y) -> clips (B,T,3,H,W) [layout 0] or
+    (B,3,T,H,W) [layout 1], uint8 as stored or fp32 normalised (data/synthetic/generate.py:18-47)"""
+    require_cuda(bank, digit, pos)
+    B = digit.numel()
+    assert bank.dtype == torch.uint8 and bank.is_contiguous() and bank.dim() == 3
+    assert digit.dtype == torch.int32 and pos.dtype == torch.int32 and tuple(pos.shape) == (B, T, 2) and pos.is_contiguous()
+    shape = (B, T, 3, H, W) if layout == 0 else (B, 3, T, H, W)
+    out = torch.empty(shape, device=bank.device, dtype=F32 if out_f32 else torch.uint8)
+    check(lib().t2v_moving_digits(ptr(bank), ptr(digit), ptr(pos), ptr(out), B, T, H, W, bank.shape[1], bank.shape[2],
+                                  1 if out_f32 else 0, layout, stream()), "t2v_moving_digits")
+    return out
+
+
+def grammar_tokens(cls, move, table):
+    """cls, move int32 (B,), table int64 (23,) -> tokens int64 (B, 8) of "digit {cls} is {a} and {b}." """
+    require_cuda(cls, move, table)
+    B = cls.numel()
+    assert cls.dtype == torch.int32 and move.dtype == torch.int32 and table.dtype == torch.int64 and table.numel() == 23
+    tokens = torch.empty((B, 8), device=cls.device, dtype=torch.int64)
+    check(lib().t2v_grammar_tokens(ptr(cls), ptr(move), ptr(table), ptr(tokens), B, stream()), "t2v_grammar_tokens")
+    return tokens

@@ -1,8 +1,9 @@
 """Caption auto-encoder pre-training: mirror of txt2vid/train/txt.py -- the sentence dataset and its
 collate function (train/txt.py:21-52), one optimisation step (train/txt.py:166-181: encode -> teacher-forced or greedy
 decode from the encoder's final state -> cross entropy against the padded targets) and the summed-loss evaluation
-(train/txt.py:54-78).  Host logic plus the Seq2Seq modules of txt2vid_b200/text.py; the recurrence runs through
-nn.LSTM (cuDNN) like the caption encoder of the GAN path."""
+(train/txt.py:54-78).  Host logic plus the Seq2Seq modules of txt2vid_b200/text.py: embedding gather, engine GEMMs and the
+length-masked recurrence kernels t2v_lstm_seq_fwd / _bwd, forward and backward (no cuDNN); parity against a fixture
+recorded from the live reference: tests/test_round2_gpu.py::test_caption_pretraining_step_vs_reference_golden."""
 import random
 
 import torch
