@@ -355,7 +355,8 @@ def run_b200(args):
     t_e2e = timed(step_e2e, args.steps, begin=e2e_begin, end=e2e_end)
 
     # the same loop fed with the frames as stored (uint8; ToTensor + Normalize run on the device inside
-    # data_prefetcher): a quarter of the bytes over PCIe.  Reported next to `e2e`, which stays on fp32 host batches.
+    # data_prefetcher): a quarter of the bytes over PCIe.  This is the line's `e2e`; the fp32-host-batch loop above is
+    # reported next to it as `e2e_fp32_host`.
     data8 = SyntheticVideoCaptions(b, 2, vocab_size=V, seed=4321 + 1000 * rank, frames=frames, size=res, as_uint8=True)
     host8 = [data8.batch(i) for i in range(2)]
     host8 = [(x.contiguous().pin_memory(), t.pin_memory(), l) for x, t, l in host8]
@@ -424,18 +425,40 @@ def run_b200(args):
     tk = kern[names[top].split(" ")[0]]
     conv_ms = sum(prof[3 * i] for i in range(NK)) / prof_steps
     conv_fl = sum(prof[3 * i + 1] for i in range(NK)) / prof_steps
+    # measured DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the
+    # committed ncu capture of one iteration at the same batch (profiles/r02_traffic_b2048.json, scripts/gpu_r02p.sh)
+    traffic, traffic_note = None, "no ncu capture at this batch / resolution"
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic_b2048.json")
+    if b == 2048 and res == 64 and os.path.exists(tpath):
+        with open(tpath) as f:
+            tj = json.load(f)
+        fam = {"igemm_fprop_kernel": "igemm_fprop", "igemm_wgrad_kernel": "igemm_wgrad", "halo_fprop_kernel": "halo_fprop",
+               "halo_wgrad_kernel": "halo_wgrad", "stem_fprop_kernel": "stem_fprop", "stem_wgrad_kernel": "stem_wgrad"}
+        key = fam[names[top].split(" ")[0]]
+        sel = [v for k, v in tj.items() if key in k]
+        nl = sum(v["launches"] for v in sel)
+        if nl > 0:
+            traffic = sum(v["dram_bytes"] for v in sel) / nl
+            fl_per_launch = prof[3 * top + 1] / max(1.0, prof[3 * top + 2])
+            traffic_note = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of every %s* launch of one iteration at "
+                            "b = 2048 (%d launches, %.1f GB in total) / launches; %.0f useful FLOP per DRAM byte -- far "
+                            "above the machine balance (~214 FLOP/B): tensor-bound, not HBM-bound"
+                            % (key, nl, sum(v["dram_bytes"] for v in sel) / 1e9, fl_per_launch / traffic))
     roof = {"bound": "tensor", "kernel": names[top], "achieved": tk["achieved"], "peak": pk["bf16_tflops_sustained"],
-            "unit": "TFLOP/s", "traffic": None,
-            "traffic_note": "per-launch DRAM bytes of these kernels on the hot shapes are in profiles/ "
-                            "(ncu --set full: dram__bytes_read.sum + dram__bytes_write.sum); the step-level kernel mixes "
-                            "~60 shapes, so no single per-launch figure applies",
+            "unit": "TFLOP/s", "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), %s" % pk["source"],
             "launches_per_step": tk["launches_per_step"], "ms_per_step_in_kernel": tk["ms_per_step_in_kernel"],
             "share_of_step": tk["share_of_step"],
-            "flops_counted": "useful MACs x2 (live taps only, padded channels included)",
+            "flops_counted": "useful MACs x2 per launch (live taps only, zero channel padding excluded), summed over "
+                             "the step's launches / summed CUDA-event durations",
             "kernels": kern,
             "conv_engine_all": {"achieved": conv_fl / (conv_ms * 1e-3) / 1e12 if conv_ms > 0 else None,
+                                "frac": conv_fl / (conv_ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"] if conv_ms > 0 else None,
                                 "ms_per_step": conv_ms, "share_of_step": conv_ms / step_ms_prof if step_ms_prof else None},
+            # whole step on the FLOPs the kernels actually issue (dead taps, the even-plane stem convolution and the
+            # skipped D weight gradients of the G step are not counted): the headline utilisation
+            "step_issued_tflops_per_gpu": conv_fl / (t_res / args.steps) / 1e12,
+            "step_issued_frac_of_sustained_peak": conv_fl / (t_res / args.steps) / 1e12 / pk["bf16_tflops_sustained"],
             "step_nominal_tflops_per_gpu": value / world * gflop_nominal / 1e3,
             "step_nominal_frac_of_sustained_peak": value / world * gflop_nominal / 1e3 / pk["bf16_tflops_sustained"]}
     roof["frac"] = roof["achieved"] / roof["peak"] if roof["achieved"] else None
@@ -461,12 +484,17 @@ def run_b200(args):
                        "parallelism": "dp%d" % world, "launch": launch_mode,
                        "l2": "per-step working set (%.1f GB peak allocated) >> 126 MB L2; "
                        "%d distinct resident batches cycled" % (mem_gb, nb)},
-            "e2e": {"value": e2e, "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
-                    "ms_per_step": t_e2e / args.steps * 1e3, "h2d_alone_ms": h2d_alone_ms,
-                    "h2d_alone_gbs": int(h2d) / h2d_alone_ms / 1e6},
-            "e2e_uint8": {"value": videos / t_e2e8, "unit": "videos/s", "h2d_bytes_per_step": int(h2d8),
-                          "d2h_bytes_per_step": 8, "ms_per_step": t_e2e8 / args.steps * 1e3,
-                          "note": "host batches hold the frames as stored (uint8); ToTensor + Normalize on the device"},
+            # headline end-to-end leg: pinned HOST batches hold the frames as stored (uint8), fed through the public
+            # loader API (data_prefetcher), ToTensor + Normalize on the device (t2v_u8_normalize, bit-exact), every
+            # step's H2D copy and loss read-back inside the timed region
+            "e2e": {"value": videos / t_e2e8, "unit": "videos/s", "h2d_bytes_per_step": int(h2d8),
+                    "d2h_bytes_per_step": 8, "ms_per_step": t_e2e8 / args.steps * 1e3,
+                    "host_batch": "uint8 frames as stored + int64 tokens (pinned); normalised on the device"},
+            # same loop with fp32 host batches (the reference loader's format: ToTensor + Normalize on CPU workers,
+            # data/__init__.py:362-364): four times the PCIe bytes
+            "e2e_fp32_host": {"value": e2e, "unit": "videos/s", "h2d_bytes_per_step": int(h2d), "d2h_bytes_per_step": 8,
+                              "ms_per_step": t_e2e / args.steps * 1e3, "h2d_alone_ms": h2d_alone_ms,
+                              "h2d_alone_gbs": int(h2d) / h2d_alone_ms / 1e6},
             "resident_again_ms_per_step": t_res2 / args.steps * 1e3,
             "gpu_launches": launches, "clocks": clk, "roofline": roof, "cpu_baseline": cpu,
             "library_baseline": libb, "peak_mem_gb": mem_gb}
