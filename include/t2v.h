@@ -191,6 +191,11 @@ int t2v_s2d_extract_wgrad(const float* dwe, float* dw, int32_t Co, int32_t Ci, i
 /* bf16 [Co][taps][Ci] -> bf16 [Ci][taps reversed][Co]: operand of the data gradient / transposed convolution of a
  * stride-1 layer made from the bf16 forward pack (tgan/gen.py:24 ConvTranspose2d k3 s1 p1, tcwyt/gen.py:14,30)   */
 int t2v_transpose_flip_bf16(const void* w, void* wT, int32_t Co, int32_t taps, int32_t Ci, void* stream);
+/* rows [N][kd*kh*kw*C] <- x[:, :kd, :kh, :kw, :] of x (N,D,H,W,C) (scatter = 0), or x <- zeros with the window
+ * written back from rows (scatter = 1): the single-output-position head convolutions of the TCWYT / TGAN critics
+ * (tcwyt/frame_discrim.py:55, motion_discrim.py:19, video_discrim.py:46) become Linear layers on the engine      */
+int t2v_window_rows(void* x, void* rows, int64_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t kd, int32_t kh,
+                    int32_t kw, int32_t elem_bytes, int32_t scatter, void* stream);
 /* out fp32 [Cp]: out[ph * creal + c] = bias[c] for ph < phases, zero beyond (bias of a transposed convolution in block form) */
 int t2v_s2d_tile_bias(const float* bias, float* out, int32_t creal, int32_t phases, int32_t Cp, void* stream);
 /* Windowed implicit GEMM on the generic tcgen05 kernels: g = geometry of the OUTPUT positions (fprop) / of dy

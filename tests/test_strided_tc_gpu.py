@@ -80,6 +80,9 @@ CASES = [
     (6, (1, 64, 64), 16, 3, 32, (1, 3, 3), (1, 1, 1), (0, 1, 1)),        # = ConvTranspose2d(32 -> 3, 3, 1, 1), tgan/gen.py:24
     (2, (16, 48, 48), 16, 3, 64, (1, 1, 1), (1, 1, 1), (0, 0, 0)),       # = ConvTranspose3d(64 -> 3, 1), tcwyt/gen.py:30
     (4, (2, 6, 6), 512, 512, 368, (2, 6, 6), (1, 1, 1), (0, 0, 0)),      # = ConvTranspose3d(356 -> 512, (2,6,6)), tcwyt/gen.py:14
+    # single-output-position heads (Cout = 1, padded to 16): the corner window gathered, then a Linear on the engine
+    (9, (1, 3, 3), 512, 512, 16, (1, 2, 2), (1, 2, 2), (0, 0, 0)),       # Conv2d(512, 1, 2, 2, 0) on 3 x 3, frame_discrim.py:55
+    (9, (1, 4, 4), 512, 512, 16, (1, 3, 3), (2, 2, 2), (0, 0, 0)),       # Conv3d(512, 1, (1,3,3), 2, 0) on (1,4,4), video_discrim.py:46
 ]
 
 

@@ -88,6 +88,7 @@ SIGNATURES = {
     "t2v_s2d_embed_weight": [_P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_s2d_extract_wgrad": [_P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_transpose_flip_bf16": [_P, _P, c_i32, c_i32, c_i32, _P],
+    "t2v_window_rows": [_P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_s2d_tile_bias": [_P, _P, c_i32, c_i32, c_i32, _P],
     "t2v_conv_fprop_win": [ctypes.POINTER(ConvGeom), _I32P, _P, _P, _P, _P, c_u32, _P],
     "t2v_conv_wgrad_win": [ctypes.POINTER(ConvGeom), _I32P, _P, _P, _P, c_int, _P],

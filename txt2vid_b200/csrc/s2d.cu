@@ -154,6 +154,24 @@ __global__ void transpose_flip_kernel(const __nv_bfloat16* __restrict__ w, __nv_
   wT[i] = w[((long long)co * taps + t) * Ci + ci];
 }
 
+// corner window x[:, :kd, :kh, :kw, :] <-> contiguous rows [N][kd*kh*kw*C] (units of 16 bytes); scatter = 1 writes the
+// rows back into x (the rest of x was zeroed by the caller): a convolution whose single output position reads that
+// window is a Linear layer over the gathered rows (tcwyt/frame_discrim.py:55, motion_discrim.py:19, video_discrim.py:46)
+__global__ void window_rows_kernel(uint4* __restrict__ x, uint4* __restrict__ rows, int D, int H, int W, int C16, int kd,
+                                   int kh, int kw, int scatter, long long total) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= total) return;
+  const int c = (int)(i % C16);
+  long long t = i / C16;
+  const int a_w = (int)(t % kw); t /= kw;
+  const int a_h = (int)(t % kh); t /= kh;
+  const int a_d = (int)(t % kd); t /= kd;
+  const long long n = t;
+  const long long xi = ((((long long)n * D + a_d) * H + a_h) * W + a_w) * C16 + c;
+  if (scatter) x[xi] = rows[i];
+  else rows[i] = x[xi];
+}
+
 __global__ void s2d_tile_bias_kernel(const float* __restrict__ bias, float* __restrict__ out, int creal, int phases,
                                      int Cp) {
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -250,6 +268,21 @@ int t2v_transpose_flip_bf16(const void* w, void* wT, int32_t Co, int32_t taps, i
       reinterpret_cast<const __nv_bfloat16*>(w), reinterpret_cast<__nv_bfloat16*>(wT), Co, taps, Ci, total);
   count_launch();
   return check_last("transpose_flip_bf16");
+}
+
+int t2v_window_rows(void* x, void* rows, int64_t N, int32_t D, int32_t H, int32_t W, int32_t C, int32_t kd, int32_t kh,
+                    int32_t kw, int32_t elem_bytes, int32_t scatter, void* stream) {
+  if (!x || !rows || N <= 0 || kd <= 0 || kh <= 0 || kw <= 0 || kd > D || kh > H || kw > W ||
+      (elem_bytes != 2 && elem_bytes != 4) || (C * elem_bytes) % 16)
+    return T2V_ERR_ARG;
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  const int C16 = C * elem_bytes / 16;
+  if (scatter) cudaMemsetAsync(x, 0, (size_t)N * D * H * W * C * elem_bytes, s);
+  const long long total = (long long)N * kd * kh * kw * C16;
+  window_rows_kernel<<<blocks_for(total, 256), 256, 0, s>>>(reinterpret_cast<uint4*>(x), reinterpret_cast<uint4*>(rows),
+                                                            D, H, W, C16, kd, kh, kw, scatter, total);
+  count_launch();
+  return check_last("window_rows");
 }
 
 int t2v_s2d_tile_bias(const float* bias, float* out, int32_t creal, int32_t phases, int32_t Cp, void* stream) {

@@ -610,15 +610,40 @@ def transpose_flip(w, flat=False):
     return wT
 
 
+def window_rows(x, k):
+    """x (N,D,H,W,C) -> (N, kd*kh*kw*C): the corner window x[:, :kd, :kh, :kw]"""
+    require_cuda(x)
+    N, D, H, W, C = x.shape
+    assert x.is_contiguous()
+    rows = torch.empty((N, k[0] * k[1] * k[2] * C), device=x.device, dtype=x.dtype)
+    check(lib().t2v_window_rows(ptr(x), ptr(rows), N, D, H, W, C, k[0], k[1], k[2], x.element_size(), 0, stream()),
+          "t2v_window_rows")
+    return rows
+
+
+def window_rows_scatter(rows, sp, C, k):
+    """adjoint of window_rows: zeros (N,*sp,C) with the corner window filled from rows"""
+    require_cuda(rows)
+    N = rows.shape[0]
+    assert rows.is_contiguous() and rows.shape[1] == k[0] * k[1] * k[2] * C
+    x = torch.empty((N, sp[0], sp[1], sp[2], C), device=rows.device, dtype=rows.dtype)
+    check(lib().t2v_window_rows(ptr(x), ptr(rows), N, sp[0], sp[1], sp[2], C, k[0], k[1], k[2], rows.element_size(), 1,
+                                stream()), "t2v_window_rows")
+    return x
+
+
 def _engine_route(t, k, s, p, in_sp):
     """'same': every axis kernel 1 / padding 0 or kernel 3 / padding 1 at stride 1 (the engine's own domain);
-    'full': the kernel covers the whole input (padding 0, one output position): a Linear layer over taps * Cin"""
+    'full': the kernel covers the whole input (padding 0, one output position): a Linear layer over taps * Cin;
+    'window': one output position whose kernel covers a corner window of the input: gather the window, then 'full'"""
     if not (GCONV_TC and t.dtype == BF16):
         return None
     if all(ss == 1 and (kk, pp) in ((1, 0), (3, 1)) for kk, ss, pp in zip(k, s, p)):
         return "same"
     if tuple(k) == tuple(in_sp) and all(pp == 0 for pp in p):
         return "full"
+    if all(pp == 0 for pp in p) and all((i - kk) // ss == 0 for i, kk, ss in zip(in_sp, k, s)):
+        return "window"                          # one output position reading the corner window of the input
     return None
 
 
@@ -639,6 +664,8 @@ def gconv_fprop(x, w, bias, k, s, p, out_f32=False, cin_real=None):
     route = _engine_route(x, k, s, p, (Di, Hi, Wi))
     if route == "same":
         return conv_fprop(x, w, bias, k=tuple(k), out_f32=out_f32)
+    if route == "window":
+        x, route = window_rows(x, k), "full"
     if route == "full":
         return conv_fprop(x.view(N, 1, 1, 1, -1), w.view(Cout, 1, -1), bias, k=(1, 1, 1), out_f32=out_f32)
     out_f32 = out_f32 or x.dtype == F32
@@ -669,11 +696,13 @@ def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False, cin_real=None):
     route = _engine_route(dy, k, s, p, tuple(in_sp))
     if route == "same":
         return conv_fprop(dy, transpose_flip(w), bias, k=tuple(k), out_f32=out_f32)
-    if route == "full":
+    if route in ("full", "window"):
         taps = w.shape[1]
         be = None if bias is None else s2d_tile_bias(bias, Cin, taps, taps * Cin)
         dx = conv_fprop(dy.view(N, 1, 1, 1, Cout), transpose_flip(w, flat=True), be, k=(1, 1, 1),
                         out_f32=out_f32)
+        if route == "window":
+            return window_rows_scatter(dx.view(N, taps * Cin), tuple(in_sp), Cin, k)
         return dx.view(N, in_sp[0], in_sp[1], in_sp[2], Cin)
     out_f32 = out_f32 or dy.dtype == F32
     dx = torch.empty((N, in_sp[0], in_sp[1], in_sp[2], Cin), device=dy.device, dtype=F32 if out_f32 else BF16)
@@ -699,6 +728,8 @@ def gconv_wgrad(dy, x, k, s, p, cin_real=None):
     route = _engine_route(x, k, s, p, (Di, Hi, Wi))
     if route == "same":
         return conv_wgrad(dy, x, k=tuple(k))
+    if route == "window":
+        x, route = window_rows(x, k), "full"
     if route == "full":
         taps = k[0] * k[1] * k[2]
         return conv_wgrad(dy.view(N, 1, 1, 1, Cout), x.view(N, 1, 1, 1, taps * Cin), k=(1, 1, 1)).view(Cout, taps, Cin)
