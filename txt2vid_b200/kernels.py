@@ -694,6 +694,8 @@ def gconv_dgrad(dy, w, bias, in_sp, k, s, p, out_f32=False, cin_real=None):
         dxs = conv_fprop_win(dy, weT, be, s2d_block_extents(tuple(in_sp), modes), ke, live, out_f32=out_f32)
         return d2s_shift(dxs, modes, tuple(in_sp), Cin, creal)
     route = _engine_route(dy, k, s, p, tuple(in_sp))
+    if route == "window" and bias is not None:
+        route = None             # a transposed convolution's bias also covers the positions outside the window
     if route == "same":
         return conv_fprop(dy, transpose_flip(w), bias, k=tuple(k), out_f32=out_f32)
     if route in ("full", "window"):
