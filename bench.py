@@ -346,11 +346,12 @@ def run_b200(args):
         step_resident(i)
     torch.cuda.synchronize()
     clocks = ClockSampler(dist.local_rank)
-    if rank == 0:
+    sample_clocks = rank == 0 and os.environ.get("T2V_BENCH_NO_CLOCKS", "0") != "1"      # (diagnosis switch)
+    if sample_clocks:
         clocks.start()
     t_res = timed(step_resident, args.steps)
     launches = launches_per_step * args.steps
-    clk = clocks.stop() if rank == 0 else None
+    clk = clocks.stop() if sample_clocks else None
     timed(step_e2e, 3, begin=e2e_begin, end=e2e_end)               # e2e warm-up (staging slots, pinned pages)
     t_e2e = timed(step_e2e, args.steps, begin=e2e_begin, end=e2e_end)
 
