@@ -247,9 +247,18 @@ def run_b200(args):
 
     nb = 4
     data = SyntheticVideoCaptions(b, nb, vocab_size=V, seed=1234 + 1000 * rank, frames=frames, size=res)
-    host = [data.batch(i) for i in range(nb)]
-    host = [(x.contiguous().pin_memory(), t.pin_memory(), l) for x, t, l in host]
-    dev = [(x.to(device), t.to(device), l) for x, t, l in host]
+    # 4 distinct RESIDENT batches; only `nh` of them are also kept in pinned host memory for the fp32-host-batch leg
+    # (3.2 GB each at b = 4096: eight ranks of one box would pin > 100 GB with all four)
+    nh = 2 if b * frames * res * res >= 4096 * 16 * 64 * 64 else nb
+    dev, host = [], []
+    for i in range(nb):
+        x, t, l = data.batch(i)
+        x = x.contiguous()
+        if i < nh:
+            x, t = x.pin_memory(), t.pin_memory()
+            host.append((x, t, l))
+        dev.append((x.to(device), t.to(device), l))
+        del x
 
     lib = _lib.lib()
     if args.eager:
@@ -282,7 +291,7 @@ def run_b200(args):
     e2e_state = {}
 
     def e2e_begin(n):
-        e2e_state["pf"] = data_prefetcher(((host[i % nb][0], host[i % nb][1], host[i % nb][2]) for i in range(n)),
+        e2e_state["pf"] = data_prefetcher(((host[i % nh][0], host[i % nh][1], host[i % nh][2]) for i in range(n)),
                                           device=device)
 
     LAG = int(os.environ.get("T2V_E2E_LAG", "2"))                  # the host logs step i-LAG while step i is enqueued
@@ -429,8 +438,8 @@ def run_b200(args):
     # measured DRAM traffic of the dominant kernel: dram__bytes_read.sum + dram__bytes_write.sum per launch from the
     # committed ncu capture of one iteration at the same batch (profiles/r02_traffic_b2048.json, scripts/gpu_r02p.sh)
     traffic, traffic_note = None, "no ncu capture at this batch / resolution"
-    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic_b2048.json")
-    if b == 2048 and res == 64 and os.path.exists(tpath):
+    tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "r02_traffic_b%d.json" % b)
+    if res == 64 and os.path.exists(tpath):
         with open(tpath) as f:
             tj = json.load(f)
         fam = {"igemm_fprop_kernel": "igemm_fprop", "igemm_wgrad_kernel": "igemm_wgrad", "halo_fprop_kernel": "halo_fprop",
@@ -442,9 +451,9 @@ def run_b200(args):
             traffic = sum(v["dram_bytes"] for v in sel) / nl
             fl_per_launch = prof[3 * top + 1] / max(1.0, prof[3 * top + 2])
             traffic_note = ("ncu dram__bytes_read.sum + dram__bytes_write.sum of every %s* launch of one iteration at "
-                            "b = 2048 (%d launches, %.1f GB in total) / launches; %.0f useful FLOP per DRAM byte -- far "
+                            "b = %d (%d launches, %.1f GB in total) / launches; %.0f useful FLOP per DRAM byte -- far "
                             "above the machine balance (~214 FLOP/B): tensor-bound, not HBM-bound"
-                            % (key, nl, sum(v["dram_bytes"] for v in sel) / 1e9, fl_per_launch / traffic))
+                            % (key, b, nl, sum(v["dram_bytes"] for v in sel) / 1e9, fl_per_launch / traffic))
     roof = {"bound": "tensor", "kernel": names[top], "achieved": tk["achieved"], "peak": pk["bf16_tflops_sustained"],
             "unit": "TFLOP/s", "traffic": traffic, "traffic_note": traffic_note,
             "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step), %s" % pk["source"],
@@ -508,7 +517,7 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"])
-    ap.add_argument("--batch", type=int, default=2048, help="videos per GPU per step (multiple of 8)")
+    ap.add_argument("--batch", type=int, default=4096, help="videos per GPU per step (multiple of 8)")
     ap.add_argument("--res", type=int, default=64, choices=[64, 128],
                     help="64: 64x64x16 clips (the metric's configuration); 128: 128x128x32 (BASELINE configs[4])")
     ap.add_argument("--cpu_batch", type=int, default=8)
