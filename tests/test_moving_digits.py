@@ -111,3 +111,44 @@ def test_moving_digits_feed_the_public_train_loop_through_the_prefetcher():
         assert float(x.min()) == -1.0 and float(x.max()) <= 1.0
         seen += 1
     assert seen == 3
+
+
+@pytest.mark.gpu
+def test_cli_entry_point_trains_on_device_generated_clips(tmp_path, capsys):
+    """The reference's launch line (scripts/run_tganv2_cond.sh:20) through txt2vid.train.gan.main -- reflection on the
+    dotted class paths, xavier init, RSGAN + gradient penalty, fused Adam, CUDA-graph iterations -- fed by the
+    on-device moving-MNIST dataset named by a `--data` json: checkpoints and samples appear, losses are logged."""
+    import json
+    import pickle
+    from txt2vid.train.gan import build_parser, main
+    from txt2vid_b200.data import MovingDigits, build_vocab
+    vocab_path, data_path = tmp_path / "vocab.pickle", tmp_path / "data.json"
+    with open(vocab_path, "wb") as f:
+        pickle.dump(build_vocab(MovingDigits.all_sentences()), f)
+    with open(data_path, "w") as f:
+        json.dump({"class": "txt2vid.data.MovingDigitsDataset",
+                   "args": {"batch_size": 8, "num_batches": 6, "seed": 300}}, f)
+    out, samples = tmp_path / "out", tmp_path / "samples"
+    argv = ["--cuda", "--seed", "100", "--G", "txt2vid.models.tganv2_cond.gen.MultiScaleGen",
+            "--D", "txt2vid.models.tganv2_cond.discrim.MultiScaleDiscrim", "--sent", "txt2vid.models.txt.basic.Seq2Seq",
+            "--D_loss", "txt2vid.gan.losses.RSGANLoss", "--frame_sizes", "8", "16", "32", "64", "--D_names", "video",
+            "--G_lr", "0.0002", "--D_lr", "0.0002", "--D_beta1", "0.5", "--D_beta2", ".999", "--G_beta1", "0.5",
+            "--G_beta2", ".999", "--init_method", "xavier", "--discrim_steps", "1", "--gp_lambda", ".5",
+            "--no_mean_discrim_loss", "--subsample_input", "--data", str(data_path), "--vocab", str(vocab_path),
+            "--epochs", "1", "--batch_size", "8", "--log_period", "2", "--save_example_period", "4",
+            "--save_model_period", "4", "--out", str(out), "--out_samples", str(samples), "--cuda_graphs"]
+    from txt2vid_b200 import _lib
+    n0 = _lib.lib().t2v_launch_count()
+    main(build_parser().parse_args(argv))
+    assert _lib.lib().t2v_launch_count() - n0 > 6 * 1500
+    text = capsys.readouterr().out
+    assert "Iter 6, Loss_D:" in text and "Loss_G:" in text
+    ckpts = [p for p in out.iterdir() if p.name.startswith("iter_4_")]
+    assert len(ckpts) == 1
+    saved = torch.load(ckpts[0], weights_only=False)
+    assert {"gen", "cond", "video", "optG", "optD"} <= set(saved.keys())
+    names = {p.name for p in samples.iterdir()}
+    assert "real_samples.png" in names and any(n.startswith("fake_samples_epoch_000_iter_000004_64x64") for n in names)
+    assert any(n.startswith("sentences_epoch000_iter_000004") for n in names)
+    words = (samples / "sentences_epoch000_iter_000004.txt").read_text().splitlines()
+    assert len(words) == 8 and all(w.startswith("<start> digit ") for w in words)

@@ -352,3 +352,22 @@ class MovingDigits(object):
     def __iter__(self):
         for _ in range(self.n):
             yield self.batch()
+
+
+class MovingDigitsDataset(MovingDigits):
+    """`--data` target of txt2vid.train.gan (created by reflection with `vocab=` and `anno=`, train/gan.py:132): the
+    on-device moving-MNIST generator over a seeded random digit bank (MNIST itself is a download; pass `bank_path`, a
+    torch.save'd {class: uint8 (n, 28, 28)} dict, for real digits).  Example config:
+        {"class": "txt2vid.data.MovingDigitsDataset", "args": {"batch_size": 64, "num_batches": 100}}"""
+
+    def __init__(self, vocab=None, anno=None, batch_size=64, num_batches=100, frames=16, size=64, seed=None,
+                 bank_path=None, bank_seed=7, per_class=3, as_uint8=False, device="cuda"):
+        import numpy as np
+        if bank_path is not None:
+            bank = {int(c): np.asarray(v, dtype=np.uint8) for c, v in torch.load(bank_path, weights_only=False).items()}
+        else:
+            rng = np.random.RandomState(bank_seed)
+            bank = {c: np.stack([rng.randint(0, 256, (28, 28)).astype(np.uint8) for _ in range(per_class)])
+                    for c in range(10)}
+        super().__init__(batch_size, num_batches, bank, vocab=vocab, frames=frames, size=size, device=device,
+                         as_uint8=as_uint8, seed=seed)
