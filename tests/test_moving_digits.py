@@ -140,7 +140,7 @@ def test_cli_entry_point_trains_on_device_generated_clips(tmp_path, capsys):
     from txt2vid_b200 import _lib
     n0 = _lib.lib().t2v_launch_count()
     main(build_parser().parse_args(argv))
-    assert _lib.lib().t2v_launch_count() - n0 > 6 * 1500
+    assert _lib.lib().t2v_launch_count() - n0 > 3 * 1500     # two eager warm-ups + the capture (replays are not counted)
     text = capsys.readouterr().out
     assert "Iter 6, Loss_D:" in text and "Loss_G:" in text
     ckpts = [p for p in out.iterdir() if p.name.startswith("iter_4_")]
