@@ -111,6 +111,20 @@ def test_moving_digits_feed_the_public_train_loop_through_the_prefetcher():
         assert float(x.min()) == -1.0 and float(x.max()) <= 1.0
         seen += 1
     assert seen == 3
+    # frames handed out as stored (uint8, resident): the prefetcher normalises them on its side stream, ordered behind
+    # the generator's kernels -- same values as the generator's own fp32 output for the same draws
+    md8, md32 = make(fx, "cuda", as_uint8=True), make(fx, "cuda")
+    md8.n = 2
+    draws = []
+    real_draw = md8.draw
+    md8.draw = lambda: draws.append(real_draw()) or draws[-1]
+    pf = data_prefetcher(md8, device="cuda")
+    B = len(fx["examples"])
+    for k in range(2):
+        x, _ = pf.next()
+        torch.cuda.synchronize()
+        want, _, _ = md32.batch(draws[k * B:(k + 1) * B])
+        assert x.dtype == torch.float32 and torch.equal(x, want)
 
 
 @pytest.mark.gpu

@@ -159,6 +159,10 @@ class data_prefetcher(object):
                     free.synchronize()
                 elif self.GUARD == "device":
                     self.stream.wait_event(free)
+            if any(isinstance(a, torch.Tensor) and a.is_cuda for a in batch):
+                # a device-resident batch (MovingDigits) was produced on the consumer's stream: order the side stream
+                # (uint8 normalisation) behind it
+                self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 self.next_x = self._to_dev(batch[0], 0)
                 if isinstance(self.next_x, torch.Tensor) and self.next_x.dtype == torch.uint8:
@@ -340,11 +344,10 @@ class MovingDigits(object):
         draws = draws if draws is not None else [self.draw() for _ in range(self.B)]
         B = len(draws)
         pos = torch.tensor([self.frame_positions(d["a"], d["b"], self.T, d["anim"]) for d in draws], dtype=torch.int32)
-        small = torch.tensor([[d["digit"], d["cls"], d["move"]] for d in draws], dtype=torch.int32)
+        small = torch.tensor([[d[k] for d in draws] for k in ("digit", "cls", "move")], dtype=torch.int32)   # (3, B)
         if self.device.type == "cuda":
             pos, small = pos.pin_memory().to(self.device, non_blocking=True), small.pin_memory().to(self.device, non_blocking=True)
         from . import kernels as K
-        small = small.t().contiguous()
         clips = K.moving_digits(self.bank, small[0], pos, self.T, self.H, self.W, out_f32=not self.as_uint8, layout=0)
         tokens = K.grammar_tokens(small[1], small[2], self.table)
         return clips, tokens, [8] * B
