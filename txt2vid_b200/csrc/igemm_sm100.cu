@@ -52,7 +52,7 @@ struct IgemmParams {
   __nv_bfloat16* h_merged;
   // wgrad only
   float* dw;
-  int taps_total, splits, tiles_total, atomic_out;
+  int taps_total, splits, tiles_total, atomic_out, tap_fast, col_fast;
 };
 
 static constexpr int kThreads = 192;
@@ -186,7 +186,9 @@ T2V_DEVINL void lstm_epilogue_row(const IgemmParams& p, uint32_t taddr, size_t p
 }
 
 // PERSISTENT: gridDim.x CTAs (a multiple of the SM count, or every tile when there are few) walk the output tiles
-// tile = blockIdx.x, + gridDim.x, ... (m fastest: CTAs running at the same time share the weight tile in L2).
+// tile = blockIdx.x, + gridDim.x, ...  Column tile fastest (col_fast): the CTAs running at the same time share the
+// ACTIVATION tile, which is then read from DRAM once instead of once per column tile (the weights of a layer, <= 19 MB,
+// stay in the 126 MB L2 either way); m fastest was round 1's order.
 // The TMA ring runs ahead ACROSS tiles (no pipeline fill / drain per tile), the accumulator is double buffered in
 // TMEM (2 x BN columns): the MMA warp starts tile i+1 while the epilogue warps drain tile i, and barrier init /
 // TMEM allocation / descriptor prefetch are paid once per CTA instead of once per 128-row tile.
@@ -208,6 +210,7 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
   const int lane = threadIdx.x & 31;
   const int mtiles = p.tn * p.td * p.th * p.tw;
   const int total = p.tiles_total;                  // mtiles * column tiles
+  const int ncols = total / mtiles;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -242,8 +245,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
       uint32_t phase = 0;
       const int nkw = p.hi_w - p.lo_w, nkh = p.hi_h - p.lo_h;
       for (int tile = blockIdx.x; tile < total; tile += gridDim.x) {
-        int mt = tile % mtiles;
-        const int col0 = (tile / mtiles) * p.BN;
+        int mt = p.col_fast ? tile / ncols : tile % mtiles;
+        const int col0 = (p.col_fast ? tile % ncols : tile / mtiles) * p.BN;
         const int tw_i = mt % p.tw; mt /= p.tw;
         const int th_i = mt % p.th; mt /= p.th;
         const int td_i = mt % p.td; mt /= p.td;
@@ -321,8 +324,8 @@ igemm_fprop_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constan
     const int id = r % p.bd; r /= p.bd;
     int it = 0;
     for (int tile = blockIdx.x; tile < total; tile += gridDim.x, ++it) {
-      int mt = tile % mtiles;
-      const int col0 = (tile / mtiles) * p.BN;
+      int mt = p.col_fast ? tile / ncols : tile % mtiles;
+      const int col0 = (p.col_fast ? tile % ncols : tile / mtiles) * p.BN;
       const int tw_i = mt % p.tw; mt /= p.tw;
       const int th_i = mt % p.th; mt /= p.th;
       const int td_i = mt % p.td; mt /= p.td;
@@ -386,13 +389,14 @@ igemm_fprop_simple_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
 
-  // tile coordinates
-  int mt = blockIdx.x;
+  // tile coordinates (1-D grid; same order as the persistent kernel)
+  const int mtiles_ = p.tn * p.td * p.th * p.tw, ncols_ = p.tiles_total / mtiles_;
+  int mt = p.col_fast ? (int)blockIdx.x / ncols_ : (int)blockIdx.x % mtiles_;
+  const int col0 = (p.col_fast ? (int)blockIdx.x % ncols_ : (int)blockIdx.x / mtiles_) * p.BN;
   const int tw_i = mt % p.tw; mt /= p.tw;
   const int th_i = mt % p.th; mt /= p.th;
   const int td_i = mt % p.td; mt /= p.td;
   const int n0 = mt * p.bn, d0 = td_i * p.bd, h0 = th_i * p.bh, w0 = tw_i * p.bw;
-  const int col0 = blockIdx.y * p.BN;
 
   if (warp == 0 && lane == 0) {
     tma_prefetch_desc(&tmA);
@@ -582,9 +586,14 @@ igemm_wgrad_kernel(const __grid_constant__ CUtensorMap tmDy, const __grid_consta
   const int lane = threadIdx.x & 31;
   const int co0 = blockIdx.x * 128;
   const int ci0 = blockIdx.y * p.BN;
-  const int split = blockIdx.z % p.splits;
-  int t = blockIdx.z / p.splits;
+  // blockIdx.z = split * ntaps + tap (tap fastest): the CTAs that share a position range (all taps and column tiles of
+  // one split) are launched together and walk it at the same pace, so the range is read from DRAM once and served to
+  // the others from L2.  With the split fastest (round 1) the taps of a range ran in different waves: ncu showed
+  // dram__bytes_read = 2-3x the operand bytes.
   const int nkw = p.hi_w - p.lo_w, nkh = p.hi_h - p.lo_h;
+  const int ntaps_live = nkw * nkh * (p.hi_d - p.lo_d);
+  const int split = p.tap_fast ? (int)blockIdx.z / ntaps_live : (int)blockIdx.z % p.splits;
+  int t = p.tap_fast ? (int)blockIdx.z % ntaps_live : (int)blockIdx.z / p.splits;
   const int a_w = t % nkw + p.lo_w; t /= nkw;
   const int a_h = t % nkh + p.lo_h; t /= nkh;
   const int a_d = t + p.lo_d;
@@ -871,6 +880,8 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
   p.relu_mask = (flags & T2V_EPI_RELU_MASK) ? 1 : 0;
   p.res_f32 = (flags & T2V_EPI_RES_F32) ? 1 : 0;
   p.tiles_total = total_ctas;
+  static const int col_fast = env_int("T2V_FPROP_COL_FAST", 1);
+  p.col_fast = col_fast;
   if (lstm) {
     p.lstm = 1; p.lstm_t = lstm->t; p.lstm_steps = lstm->steps; p.lstm_plane = g->D * g->H * g->W;
     p.c_prev = lstm->c_prev; p.c_out = lstm->c_out; p.gates_out = lstm->gates;
@@ -894,7 +905,7 @@ int igemm_fprop_launch_aux(const t2v_conv_geom* g, const void* x, const void* w,
 
   const size_t smem = (size_t)p.stages * p.stage_bytes + 1024 + (2 * p.stages + 4) * 8 + 16;
   if (!persist) {                               // one tile per CTA (grid = m tiles x column tiles)
-    dim3 grid2((unsigned)mtiles_total, (unsigned)((g->Cout + p.BN - 1) / p.BN), 1);
+    dim3 grid2((unsigned)total_ctas, 1, 1);
     auto launch2 = [&](auto kern) {
       cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
       kern<<<grid2, kThreads, smem, stream>>>(tmA, tmB, tmA2, tmB2, p);
@@ -989,6 +1000,8 @@ int igemm_wgrad_launch(const t2v_conv_geom* g, const void* dy, const void* x, fl
   p.idesc = make_idesc_bf16(128, (uint32_t)p.BN, 1, 1);
   p.tmem_cols = (uint32_t)(p.BN < 32 ? 32 : p.BN);
   p.dw = dw;
+  static const int tap_fast = env_int("T2V_WGRAD_TAP_FAST", 1);
+  p.tap_fast = tap_fast;
   p.atomic_out = (splits > 1 || accumulate) ? 1 : 0;
 
   const size_t dw_elems = (size_t)g->Cout * p.taps_total * g->Cin;
