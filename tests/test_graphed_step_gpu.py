@@ -122,3 +122,28 @@ def test_public_train_loop_with_graphs(tmp_path, capsys):
     assert all(np.isfinite(a) and np.isfinite(b) for a, b in seen)
     assert len({round(a, 4) for a, _ in seen}) > 3
     assert "Iter 3" in out and "Iter 6" in out
+
+
+def test_uint8_frames_are_normalised_into_the_graph_input():
+    """Frames handed out as stored (data_prefetcher(normalize=False)): eager warm-ups and the capture normalise them
+    with t2v_u8_normalize, replays fuse ToTensor + Normalize(0.5, 0.5) (data/__init__.py:362-364) into the fill of the
+    graph's static input -- bit-identical to the CPU transform."""
+    from txt2vid_b200.data import SyntheticVideoCaptions, data_prefetcher
+    from txt2vid_b200.trainer import GraphedTrainStep
+    B = 8
+    dev, gan, losses, optD, optG, params, _ = _setup(B)
+    step = GraphedTrainStep(gan, optD, optG, params, losses, dev, warmup=2)
+    pf = data_prefetcher(SyntheticVideoCaptions(B, 5, vocab_size=1000, as_uint8=True), device=dev, normalize=False)
+    last, seen = None, []
+    while True:
+        x, y = pf.next()
+        if x is None:
+            break
+        assert x.dtype == torch.uint8 and x.is_cuda
+        ld, lg = step(x, y)
+        seen.append((float(ld), float(lg)))
+        last = x.clone()
+    assert step.graphs is not None and step.replays >= 3 and all(np.isfinite(v) for p in seen for v in p)
+    torch.cuda.synchronize()
+    want = last.cpu().float().div(255.0).sub(0.5).div(0.5)
+    assert step.static_x.dtype == torch.float32 and torch.equal(step.static_x.cpu(), want)

@@ -96,7 +96,11 @@ class data_prefetcher(object):
     GUARD = "host"
     SM_COPY_CTAS = int(os.environ.get("T2V_PF_SM_COPY_CTAS", "0"))   # > 0: bulk copy by an SM kernel over UVA (experimental)
 
-    def __init__(self, loader, device=None):
+    def __init__(self, loader, device=None, normalize=True):
+        # normalize=False: uint8 frames are handed out as stored; the consumer normalises them where it needs them
+        # (trainer.GraphedTrainStep fuses ToTensor + Normalize into the fill of its static input: one pass reading
+        # 1 byte and writing 4 per pixel instead of a side-stream pass plus a 4-byte copy)
+        self.normalize = normalize
         self.loader = iter(loader)
         self.device = torch.device(device if device is not None else
                                    ('cuda' if torch.cuda.is_available() else 'cpu'))
@@ -165,7 +169,7 @@ class data_prefetcher(object):
                 self.stream.wait_stream(torch.cuda.current_stream())
             with torch.cuda.stream(self.stream):
                 self.next_x = self._to_dev(batch[0], 0)
-                if isinstance(self.next_x, torch.Tensor) and self.next_x.dtype == torch.uint8:
+                if self.normalize and isinstance(self.next_x, torch.Tensor) and self.next_x.dtype == torch.uint8:
                     self.next_x = self._normalize(self.next_x)
                 self.next_y = [self._to_dev(a, 1 + i) for i, a in enumerate(batch[1:])]
         else:

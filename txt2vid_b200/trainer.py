@@ -179,6 +179,8 @@ def train_iteration(gan, x, y, device, optD, optG, params, losses, channel_first
     """Body of one `train()` iteration (gan/trainer.py:199-267).  x: (B,T,C,H,W) loader order.
     Returns (lossD, lossG, fake, real_levels, conds) with the losses as 0-d device tensors (no host sync)."""
     from . import hostrng
+    if torch.is_tensor(x) and x.dtype == torch.uint8:       # frames as stored: ToTensor + Normalize(0.5, 0.5) on the device
+        x = K.u8_normalize(x.contiguous())
     hostrng.CURRENT.begin_iteration()
     cond = encode_captions(gan, y, end2end)
     st, total_d, total_g = None, 0, 0
@@ -303,10 +305,13 @@ class GraphedTrainStep(object):
             self.draws = hostrng.StaticDraws(self._calls_rec, self.device)
             hostrng.set_current(self.draws)
             try:
-                self._capture(x, cond)
+                self._capture(K.u8_normalize(x.contiguous()) if x.dtype == torch.uint8 else x, cond)
             finally:
                 hostrng.set_current(hostrng.EagerDraws())
-        if x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and self.static_x.is_contiguous():
+        if x.is_cuda and x.dtype == torch.uint8 and x.is_contiguous() and self.static_x.is_contiguous():
+            # frames as stored: ToTensor + Normalize fused into the fill of the graph's static input (t2v_u8_normalize)
+            K.u8_normalize(x, out=self.static_x)
+        elif x.is_cuda and x.dtype == torch.float32 and x.is_contiguous() and self.static_x.is_contiguous():
             # an SM copy kernel, not cudaMemcpyAsync: a copy-engine D2D copy would queue behind the prefetcher's
             # H2D chunks of the NEXT batch (data.data_prefetcher) and delay this step by the whole transfer
             K.multi_copy([x], [self.static_x])
@@ -437,7 +442,7 @@ def train(gan=None, num_epoch=None, dataset=None, device=None, optD=None, optG=N
         data_load_watch.start()
         iter_watch.start()
         i = 0
-        prefetcher = data_prefetcher(dataset, device=device)
+        prefetcher = data_prefetcher(dataset, device=device, normalize=graphed is None)
         x, y = prefetcher.next(preload=False)
         while x is not None:
             iteration = epoch * len(dataset) + i + 1
