@@ -64,7 +64,7 @@ def synth_batch(B, V, T=16, S=64, seed=1234):
     return x, tokens, lengths
 
 
-def build_reference_models(conditional, V=1000, seed=100):
+def build_reference_models(conditional, V=1000, seed=100, size=64, frames=16):
     """Construction + init order of train/gan.py:28-70."""
     import contextlib
     import io
@@ -78,7 +78,7 @@ def build_reference_models(conditional, V=1000, seed=100):
             from txt2vid.models.tganv2_cond.discrim import MultiScaleDiscrim
             txt = Seq2Seq(vocab_size=V)
             init(txt, "xavier")
-            gen = MultiScaleGen(width=64, height=64, cond_dim=256)
+            gen = MultiScaleGen(width=size, height=size, cond_dim=256, num_frames=frames)
             dis = MultiScaleDiscrim(cond_dim=256)
         else:
             from txt2vid.models.tganv2.gen import MultiScaleGen
@@ -146,17 +146,21 @@ def reference_iteration(L, txt, gen, dis, x, tokens, lengths, conditional, gp_la
     return out
 
 
-def run_config(L, conditional, out_dir, B=8, V=1000):
+def run_config(L, conditional, out_dir, B=8, V=1000, size=64, frames=16, frame_sizes=(8, 16, 32, 64)):
+    """size / frames / frame_sizes: BASELINE configs[4] is the conditional model at 128 x 128 x 32 with the pyramid
+    16 / 32 / 64 / 128 (the ConvLSTM plane becomes 2 x 2, tganv2_cond/gen.py:32-33)."""
     import oracle.txt2vid_oracle as O
     name = "tganv2_cond" if conditional else "tganv2_uncond"
+    if size != 64:
+        name += "_%dx%dx%d" % (size, size, frames)
     t0 = time.time()
-    txt, gen, dis = build_reference_models(conditional, V)
+    txt, gen, dis = build_reference_models(conditional, V, size=size, frames=frames)
     init_sd = {"gen": {k: v.detach().clone() for k, v in gen.state_dict().items()},
                "dis": {k: v.detach().clone() for k, v in dis.state_dict().items()},
                "txt": None if txt is None else {k: v.detach().clone() for k, v in txt.state_dict().items()}}
-    x, tokens, lengths = synth_batch(B, V)
+    x, tokens, lengths = synth_batch(B, V, T=frames, S=size)
     rng_t, rng_n = torch.get_rng_state(), np.random.get_state()
-    ref = reference_iteration(L, txt, gen, dis, x, tokens, lengths, conditional)
+    ref = reference_iteration(L, txt, gen, dis, x, tokens, lengths, conditional, frame_sizes=frame_sizes)
     print("[%s] reference iteration: lossD %.6f lossG %.6f (%.1fs)" % (name, ref["lossD"], ref["lossG"], time.time() - t0))
 
     # ---- the oracle on the same weights, inputs and RNG stream
@@ -173,7 +177,8 @@ def run_config(L, conditional, out_dir, B=8, V=1000):
     opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
     opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
     t1 = time.time()
-    orc = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
+    orc = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d,
+                            frame_sizes=frame_sizes, num_frames=frames)
     print("[%s] oracle iteration:    lossD %.6f lossG %.6f (%.1fs)" % (name, orc["lossD"], orc["lossG"], time.time() - t1))
 
     def l2rel(a, b):
@@ -192,8 +197,8 @@ def run_config(L, conditional, out_dir, B=8, V=1000):
     assert set(orc["gradD"]) == set(ref["gradD"]) and set(orc["gradG"]) == set(ref["gradG"])
 
     fixture = {
-        "config": {"model": name, "B": B, "V": V, "seed": 100, "data_seed": 1234, "frame_sizes": [8, 16, 32, 64],
-                   "gp_lambda": 0.5, "loss": "RSGAN", "lr": 2e-4, "betas": [0.5, 0.999]},
+        "config": {"model": name, "B": B, "V": V, "seed": 100, "data_seed": 1234, "frame_sizes": list(frame_sizes),
+                   "size": size, "frames": frames, "gp_lambda": 0.5, "loss": "RSGAN", "lr": 2e-4, "betas": [0.5, 0.999]},
         "generated_by": "oracle/make_golden.py from the live reference at /root/reference, torch %s" % torch.__version__,
         "init": {part: (None if sd is None else {k: checksum(v) for k, v in sd.items() if v.dtype.is_floating_point})
                  for part, sd in init_sd.items()},
@@ -256,3 +261,5 @@ if __name__ == "__main__":
         run_config(Lmod, True, a.out)
     if a.only in (None, "uncond"):
         run_config(Lmod, False, a.out)
+    if a.only in (None, "cond128"):
+        run_config(Lmod, True, a.out, size=128, frames=32, frame_sizes=(16, 32, 64, 128))

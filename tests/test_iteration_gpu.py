@@ -78,10 +78,14 @@ def test_config5_128x128x32_iteration_on_b200():
     test; exercises the kernels on the larger planes (all four pyramid levels take the stride-(2,1,1) stem conv)."""
     from txt2vid_b200 import ops
     ops.PACKS.clear()
-    fx = {"config": dict(golden("tganv2_cond_B8.json")["config"])}
+    fx = golden("tganv2_cond_128x128x32_B8.json")         # recorded from the LIVE reference at this size (make_golden.py)
     orc, got = run_product_iteration(True, fx, "cuda", size=128, frames=32, frame_sizes=(16, 32, 64, 128))
     loss_tol, g_l2, g_cos, fake_tol, d_l2, d_cos = bf16_bars("cond_g0")      # same network, larger planes
     rep = compare(orc, got, loss_tol, g_l2, g_cos, fake_tol)
+    # the reference's own recorded losses (the oracle reproduces them to 6e-8 / 0 on the CPU: test_oracle_golden.py)
+    assert abs(orc["lossD"] - fx["lossD"]) < 2e-5 and abs(orc["lossG"] - fx["lossG"]) < 2e-5
+    assert abs(got["lossD"] - fx["lossD"]) <= loss_tol * abs(fx["lossD"]), (got["lossD"], fx["lossD"])
+    assert abs(got["lossG"] - fx["lossG"]) <= loss_tol * abs(fx["lossG"]), (got["lossG"], fx["lossG"])
     assert rep["gradD"]["l2"] < d_l2 and rep["gradD"]["cos"] > d_cos, rep
     import json, os
     os.makedirs("gpurun_out", exist_ok=True)

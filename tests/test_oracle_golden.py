@@ -12,12 +12,16 @@ def _close(a, b, rel=1e-6, abs_=1e-6):
     return abs(a - b) <= abs_ + rel * abs(b)
 
 
-@pytest.mark.parametrize("name,conditional", [("tganv2_cond_B8.json", True), ("tganv2_uncond_B8.json", False)])
+@pytest.mark.parametrize("name,conditional", [("tganv2_cond_B8.json", True), ("tganv2_uncond_B8.json", False),
+                                              ("tganv2_cond_128x128x32_B8.json", True)])
 def test_init_parity_and_oracle_vs_reference(name, conditional):
+    """the third case is BASELINE configs[4] (128 x 128 x 32, pyramid 16 / 32 / 64 / 128, 2 x 2 ConvLSTM plane)"""
     import oracle.txt2vid_oracle as O
     fx = golden(name)
+    size, frames = fx["config"].get("size", 64), fx["config"].get("frames", 16)
     torch.set_num_threads(max(1, torch.get_num_threads()))
-    txt, gen, dis = build_product_models(conditional, V=fx["config"]["V"], seed=fx["config"]["seed"])
+    txt, gen, dis = build_product_models(conditional, V=fx["config"]["V"], seed=fx["config"]["seed"], width=size,
+                                         height=size, num_frames=frames)
     sds = {"gen": state_to_cpu(gen), "dis": state_to_cpu(dis), "txt": None if txt is None else state_to_cpu(txt)}
     # ---- init parity: every tensor of the reference's state_dict, same name, same values
     for part in ("gen", "dis", "txt"):
@@ -34,7 +38,7 @@ def test_init_parity_and_oracle_vs_reference(name, conditional):
             assert np.allclose(m["first"], c["first"], rtol=0, atol=0), k
     # ---- the oracle on those weights against the reference's recorded iteration
     B = fx["config"]["B"]
-    x, tokens, lengths = synth_batch(B, fx["config"]["V"], seed=fx["config"]["data_seed"])
+    x, tokens, lengths = synth_batch(B, fx["config"]["V"], T=frames, S=size, seed=fx["config"]["data_seed"])
     assert tokens.tolist() == fx["tokens"] and lengths == fx["lengths"]
     assert _close(checksum(x)["wsum"], fx["x"]["wsum"], abs_=1e-3)
     d = fx["draws"]
@@ -48,7 +52,8 @@ def test_init_parity_and_oracle_vs_reference(name, conditional):
     sd_t = None if sds["txt"] is None else O.as_leaves(sds["txt"])
     opt_g = O.Adam(O.param_names(sd_g), 2e-4, (0.5, 0.999))
     opt_d = O.Adam(O.param_names(sd_d), 2e-4, (0.5, 0.999))
-    out = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d)
+    out = O.train_iteration(sd_g, sd_d, sd_t, x, tokens, lengths, z, draws, opt_g=opt_g, opt_d=opt_d,
+                            frame_sizes=tuple(fx["config"]["frame_sizes"]), num_frames=frames)
     assert abs(out["lossD"] - fx["lossD"]) < 2e-5 and abs(out["lossG"] - fx["lossG"]) < 2e-5
     for lvl, f in zip(out["fake"], fx["fake"]):
         assert list(lvl.shape) == f["shape"]
@@ -66,7 +71,9 @@ def test_init_parity_and_oracle_vs_reference(name, conditional):
 def _redraw_z(fx, conditional):
     """Replays the reference's RNG stream up to z: seed, construct + init (done by the caller in the same
     process state is gone), so rebuild once more -- cheap relative to the iteration."""
-    build_product_models(conditional, V=fx["config"]["V"], seed=fx["config"]["seed"])
+    size, frames = fx["config"].get("size", 64), fx["config"].get("frames", 16)
+    build_product_models(conditional, V=fx["config"]["V"], seed=fx["config"]["seed"], width=size, height=size,
+                         num_frames=frames)
     import oracle.txt2vid_oracle as O
     bt = O.draw_real(4, True)
     assert bt == fx["draws"]["bt_real"]
