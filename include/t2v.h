@@ -287,6 +287,13 @@ int t2v_attention_fwd(const void* theta, const void* phi, const void* g, void* o
 int t2v_attention_bwd(const void* theta, const void* phi, const void* g, const void* dout, void* dtheta, void* dphi,
                       void* dg, int64_t N, int32_t D, int32_t H, int32_t W, int32_t c8, int32_t c2, int32_t C8p,
                       int32_t C2p, void* stream);
+/* the same for maps beyond one CTA of the backward kernel (2 * pooled keys > 512; c8 = 4, c2 = 16, rows padded to 16;
+ * up to 2560 pooled keys): two launches (thread = query, then thread = key x query quarter), deterministic;
+ * stats_ws = fp32 workspace [N * D*H*W * 3] (softmax maximum, 1 / sum, D_q per query).  BASELINE configs[4]: the
+ * generator's block sits on a 64 x 64 map (4096 queries x 1024 keys) there.                                        */
+int t2v_attention_bwd_large(const void* theta, const void* phi, const void* g, const void* dout, void* dtheta, void* dphi,
+                            void* dg, float* stats_ws, int64_t N, int32_t D, int32_t H, int32_t W, int32_t c8, int32_t c2,
+                            int32_t C8p, int32_t C2p, void* stream);
 
 /* RenderBlock tail: tanh + (B*T,H,W,Cp) bf16 -> (B,C,T,H,W) fp32 (layers.py:252, gen.py:116-119)  */
 int t2v_render_fwd(const void* pre, float* y, int32_t B, int32_t T, int32_t H, int32_t W, int32_t C, int32_t Cp,

@@ -349,6 +349,14 @@ def _attn_parts(theta, phi, g, c8, c2):
     return th, mp(phi, c8), mp(g, c2)
 
 
+def attention_fused_ok(D, H, W, c8, c2):
+    if c8 > 8 or c2 > 16:
+        return False
+    if D * H * W <= 1024:
+        return True
+    return c8 == 4 and c2 == 16 and D * (H // 2) * (W // 2) <= 2560
+
+
 def attention_fwd(theta, phi, g, c8, c2):
     N, D, H, W, _ = theta.shape
     th, ph, gp = _attn_parts(theta, phi, g, c8, c2)

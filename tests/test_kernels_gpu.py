@@ -69,7 +69,10 @@ def test_im2col3_and_adjoint(shape):
 
 
 @pytest.mark.parametrize("shape,c8,c2", [((5, 1, 32, 32), 4, 16), ((3, 1, 8, 12), 4, 16), ((2, 2, 4, 6), 8, 16),
-                                         ((4, 1, 16, 16), 2, 8)])
+                                         ((4, 1, 16, 16), 2, 8),
+                                         # maps beyond one CTA of the backward kernel (t2v_attention_bwd_large): the 64 x 64
+                                         # map of BASELINE configs[4], and a key count that is not a multiple of 64
+                                         ((3, 1, 64, 64), 4, 16), ((2, 1, 48, 40), 4, 16), ((2, 2, 24, 28), 4, 16)])
 def test_attention_core(shape, c8, c2):
     """fused non-local core (max-pool + QK^T + softmax + beta.g) and its gradient vs the composite torch formulation"""
     N, D, H, W = shape

@@ -121,6 +121,8 @@ SIGNATURES = {
     "t2v_bn_bwd": [_P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_attention_fwd": [_P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_attention_bwd": [_P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
+    "t2v_attention_bwd_large": [_P, _P, _P, _P, _P, _P, _P, _P, c_i64, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32,
+                                _P],
     "t2v_render_fwd": [_P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_render_bwd": [_P, _P, _P, c_i32, c_i32, c_i32, c_i32, c_i32, c_i32, _P],
     "t2v_gather_frames": [_P, _P, c_i32, c_i32, c_i64, c_i32, c_i32, c_i32, _P, c_i32, _P],

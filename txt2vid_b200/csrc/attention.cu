@@ -233,11 +233,13 @@ __device__ __forceinline__ void st16_bf16(__nv_bfloat16* p, const float4* v, flo
 }
 
 // pooled keys / values of one map -> shared memory (+ arg-max of every channel for the backward pass)
+// (k0, nk: the key range [k0, k0 + nk) of the map, stored at local index k - k0; default: all keys)
 __device__ __forceinline__ void build_keys_fast(const AttnParams& p, long long map0, float4* s_phi, float4* s_g,
-                                                unsigned char* s_aphi, unsigned char* s_ag) {
-  for (int k = threadIdx.x; k < p.Kp; k += blockDim.x) {
+                                                unsigned char* s_aphi, unsigned char* s_ag, int k0 = 0, int nk = -1) {
+  if (nk < 0) nk = p.Kp;
+  for (int k = threadIdx.x; k < nk; k += blockDim.x) {
     int pos4[4];
-    pooled_window(p, k, pos4);
+    pooled_window(p, k0 + k, pos4);
     float4 bp = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
     float4 bg[4];
     unsigned char ap[4] = {0, 0, 0, 0}, ag[16];
@@ -426,6 +428,147 @@ __global__ void __launch_bounds__(512) attn_bwd_fast_kernel(const AttnParams p) 
   }
 }
 
+// ---- maps too large for one CTA (the 64 x 64 map of the 128 x 128 x 32 configuration: 4096 queries x 1024 keys) ----
+// Same math in two launches.  A: grid (maps, query blocks of 256), thread = query, all keys in shared memory: softmax
+// statistics, D_q and d theta; {m, 1/l, D_q} go to a workspace.  B: grid (maps, key blocks of 64), thread = (key, query
+// quarter): the queries stream through shared memory in tiles of 256 (theta, dy and the statistics of A), every thread
+// sums d phi_k / d g_k over its quarter of each tile, the four quarters are combined through shared memory and routed
+// to the arg-max voxel of the pooling window.  No atomics: deterministic.
+static constexpr int kLargeKeys = 64, kLargeTile = 256;
+
+__global__ void __launch_bounds__(256) attn_bwd_large_a_kernel(const AttnParams p, float* __restrict__ stats) {
+  extern __shared__ float4 smem_v[];
+  float4* s_phi = smem_v;              // [Kp]
+  float4* s_g = s_phi + p.Kp;          // [Kp][4]
+  const long long map0 = (long long)blockIdx.x * p.P;
+  build_keys_fast(p, map0, s_phi, s_g, nullptr, nullptr);
+  __syncthreads();
+  const int q = blockIdx.y * 256 + threadIdx.x;
+  if (q >= p.P) return;
+  const float4 th = ld4_bf16(p.theta + (map0 + q) * 16);
+  float4 dy[4];
+  ld16_bf16(p.dout + (map0 + q) * 16, dy);
+  float m = -INFINITY;
+  for (int k = 0; k < p.Kp; ++k) m = fmaxf(m, dot4(th, s_phi[k]));
+  float l = 0.f, ws = 0.f;
+  for (int k = 0; k < p.Kp; ++k) {
+    const float e = __expf(dot4(th, s_phi[k]) - m);
+    l += e;
+    ws = fmaf(e, dot16(dy, s_g + 4 * k), ws);
+  }
+  const float il = 1.f / l, dq = ws * il;
+  float4 dth = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int k = 0; k < p.Kp; ++k) {
+    const float4 ph = s_phi[k];
+    const float ds = __expf(dot4(th, ph) - m) * il * (dot16(dy, s_g + 4 * k) - dq);
+    fma4(dth, ds, ph);
+  }
+  float* st = stats + (map0 + q) * 3;
+  st[0] = m; st[1] = il; st[2] = dq;
+  reinterpret_cast<uint4*>(p.dtheta + (map0 + q) * 16)[0] =
+      make_uint4(pack_bf16x2(dth.x, dth.y), pack_bf16x2(dth.z, dth.w), 0u, 0u);
+  reinterpret_cast<uint4*>(p.dtheta + (map0 + q) * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+}
+
+__global__ void __launch_bounds__(256) attn_bwd_large_b_kernel(const AttnParams p, const float* __restrict__ stats) {
+  extern __shared__ float4 smem_v[];
+  float4* s_phi = smem_v;                                   // [64]
+  float4* s_g = s_phi + kLargeKeys;                         // [64][4]
+  float4* s_th = s_g + 4 * kLargeKeys;                      // [256]
+  float4* s_do = s_th + kLargeTile;                         // [256][4]
+  float4* s_part = s_do + 4 * kLargeTile;                   // [3][64][5]
+  float* s_st = reinterpret_cast<float*>(s_part + 3 * kLargeKeys * 5);     // [256][3]
+  unsigned char* s_aphi = reinterpret_cast<unsigned char*>(s_st + 3 * kLargeTile);   // [64][4]
+  unsigned char* s_ag = s_aphi + 4 * kLargeKeys;                                      // [64][16]
+  const long long map0 = (long long)blockIdx.x * p.P;
+  const int k0 = blockIdx.y * kLargeKeys;
+  const int nk = min(kLargeKeys, p.Kp - k0);
+  build_keys_fast(p, map0, s_phi, s_g, s_aphi, s_ag, k0, nk);
+  const int kl = threadIdx.x % kLargeKeys, quarter = threadIdx.x / kLargeKeys;
+  const bool active = kl < nk;
+  float4 dph = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 dgk[4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i) dgk[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int t0 = 0; t0 < p.P; t0 += kLargeTile) {
+    __syncthreads();                             // keys built / previous tile consumed
+    {
+      const int q = t0 + threadIdx.x;
+      if (q < p.P) {
+        s_th[threadIdx.x] = ld4_bf16(p.theta + (map0 + q) * 16);
+        ld16_bf16(p.dout + (map0 + q) * 16, s_do + 4 * threadIdx.x);
+        const float* st = stats + (map0 + q) * 3;
+        s_st[3 * threadIdx.x] = st[0]; s_st[3 * threadIdx.x + 1] = st[1]; s_st[3 * threadIdx.x + 2] = st[2];
+      } else {                                   // past the map: 1/l = 0 -> beta = 0, contributes nothing
+        s_th[threadIdx.x] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) s_do[4 * threadIdx.x + i] = make_float4(0.f, 0.f, 0.f, 0.f);
+        s_st[3 * threadIdx.x] = 0.f; s_st[3 * threadIdx.x + 1] = 0.f; s_st[3 * threadIdx.x + 2] = 0.f;
+      }
+    }
+    __syncthreads();
+    if (active) {
+      const float4 ph = s_phi[kl];
+      float4 gk[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) gk[i] = s_g[4 * kl + i];
+      const int qb = quarter * (kLargeTile / 4);
+      for (int qq = qb; qq < qb + kLargeTile / 4; ++qq) {
+        const float4 th = s_th[qq];
+        float4 dy[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dy[i] = s_do[4 * qq + i];
+        const float beta = __expf(dot4(th, ph) - s_st[3 * qq]) * s_st[3 * qq + 1];
+        const float ds = beta * (dot16(dy, gk) - s_st[3 * qq + 2]);
+        fma4(dph, ds, th);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) fma4(dgk[i], beta, dy[i]);
+      }
+    }
+  }
+  if (active && quarter > 0) {
+    float4* dst = s_part + ((quarter - 1) * kLargeKeys + kl) * 5;
+    dst[0] = dph;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) dst[1 + i] = dgk[i];
+  }
+  __syncthreads();
+  if (active && quarter == 0) {
+    for (int s = 0; s < 3; ++s) {
+      const float4* src = s_part + (s * kLargeKeys + kl) * 5;
+      dph.x += src[0].x; dph.y += src[0].y; dph.z += src[0].z; dph.w += src[0].w;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        dgk[i].x += src[1 + i].x; dgk[i].y += src[1 + i].y; dgk[i].z += src[1 + i].z; dgk[i].w += src[1 + i].w;
+      }
+    }
+    int pos4[4];
+    pooled_window(p, k0 + kl, pos4);
+    const float dp[4] = {dph.x, dph.y, dph.z, dph.w};
+    const float* dgf = reinterpret_cast<const float*>(dgk);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      float v[16];
+#pragma unroll
+      for (int c = 0; c < 4; ++c) v[c] = s_aphi[4 * kl + c] == j ? dp[c] : 0.f;
+      reinterpret_cast<uint4*>(p.dphi + (map0 + pos4[j]) * 16)[0] =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), 0u, 0u);
+      reinterpret_cast<uint4*>(p.dphi + (map0 + pos4[j]) * 16)[1] = make_uint4(0u, 0u, 0u, 0u);
+#pragma unroll
+      for (int c = 0; c < 16; ++c) v[c] = s_ag[16 * kl + c] == j ? dgf[c] : 0.f;
+      reinterpret_cast<uint4*>(p.dg + (map0 + pos4[j]) * 16)[0] =
+          make_uint4(pack_bf16x2(v[0], v[1]), pack_bf16x2(v[2], v[3]), pack_bf16x2(v[4], v[5]), pack_bf16x2(v[6], v[7]));
+      reinterpret_cast<uint4*>(p.dg + (map0 + pos4[j]) * 16)[1] =
+          make_uint4(pack_bf16x2(v[8], v[9]), pack_bf16x2(v[10], v[11]), pack_bf16x2(v[12], v[13]),
+                     pack_bf16x2(v[14], v[15]));
+    }
+  }
+}
+
+static bool attn_fast_cfg(const AttnParams& p) {
+  return p.c8 == 4 && p.c2 == 16 && p.C8p == 16 && p.C2p == 16;
+}
+
 static bool attn_fast_ok(const AttnParams& p) {
   // phase B of the backward kernel needs both halves of a key in the same sweep (see the kernel)
   return p.c8 == 4 && p.c2 == 16 && p.C8p == 16 && p.C2p == 16 && 2 * p.Kp <= 512;
@@ -455,7 +598,7 @@ int t2v_attention_fwd(const void* theta, const void* phi, const void* g, void* o
   p.g = reinterpret_cast<const __nv_bfloat16*>(g);
   p.o = reinterpret_cast<__nv_bfloat16*>(o);
   static const bool fast_off = getenv("T2V_ATTN_GENERIC") != nullptr;
-  if (!fast_off && attn_fast_ok(p)) {
+  if (!fast_off && attn_fast_cfg(p)) {          // (two queries per thread over grid.y: any number of queries)
     const size_t sm = sizeof(float4) * (size_t)p.Kp * 5;
     if (sm <= 200 * 1024) {
       cudaFuncSetAttribute(attn_fwd_fast_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
@@ -504,6 +647,35 @@ int t2v_attention_bwd(const void* theta, const void* phi, const void* g, const v
   attn_bwd_kernel<<<(unsigned)N, 256, smem, reinterpret_cast<cudaStream_t>(stream)>>>(p);
   count_launch();
   return check_last("attention_bwd");
+}
+
+/* t2v_attention_bwd for maps beyond one CTA (up to 2560 pooled keys): stats_ws = fp32 [N * D*H*W * 3] workspace */
+int t2v_attention_bwd_large(const void* theta, const void* phi, const void* g, const void* dout, void* dtheta, void* dphi,
+                            void* dg, float* stats_ws, int64_t N, int32_t D, int32_t H, int32_t W, int32_t c8, int32_t c2,
+                            int32_t C8p, int32_t C2p, void* stream) {
+  AttnParams p{};
+  int rc = attn_fill(p, N, D, H, W, c8, c2, C8p, C2p);
+  if (rc) return rc;
+  if (!stats_ws || !attn_fast_cfg(p)) return T2V_ERR_ARG;
+  const size_t sm_a = sizeof(float4) * (size_t)p.Kp * 5;
+  if (sm_a > 200 * 1024) return T2V_ERR_ARG;
+  p.theta = reinterpret_cast<const __nv_bfloat16*>(theta);
+  p.phi = reinterpret_cast<const __nv_bfloat16*>(phi);
+  p.g = reinterpret_cast<const __nv_bfloat16*>(g);
+  p.dout = reinterpret_cast<const __nv_bfloat16*>(dout);
+  p.dtheta = reinterpret_cast<__nv_bfloat16*>(dtheta);
+  p.dphi = reinterpret_cast<__nv_bfloat16*>(dphi);
+  p.dg = reinterpret_cast<__nv_bfloat16*>(dg);
+  cudaStream_t s = reinterpret_cast<cudaStream_t>(stream);
+  cudaFuncSetAttribute(attn_bwd_large_a_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_a);
+  attn_bwd_large_a_kernel<<<dim3((unsigned)N, (unsigned)((p.P + 255) / 256), 1), 256, sm_a, s>>>(p, stats_ws);
+  const size_t sm_b = sizeof(float4) * (5 * kLargeKeys + 5 * kLargeTile + 15 * kLargeKeys) + sizeof(float) * 3 * kLargeTile +
+                      20 * kLargeKeys;
+  cudaFuncSetAttribute(attn_bwd_large_b_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_b);
+  attn_bwd_large_b_kernel<<<dim3((unsigned)N, (unsigned)((p.Kp + kLargeKeys - 1) / kLargeKeys), 1), 256, sm_b, s>>>(
+      p, stats_ws);
+  count_launch(2);
+  return check_last("attention_bwd_large");
 }
 
 }  // extern "C"

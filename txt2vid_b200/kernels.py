@@ -1040,9 +1040,30 @@ def attention_bwd(theta, phi, g, dout, c8, c2):
     C2p = g.shape[-1]
     assert dout.dtype == BF16 and dout.is_contiguous()
     dtheta, dphi, dg = torch.empty_like(theta), torch.empty_like(phi), torch.empty_like(g)
+    if attention_is_large(D, H, W):            # beyond one CTA per map: the two-launch form with a statistics workspace
+        stats = torch.empty((N * D * H * W * 3,), device=theta.device, dtype=F32)
+        check(lib().t2v_attention_bwd_large(ptr(theta), ptr(phi), ptr(g), ptr(dout), ptr(dtheta), ptr(dphi), ptr(dg),
+                                            ptr(stats), N, D, H, W, c8, c2, C8p, C2p, stream()),
+              "t2v_attention_bwd_large")
+        return dtheta, dphi, dg
     check(lib().t2v_attention_bwd(ptr(theta), ptr(phi), ptr(g), ptr(dout), ptr(dtheta), ptr(dphi), ptr(dg), N, D, H, W,
                                   c8, c2, C8p, C2p, stream()), "t2v_attention_bwd")
     return dtheta, dphi, dg
+
+
+def attention_is_large(D, H, W):
+    """pooled keys of a map beyond the one-CTA backward kernel (2 * Kp > 512)"""
+    return 2 * D * (H // 2) * (W // 2) > 512
+
+
+def attention_fused_ok(D, H, W, c8, c2):
+    """shapes the fused generator-attention kernels take: any map of <= 1024 voxels with c8 <= 8, c2 <= 16; larger maps
+    (up to 2560 pooled keys: shared memory) in the compile-time configuration c8 = 4, c2 = 16"""
+    if c8 > 8 or c2 > 16:
+        return False
+    if D * H * W <= 1024:
+        return True
+    return c8 == 4 and c2 == 16 and D * (H // 2) * (W // 2) <= 2560
 
 
 # ------------------------------------------------------------------------------------- render / index

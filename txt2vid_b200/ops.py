@@ -1394,14 +1394,15 @@ def nonlocal_block(x, w_theta, w_phi, w_g, w_o, gamma, pool=(1, 2, 2), fused=Fal
     """SA-GAN / non-local block (models/layers.py:23-36 2-D, :52-68 3-D) on a CL tensor.
 
     The four 1x1(x1) convs run on the tcgen05 engine (channel counts < 16 are zero-padded).  The attention core is the
-    fused kernel pair t2v_attention_fwd / _bwd where it applies (the generator's block: first-order autograd, bf16
-    storage, c8 <= 8, <= 1024 positions) and the differentiable primitive composition of attention_core otherwise (the
-    discriminator's block, which the gradient penalty differentiates twice; large maps; fp32 storage)."""
+    fused kernel pair t2v_attention_fwd / _bwd (_bwd_large) where it applies (the generator's block: first-order
+    autograd, bf16 storage, kernels.attention_fused_ok: up to 64 x 64 maps in its c8 = 4 / c2 = 16 configuration) and the
+    differentiable primitive composition of attention_core otherwise (the discriminator's block, which the gradient
+    penalty differentiates twice; fp32 storage)."""
     N, D, H, W, C = x.shape
     c8, c2 = w_theta.shape[0], w_g.shape[0]
     assert tuple(pool) == (1, 2, 2) and H % 2 == 0 and W % 2 == 0
     theta, phi, g = conv(x, w_theta), conv(x, w_phi), conv(x, w_g)
-    if fused and x.dtype == BF16 and c8 <= 8 and c2 <= 16 and D * H * W <= 1024:   # kernels' shared-memory bound
+    if fused and x.dtype == BF16 and K.attention_fused_ok(D, H, W, c8, c2):        # kernels' shared-memory bound
         o = AttentionCoreF.apply(theta, phi, g, c8, c2)
     else:
         o = attention_core(theta, phi, g, c8, c2)
