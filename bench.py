@@ -351,7 +351,7 @@ def run_b200(args):
     step_resident(1)                                              # eager warm-ups (graph mode: then capture)
     l1 = lib.t2v_launch_count()
     launches_per_step = int(l1 - l0) // 2
-    for i in range(2, max(3, args.warmup)):
+    for i in range(2, max(5, args.warmup)):
         step_resident(i)
     torch.cuda.synchronize()
     clocks = ClockSampler(dist.local_rank)
@@ -488,7 +488,7 @@ def run_b200(args):
         c = cpu_baseline(steps=2, warmup=1, batch=args.cpu_batch)
         cpu = {k: c[k] for k in ("value", "unit", "cores", "kind", "sample")}
     line = {"metric": "TGANv2-cond G+D train videos/sec", "value": value, "unit": "videos/s", "n_gpus": world,
-            "steps": args.steps, "warmup": max(3, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
+            "steps": args.steps, "warmup": max(5, args.warmup), "ms_per_step": t_res / args.steps * 1e3,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16", "data": "synthetic",
             "config": {"workload": workload, "batch_per_gpu": b, "global_batch": world * b,
                        "parallelism": "dp%d" % world, "launch": launch_mode,
