@@ -516,7 +516,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=10)
-    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference", "torch_cuda"])
     ap.add_argument("--batch", type=int, default=4096, help="videos per GPU per step (multiple of 8)")
     ap.add_argument("--res", type=int, default=64, choices=[64, 128],
