@@ -633,3 +633,91 @@ def embedding_bwd(tokens, dout, V):
     dw = torch.zeros((V, dout.shape[-1]))
     dw.index_add_(0, tokens.reshape(-1), dout.float().reshape(-1, dout.shape[-1]))
     return dw
+
+
+# ---- executable spec of csrc/s2d.cu (stride-2 layers as dense kernel-2 convolutions over shifted blocks) -----------
+def _s2d_phases(modes):
+    return 2 ** sum(1 for m in modes if m == 2)
+
+
+def s2d_shift(x, modes, creal=None):
+    """(N,D,H,W,C) -> (N,D',H',W',round16(P*creal)): block b of a strided axis = samples (2b-1, 2b), zero outside"""
+    N, D, H, W, C = x.shape
+    creal = C if creal is None else creal
+    xr = x[..., :creal]
+    pads = []
+    for m in reversed(modes):
+        pads += [1, 1] if m == 2 else [0, 0]
+    xr = F.pad(xr, [0, 0] + pads)
+    f = [2 if m == 2 else 1 for m in modes]
+    Db, Hb, Wb = xr.shape[1] // f[0], xr.shape[2] // f[1], xr.shape[3] // f[2]
+    xr = xr.reshape(N, Db, f[0], Hb, f[1], Wb, f[2], creal).permute(0, 1, 3, 5, 2, 4, 6, 7)
+    xr = xr.reshape(N, Db, Hb, Wb, f[0] * f[1] * f[2] * creal)
+    Cp = (xr.shape[-1] + 15) // 16 * 16
+    return F.pad(xr, [0, Cp - xr.shape[-1]]).contiguous()
+
+
+def d2s_shift(xs, modes, sp, C, creal=None):
+    """inverse of s2d_shift (channels >= creal zero)"""
+    N = xs.shape[0]
+    creal = C if creal is None else creal
+    f = [2 if m == 2 else 1 for m in modes]
+    Db, Hb, Wb = xs.shape[1:4]
+    t = xs[..., :f[0] * f[1] * f[2] * creal].reshape(N, Db, Hb, Wb, f[0], f[1], f[2], creal)
+    t = t.permute(0, 1, 4, 2, 5, 3, 6, 7).reshape(N, Db * f[0], Hb * f[1], Wb * f[2], creal)
+    sl = [slice(1, 1 + e) if m == 2 else slice(0, e) for m, e in zip(modes, sp)]
+    t = t[:, sl[0], sl[1], sl[2]]
+    return F.pad(t, [0, C - creal]).contiguous()
+
+
+def s2d_embed_weight(w, modes, creal=None, transposed=False):
+    """w (Co, k taps, Ci), k = 4 per strided axis -> (Co, 3^s, Cp): engine tap t = block offset j + 1, channel =
+    phase * creal + c with kernel index 2 j + phase per axis; transposed: (Cp, 3^s reversed, Co)"""
+    Co, taps, Ci = w.shape
+    creal = Ci if creal is None else creal
+    kk = [4 if m == 2 else 1 for m in modes]
+    ke = [3 if m == 2 else 1 for m in modes]
+    P = _s2d_phases(modes)
+    Cp = (P * creal + 15) // 16 * 16
+    w6 = w.reshape(Co, kk[0], kk[1], kk[2], Ci)
+    we = torch.zeros((Co, ke[0], ke[1], ke[2], Cp), dtype=w.dtype, device=w.device)
+    rng = [(0, 1) if m == 2 else (0,) for m in modes]
+    for jd in rng[0]:
+        for jh in rng[1]:
+            for jw in rng[2]:
+                for pd in rng[0]:
+                    for ph in rng[1]:
+                        for pw in rng[2]:
+                            phase = 0
+                            for m, pp in zip(modes, (pd, ph, pw)):
+                                if m == 2:
+                                    phase = phase * 2 + pp
+                            td, th, tw = [j + 1 if m == 2 else 0 for m, j in zip(modes, (jd, jh, jw))]
+                            ad, ah, aw = [2 * j + pp if m == 2 else 0 for m, j, pp in zip(modes, (jd, jh, jw), (pd, ph, pw))]
+                            we[:, td, th, tw, phase * creal:(phase + 1) * creal] = w6[:, ad, ah, aw, :creal]
+    we = we.reshape(Co, ke[0] * ke[1] * ke[2], Cp)
+    if transposed:
+        we = we.flip(1).permute(2, 1, 0).contiguous()
+    return we
+
+
+def s2d_extract_wgrad(dwe, modes, Ci, creal=None):
+    """(Co, 3^s, Cp) -> (Co, k taps, Ci): the adjoint gather of s2d_embed_weight"""
+    Co, ntap, Cp = dwe.shape
+    creal = Ci if creal is None else creal
+    kk = [4 if m == 2 else 1 for m in modes]
+    ke = [3 if m == 2 else 1 for m in modes]
+    d5 = dwe.reshape(Co, ke[0], ke[1], ke[2], Cp)
+    dw = torch.zeros((Co, kk[0], kk[1], kk[2], Ci), dtype=dwe.dtype, device=dwe.device)
+    for ad in range(kk[0]):
+        for ah in range(kk[1]):
+            for aw in range(kk[2]):
+                phase, t = 0, []
+                for m, a in zip(modes, (ad, ah, aw)):
+                    if m == 2:
+                        phase = phase * 2 + (a & 1)
+                        t.append(a // 2 + 1)
+                    else:
+                        t.append(0)
+                dw[:, ad, ah, aw, :creal] = d5[:, t[0], t[1], t[2], phase * creal:(phase + 1) * creal]
+    return dw.reshape(Co, kk[0] * kk[1] * kk[2], Ci)
