@@ -48,8 +48,29 @@ def _worker(rank, world, port, out):
     bts = [hostrng.EagerDraws().bt(2) for _ in range(7)]
     perm = hostrng.EagerDraws().perm(8, "cpu").tolist()
     assert ctx.last_bucket_bytes == 4 * (sum(p.numel() for p in params[:-1]) + 6 * 4)
+    # ---- the helpers of the multi-rank CLI path (txt2vid/train/gan.py under torchrun)
+    # replicas that were initialised differently start from rank 0's weights and buffers
+    torch.manual_seed(500 + rank)
+    net = torch.nn.Sequential(torch.nn.Conv2d(3, 4, 3), torch.nn.BatchNorm2d(4))
+    net[1].running_mean.add_(float(rank + 1))
+    ctx.broadcast_module(net)
+    ctx.broadcast_module(None)
+    state = [t.detach().clone() for t in list(net.parameters()) + list(net.buffers())]
+    # per-rank random streams with a SHARED torch CPU generator (frame offsets), after seed_ranks
+    ctx.seed_ranks(77)
+    import random
+    shared, own_np, own_py = float(torch.rand(())), float(np.random.rand()), random.random()
+    # every rank iterates its own stride of the batches, equal counts (7 batches, world 2 -> 3 each)
+    mine = list(ctx.shard(list(range(7))))
+    assert len(ctx.shard(list(range(7)))) == 3 and ctx.is_main == (rank == 0)
+    # summed (multi-scale) penalties are rescaled for gradient averaging, batch-mean penalties are not
+    ms, plain = type("MS", (), {"sub_discrims": [1]})(), object()
+    lam = (ctx.gp_lambda_for(0.5, [ms]), ctx.gp_lambda_for(0.5, [plain]), ctx.gp_lambda_for(0.5, [ms, plain]),
+           ctx.gp_lambda_for(-1.0, [ms]))
+    assert lam == (0.5 * world, 0.5, 0.5, -1.0), lam
     out[rank] = {"local": local, "reduced": [p.grad.clone() for p in params], "bts": bts, "perm": perm,
-                 "strides": [p.grad.stride() for p in params]}
+                 "strides": [p.grad.stride() for p in params], "state": state, "shared": shared, "own": (own_np, own_py),
+                 "mine": mine}
     torch.distributed.barrier()
     torch.distributed.destroy_process_group()
 
@@ -73,4 +94,8 @@ def test_reduce_grads_world2():
             assert torch.equal(m0[:, :, keep], a[:, :, keep]) and torch.equal(m1[:, :, keep], b[:, :, keep])
     assert r0["bts"] == r1["bts"]
     assert r0["perm"] != r1["perm"]
+    assert all(torch.equal(a, b) for a, b in zip(r0["state"], r1["state"]))           # broadcast_module
+    assert float(r1["state"][-3].mean()) == 1.0                                        # ... rank 0's running_mean (0 + 1), not rank 1's (2)
+    assert r0["shared"] == r1["shared"] and r0["own"][0] != r1["own"][0] and r0["own"][1] != r1["own"][1]
+    assert r0["mine"] == [0, 2, 4] and r1["mine"] == [1, 3, 5]                          # shard: strided, truncated
     assert r0["strides"][0] == r1["strides"][0] and r0["strides"][0][1] == 1      # layout preserved (channels-last)
